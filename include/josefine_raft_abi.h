@@ -1,0 +1,329 @@
+/*
+ * josefine_raft_abi.h -- C ABI of the B200 batched Chained-Raft engine.
+ *
+ * This is the drop-in boundary for josefine's Raft step path.  Every entry
+ * point names the reference interface it stands in for (paths are relative to
+ * the reference checkout, tychedelia/josefine @ 28b42c9):
+ *
+ *   jr_engine_create   <- RaftHandle::new                 src/raft/mod.rs:428-435
+ *                         (Raft::<Follower>::new          src/raft/follower.rs:68-91,
+ *                          Chain::new                     src/raft/chain.rs:117-137)
+ *   jr_step            <- Apply::apply(self, Command)     src/raft/mod.rs:483-489,471-479
+ *                         as called by event_loop         src/raft/server.rs:125,133,135,143,159
+ *   jr_step outputs    <- rpc_tx.send(Message)            src/raft/mod.rs:390-400
+ *                         fsm_tx.send(Instruction)        src/raft/leader.rs:94,184; follower.rs:205
+ *   jr_run             <- N consecutive event_loop turns with no host traffic (Tick + peer mail)
+ *   jr_query           <- pub fields id/state/role/chain  src/raft/mod.rs:326-341,437-447;
+ *                         Chain::get_head/get_commit      src/raft/chain.rs:230-236
+ *   jr_chain_read      <- Chain::range / Chain::has       src/raft/chain.rs:155-157,208-228
+ *   jr_compact         <- Chain::compact                  src/raft/chain.rs:239-253
+ *   jr_leader_table    <- Leader::write_state             src/raft/leader.rs:101-121
+ *   jr_set_alive       <- process death (no reference API; a node that stops calling apply)
+ *
+ * One engine = G independent Raft groups x R replicas, all resident in one GPU's
+ * HBM.  The reference is one group, one node per process; the group dimension is
+ * new.  Role is a field here, not a type (reference: RaftHandle enum,
+ * mod.rs:417-424).
+ *
+ * Declared deviations from the reference ("Deviations"):
+ *   D1  time: `now` is an explicit u64 input in milliseconds instead of
+ *       Instant::now() (mod.rs:354; follower.rs:112,141; leader.rs:79,83).
+ *   D2  randomness: election timeouts come from a counter-based generator keyed
+ *       (seed, group, node, draw#) (jr_election_timeout below) instead of
+ *       rand::thread_rng (follower.rs:103-108).
+ *   D3  panics / Err returns of the reference become a sticky per-replica
+ *       fault code (JR_FAULT_*); a faulted replica stops like a dead process.
+ *   D4  node ids are 1..65535 (reference: any non-zero u32, config.rs:64);
+ *       block ids must be < chain_capacity (reference: any u64).
+ *   D5  Block.data (Vec<u8>) is represented on the device by a 64-bit token the
+ *       host maps to the payload bytes; ClientRequest.id (Uuid) likewise.
+ *   D6  the sled "commit" key shares the block keyspace in the reference
+ *       (chain.rs:198), so an unbounded Chain::range that runs past the last
+ *       block hits it and panics in bincode (chain.rs:222-226).  That is
+ *       reproduced only when JR_F_SLED_COMMIT_KEY_STRICT is set; by default the
+ *       block map holds blocks only.
+ *
+ * All structs are plain data, little endian, naturally aligned.  No callbacks.
+ * Buffers passed to jr_step are HOST memory owned by the caller.
+ */
+#ifndef JOSEFINE_RAFT_ABI_H
+#define JOSEFINE_RAFT_ABI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JR_ABI_VERSION 1u
+
+/* ---- limits ------------------------------------------------------------ */
+#define JR_MAX_REPLICAS 8u        /* R <= 8 (reference configs use 3, 5, 7)         */
+#define JR_MAX_AE_BLOCKS 5u       /* MAX_INFLIGHT, src/raft/progress.rs:117          */
+#define JR_MAX_NODE_ID 65535u     /* deviation D4                                    */
+#define JR_CLIENT_QUEUE_CAP 4u    /* queued_reqs bound per replica (reference: Vec)  */
+
+/* ---- status codes (API misuse / resources; never consensus outcomes) ---- */
+typedef enum jr_status {
+  JR_OK = 0,
+  JR_E_INVAL = 1,        /* bad argument / config (RaftConfig::validate, config.rs:60-84) */
+  JR_E_NOMEM = 2,
+  JR_E_CUDA = 3,         /* CUDA runtime error; jr_last_error() has the text            */
+  JR_E_CAPACITY = 4,     /* caller output buffer too small; n_* hold the needed counts  */
+  JR_E_UNKNOWN_NODE = 5, /* message addressed to / naming a node outside the group     */
+  JR_E_NO_DEVICE = 6     /* no CUDA device: there is NO CPU fallback in this library   */
+} jr_status;
+
+/* ---- roles (RaftRole, src/raft/mod.rs:403-407) --------------------------- */
+enum { JR_ROLE_FOLLOWER = 0, JR_ROLE_CANDIDATE = 1, JR_ROLE_LEADER = 2 };
+
+/* ---- Command discriminants, in the order of `enum Command` (mod.rs:160-227) */
+enum {
+  JR_CMD_TICK = 0,
+  JR_CMD_PROPOSE = 1,            /* unused by the reference state machine */
+  JR_CMD_VOTE_REQUEST = 2,
+  JR_CMD_VOTE_RESPONSE = 3,
+  JR_CMD_APPEND_ENTRIES = 4,
+  JR_CMD_APPEND_RESPONSE = 5,
+  JR_CMD_HEARTBEAT = 6,
+  JR_CMD_HEARTBEAT_RESPONSE = 7,
+  JR_CMD_TIMEOUT = 8,
+  JR_CMD_NOOP = 9,
+  JR_CMD_CLIENT_REQUEST = 10,
+  JR_CMD_CLIENT_RESPONSE = 11
+};
+
+/* ---- Address (src/raft/rpc.rs:5-14) ------------------------------------- */
+enum { JR_ADDR_PEERS = 0, JR_ADDR_PEER = 1, JR_ADDR_LOCAL = 2, JR_ADDR_CLIENT = 3 };
+
+/* ---- sticky per-replica fault codes (deviation D3) ------------------------
+ * 1..31: one per reference panic!/assert!/unimplemented!/Err site on the path. */
+enum {
+  JR_FAULT_NONE = 0,
+  JR_FAULT_AE_STALE_LEADER = 1,       /* assert!, follower.rs:149-153                        */
+  JR_FAULT_EXTEND_PARENT_MISSING = 2, /* Err from Chain::extend chain.rs:180-185 via follower.rs:159 `?` */
+  JR_FAULT_APPEND_ID_NOT_GT_HEAD = 3, /* assert!(id > self.head), chain.rs:163               */
+  JR_FAULT_COMMIT_BLOCK_MISSING = 4,  /* panic!(""), chain.rs:200-202                        */
+  JR_FAULT_PROGRESS_UNKNOWN_NODE = 5, /* expect("the node does not exist"), progress.rs:43   */
+  JR_FAULT_LEADER_TERM_UNIMPLEMENTED = 6, /* unimplemented!(), leader.rs:33-35 via leader.rs:203 */
+  JR_FAULT_CANDIDATE_TICK_ELECTED = 7,/* panic!("this should never happen"), candidate.rs:63 */
+  JR_FAULT_RANGE_COMMIT_KEY = 8,      /* bincode panic on the "commit" key, chain.rs:222-226 (D6) */
+  /* 64..: engine limits, not reference behaviour */
+  JR_FAULT_ENGINE_CHAIN_CAPACITY = 64,   /* block id >= chain_capacity                       */
+  JR_FAULT_ENGINE_MAILBOX_OVERFLOW = 65, /* a replica emitted more than mailbox_units units  */
+  JR_FAULT_ENGINE_FSM_OVERFLOW = 66,     /* more than fsm_units instructions in one launch   */
+  JR_FAULT_ENGINE_QUEUE_OVERFLOW = 67    /* more than JR_CLIENT_QUEUE_CAP queued requests    */
+};
+
+/* ---- engine flags ---------------------------------------------------------- */
+enum {
+  JR_F_SLED_COMMIT_KEY_STRICT = 1u << 0, /* deviation D6 off: reproduce the commit-key panic */
+  JR_F_CAPTURE_MESSAGES = 1u << 1,       /* jr_step may return every emitted Message (rpc_rx) */
+  JR_F_CAPTURE_FSM = 1u << 2             /* jr_step may return every Instruction (fsm_rx)     */
+};
+
+/* ---- configuration (RaftConfig, src/raft/config.rs:14-41, batched) --------- */
+typedef struct jr_config {
+  uint32_t abi_version;        /* JR_ABI_VERSION                                         */
+  uint32_t n_groups;           /* G, groups resident in this engine                      */
+  uint32_t n_replicas;         /* R; node ids of every group are 1..R (config.rs:64: !=0) */
+  int32_t  device;             /* CUDA device ordinal                                    */
+  uint64_t seed;               /* D2                                                     */
+  uint64_t group_offset;       /* global id of local group 0 (sharding keeps D2 stable)  */
+  uint32_t election_min_ms;    /* State::min_election_timeout, mod.rs:318 (500)          */
+  uint32_t election_max_ms;    /* State::max_election_timeout, mod.rs:319 (1000)         */
+  uint32_t heartbeat_ms;       /* RaftConfig::heartbeat_timeout, config.rs:104 (100)     */
+  uint32_t chain_capacity;     /* blocks per replica block table (D4)                    */
+  uint32_t mailbox_units;      /* 16-byte units one replica may emit per step            */
+  uint32_t fsm_units;          /* Instructions one replica may emit per launch           */
+  uint32_t flags;              /* JR_F_*                                                 */
+  uint32_t reserved;
+} jr_config;
+
+/* Block (src/raft/chain.rs:86-91); `data` is the payload token (D5). */
+typedef struct jr_block {
+  uint64_t id;
+  uint64_t next;
+  uint64_t data;
+} jr_block;
+
+/*
+ * Message{from,to,command} (src/raft/rpc.rs:17-21) with Command flattened.
+ * Field use per command (all others zero):
+ *   VOTE_REQUEST       term, node_id=candidate_id, last_term, block=head
+ *   VOTE_RESPONSE      term, node_id=from, flag=granted
+ *   APPEND_ENTRIES     term, node_id=leader_id, n_blocks, blocks[]
+ *   APPEND_RESPONSE    node_id, term, block=head, flag=success
+ *   HEARTBEAT          term, block=commit, node_id=leader_id
+ *   HEARTBEAT_RESPONSE block=commit, flag=has_committed
+ *   CLIENT_REQUEST     token=request/payload token (D5), client_kind/client_id=address
+ *   CLIENT_RESPONSE    token
+ *   TICK, TIMEOUT, NOOP, PROPOSE: no fields
+ */
+typedef struct jr_msg {
+  uint32_t group;
+  uint8_t  from_kind;   /* JR_ADDR_* */
+  uint8_t  to_kind;
+  uint8_t  kind;        /* JR_CMD_*  */
+  uint8_t  flag;
+  uint32_t from_id;
+  uint32_t to_id;
+  uint32_t node_id;
+  uint8_t  n_blocks;
+  uint8_t  client_kind;
+  uint16_t reserved;
+  uint32_t client_id;
+  uint32_t reserved2;
+  uint64_t term;
+  uint64_t last_term;
+  uint64_t block;
+  uint64_t token;
+  jr_block blocks[JR_MAX_AE_BLOCKS];
+} jr_msg;
+
+/* Instruction (src/raft/fsm.rs:19-29). */
+enum { JR_FSM_APPLY = 0, JR_FSM_NOTIFY = 1 };
+typedef struct jr_fsm_instr {
+  uint32_t group;
+  uint32_t node;        /* the replica whose fsm_tx this was sent on */
+  uint8_t  kind;        /* JR_FSM_*                                   */
+  uint8_t  client_kind; /* Notify.client_address                      */
+  uint16_t reserved;
+  uint32_t client_id;
+  jr_block block;       /* Apply: the Block; Notify: block.id = block_id, block.data = request token */
+} jr_fsm_instr;
+
+/* One dense client proposal per group: ClientRequest applied to `node` (0 = none).
+ * Reference: event_loop client arm, src/raft/server.rs:156-160. */
+typedef struct jr_proposal {
+  uint64_t token;
+  uint32_t node;
+  uint32_t reserved;
+} jr_proposal;
+
+/* jr_step flags */
+enum {
+  JR_STEP_DELIVER = 1u << 0,  /* apply peer mail emitted in the previous step        */
+  JR_STEP_TICK = 1u << 1,     /* then apply Command::Tick on every replica           */
+  JR_STEP_SYNTH_PROPOSALS = 1u << 2 /* every current Leader receives n_synth ClientRequests */
+};
+
+/*
+ * Per replica and step, commands are applied in this fixed order (our synthetic
+ * schedule; the reference's is arrival order off tokio channels):
+ *   1. JR_STEP_DELIVER: peer mail of the previous step, ascending sender id,
+ *      FIFO per sender (only mail addressed to Peers or to this node);
+ *   2. `inject[]` entries addressed to this replica, in array order;
+ *   3. the dense `proposals[group]` entry if it names this node, then the
+ *      synthetic proposals;
+ *   4. JR_STEP_TICK: Command::Tick.
+ * Mail of the previous step that is not delivered is dropped.
+ */
+typedef struct jr_step_args {
+  uint64_t now_ms;               /* D1 */
+  uint32_t flags;                /* JR_STEP_* */
+  uint32_t n_synth;              /* proposals per leader per step with JR_STEP_SYNTH_PROPOSALS */
+  const jr_msg* inject;          /* host; to_kind must be JR_ADDR_PEER and to_id in 1..R */
+  size_t n_inject;
+  const jr_proposal* proposals;  /* host; NULL or n_groups entries */
+  /* outputs (host).  NULL/0 to skip.  With capture flags off these must be NULL. */
+  jr_msg* out_msgs;
+  size_t cap_msgs;
+  size_t n_msgs;                 /* out: messages emitted this step, group-major, sender asc, FIFO */
+  jr_fsm_instr* out_fsm;
+  size_t cap_fsm;
+  size_t n_fsm;                  /* out: instructions, group-major, node asc, FIFO */
+} jr_step_args;
+
+/* Introspection: Raft<T> pub fields (mod.rs:326-341) + role state. */
+typedef struct jr_replica_state {
+  uint64_t current_term;      /* State.current_term, mod.rs:276            */
+  uint32_t voted_for;         /* State.voted_for, 0 = None                 */
+  uint32_t leader_id;         /* Follower.leader_id, 0 = None              */
+  uint64_t election_time_ms;  /* State.election_time (D1)                  */
+  uint32_t election_timeout_ms;
+  uint32_t rng_draws;
+  uint64_t head;              /* Chain.head                                */
+  uint64_t commit;            /* Chain.commit                              */
+  uint64_t id_gen;            /* Chain.id_gen                              */
+  uint64_t max_key;           /* largest block id present                  */
+  uint64_t heartbeat_time_ms; /* Leader.heartbeat_time                     */
+  uint32_t votes_seen;        /* Election.votes keys, bit (id-1)           */
+  uint32_t votes_granted;     /* Election.votes == true, bit (id-1)        */
+  uint64_t progress_head[JR_MAX_REPLICAS]; /* ReplicationProgress heads, index id-1 */
+  uint32_t progress_replicate;/* bit (id-1): NodeProgress::Replicate (else Probe) */
+  uint8_t  role;              /* JR_ROLE_*                                 */
+  uint8_t  fault;             /* JR_FAULT_*                                */
+  uint8_t  alive;
+  uint8_t  n_queued;          /* queued_reqs.len()                         */
+} jr_replica_state;
+
+/* Leader::write_state record (leader.rs:103-107), one per group. */
+typedef struct jr_leader_entry {
+  uint64_t term;
+  uint32_t leader_id;   /* 0 = the group has no live leader */
+  uint32_t commit;
+} jr_leader_entry;
+
+typedef struct jr_engine jr_engine;
+
+/* ---- lifecycle ------------------------------------------------------------- */
+jr_status jr_engine_create(const jr_config* cfg, jr_engine** out);
+void      jr_engine_destroy(jr_engine* e);
+/* Run all engine work on `cuda_stream` (a cudaStream_t); NULL = the engine's own. */
+jr_status jr_engine_set_stream(jr_engine* e, void* cuda_stream);
+jr_status jr_engine_sync(jr_engine* e);
+const char* jr_last_error(void);
+/* Fills the defaults the reference uses (500/1000/100 ms) and engine sizing. */
+void      jr_config_default(jr_config* cfg, uint32_t n_groups, uint32_t n_replicas);
+
+/* ---- stepping -------------------------------------------------------------- */
+jr_status jr_step(jr_engine* e, jr_step_args* args);
+/*
+ * n_steps fused steps with no host traffic: step k uses now = now0 + k*dt_ms and
+ * flags DELIVER|TICK (+SYNTH_PROPOSALS when n_synth > 0).  Asynchronous on the
+ * engine stream.  Equivalent to n_steps jr_step calls, bit for bit.
+ */
+jr_status jr_run(jr_engine* e, uint64_t now0_ms, uint32_t dt_ms, uint32_t n_steps, uint32_t n_synth);
+/* Drop and return the Instructions accumulated by jr_run (same order as jr_step). */
+jr_status jr_drain_fsm(jr_engine* e, jr_fsm_instr* out, size_t cap, size_t* n);
+
+/* ---- introspection --------------------------------------------------------- */
+jr_status jr_query(jr_engine* e, uint32_t group, uint32_t node, jr_replica_state* out);
+/* blocks with first_id <= id < first_id+n of one replica; present[i]=0 if absent. */
+jr_status jr_chain_read(jr_engine* e, uint32_t group, uint32_t node, uint64_t first_id,
+                        uint32_t n, jr_block* out, uint8_t* present);
+/* order-independent digest of all replica state + block tables, computed on the device */
+jr_status jr_state_digest(jr_engine* e, uint64_t* out);
+/* cumulative digests of every Message / Instruction emitted so far (order sensitive per replica) */
+jr_status jr_stream_digest(jr_engine* e, uint64_t* msg_digest, uint64_t* fsm_digest,
+                           uint64_t* n_msgs, uint64_t* n_fsm);
+jr_status jr_fault_count(jr_engine* e, uint64_t* n_faulted);
+
+/* ---- maintenance ----------------------------------------------------------- */
+jr_status jr_compact(jr_engine* e);                                    /* every replica */
+jr_status jr_set_alive(jr_engine* e, uint32_t group, uint32_t node, int alive);
+/* Silence the current leader of every group g with hash(seed,g,salt) % 1000 < permille. */
+jr_status jr_kill_leaders(jr_engine* e, uint64_t salt, uint32_t permille, uint64_t* n_killed);
+
+/* ---- leader announce ------------------------------------------------------- */
+/* Writes n_groups entries to DEVICE memory `dev_out` (for a collective) */
+jr_status jr_leader_table_device(jr_engine* e, void* dev_out);
+/* ... or to HOST memory. */
+jr_status jr_leader_table(jr_engine* e, jr_leader_entry* host_out);
+
+/* ---- deviation D2, normative ------------------------------------------------
+ * draw-th election timeout of (group, node):
+ *   x = mix(mix(mix(seed ^ 0x6a09e667f3bcc908) + group) + ((uint64)node << 32 | draw))
+ *   timeout = min + (((x >> 32) * (max - min)) >> 32)
+ * mix = splitmix64 finaliser: x += 0x9e3779b97f4a7c15; x = (x ^ x>>30) * 0xbf58476d1ce4e5b9;
+ *       x = (x ^ x>>27) * 0x94d049bb133111eb; x ^= x>>31.
+ */
+uint32_t jr_election_timeout(uint64_t seed, uint64_t group, uint32_t node, uint32_t draw,
+                             uint32_t min_ms, uint32_t max_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JOSEFINE_RAFT_ABI_H */
