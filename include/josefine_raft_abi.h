@@ -33,7 +33,7 @@
  *       rand::thread_rng (follower.rs:103-108).
  *   D3  panics / Err returns of the reference become a sticky per-replica
  *       fault code (JR_FAULT_*); a faulted replica stops like a dead process.
- *   D4  node ids are 1..65535 (reference: any non-zero u32, config.rs:64);
+ *   D4  node ids are 1..65534 (reference: any non-zero u32, config.rs:64);
  *       block ids must be < chain_capacity (reference: any u64).
  *   D5  Block.data (Vec<u8>) is represented on the device by a 64-bit token the
  *       host maps to the payload bytes; ClientRequest.id (Uuid) likewise.
@@ -61,7 +61,7 @@ extern "C" {
 /* ---- limits ------------------------------------------------------------ */
 #define JR_MAX_REPLICAS 8u        /* R <= 8 (reference configs use 3, 5, 7)         */
 #define JR_MAX_AE_BLOCKS 5u       /* MAX_INFLIGHT, src/raft/progress.rs:117          */
-#define JR_MAX_NODE_ID 65535u     /* deviation D4                                    */
+#define JR_MAX_NODE_ID 65534u     /* deviation D4                                    */
 #define JR_CLIENT_QUEUE_CAP 4u    /* queued_reqs bound per replica (reference: Vec)  */
 
 /* ---- status codes (API misuse / resources; never consensus outcomes) ---- */
@@ -120,7 +120,8 @@ enum {
 enum {
   JR_F_SLED_COMMIT_KEY_STRICT = 1u << 0, /* deviation D6 off: reproduce the commit-key panic */
   JR_F_CAPTURE_MESSAGES = 1u << 1,       /* jr_step may return every emitted Message (rpc_rx) */
-  JR_F_CAPTURE_FSM = 1u << 2             /* jr_step may return every Instruction (fsm_rx)     */
+  JR_F_CAPTURE_FSM = 1u << 2,            /* Instructions are stored (jr_step / jr_drain_fsm)  */
+  JR_F_STREAM_DIGEST = 1u << 3           /* keep the running digests jr_stream_digest returns  */
 };
 
 /* ---- configuration (RaftConfig, src/raft/config.rs:14-41, batched) --------- */

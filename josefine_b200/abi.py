@@ -10,7 +10,7 @@ import ctypes as C
 ABI_VERSION = 1
 MAX_REPLICAS = 8
 MAX_AE_BLOCKS = 5
-MAX_NODE_ID = 65535
+MAX_NODE_ID = 65534
 CLIENT_QUEUE_CAP = 4
 
 # jr_status
@@ -48,6 +48,7 @@ FAULT_ENGINE_QUEUE_OVERFLOW = 67
 F_SLED_COMMIT_KEY_STRICT = 1 << 0
 F_CAPTURE_MESSAGES = 1 << 1
 F_CAPTURE_FSM = 1 << 2
+F_STREAM_DIGEST = 1 << 3
 
 # step flags
 STEP_DELIVER = 1 << 0

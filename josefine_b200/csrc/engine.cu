@@ -1,0 +1,869 @@
+// engine.cu -- kernels + C ABI of the B200 batched Chained-Raft engine.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a (see __graft_entry__.build).
+// No CPU fallback: without a CUDA device jr_engine_create returns JR_E_NO_DEVICE.
+//
+// Reference interfaces replaced are cited in include/josefine_raft_abi.h; the
+// replica state machine is in raft_device.cuh.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "raft_device.cuh"
+
+using namespace jr;
+
+// ============================================================================
+// kernels
+// ============================================================================
+
+// One jr_step phase set for every replica.  CTA = 32 groups x R warps.
+template <int R>
+__global__ void __launch_bounds__(32 * R) step_kernel(const Dev d, const StepParams p) {
+  const uint32_t r = threadIdx.x >> 5;
+  const uint32_t g = blockIdx.x * GROUPS_PER_CTA + (threadIdx.x & 31u);
+  if (g >= d.G) return;
+  Replica<R> rep(d, r, g);
+  rep.now = p.now;
+  rep.cur = p.cur;
+  rep.load(p.phases & PH_RESET_OUT, p.phases & PH_RESET_FSM);
+  rep.run_step(p);
+  rep.store();
+}
+
+// Host-injected commands: one thread per distinct target replica, commands in
+// array order.  targets[i] = {group, replica index, first, count}.
+template <int R>
+__global__ void inject_kernel(const Dev d, const StepParams p, const jr_msg* msgs, const uint4* targets,
+                              uint32_t n_targets) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_targets) return;
+  const uint4 t = targets[i];
+  Replica<R> rep(d, t.y, t.x);
+  rep.now = p.now;
+  rep.cur = p.cur;
+  rep.load(false, false);
+  for (uint32_t k = 0; k < t.w; ++k) {
+    const jr_msg* m = msgs + t.z + k;
+    Cmd c;
+    c.kind = m->kind; c.flag = m->flag ? 1u : 0u; c.node_id = m->node_id; c.block = (uint32_t)m->block;
+    c.nblk = m->n_blocks; c.addr = ((uint32_t)m->client_kind << 16) | (m->client_id & 0xffffu);
+    c.term = m->term; c.last_term = m->last_term; c.token = m->token;
+    c.blk_units = nullptr; c.blk_stride = 0; c.host_msg = m;
+    rep.apply(c);
+  }
+  rep.store();
+}
+
+// RaftHandle::new for every replica (mod.rs:428-435; follower.rs:68-95; chain.rs:117-153).
+__global__ void init_kernel(const Dev d) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t plane = (size_t)d.R * d.Gp;
+  if (i >= plane) return;
+  const uint32_t r = (uint32_t)(i / d.Gp), g = (uint32_t)(i % d.Gp);
+  const uint32_t timeout = election_timeout_draw(d.seed, d.goff + g, r + 1, 0, d.emin, d.emax);
+  d.p0[i] = make_uint4(0, 0, 0, 0);
+  d.p1[i] = make_uint4(0, 0, timeout, 1);                 // init(): first draw, election_time = 0
+  d.p2[i] = make_uint4(0, 0, 1, JR_ROLE_FOLLOWER);        // head 0, commit 0, id_gen 1
+  d.p3[i] = make_uint4(0, 0, 0, 0);
+  d.mk[i] = 0;
+  d.cnext[i] = 0;                                         // genesis block 0 -> 0 (chain.rs:139-153)
+  d.ctok[i] = 0;
+  d.oc[0][i] = 0;
+  d.oc[1][i] = 0;
+  d.fc[i] = 0;
+  const uint64_t tag = mix64(((d.goff + g) << 8) | (r + 1));
+  d.dg[i] = make_uint4((uint32_t)tag, (uint32_t)(tag >> 32), (uint32_t)tag, (uint32_t)(tag >> 32));
+  d.cn[i] = make_uint2(0, 0);
+}
+
+// Chain::compact for every live replica (chain.rs:239-253).
+__global__ void compact_kernel(const Dev d) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t plane = (size_t)d.R * d.Gp;
+  if (i >= plane || (uint32_t)(i % d.Gp) >= d.G) return;
+  const uint4 c = d.p2[i];
+  const uint32_t meta = c.w;
+  if (((meta >> 8) & 255u) != 0 || ((meta >> 27) & 1u)) return;  // faulted or dead
+  bool have = false;
+  uint32_t expect = 0;
+  for (uint32_t b = c.y; b-- > 0;) {  // ids in [0, commit), descending
+    const uint32_t nx = d.cnext[(size_t)b * plane + i];
+    if (nx == ABSENT) continue;
+    if (have && b != expect) d.cnext[(size_t)b * plane + i] = ABSENT;
+    expect = nx;  // even for a removed block
+    have = true;
+  }
+}
+
+// Adds every thread's v into *out (one atomic per CTA on the device).
+__device__ inline void block_add(unsigned long long* out, uint64_t v, uint64_t* smem) {
+#ifdef JR_EMU
+  (void)smem;
+  atomicAdd(out, (unsigned long long)v);
+#else
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    uint64_t t = threadIdx.x < (blockDim.x >> 5) ? smem[threadIdx.x] : 0;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) atomicAdd(out, (unsigned long long)t);
+  }
+  __syncthreads();
+#endif
+}
+
+// Normative state digest (DESIGN.md "Digests"); must equal jro_state_digest.
+__global__ void state_digest_kernel(const Dev d, unsigned long long* out) {
+  __shared__ uint64_t sm[32];
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t plane = (size_t)d.R * d.Gp;
+  uint64_t h = 0;
+  if (i < plane && (uint32_t)(i % d.Gp) < d.G) {
+    const uint32_t r = (uint32_t)(i / d.Gp), g = (uint32_t)(i % d.Gp);
+    const uint4 a = d.p0[i], b = d.p1[i], c = d.p2[i];
+    const uint32_t role = c.w & 255u, fault = (c.w >> 8) & 255u, prmask = (c.w >> 16) & 255u;
+    const uint32_t nq = (c.w >> 24) & 7u, dead = (c.w >> 27) & 1u;
+    h = mix64(0x243f6a8885a308d3ull ^ (((d.goff + g) << 8) | (r + 1)));
+    h = fold(h, (uint64_t)a.x | ((uint64_t)a.y << 32));
+    h = fold(h, a.z);
+    h = fold(h, (uint64_t)role | ((uint64_t)fault << 8) | ((uint64_t)(dead ? 0 : 1) << 16) | ((uint64_t)nq << 24));
+    h = fold(h, (uint64_t)b.x | ((uint64_t)b.y << 32));
+    h = fold(h, (uint64_t)b.z | ((uint64_t)b.w << 32));
+    h = fold(h, c.x);
+    h = fold(h, c.y);
+    h = fold(h, c.z);
+    if (role == JR_ROLE_FOLLOWER) h = fold(h, a.w);
+    if (role == JR_ROLE_CANDIDATE) {
+      const uint4 e = d.p3[i];
+      h = fold(h, (uint64_t)e.z | ((uint64_t)e.w << 32));
+    }
+    if (role == JR_ROLE_LEADER) {
+      const uint4 e = d.p3[i];
+      h = fold(h, (uint64_t)e.x | ((uint64_t)e.y << 32));
+      for (uint32_t k = 0; k < d.R; ++k) {
+        const uint4 v = d.pr[(size_t)(k / 4) * plane + i];
+        const uint32_t ph = (k & 3) == 0 ? v.x : (k & 3) == 1 ? v.y : (k & 3) == 2 ? v.z : v.w;
+        h = fold(h, ph);
+      }
+      h = fold(h, prmask);
+    }
+    for (uint32_t q = 0; q < nq; ++q) {
+      const uint4 e = d.qt[(size_t)q * plane + i];
+      h = fold(h, (uint64_t)e.x | ((uint64_t)e.y << 32));
+      h = fold(h, (uint64_t)(e.z >> 16) | ((uint64_t)(e.z & 0xffffu) << 8));
+    }
+    uint64_t chain = 0;
+    const uint32_t mk = d.mk[i];
+    for (uint32_t bid = 0; bid <= mk; ++bid) {
+      const uint32_t nx = d.cnext[(size_t)bid * plane + i];
+      if (nx == ABSENT) continue;
+      const uint64_t tok = d.ctok[(size_t)bid * plane + i];
+      chain += mix64(mix64((uint64_t)bid + 0x13198a2e03707344ull) ^ ((uint64_t)nx * 0xa4093822299f31d1ull) ^ tok);
+    }
+    h = fold(h, chain);
+  }
+  block_add(out, h, sm);
+}
+
+// out[0..3] = sum msg digest, sum fsm digest, n msgs, n fsm; out[4] = faulted replicas
+__global__ void stream_digest_kernel(const Dev d, unsigned long long* out) {
+  __shared__ uint64_t sm[32];
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t plane = (size_t)d.R * d.Gp;
+  uint64_t a = 0, b = 0, x = 0, y = 0, f = 0;
+  if (i < plane && (uint32_t)(i % d.Gp) < d.G) {
+    const uint4 v = d.dg[i];
+    const uint2 n = d.cn[i];
+    a = (uint64_t)v.x | ((uint64_t)v.y << 32);
+    b = (uint64_t)v.z | ((uint64_t)v.w << 32);
+    x = n.x;
+    y = n.y;
+    f = ((d.p2[i].w >> 8) & 255u) != 0;
+  }
+  block_add(out + 0, a, sm);
+  block_add(out + 1, b, sm);
+  block_add(out + 2, x, sm);
+  block_add(out + 3, y, sm);
+  block_add(out + 4, f, sm);
+}
+
+// Leader::write_state (leader.rs:101-121) for every group: the live leader with
+// the highest (term, id).  One thread per group.
+__global__ void leader_table_kernel(const Dev d, jr_leader_entry* out) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= d.G) return;
+  jr_leader_entry e{0, 0, 0};
+  for (uint32_t r = 0; r < d.R; ++r) {
+    const size_t i = (size_t)r * d.Gp + g;
+    const uint4 c = d.p2[i];
+    const uint32_t role = c.w & 255u, fault = (c.w >> 8) & 255u, dead = (c.w >> 27) & 1u;
+    if (role != JR_ROLE_LEADER || fault || dead) continue;
+    const uint4 a = d.p0[i];
+    const uint64_t term = (uint64_t)a.x | ((uint64_t)a.y << 32);
+    if (e.leader_id == 0 || term >= e.term) {
+      e.term = term;
+      e.leader_id = r + 1;
+      e.commit = c.y;
+    }
+  }
+  out[g] = e;
+}
+
+__global__ void kill_leaders_kernel(const Dev d, uint64_t base, uint32_t permille, unsigned long long* n_killed) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= d.G) return;
+  if (mix64(base + d.goff + g) % 1000 >= permille) return;
+  for (uint32_t r = 0; r < d.R; ++r) {
+    const size_t i = (size_t)r * d.Gp + g;
+    const uint32_t m = d.p2[i].w;
+    if ((m & 255u) == JR_ROLE_LEADER && ((m >> 8) & 255u) == 0 && ((m >> 27) & 1u) == 0) {
+      d.p2[i].w = m | (1u << 27);
+      atomicAdd(n_killed, 1ull);
+    }
+  }
+}
+
+__global__ void set_alive_kernel(const Dev d, uint32_t g, uint32_t r, int alive) {
+  const size_t i = (size_t)r * d.Gp + g;
+  uint32_t m = d.p2[i].w;
+  d.p2[i].w = alive ? (m & ~(1u << 27)) : (m | (1u << 27));
+}
+
+__global__ void query_kernel(const Dev d, uint32_t g, uint32_t r, jr_replica_state* o) {
+  const size_t plane = (size_t)d.R * d.Gp;
+  const size_t i = (size_t)r * d.Gp + g;
+  const uint4 a = d.p0[i], b = d.p1[i], c = d.p2[i], e = d.p3[i];
+  jr_replica_state s;
+  memset(&s, 0, sizeof s);
+  s.current_term = (uint64_t)a.x | ((uint64_t)a.y << 32);
+  s.voted_for = a.z;
+  s.role = c.w & 255u;
+  s.leader_id = s.role == JR_ROLE_FOLLOWER ? a.w : 0;
+  s.election_time_ms = (uint64_t)b.x | ((uint64_t)b.y << 32);
+  s.election_timeout_ms = b.z;
+  s.rng_draws = b.w;
+  s.head = c.x;
+  s.commit = c.y;
+  s.id_gen = c.z;
+  s.max_key = d.mk[i];
+  s.fault = (c.w >> 8) & 255u;
+  s.alive = ((c.w >> 27) & 1u) ? 0 : 1;
+  s.n_queued = (c.w >> 24) & 7u;
+  if (s.role == JR_ROLE_LEADER) {
+    s.heartbeat_time_ms = (uint64_t)e.x | ((uint64_t)e.y << 32);
+    s.progress_replicate = (c.w >> 16) & 255u;
+    for (uint32_t k = 0; k < d.R; ++k) {
+      const uint4 v = d.pr[(size_t)(k / 4) * plane + i];
+      s.progress_head[k] = (k & 3) == 0 ? v.x : (k & 3) == 1 ? v.y : (k & 3) == 2 ? v.z : v.w;
+    }
+  }
+  if (s.role == JR_ROLE_CANDIDATE) {
+    s.votes_seen = e.z;
+    s.votes_granted = e.w;
+  }
+  *o = s;
+}
+
+__global__ void chain_read_kernel(const Dev d, uint32_t g, uint32_t r, uint32_t first, uint32_t n, jr_block* out,
+                                  uint8_t* present) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const size_t plane = (size_t)d.R * d.Gp;
+  const size_t i = (size_t)r * d.Gp + g;
+  const uint64_t bid = (uint64_t)first + k;
+  uint32_t nx = ABSENT;
+  if (bid < d.cap) nx = d.cnext[(size_t)bid * plane + i];
+  present[k] = nx != ABSENT;
+  out[k] = jr_block{bid, nx != ABSENT ? nx : 0ull, nx != ABSENT ? d.ctok[(size_t)bid * plane + i] : 0ull};
+}
+
+__global__ void max_u32_kernel(const uint32_t* v, size_t n, uint32_t* out) {
+  uint32_t m = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    m = max(m, v[i]);
+#ifndef JR_EMU
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0)
+#endif
+    atomicMax(out, m);
+}
+
+// ============================================================================
+// host side
+// ============================================================================
+
+static thread_local char g_err[512] = "";
+static void set_err(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+#define CK(call)                                                                      \
+  do {                                                                                \
+    cudaError_t _e = (call);                                                          \
+    if (_e != cudaSuccess) {                                                          \
+      set_err("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e));     \
+      return JR_E_CUDA;                                                               \
+    }                                                                                 \
+  } while (0)
+
+struct jr_engine {
+  jr_config cfg;
+  Dev d;
+  cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
+  int cur = 0;               // outbox index the NEXT step writes
+  uint64_t step_index = 0;
+  std::vector<void*> allocs;
+  // scratch
+  unsigned long long* scratch = nullptr;  // 8 x u64 (device)
+  jr_replica_state* q_state = nullptr;    // device
+  jr_msg* inj_msgs = nullptr;             // device, grows
+  uint4* inj_targets = nullptr;
+  size_t inj_cap = 0;
+  jr_proposal* prop = nullptr;            // device, G entries
+  jr_leader_entry* leaders = nullptr;     // device, G entries
+  jr_block* cr_blocks = nullptr;          // device scratch for chain_read
+  uint8_t* cr_present = nullptr;
+  uint32_t cr_cap = 0;
+};
+
+template <typename T>
+static jr_status dalloc(jr_engine* e, T** p, size_t n) {
+  void* q = nullptr;
+  cudaError_t err = cudaMalloc(&q, n * sizeof(T));
+  if (err != cudaSuccess) {
+    set_err("cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(err));
+    return err == cudaErrorMemoryAllocation ? JR_E_NOMEM : JR_E_CUDA;
+  }
+  e->allocs.push_back(q);
+  *p = (T*)q;
+  return JR_OK;
+}
+
+#define DISPATCH_R(R_, CALL)           \
+  switch (R_) {                        \
+    case 1: { constexpr int RR = 1; CALL; } break; \
+    case 2: { constexpr int RR = 2; CALL; } break; \
+    case 3: { constexpr int RR = 3; CALL; } break; \
+    case 4: { constexpr int RR = 4; CALL; } break; \
+    case 5: { constexpr int RR = 5; CALL; } break; \
+    case 6: { constexpr int RR = 6; CALL; } break; \
+    case 7: { constexpr int RR = 7; CALL; } break; \
+    default: { constexpr int RR = 8; CALL; } break; \
+  }
+
+static jr_status launch_step(jr_engine* e, const StepParams& p) {
+  const uint32_t grid = e->d.Gp / GROUPS_PER_CTA;
+  DISPATCH_R(e->cfg.n_replicas, (JR_LAUNCH(step_kernel<RR>, grid, 32 * RR, e->stream, e->d, p)));
+  CK(cudaGetLastError());
+  return JR_OK;
+}
+
+extern "C" {
+
+const char* jr_last_error(void) { return g_err; }
+
+void jr_config_default(jr_config* cfg, uint32_t n_groups, uint32_t n_replicas) {
+  if (!cfg) return;
+  memset(cfg, 0, sizeof *cfg);
+  cfg->abi_version = JR_ABI_VERSION;
+  cfg->n_groups = n_groups;
+  cfg->n_replicas = n_replicas;
+  cfg->election_min_ms = 500;   // mod.rs:318
+  cfg->election_max_ms = 1000;  // mod.rs:319
+  cfg->heartbeat_ms = 100;      // config.rs:104
+  cfg->chain_capacity = 4096;
+  cfg->mailbox_units = 64;
+  cfg->fsm_units = 64;
+}
+
+uint32_t jr_election_timeout(uint64_t seed, uint64_t group, uint32_t node, uint32_t draw, uint32_t mn,
+                             uint32_t mx) {
+  return election_timeout_draw(seed, group, node, draw, mn, mx);
+}
+
+jr_status jr_engine_create(const jr_config* cfg, jr_engine** out) {
+  if (!cfg || !out) return JR_E_INVAL;
+  // RaftConfig::validate analogue (config.rs:60-84)
+  if (cfg->abi_version != JR_ABI_VERSION) { set_err("abi_version mismatch"); return JR_E_INVAL; }
+  if (cfg->n_replicas < 1 || cfg->n_replicas > JR_MAX_REPLICAS || cfg->n_groups < 1) { set_err("bad G/R"); return JR_E_INVAL; }
+  if (cfg->election_max_ms <= cfg->election_min_ms) { set_err("empty election timeout range"); return JR_E_INVAL; }
+  if (cfg->chain_capacity < 2 || cfg->chain_capacity > 0x7fffffffu) { set_err("chain_capacity out of range"); return JR_E_INVAL; }
+  if (cfg->mailbox_units < 8 || cfg->fsm_units < 1) { set_err("mailbox_units >= 8, fsm_units >= 1"); return JR_E_INVAL; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_err("no CUDA device; this library has no CPU fallback");
+    return JR_E_NO_DEVICE;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) { set_err("device ordinal %d out of range", cfg->device); return JR_E_INVAL; }
+  CK(cudaSetDevice(cfg->device));
+  jr_engine* e = new (std::nothrow) jr_engine();
+  if (!e) return JR_E_NOMEM;
+  e->cfg = *cfg;
+  Dev& d = e->d;
+  memset(&d, 0, sizeof d);
+  d.G = cfg->n_groups;
+  d.Gp = (cfg->n_groups + GROUPS_PER_CTA - 1) / GROUPS_PER_CTA * GROUPS_PER_CTA;
+  d.R = cfg->n_replicas;
+  d.cap = cfg->chain_capacity;
+  d.U = cfg->mailbox_units;
+  d.F = cfg->fsm_units;
+  d.flags = cfg->flags;
+  d.emin = cfg->election_min_ms;
+  d.emax = cfg->election_max_ms;
+  d.hb = cfg->heartbeat_ms;
+  d.seed = cfg->seed;
+  d.goff = cfg->group_offset;
+  const size_t plane = (size_t)d.R * d.Gp;
+  jr_status st = JR_OK;
+#define A(ptr, n) if (st == JR_OK) st = dalloc(e, &(ptr), (n))
+  A(d.p0, plane); A(d.p1, plane); A(d.p2, plane); A(d.p3, plane);
+  A(d.pr, plane * ((d.R + 3) / 4));
+  A(d.mk, plane);
+  A(d.qt, plane * JR_CLIENT_QUEUE_CAP);
+  A(d.dg, plane); A(d.cn, plane);
+  A(d.cnext, plane * (size_t)d.cap);
+  A(d.ctok, plane * (size_t)d.cap);
+  A(d.ob[0], plane * (size_t)d.U); A(d.ob[1], plane * (size_t)d.U);
+  A(d.oc[0], plane); A(d.oc[1], plane);
+  A(d.fs, plane * (size_t)((d.flags & JR_F_CAPTURE_FSM) ? d.F : 1));
+  A(d.fc, plane);
+  A(e->scratch, 8);
+  A(e->q_state, 1);
+  A(e->prop, d.G);
+  A(e->leaders, d.G);
+#undef A
+  if (st != JR_OK) { jr_engine_destroy(e); return st; }
+  if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    set_err("cudaStreamCreate failed");
+    jr_engine_destroy(e);
+    return JR_E_CUDA;
+  }
+  e->stream = e->own_stream;
+  // block tables start empty (all keys absent); pr / qt zero
+  cudaMemsetAsync(d.cnext, 0xFF, plane * (size_t)d.cap * sizeof(uint32_t), e->stream);
+  cudaMemsetAsync(d.pr, 0, plane * ((d.R + 3) / 4) * sizeof(uint4), e->stream);
+  cudaMemsetAsync(d.qt, 0, plane * JR_CLIENT_QUEUE_CAP * sizeof(uint4), e->stream);
+  JR_LAUNCH(init_kernel, (unsigned)((plane + 255) / 256), 256, e->stream, d);
+  cudaError_t err = cudaStreamSynchronize(e->stream);
+  if (err != cudaSuccess) {
+    set_err("engine init: %s", cudaGetErrorString(err));
+    jr_engine_destroy(e);
+    return JR_E_CUDA;
+  }
+  *out = e;
+  return JR_OK;
+}
+
+void jr_engine_destroy(jr_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  for (void* p : e->allocs) cudaFree(p);
+  if (e->inj_msgs) cudaFree(e->inj_msgs);
+  if (e->inj_targets) cudaFree(e->inj_targets);
+  if (e->cr_blocks) cudaFree(e->cr_blocks);
+  if (e->cr_present) cudaFree(e->cr_present);
+  if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  delete e;
+}
+
+jr_status jr_engine_set_stream(jr_engine* e, void* s) {
+  if (!e) return JR_E_INVAL;
+  CK(cudaStreamSynchronize(e->stream));
+  e->stream = s ? (cudaStream_t)s : e->own_stream;
+  return JR_OK;
+}
+
+jr_status jr_engine_sync(jr_engine* e) {
+  if (!e) return JR_E_INVAL;
+  CK(cudaStreamSynchronize(e->stream));
+  return JR_OK;
+}
+
+// ---- capture: decode raw mailboxes / FIFOs on the host --------------------------------
+
+static void decode_unit(const uint4& h, uint32_t group, uint32_t sender, const uint4* blocks, size_t stride,
+                        std::vector<jr_msg>& out) {
+  const uint32_t kind = h.x & 15u, flag = (h.x >> 4) & 1u, aux = (h.x >> 8) & 255u, to = h.x >> 16;
+  jr_msg m;
+  memset(&m, 0, sizeof m);
+  m.group = group;
+  m.from_kind = JR_ADDR_PEER;
+  m.from_id = sender;
+  m.to_kind = to == TO_PEERS ? JR_ADDR_PEERS : (to == TO_CLIENT ? JR_ADDR_CLIENT : JR_ADDR_PEER);
+  m.to_id = m.to_kind == JR_ADDR_PEER ? to : 0;
+  m.kind = (uint8_t)kind;
+  const uint64_t t = (uint64_t)h.y | ((uint64_t)h.z << 32);
+  uint32_t copies = 1;
+  switch (kind) {
+    case JR_CMD_VOTE_REQUEST: m.term = t; m.node_id = sender; m.last_term = t; m.block = h.w; copies = aux; break;
+    case JR_CMD_VOTE_RESPONSE: m.term = t; m.node_id = sender; m.flag = flag; break;
+    case JR_CMD_APPEND_ENTRIES:
+      m.term = t; m.node_id = sender; m.n_blocks = (uint8_t)aux;
+      for (uint32_t k = 0; k < aux && k < JR_MAX_AE_BLOCKS; ++k) {
+        const uint4& b = blocks[(size_t)k * stride];
+        m.blocks[k] = jr_block{b.x, b.y, (uint64_t)b.z | ((uint64_t)b.w << 32)};
+      }
+      break;
+    case JR_CMD_APPEND_RESPONSE: m.node_id = sender; m.term = t; m.block = h.w; m.flag = flag; break;
+    case JR_CMD_HEARTBEAT: m.term = t; m.block = h.w; m.node_id = sender; break;
+    case JR_CMD_HEARTBEAT_RESPONSE: m.block = h.w; m.flag = flag; break;
+    case JR_CMD_CLIENT_REQUEST: m.token = t; m.client_kind = (uint8_t)(h.w >> 16); m.client_id = h.w & 0xffffu; break;
+    case JR_CMD_CLIENT_RESPONSE: m.token = t; break;
+    default: break;
+  }
+  for (uint32_t k = 0; k < copies; ++k) out.push_back(m);
+}
+
+static jr_status device_max(jr_engine* e, const uint32_t* v, size_t n, uint32_t* out) {
+  uint32_t* s = reinterpret_cast<uint32_t*>(e->scratch);
+  CK(cudaMemsetAsync(s, 0, sizeof(uint32_t), e->stream));
+  JR_LAUNCH(max_u32_kernel, 64, 256, e->stream, v, n, s);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, s, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return JR_OK;
+}
+
+static jr_status capture_messages(jr_engine* e, int buf, std::vector<jr_msg>& out) {
+  const Dev& d = e->d;
+  const size_t plane = (size_t)d.R * d.Gp;
+  uint32_t mx = 0;
+  jr_status st = device_max(e, d.oc[buf], plane, &mx);
+  if (st != JR_OK) return st;
+  std::vector<uint32_t> cnt(plane);
+  CK(cudaMemcpyAsync(cnt.data(), d.oc[buf], plane * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+  std::vector<uint4> units((size_t)mx * plane);
+  if (mx) CK(cudaMemcpyAsync(units.data(), d.ob[buf], units.size() * sizeof(uint4), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  for (uint32_t g = 0; g < d.G; ++g)
+    for (uint32_t r = 0; r < d.R; ++r) {
+      const size_t i = (size_t)r * d.Gp + g;
+      for (uint32_t u = 0; u < cnt[i];) {
+        const uint4& h = units[(size_t)u * plane + i];
+        const uint32_t kind = h.x & 15u, aux = (h.x >> 8) & 255u;
+        const uint32_t span = 1 + (kind == JR_CMD_APPEND_ENTRIES ? aux : 0u);
+        decode_unit(h, g, r + 1, span > 1 ? &units[(size_t)(u + 1) * plane + i] : nullptr, plane, out);
+        u += span;
+      }
+    }
+  return JR_OK;
+}
+
+static jr_status capture_fsm(jr_engine* e, std::vector<jr_fsm_instr>& out) {
+  const Dev& d = e->d;
+  if (!(d.flags & JR_F_CAPTURE_FSM)) return JR_OK;
+  const size_t plane = (size_t)d.R * d.Gp;
+  uint32_t mx = 0;
+  jr_status st = device_max(e, d.fc, plane, &mx);
+  if (st != JR_OK) return st;
+  std::vector<uint32_t> cnt(plane);
+  CK(cudaMemcpyAsync(cnt.data(), d.fc, plane * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+  std::vector<uint4> units((size_t)mx * plane);
+  if (mx) CK(cudaMemcpyAsync(units.data(), d.fs, units.size() * sizeof(uint4), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  for (uint32_t g = 0; g < d.G; ++g)
+    for (uint32_t r = 0; r < d.R; ++r) {
+      const size_t i = (size_t)r * d.Gp + g;
+      for (uint32_t u = 0; u < cnt[i]; ++u) {
+        const uint4& v = units[(size_t)u * plane + i];
+        jr_fsm_instr f;
+        memset(&f, 0, sizeof f);
+        f.group = g;
+        f.node = r + 1;
+        const uint64_t tok = (uint64_t)v.z | ((uint64_t)v.w << 32);
+        if (v.x & 0x80000000u) {
+          f.kind = JR_FSM_NOTIFY;
+          f.client_kind = (uint8_t)(v.y >> 16);
+          f.client_id = v.y & 0xffffu;
+          f.block = jr_block{v.x & 0x7fffffffu, 0, tok};
+        } else {
+          f.kind = JR_FSM_APPLY;
+          f.block = jr_block{v.x, v.y, tok};
+        }
+        out.push_back(f);
+      }
+    }
+  return JR_OK;
+}
+
+// ---- jr_step ------------------------------------------------------------------------------
+
+jr_status jr_step(jr_engine* e, jr_step_args* a) {
+  if (!e || !a) return JR_E_INVAL;
+  CK(cudaSetDevice(e->cfg.device));
+  const Dev& d = e->d;
+  const uint32_t R = d.R, G = d.G;
+  if (a->n_synth > 8) { set_err("n_synth <= 8"); return JR_E_INVAL; }
+  if ((a->out_msgs && !(d.flags & JR_F_CAPTURE_MESSAGES)) || (a->out_fsm && !(d.flags & JR_F_CAPTURE_FSM))) {
+    set_err("output buffer given but capture flag not set at create");
+    return JR_E_INVAL;
+  }
+  // ---- validate + bucket injected commands by target, stable
+  std::vector<jr_msg> sorted;
+  std::vector<uint4> targets;
+  if (a->n_inject) {
+    if (!a->inject) return JR_E_INVAL;
+    std::vector<uint32_t> order(a->n_inject);
+    for (size_t i = 0; i < a->n_inject; ++i) {
+      const jr_msg& m = a->inject[i];
+      if (m.group >= G || m.to_kind != JR_ADDR_PEER) { set_err("inject[%zu]: bad group / to_kind", i); return JR_E_INVAL; }
+      if (m.to_id < 1 || m.to_id > R) return JR_E_UNKNOWN_NODE;
+      if (m.node_id > JR_MAX_NODE_ID || m.from_id > JR_MAX_NODE_ID || m.client_id > JR_MAX_NODE_ID) return JR_E_INVAL;
+      if (m.kind == JR_CMD_VOTE_RESPONSE && (m.node_id < 1 || m.node_id > 32)) return JR_E_UNKNOWN_NODE;
+      if (m.n_blocks > JR_MAX_AE_BLOCKS) return JR_E_INVAL;
+      if (m.block >= 0xffffffffull) { set_err("inject[%zu]: block id >= 2^32-1 (D4)", i); return JR_E_INVAL; }
+      for (unsigned k = 0; k < m.n_blocks; ++k)
+        if (m.blocks[k].id >= 0xffffffffull || m.blocks[k].next >= 0xffffffffull) return JR_E_INVAL;
+      order[i] = (uint32_t)i;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+      const jr_msg &p = a->inject[x], &q = a->inject[y];
+      return p.group != q.group ? p.group < q.group : p.to_id < q.to_id;
+    });
+    sorted.reserve(a->n_inject);
+    for (uint32_t idx : order) {
+      const jr_msg& m = a->inject[idx];
+      if (targets.empty() || targets.back().x != m.group || targets.back().y != m.to_id - 1)
+        targets.push_back(make_uint4(m.group, m.to_id - 1, (uint32_t)sorted.size(), 0));
+      targets.back().w++;
+      sorted.push_back(m);
+    }
+  }
+  if (a->proposals)
+    for (uint32_t g = 0; g < G; ++g)
+      if (a->proposals[g].node > R) return JR_E_UNKNOWN_NODE;
+
+  StepParams p;
+  p.now = a->now_ms;
+  p.step_index = e->step_index;
+  p.n_synth = (a->flags & JR_STEP_SYNTH_PROPOSALS) ? a->n_synth : 0;
+  p.cur = e->cur;
+  p.proposals = nullptr;
+  if (a->proposals) {
+    CK(cudaMemcpyAsync(e->prop, a->proposals, (size_t)G * sizeof(jr_proposal), cudaMemcpyHostToDevice, e->stream));
+    p.proposals = e->prop;
+  }
+  const uint32_t ph_first = PH_RESET_OUT | PH_RESET_FSM | ((a->flags & JR_STEP_DELIVER) ? PH_DRAIN : 0u);
+  const uint32_t ph_last = ((p.proposals || p.n_synth) ? PH_PROPOSE : 0u) | ((a->flags & JR_STEP_TICK) ? PH_TICK : 0u);
+  jr_status st;
+  if (targets.empty()) {
+    p.phases = ph_first | ph_last;
+    if ((st = launch_step(e, p)) != JR_OK) return st;
+  } else {
+    if (sorted.size() > e->inj_cap) {
+      if (e->inj_msgs) cudaFree(e->inj_msgs);
+      if (e->inj_targets) cudaFree(e->inj_targets);
+      e->inj_msgs = nullptr; e->inj_targets = nullptr;
+      e->inj_cap = std::max<size_t>(sorted.size() * 2, 64);
+      CK(cudaMalloc(&e->inj_msgs, e->inj_cap * sizeof(jr_msg)));
+      CK(cudaMalloc(&e->inj_targets, e->inj_cap * sizeof(uint4)));
+    }
+    CK(cudaMemcpyAsync(e->inj_msgs, sorted.data(), sorted.size() * sizeof(jr_msg), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->inj_targets, targets.data(), targets.size() * sizeof(uint4), cudaMemcpyHostToDevice, e->stream));
+    p.phases = ph_first;
+    if ((st = launch_step(e, p)) != JR_OK) return st;
+    const uint32_t nt = (uint32_t)targets.size();
+    DISPATCH_R(R, (JR_LAUNCH(inject_kernel<RR>, (nt + 63) / 64, 64, e->stream, e->d, p, e->inj_msgs, e->inj_targets, nt)));
+    CK(cudaGetLastError());
+    if (ph_last) {
+      p.phases = ph_last;
+      if ((st = launch_step(e, p)) != JR_OK) return st;
+    }
+    CK(cudaStreamSynchronize(e->stream));  // `sorted` / `targets` are stack-owned host buffers
+  }
+  const int written = e->cur;
+  e->cur ^= 1;
+  e->step_index++;
+
+  // ---- capture (synchronises)
+  a->n_msgs = 0;
+  a->n_fsm = 0;
+  bool ovf = false;
+  if (a->out_msgs) {
+    std::vector<jr_msg> msgs;
+    if ((st = capture_messages(e, written, msgs)) != JR_OK) return st;
+    a->n_msgs = msgs.size();
+    memcpy(a->out_msgs, msgs.data(), std::min(msgs.size(), a->cap_msgs) * sizeof(jr_msg));
+    ovf |= msgs.size() > a->cap_msgs;
+  }
+  if (a->out_fsm) {
+    std::vector<jr_fsm_instr> fsm;
+    if ((st = capture_fsm(e, fsm)) != JR_OK) return st;
+    a->n_fsm = fsm.size();
+    memcpy(a->out_fsm, fsm.data(), std::min(fsm.size(), a->cap_fsm) * sizeof(jr_fsm_instr));
+    ovf |= fsm.size() > a->cap_fsm;
+  }
+  return ovf ? JR_E_CAPACITY : JR_OK;
+}
+
+jr_status jr_run(jr_engine* e, uint64_t now0, uint32_t dt, uint32_t n_steps, uint32_t n_synth) {
+  if (!e) return JR_E_INVAL;
+  if (n_synth > 8) { set_err("n_synth <= 8"); return JR_E_INVAL; }
+  CK(cudaSetDevice(e->cfg.device));
+  for (uint32_t k = 0; k < n_steps; ++k) {
+    StepParams p;
+    p.now = now0 + (uint64_t)k * dt;
+    p.step_index = e->step_index;
+    p.n_synth = n_synth;
+    p.cur = e->cur;
+    p.proposals = nullptr;
+    p.phases = PH_RESET_OUT | (k == 0 ? PH_RESET_FSM : 0u) | PH_DRAIN | (n_synth ? PH_PROPOSE : 0u) | PH_TICK;
+    jr_status st = launch_step(e, p);
+    if (st != JR_OK) return st;
+    e->cur ^= 1;
+    e->step_index++;
+  }
+  return JR_OK;
+}
+
+jr_status jr_drain_fsm(jr_engine* e, jr_fsm_instr* out, size_t cap, size_t* n) {
+  if (!e || !n) return JR_E_INVAL;
+  CK(cudaSetDevice(e->cfg.device));
+  std::vector<jr_fsm_instr> fsm;
+  jr_status st = capture_fsm(e, fsm);
+  if (st != JR_OK) return st;
+  *n = fsm.size();
+  if (out) memcpy(out, fsm.data(), std::min(fsm.size(), cap) * sizeof(jr_fsm_instr));
+  return (out && fsm.size() > cap) ? JR_E_CAPACITY : JR_OK;
+}
+
+// ---- introspection ----------------------------------------------------------------------------
+
+jr_status jr_query(jr_engine* e, uint32_t group, uint32_t node, jr_replica_state* out) {
+  if (!e || !out || group >= e->d.G || node < 1 || node > e->d.R) return JR_E_INVAL;
+  CK(cudaSetDevice(e->cfg.device));
+  JR_LAUNCH(query_kernel, 1, 1, e->stream, e->d, group, node - 1, e->q_state);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, e->q_state, sizeof *out, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return JR_OK;
+}
+
+jr_status jr_chain_read(jr_engine* e, uint32_t group, uint32_t node, uint64_t first, uint32_t n, jr_block* out,
+                        uint8_t* present) {
+  if (!e || group >= e->d.G || node < 1 || node > e->d.R) return JR_E_INVAL;
+  if (n == 0) return JR_OK;
+  if (first + n > 0xffffffffull) return JR_E_INVAL;
+  CK(cudaSetDevice(e->cfg.device));
+  if (n > e->cr_cap) {
+    if (e->cr_blocks) cudaFree(e->cr_blocks);
+    if (e->cr_present) cudaFree(e->cr_present);
+    e->cr_blocks = nullptr; e->cr_present = nullptr;
+    e->cr_cap = std::max(n, 256u);
+    CK(cudaMalloc(&e->cr_blocks, (size_t)e->cr_cap * sizeof(jr_block)));
+    CK(cudaMalloc(&e->cr_present, e->cr_cap));
+  }
+  JR_LAUNCH(chain_read_kernel, (n + 127) / 128, 128, e->stream, e->d, group, node - 1, (uint32_t)first, n, e->cr_blocks,
+                                                            e->cr_present);
+  CK(cudaGetLastError());
+  if (out) CK(cudaMemcpyAsync(out, e->cr_blocks, (size_t)n * sizeof(jr_block), cudaMemcpyDeviceToHost, e->stream));
+  if (present) CK(cudaMemcpyAsync(present, e->cr_present, n, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return JR_OK;
+}
+
+jr_status jr_state_digest(jr_engine* e, uint64_t* out) {
+  if (!e || !out) return JR_E_INVAL;
+  CK(cudaSetDevice(e->cfg.device));
+  const size_t plane = (size_t)e->d.R * e->d.Gp;
+  CK(cudaMemsetAsync(e->scratch, 0, 8 * sizeof(unsigned long long), e->stream));
+  JR_LAUNCH(state_digest_kernel, (unsigned)((plane + 255) / 256), 256, e->stream, e->d, e->scratch);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, e->scratch, sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return JR_OK;
+}
+
+static jr_status stream_sums(jr_engine* e, uint64_t v[5]) {
+  CK(cudaSetDevice(e->cfg.device));
+  const size_t plane = (size_t)e->d.R * e->d.Gp;
+  CK(cudaMemsetAsync(e->scratch, 0, 8 * sizeof(unsigned long long), e->stream));
+  JR_LAUNCH(stream_digest_kernel, (unsigned)((plane + 255) / 256), 256, e->stream, e->d, e->scratch);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(v, e->scratch, 5 * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return JR_OK;
+}
+
+jr_status jr_stream_digest(jr_engine* e, uint64_t* md, uint64_t* fd, uint64_t* nm, uint64_t* nf) {
+  if (!e) return JR_E_INVAL;
+  if (!(e->d.flags & JR_F_STREAM_DIGEST)) { set_err("engine created without JR_F_STREAM_DIGEST"); return JR_E_INVAL; }
+  uint64_t v[5];
+  jr_status st = stream_sums(e, v);
+  if (st != JR_OK) return st;
+  if (md) *md = v[0];
+  if (fd) *fd = v[1];
+  if (nm) *nm = v[2];
+  if (nf) *nf = v[3];
+  return JR_OK;
+}
+
+jr_status jr_fault_count(jr_engine* e, uint64_t* n) {
+  if (!e || !n) return JR_E_INVAL;
+  uint64_t v[5];
+  jr_status st = stream_sums(e, v);
+  if (st != JR_OK) return st;
+  *n = v[4];
+  return JR_OK;
+}
+
+// ---- maintenance ------------------------------------------------------------------------------
+
+jr_status jr_compact(jr_engine* e) {
+  if (!e) return JR_E_INVAL;
+  CK(cudaSetDevice(e->cfg.device));
+  const size_t plane = (size_t)e->d.R * e->d.Gp;
+  JR_LAUNCH(compact_kernel, (unsigned)((plane + 127) / 128), 128, e->stream, e->d);
+  CK(cudaGetLastError());
+  return JR_OK;
+}
+
+jr_status jr_set_alive(jr_engine* e, uint32_t group, uint32_t node, int alive) {
+  if (!e || group >= e->d.G || node < 1 || node > e->d.R) return JR_E_INVAL;
+  CK(cudaSetDevice(e->cfg.device));
+  JR_LAUNCH(set_alive_kernel, 1, 1, e->stream, e->d, group, node - 1, alive);
+  CK(cudaGetLastError());
+  return JR_OK;
+}
+
+jr_status jr_kill_leaders(jr_engine* e, uint64_t salt, uint32_t permille, uint64_t* n_killed) {
+  if (!e) return JR_E_INVAL;
+  CK(cudaSetDevice(e->cfg.device));
+  CK(cudaMemsetAsync(e->scratch, 0, sizeof(unsigned long long), e->stream));
+  JR_LAUNCH(kill_leaders_kernel, (e->d.G + 127) / 128, 128, e->stream, e->d, mix64(e->d.seed ^ salt), permille, e->scratch);
+  CK(cudaGetLastError());
+  uint64_t k = 0;
+  CK(cudaMemcpyAsync(&k, e->scratch, sizeof k, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  if (n_killed) *n_killed = k;
+  return JR_OK;
+}
+
+jr_status jr_leader_table_device(jr_engine* e, void* dev_out) {
+  if (!e || !dev_out) return JR_E_INVAL;
+  CK(cudaSetDevice(e->cfg.device));
+  JR_LAUNCH(leader_table_kernel, (e->d.G + 127) / 128, 128, e->stream, e->d, (jr_leader_entry*)dev_out);
+  CK(cudaGetLastError());
+  return JR_OK;
+}
+
+jr_status jr_leader_table(jr_engine* e, jr_leader_entry* host_out) {
+  if (!e || !host_out) return JR_E_INVAL;
+  jr_status st = jr_leader_table_device(e, e->leaders);
+  if (st != JR_OK) return st;
+  CK(cudaMemcpyAsync(host_out, e->leaders, (size_t)e->d.G * sizeof(jr_leader_entry), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return JR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,744 @@
+// raft_device.cuh -- device-side Chained-Raft replica state machine (sm_100a).
+//
+// One lane owns one replica.  A CTA is GROUPS_PER_CTA(=32) consecutive groups x R
+// replicas; warp w holds replica index w of those 32 groups, so every state
+// plane [replica][group] is read with one coalesced 128-bit load per lane and a
+// warp normally executes ONE role's code path (all leaders or all followers).
+//
+// Behaviour follows josefine src/raft (file:line cited per function, paths
+// relative to the reference).  Data layout and control structure are ours.
+#pragma once
+#include <stdint.h>
+
+#include "jr_cuda.h"
+
+#include "../../include/josefine_raft_abi.h"
+
+namespace jr {
+
+constexpr uint32_t ABSENT = 0xFFFFFFFFu;     // block table: no such key
+constexpr uint32_t TO_PEERS = 0u;            // Address::Peers
+constexpr uint32_t TO_CLIENT = 0xFFFFu;      // Address::Client
+constexpr uint32_t GROUPS_PER_CTA = 32;
+
+// phases of one dense launch
+enum : uint32_t {
+  PH_RESET_OUT = 1u << 0,  // start a new outbox (count = 0)
+  PH_RESET_FSM = 1u << 1,  // start a new Instruction FIFO
+  PH_DRAIN = 1u << 2,      // apply peer mail of the previous step
+  PH_PROPOSE = 1u << 3,    // dense + synthetic proposals
+  PH_TICK = 1u << 4,       // Command::Tick
+  PH_DROP_PREV = 1u << 5   // previous outbox is discarded (no DELIVER)
+};
+
+// Mailbox unit (16 B): x = kind[0:4) | flag[4] | aux[8:16) | to[16:32); y,z = term / token; w = block id.
+// AppendEntries: header (aux = n_blocks) followed by n_blocks block units {id, next, token}.
+__host__ __device__ inline uint32_t unit_hdr(uint32_t kind, uint32_t flag, uint32_t aux, uint32_t to) {
+  return (kind & 15u) | ((flag & 1u) << 4) | ((aux & 255u) << 8) | (to << 16);
+}
+
+struct Dev {
+  uint4 *p0, *p1, *p2, *p3, *pr;   // state planes, [plane][replica][group]
+  uint32_t* mk;                    // max block id present
+  uint4* qt;                       // queued client requests [q][replica][group]
+  uint4* dg;                       // stream digests {msg, fsm}
+  uint2* cn;                       // stream counts {msgs, fsm}
+  uint32_t* cnext;                 // block table: next pointer, [id][replica][group]
+  unsigned long long* ctok;        // block table: payload token
+  uint4* ob[2];                    // mailboxes [unit][replica][group], double buffered
+  uint32_t* oc[2];                 // units used per replica
+  uint4* fs;                       // Instruction FIFO [unit][replica][group]
+  uint32_t* fc;
+  uint32_t G, Gp, R, cap, U, F, flags;
+  uint32_t emin, emax, hb;
+  uint64_t seed, goff;
+};
+
+struct StepParams {
+  uint64_t now;
+  uint64_t step_index;
+  uint32_t phases;
+  uint32_t n_synth;
+  int cur;                       // outbox written this step; 1-cur is read
+  const jr_proposal* proposals;  // device, G entries or null
+};
+
+__host__ __device__ inline uint64_t mix64(uint64_t x) {
+  x += 0x9e3779b97f4a7c15ull;
+  x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+  x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+  return x ^ (x >> 31);
+}
+__host__ __device__ inline uint64_t fold(uint64_t h, uint64_t w) { return mix64(h ^ w); }
+
+// Deviation D2 (normative text in the ABI header).
+__host__ __device__ inline uint32_t election_timeout_draw(uint64_t seed, uint64_t group, uint32_t node,
+                                                          uint32_t draw, uint32_t mn, uint32_t mx) {
+  uint64_t x = mix64(seed ^ 0x6a09e667f3bcc908ull);
+  x = mix64(x + group);
+  x = mix64(x + (((uint64_t)node << 32) | draw));
+  return mn + (uint32_t)(((x >> 32) * (uint64_t)(mx - mn)) >> 32);
+}
+
+__host__ __device__ inline uint64_t synth_token(uint64_t step_index, uint32_t i, uint64_t g_global) {
+  return ((step_index * 8 + i + 1) << 32) | (g_global & 0xffffffffull);
+}
+
+// A decoded command as the handlers see it.  Blocks come either from mailbox
+// units (strided) or from a host jr_msg copied to the device.
+struct Cmd {
+  uint32_t kind, flag, node_id, block, nblk, addr;  // addr = client address kind<<16 | id
+  uint64_t term, last_term, token;
+  const uint4* blk_units;  // first block unit (mailbox) or null
+  size_t blk_stride;       // in uint4
+  const jr_msg* host_msg;  // injected command or null
+};
+
+#ifdef JR_DEVICE_CODE
+
+// Stream digest of one Message (normative: DESIGN.md "Digests").  Kept out of
+// line: it is only live with JR_F_STREAM_DIGEST and would otherwise be inlined
+// at every send site.
+__device__ __noinline__ uint64_t digest_message_fn(uint64_t h, uint32_t kind, uint32_t to, uint32_t flag,
+                                                   uint32_t nblk, uint32_t node_id, uint64_t t,
+                                                   uint64_t last_term, uint64_t block, uint64_t token,
+                                                   uint32_t addr) {
+  uint32_t to_kind = to == TO_PEERS ? JR_ADDR_PEERS : (to == TO_CLIENT ? JR_ADDR_CLIENT : JR_ADDR_PEER);
+  uint32_t to_id = to_kind == JR_ADDR_PEER ? to : 0u;
+  h = fold(h, (uint64_t)kind | ((uint64_t)to_kind << 8) | ((uint64_t)(flag & 1u) << 16) |
+                  ((uint64_t)nblk << 24) | ((uint64_t)to_id << 32));
+  h = fold(h, node_id);
+  h = fold(h, t);
+  h = fold(h, last_term);
+  h = fold(h, block);
+  h = fold(h, token);
+  h = fold(h, (uint64_t)(addr >> 16) | ((uint64_t)(addr & 0xffffu) << 8));
+  return h;
+}
+
+__device__ __noinline__ uint64_t digest_send_fn(uint64_t h, uint32_t self, uint32_t kind, uint32_t to,
+                                                uint32_t flag, uint32_t aux, uint64_t t, uint32_t w,
+                                                uint32_t* n_out) {
+  uint32_t n = 1;
+  switch (kind) {
+    case JR_CMD_VOTE_REQUEST:
+      n = aux;
+      for (uint32_t k = 0; k < aux; ++k) h = digest_message_fn(h, kind, to, 0, 0, self, t, t, w, 0, 0);
+      break;
+    case JR_CMD_VOTE_RESPONSE: h = digest_message_fn(h, kind, to, flag, 0, self, t, 0, 0, 0, 0); break;
+    case JR_CMD_APPEND_RESPONSE: h = digest_message_fn(h, kind, to, flag, 0, self, t, 0, w, 0, 0); break;
+    case JR_CMD_HEARTBEAT: h = digest_message_fn(h, kind, to, 0, 0, self, t, 0, w, 0, 0); break;
+    case JR_CMD_HEARTBEAT_RESPONSE: h = digest_message_fn(h, kind, to, flag, 0, 0, 0, 0, w, 0, 0); break;
+    case JR_CMD_CLIENT_REQUEST: h = digest_message_fn(h, kind, to, 0, 0, 0, 0, 0, 0, t, w); break;
+    default: h = digest_message_fn(h, kind, to, 0, 0, 0, 0, 0, 0, t, 0); break;  // ClientResponse
+  }
+  *n_out = n;
+  return h;
+}
+
+__device__ __noinline__ uint64_t digest_fsm_fn(uint64_t h, bool notify, uint32_t bid, uint32_t next_or_addr,
+                                               uint64_t tok) {
+  if (notify) {
+    h = fold(h, (uint64_t)JR_FSM_NOTIFY | ((uint64_t)(next_or_addr >> 16) << 8) |
+                    ((uint64_t)(next_or_addr & 0xffffu) << 32));
+    h = fold(h, bid);
+    h = fold(h, 0);
+  } else {
+    h = fold(h, (uint64_t)JR_FSM_APPLY);
+    h = fold(h, bid);
+    h = fold(h, next_or_addr);
+  }
+  return fold(h, tok);
+}
+
+template <int R>
+struct Replica {
+  const Dev& d;
+  const uint32_t r, g;   // replica index (node id - 1), local group
+  const size_t rg;       // r * Gp + g
+  const size_t plane;    // R * Gp
+  uint64_t now;
+  int cur;
+  // ---- State (mod.rs:271-287) + role state + Chain scalars (chain.rs:99-104)
+  uint64_t term, etime, hbtime;
+  uint32_t voted, leader, etimeout, draws, head, commit, idgen, maxkey;
+  uint32_t role, fault, prmask, nq, dead, ckey, seen, granted;
+  uint32_t ph[R];
+  // ---- output cursors
+  uint32_t ocnt, fcnt, nmsg, nfsm;
+  uint64_t mdig, fdig;
+
+  __device__ __forceinline__ Replica(const Dev& dv, uint32_t r_, uint32_t g_)
+      : d(dv), r(r_), g(g_), rg((size_t)r_ * dv.Gp + g_), plane((size_t)R * dv.Gp) {}
+
+  __device__ __forceinline__ uint32_t id() const { return r + 1; }
+  __device__ __forceinline__ bool live() const { return !dead && fault == 0; }
+  __device__ __forceinline__ bool digest_on() const { return d.flags & JR_F_STREAM_DIGEST; }
+
+  // ------------------------------------------------------------------ load/store
+  __device__ __forceinline__ void load(bool reset_out, bool reset_fsm) {
+    uint4 a = d.p0[rg], b = d.p1[rg], c = d.p2[rg];
+    term = (uint64_t)a.x | ((uint64_t)a.y << 32); voted = a.z; leader = a.w;
+    etime = (uint64_t)b.x | ((uint64_t)b.y << 32); etimeout = b.z; draws = b.w;
+    head = c.x; commit = c.y; idgen = c.z;
+    uint32_t m = c.w;
+    role = m & 255u; fault = (m >> 8) & 255u; prmask = (m >> 16) & 255u;
+    nq = (m >> 24) & 7u; dead = (m >> 27) & 1u; ckey = (m >> 28) & 1u;
+    maxkey = d.mk[rg];
+    hbtime = 0; seen = granted = 0;
+#pragma unroll
+    for (int i = 0; i < R; ++i) ph[i] = 0;
+    if (role != JR_ROLE_FOLLOWER) {
+      uint4 e = d.p3[rg];
+      hbtime = (uint64_t)e.x | ((uint64_t)e.y << 32); seen = e.z; granted = e.w;
+      if (role == JR_ROLE_LEADER) {
+#pragma unroll
+        for (int q = 0; q < (R + 3) / 4; ++q) {
+          uint4 v = d.pr[(size_t)q * plane + rg];
+          if (q * 4 + 0 < R) ph[q * 4 + 0] = v.x;
+          if (q * 4 + 1 < R) ph[q * 4 + 1] = v.y;
+          if (q * 4 + 2 < R) ph[q * 4 + 2] = v.z;
+          if (q * 4 + 3 < R) ph[q * 4 + 3] = v.w;
+        }
+      }
+    }
+    ocnt = reset_out ? 0u : d.oc[cur][rg];
+    fcnt = reset_fsm ? 0u : d.fc[rg];
+    mdig = fdig = 0; nmsg = nfsm = 0;
+    if (digest_on()) {
+      uint4 v = d.dg[rg];
+      mdig = (uint64_t)v.x | ((uint64_t)v.y << 32);
+      fdig = (uint64_t)v.z | ((uint64_t)v.w << 32);
+      uint2 n = d.cn[rg];
+      nmsg = n.x; nfsm = n.y;
+    }
+  }
+
+  __device__ __forceinline__ void store() {
+    d.p0[rg] = make_uint4((uint32_t)term, (uint32_t)(term >> 32), voted, leader);
+    d.p1[rg] = make_uint4((uint32_t)etime, (uint32_t)(etime >> 32), etimeout, draws);
+    uint32_t m = role | (fault << 8) | (prmask << 16) | (nq << 24) | (dead << 27) | (ckey << 28);
+    d.p2[rg] = make_uint4(head, commit, idgen, m);
+    d.mk[rg] = maxkey;
+    if (role != JR_ROLE_FOLLOWER) {
+      d.p3[rg] = make_uint4((uint32_t)hbtime, (uint32_t)(hbtime >> 32), seen, granted);
+      if (role == JR_ROLE_LEADER) {
+#pragma unroll
+        for (int q = 0; q < (R + 3) / 4; ++q) {
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if (q * 4 + 0 < R) v.x = ph[q * 4 + 0];
+          if (q * 4 + 1 < R) v.y = ph[q * 4 + 1];
+          if (q * 4 + 2 < R) v.z = ph[q * 4 + 2];
+          if (q * 4 + 3 < R) v.w = ph[q * 4 + 3];
+          d.pr[(size_t)q * plane + rg] = v;
+        }
+      }
+    }
+    d.oc[cur][rg] = ocnt;
+    d.fc[rg] = fcnt;
+    if (digest_on()) {
+      d.dg[rg] = make_uint4((uint32_t)mdig, (uint32_t)(mdig >> 32), (uint32_t)fdig, (uint32_t)(fdig >> 32));
+      d.cn[rg] = make_uint2(nmsg, nfsm);
+    }
+  }
+
+  // ------------------------------------------------------------------ block table (chain.rs)
+  __device__ __forceinline__ size_t tix(uint32_t bid) const { return (size_t)bid * plane + rg; }
+  __device__ __forceinline__ uint32_t tbl_next(uint32_t bid) const { return d.cnext[tix(bid)]; }
+  __device__ __forceinline__ uint64_t tbl_tok(uint32_t bid) const { return d.ctok[tix(bid)]; }
+  // chain.rs:155-157
+  __device__ __forceinline__ bool has(uint32_t bid) const { return bid < d.cap && tbl_next(bid) != ABSENT; }
+  __device__ __forceinline__ void tbl_put(uint32_t bid, uint32_t next, uint64_t tok) {
+    d.cnext[tix(bid)] = next;
+    d.ctok[tix(bid)] = tok;
+    if (bid > maxkey) maxkey = bid;
+  }
+  // chain.rs:160-175; returns false on fault
+  __device__ __forceinline__ bool chain_append(uint64_t tok, uint32_t& out_id) {
+    uint32_t bid = idgen++;  // fetch_add precedes the assert
+    if (!(bid > head)) { fault = JR_FAULT_APPEND_ID_NOT_GT_HEAD; return false; }
+    if (bid >= d.cap) { fault = JR_FAULT_ENGINE_CHAIN_CAPACITY; return false; }
+    tbl_put(bid, head, tok);
+    head = bid;
+    out_id = bid;
+    return true;
+  }
+  // chain.rs:178-192
+  __device__ __forceinline__ bool chain_extend(uint32_t bid, uint32_t next, uint64_t tok) {
+    if (!has(next)) { fault = JR_FAULT_EXTEND_PARENT_MISSING; return false; }
+    if (bid >= d.cap) { fault = JR_FAULT_ENGINE_CHAIN_CAPACITY; return false; }
+    tbl_put(bid, next, tok);
+    head = bid;
+    return true;
+  }
+  // chain.rs:195-205
+  __device__ __forceinline__ bool chain_commit(uint32_t bid) {
+    if (!has(bid)) { fault = JR_FAULT_COMMIT_BLOCK_MISSING; return false; }
+    ckey = 1;  // db.insert("commit", ..)
+    commit = bid;
+    return true;
+  }
+
+  // ------------------------------------------------------------------ outputs
+  __device__ __forceinline__ bool put_unit(uint32_t slot, uint4 v) {
+    if (slot >= d.U) { fault = JR_FAULT_ENGINE_MAILBOX_OVERFLOW; return false; }
+    d.ob[cur][((size_t)slot * R + r) * d.Gp + g] = v;
+    return true;
+  }
+
+  // mod.rs:390-400 for every single-unit command.
+  __device__ __forceinline__ void send(uint32_t kind, uint32_t to, uint32_t flag, uint32_t aux, uint64_t t, uint32_t w) {
+    if (!put_unit(ocnt, make_uint4(unit_hdr(kind, flag, aux, to), (uint32_t)t, (uint32_t)(t >> 32), w))) return;
+    ++ocnt;
+    if (digest_on()) {
+      uint32_t n;
+      mdig = digest_send_fn(mdig, id(), kind, to, flag, aux, t, w, &n);
+      nmsg += n;
+    }
+  }
+
+  // fsm_tx.send(Instruction) (fsm.rs:19-29)
+  __device__ __forceinline__ void fsm_emit(bool notify, uint32_t bid, uint32_t next_or_addr, uint64_t tok) {
+    if (d.flags & JR_F_CAPTURE_FSM) {
+      if (fcnt >= d.F) { fault = JR_FAULT_ENGINE_FSM_OVERFLOW; return; }
+      d.fs[((size_t)fcnt * R + r) * d.Gp + g] =
+          make_uint4(bid | (notify ? 0x80000000u : 0u), next_or_addr, (uint32_t)tok, (uint32_t)(tok >> 32));
+      ++fcnt;
+    }
+    if (digest_on()) {
+      fdig = digest_fsm_fn(fdig, notify, bid, next_or_addr, tok);
+      ++nfsm;
+    }
+  }
+
+  // ------------------------------------------------------------------ mod.rs
+  // mod.rs:352-357 (Instant::elapsed saturates)
+  __device__ __forceinline__ bool needs_election() const {
+    uint64_t el = now >= etime ? now - etime : 0;
+    return el > (uint64_t)etimeout;
+  }
+  // mod.rs:360-365 + Role::term (follower.rs:27-29, candidate.rs:161-163, leader.rs:33-35)
+  __device__ __forceinline__ bool set_term(uint64_t t) {
+    voted = 0;
+    term = t;
+    if (role == JR_ROLE_FOLLOWER) leader = 0;
+    else if (role == JR_ROLE_CANDIDATE) seen = granted = 0;
+    else { fault = JR_FAULT_LEADER_TERM_UNIMPLEMENTED; return false; }
+    return true;
+  }
+  // follower.rs:103-113 (D2)
+  __device__ __forceinline__ void set_election_timeout() {
+    etimeout = election_timeout_draw(d.seed, d.goff + g, id(), draws++, d.emin, d.emax);
+    etime = now;
+  }
+
+  // ------------------------------------------------------------------ queue (follower.rs:23, candidate.rs:20)
+  __device__ __forceinline__ bool queue_push(uint64_t tok, uint32_t addr) {
+    if (nq >= JR_CLIENT_QUEUE_CAP) { fault = JR_FAULT_ENGINE_QUEUE_OVERFLOW; return false; }
+    d.qt[(size_t)nq * plane + rg] = make_uint4((uint32_t)tok, (uint32_t)(tok >> 32), addr, 0);
+    ++nq;
+    return true;
+  }
+
+  // ------------------------------------------------------------------ election.rs
+  __device__ __forceinline__ void vote(uint32_t from, bool v) {  // election.rs:33-35, last write wins
+    uint32_t bit = 1u << ((from - 1) & 31u);
+    seen |= bit;
+    granted = v ? (granted | bit) : (granted & ~bit);
+  }
+  // election.rs:37-73: 0 Elected, 1 Voting, 2 Defeated
+  __device__ __forceinline__ int election_status() const {
+    const int q = (R == 1) ? 0 : (R / 2 + 1);
+    int votes = __popc(granted), total = __popc(seen);
+    if (votes >= q) return 0;
+    if (total - votes == q) return 2;
+    return 1;
+  }
+
+  // ------------------------------------------------------------------ progress.rs
+  __device__ __forceinline__ uint32_t get_ph(uint32_t i) const {
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < R; ++k) if (k == (int)i) v = ph[k];
+    return v;
+  }
+  // progress.rs:42-46,76-94,133-140
+  __device__ __forceinline__ bool progress_advance(uint32_t node, uint32_t bid) {
+    if (node < 1 || node > (uint32_t)R) { fault = JR_FAULT_PROGRESS_UNKNOWN_NODE; return false; }
+    uint32_t i = node - 1;
+    bool inc = false;
+#pragma unroll
+    for (int k = 0; k < R; ++k)
+      if (k == (int)i && ph[k] < bid) { ph[k] = bid; inc = true; }
+    prmask = inc ? (prmask | (1u << i)) : (prmask & ~(1u << i));  // Replicate iff incremented
+    return true;
+  }
+  // progress.rs:48-60: heads sorted descending, element [R/2]
+  __device__ __forceinline__ uint32_t committed_index() const {
+    uint32_t v[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) v[i] = ph[i];
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+#pragma unroll
+      for (int j = 0; j + 1 < R - i; ++j) {
+        uint32_t a = v[j], b = v[j + 1];
+        v[j] = max(a, b);
+        v[j + 1] = min(a, b);
+      }
+    return v[R / 2];
+  }
+
+  // ------------------------------------------------------------------ transitions
+  __device__ __forceinline__ void become_candidate() {  // follower.rs:285-304
+    seen = granted = 0;
+    nq = 0;      // Candidate { queued_reqs: Vec::new() }
+    leader = 0;
+    role = JR_ROLE_CANDIDATE;
+  }
+  __device__ __forceinline__ void candidate_to_follower() {  // candidate.rs:198-214
+    leader = 0;
+    role = JR_ROLE_FOLLOWER;
+  }
+  __device__ __forceinline__ void candidate_to_leader() {  // candidate.rs:216-238
+#pragma unroll
+    for (int i = 0; i < R; ++i) ph[i] = 0;
+    prmask = 0;
+    hbtime = now;
+    nq = 0;
+    role = JR_ROLE_LEADER;
+  }
+
+  // ------------------------------------------------------------------ follower.rs
+  __device__ __forceinline__ void cmd_block(const Cmd& c, uint32_t k, uint32_t& bid, uint32_t& next, uint64_t& tok) const {
+    if (c.host_msg) {
+      bid = (uint32_t)c.host_msg->blocks[k].id;
+      next = (uint32_t)c.host_msg->blocks[k].next;
+      tok = c.host_msg->blocks[k].data;
+    } else {
+      uint4 u = c.blk_units[(size_t)k * c.blk_stride];
+      bid = u.x; next = u.y; tok = (uint64_t)u.z | ((uint64_t)u.w << 32);
+    }
+  }
+
+  __device__ __forceinline__ void follower_append_entries(const Cmd& c) {  // follower.rs:130-176
+    uint32_t ldr = c.node_id;
+    if (voted == 0 && c.term >= term) {
+      set_term(c.term);
+      etime = now;  // timer restarted, timeout kept
+      leader = ldr;
+      voted = ldr;
+    }
+    if (voted != 0 && voted != ldr && c.term < term) { fault = JR_FAULT_AE_STALE_LEADER; return; }
+    if (c.nblk) {
+      for (uint32_t k = 0; k < c.nblk; ++k) {
+        uint32_t bid, next; uint64_t tok;
+        cmd_block(c, k, bid, next, tok);
+        if (!chain_extend(bid, next, tok)) return;  // Err -> `?` -> node stops
+      }
+      send(JR_CMD_APPEND_RESPONSE, ldr, 1, 0, term, head);
+    }
+  }
+
+  __device__ __forceinline__ void follower_heartbeat(const Cmd& c) {  // follower.rs:178-217
+    uint32_t ldr = c.node_id;
+    set_election_timeout();
+    set_term(c.term);  // unconditional
+    leader = ldr;
+    voted = ldr;
+    for (uint32_t q = 0; q < nq; ++q) {  // follower.rs:190-197
+      uint4 e = d.qt[(size_t)q * plane + rg];
+      send(JR_CMD_CLIENT_REQUEST, ldr, 0, 0, (uint64_t)e.x | ((uint64_t)e.y << 32), e.z);
+      if (fault) return;
+    }
+    nq = 0;
+    bool hasc = has(c.block);
+    if (hasc && c.block > commit) {
+      uint32_t prev = commit;
+      chain_commit(c.block);
+      for (uint32_t b = prev; b < c.block; ++b) {  // range(prev..commit), key order
+        uint32_t nx = tbl_next(b);
+        if (nx != ABSENT) { fsm_emit(false, b, nx, tbl_tok(b)); if (fault) return; }
+      }
+    }
+    send(JR_CMD_HEARTBEAT_RESPONSE, ldr, hasc ? 1 : 0, 0, 0, commit);
+  }
+
+  __device__ __forceinline__ void follower_vote_request(const Cmd& c) {  // follower.rs:97-101,219-246
+    bool can = !(voted != 0 || term > c.last_term || commit > c.block);
+    send(JR_CMD_VOTE_RESPONSE, c.node_id, can ? 1 : 0, 0, term, 0);
+    if (fault) return;
+    if (can) voted = c.node_id;
+  }
+
+  __device__ __forceinline__ void follower_client_request(uint64_t tok) {  // follower.rs:258-269
+    uint32_t addr = ((uint32_t)JR_ADDR_PEER << 16) | id();  // req.address = Peer(self.id)
+    if (leader != 0) send(JR_CMD_CLIENT_REQUEST, leader, 0, 0, tok, addr);
+    else queue_push(tok, addr);
+  }
+
+  // ------------------------------------------------------------------ candidate.rs
+  // candidate.rs:91-113.  Returns through state: may become Leader (+ heartbeat) or Follower.
+  __device__ __forceinline__ void candidate_vote_response(uint32_t from, bool g_) {
+    vote(from, g_);
+    int st = election_status();
+    if (st == 0) {  // elect(): Raft::from(self) then heartbeat()
+      candidate_to_leader();
+      heartbeat();
+    } else if (st == 2) {
+      voted = 0;
+      candidate_to_follower();
+    }
+  }
+
+  __device__ __forceinline__ void candidate_vote_request(const Cmd& c) {  // candidate.rs:71-88
+    if (c.term > term) {
+      set_term(c.term);
+      candidate_to_follower();
+      return;
+    }
+    send(JR_CMD_VOTE_RESPONSE, c.node_id, 0, 0, term, 0);
+  }
+
+  __device__ __forceinline__ void candidate_heartbeat(const Cmd& c) {  // candidate.rs:137-157
+    bool hasc = has(c.block);
+    uint32_t own = commit;
+    set_term(c.term);
+    voted = c.node_id;
+    candidate_to_follower();
+    send(JR_CMD_HEARTBEAT_RESPONSE, c.node_id, hasc ? 1 : 0, 0, 0, own);
+  }
+
+  // ------------------------------------------------------------------ leader.rs
+  __device__ __forceinline__ void heartbeat() {  // leader.rs:44-51
+    send(JR_CMD_HEARTBEAT, TO_PEERS, 0, 0, term, commit);
+  }
+
+  __device__ __forceinline__ void leader_commit() {  // leader.rs:87-99
+    uint32_t q = committed_index();
+    if (q > commit) {
+      uint32_t prev = commit;
+      if (!chain_commit(q)) return;
+      bool first = true;
+      for (uint32_t b = prev; b <= q; ++b) {  // range(prev..=new).skip(1), key order
+        uint32_t nx = tbl_next(b);
+        if (nx == ABSENT) continue;
+        if (first) { first = false; continue; }
+        fsm_emit(false, b, nx, tbl_tok(b));
+        if (fault) return;
+      }
+    }
+  }
+
+  // leader.rs:124-174.  Probe: range(head..).nth(1); Replicate: range(head..).skip(1).take(5).
+  __device__ __forceinline__ void replicate() {
+#pragma unroll
+    for (int p = 0; p < R; ++p) {
+      if (p == (int)r) continue;  // config.nodes holds peers only
+      const uint32_t take = (prmask >> p) & 1u ? JR_MAX_AE_BLOCKS : 1u;
+      uint32_t bid = ph[p], pulled = 0, nb = 0;
+      while (pulled < 1 + take) {
+        uint32_t nx = ABSENT;
+        while (bid <= maxkey && (nx = tbl_next(bid)) == ABSENT) ++bid;
+        if (bid > maxkey) {
+          // sled would now yield the "commit" key and bincode panics (D6)
+          if ((d.flags & JR_F_SLED_COMMIT_KEY_STRICT) && ckey) { fault = JR_FAULT_RANGE_COMMIT_KEY; return; }
+          break;
+        }
+        if (pulled >= 1) {
+          uint64_t tok = tbl_tok(bid);
+          if (!put_unit(ocnt + 1 + nb, make_uint4(bid, nx, (uint32_t)tok, (uint32_t)(tok >> 32)))) return;
+          ++nb;
+        }
+        ++pulled;
+        ++bid;
+      }
+      if (!put_unit(ocnt, make_uint4(unit_hdr(JR_CMD_APPEND_ENTRIES, 0, nb, p + 1), (uint32_t)term,
+                                     (uint32_t)(term >> 32), 0)))
+        return;
+      if (digest_on()) {
+        uint64_t h = digest_message_fn(mdig, JR_CMD_APPEND_ENTRIES, p + 1, 0, nb, id(), term, 0, 0, 0, 0);
+        ++nmsg;
+        for (uint32_t k = 0; k < nb; ++k) {
+          uint4 u = d.ob[cur][((size_t)(ocnt + 1 + k) * R + r) * d.Gp + g];
+          h = fold(h, u.x);
+          h = fold(h, u.y);
+          h = fold(h, (uint64_t)u.z | ((uint64_t)u.w << 32));
+        }
+        mdig = h;
+      }
+      ocnt += 1 + nb;
+    }
+  }
+
+  // ------------------------------------------------------------------ Apply::apply (mod.rs:471-479)
+  // Single entry for every Command.  The three heavy continuations the
+  // reference reaches from several places are shared tails here so each is
+  // instantiated once:
+  //   timeout tail   = Raft<Follower>::apply_timeout -> seek_election (follower.rs:248-256, candidate.rs:24-45)
+  //   advance tail   = ReplicationProgress::advance + Leader::commit (leader.rs:211-219, also 191-196)
+  //   replicate tail = Leader::replicate (leader.rs:124-174, reached from 228 and 242)
+  __device__ __forceinline__ void apply(const Cmd& c) {
+    if (!live()) return;
+    bool t_timeout = false, t_replicate = false, t_advance = false;
+    uint32_t adv_node = 0, adv_block = 0;
+    if (role == JR_ROLE_FOLLOWER) {  // follower.rs:38-63
+      switch (c.kind) {
+        case JR_CMD_TICK: t_timeout = needs_election(); break;  // follower.rs:121-128
+        case JR_CMD_TIMEOUT: t_timeout = true; break;
+        case JR_CMD_APPEND_ENTRIES: follower_append_entries(c); break;
+        case JR_CMD_HEARTBEAT: follower_heartbeat(c); break;
+        case JR_CMD_VOTE_REQUEST: follower_vote_request(c); break;
+        case JR_CMD_CLIENT_REQUEST: follower_client_request(c.token); break;
+        case JR_CMD_CLIENT_RESPONSE: send(JR_CMD_CLIENT_RESPONSE, TO_CLIENT, 0, 0, c.token, 0); break;  // follower.rs:271-282
+        default: break;
+      }
+    } else if (role == JR_ROLE_CANDIDATE) {  // candidate.rs:170-196
+      switch (c.kind) {
+        case JR_CMD_TICK:  // candidate.rs:48-68
+          if (needs_election()) {
+            if (election_status() == 0) { fault = JR_FAULT_CANDIDATE_TICK_ELECTED; break; }
+            voted = 0;
+            candidate_to_follower();
+            t_timeout = true;  // raft.apply(Command::Timeout) as a Follower
+          }
+          break;
+        case JR_CMD_VOTE_REQUEST: candidate_vote_request(c); break;
+        case JR_CMD_VOTE_RESPONSE: candidate_vote_response(c.node_id, c.flag != 0); break;
+        case JR_CMD_APPEND_ENTRIES: if (c.term >= term) candidate_to_follower(); break;  // candidate.rs:116-134
+        case JR_CMD_HEARTBEAT: candidate_heartbeat(c); break;
+        case JR_CMD_CLIENT_REQUEST: queue_push(c.token, c.addr); break;
+        default: break;
+      }
+    } else {  // leader.rs:248-266
+      switch (c.kind) {
+        case JR_CMD_TICK: {  // leader.rs:234-245
+          uint64_t el = now >= hbtime ? now - hbtime : 0;
+          if (el > (uint64_t)d.hb) {
+            heartbeat();
+            hbtime = now;
+          }
+          t_replicate = true;
+          break;
+        }
+        case JR_CMD_HEARTBEAT_RESPONSE: t_replicate = !c.flag && c.block > 0; break;  // leader.rs:222-231
+        case JR_CMD_APPEND_RESPONSE: t_advance = true; adv_node = c.node_id; adv_block = c.block; break;
+        case JR_CMD_APPEND_ENTRIES: if (c.term > term) set_term(c.term); break;  // leader.rs:200-208
+        case JR_CMD_CLIENT_REQUEST: {  // leader.rs:177-197
+          uint32_t bid;
+          if (!chain_append(c.token, bid)) break;
+          fsm_emit(true, bid, c.addr, c.token);
+          t_advance = true; adv_node = id(); adv_block = head;  // self AppendResponse
+          break;
+        }
+        default: break;
+      }
+    }
+    if (fault) return;
+    if (t_timeout && voted == 0) {  // follower.rs:248-256
+      set_election_timeout();
+      become_candidate();
+      // seek_election, candidate.rs:24-45
+      voted = id();
+      term += 1;
+      // N-1 broadcasts of the same VoteRequest: one unit with aux = copies
+      if (R > 1) send(JR_CMD_VOTE_REQUEST, TO_PEERS, 0, R - 1, term, head);
+      if (fault) return;
+      candidate_vote_response(id(), true);
+    }
+    if (t_advance) {
+      if (progress_advance(adv_node, adv_block)) leader_commit();
+    }
+    if (t_replicate && !fault) replicate();
+  }
+
+  // ------------------------------------------------------------------ the step schedule (jr_step_args)
+  // A cursor that yields this replica's commands of one step in order:
+  // peer mail (ascending sender, FIFO) -> dense proposal -> synthetic proposals -> Tick.
+  struct Cursor {
+    uint32_t stage, s, u, cnt, reps, synth_i;
+  };
+
+  __device__ __forceinline__ void cursor_init(Cursor& k, uint32_t phases) const {
+    k.stage = (phases & PH_DRAIN) ? 0u : 1u;
+    k.s = 0xFFFFFFFFu; k.u = 0; k.cnt = 0; k.reps = 0; k.synth_i = 0;
+  }
+
+  __device__ __forceinline__ bool next_cmd(Cursor& k, Cmd& c, const StepParams& p) {
+    const int prv = 1 - cur;
+    for (;;) {
+      if (k.stage == 0) {
+        if (k.reps) { --k.reps; return true; }  // another copy of the same VoteRequest broadcast
+        if (k.u >= k.cnt) {
+          ++k.s;
+          if (k.s == r) ++k.s;
+          if (k.s >= (uint32_t)R) { k.stage = 1; continue; }
+          k.cnt = d.oc[prv][(size_t)k.s * d.Gp + g];
+          k.u = 0;
+          continue;
+        }
+        const uint4* base = d.ob[prv] + (size_t)k.s * d.Gp + g;
+        const uint4 h = __ldg(base + (size_t)k.u * plane);
+        const uint32_t kind = h.x & 15u, flag = (h.x >> 4) & 1u, aux = (h.x >> 8) & 255u, to = h.x >> 16;
+        const uint32_t at = k.u;
+        k.u += 1 + (kind == JR_CMD_APPEND_ENTRIES ? aux : 0u);
+        if (to != TO_PEERS && to != id()) continue;
+        c.kind = kind; c.flag = flag; c.node_id = k.s + 1; c.block = h.w; c.nblk = 0; c.addr = 0;
+        c.term = (uint64_t)h.y | ((uint64_t)h.z << 32); c.last_term = c.term; c.token = 0;
+        c.blk_units = nullptr; c.blk_stride = plane; c.host_msg = nullptr;
+        if (kind == JR_CMD_APPEND_ENTRIES) {
+          c.nblk = aux;
+          c.blk_units = base + (size_t)(at + 1) * plane;
+        } else if (kind == JR_CMD_CLIENT_REQUEST || kind == JR_CMD_CLIENT_RESPONSE) {
+          c.token = c.term; c.term = 0; c.last_term = 0; c.addr = h.w; c.block = 0;
+        } else if (kind == JR_CMD_VOTE_REQUEST) {
+          k.reps = aux ? aux - 1 : 0;  // N-1 identical broadcasts, candidate.rs:30-37
+        }
+        return true;
+      }
+      c.flag = 0; c.node_id = 0; c.block = 0; c.nblk = 0; c.term = c.last_term = 0;
+      c.blk_units = nullptr; c.blk_stride = 0; c.host_msg = nullptr;
+      if (k.stage == 1) {  // event_loop client arm, server.rs:156-160
+        k.stage = 2;
+        if ((p.phases & PH_PROPOSE) && p.proposals) {
+          const uint4 pr = __ldg(reinterpret_cast<const uint4*>(p.proposals) + g);
+          if (pr.z == id()) {
+            c.kind = JR_CMD_CLIENT_REQUEST; c.addr = (uint32_t)JR_ADDR_CLIENT << 16;
+            c.token = (uint64_t)pr.x | ((uint64_t)pr.y << 32);
+            return true;
+          }
+        }
+        continue;
+      }
+      if (k.stage == 2) {
+        if ((p.phases & PH_PROPOSE) && k.synth_i < p.n_synth && role == JR_ROLE_LEADER && live()) {
+          c.kind = JR_CMD_CLIENT_REQUEST; c.addr = (uint32_t)JR_ADDR_CLIENT << 16;
+          c.token = synth_token(p.step_index, k.synth_i, d.goff + g);
+          ++k.synth_i;
+          return true;
+        }
+        k.stage = 3;
+        continue;
+      }
+      if (k.stage == 3) {
+        k.stage = 4;
+        if (p.phases & PH_TICK) { c.kind = JR_CMD_TICK; c.addr = 0; c.token = 0; return true; }
+        continue;
+      }
+      return false;
+    }
+  }
+
+  __device__ __forceinline__ void run_step(const StepParams& p) {
+    if (!live()) return;
+    Cursor k;
+    cursor_init(k, p.phases);
+    Cmd c;
+    c.kind = JR_CMD_NOOP; c.flag = 0; c.node_id = 0; c.block = 0; c.nblk = 0; c.addr = 0;
+    c.term = c.last_term = c.token = 0; c.blk_units = nullptr; c.blk_stride = 0; c.host_msg = nullptr;
+    while (live() && next_cmd(k, c, p)) apply(c);
+  }
+};
+
+#endif  // JR_DEVICE_CODE
+}  // namespace jr

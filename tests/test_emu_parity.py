@@ -1,0 +1,60 @@
+"""CPU suite: the engine's DEVICE CODE (compiled for the host through
+tests/emu/cuda_emu.h) against the C++ restatement oracle, bit for bit.
+The GPU suite (test_gpu_parity.py) runs the same scenarios through the real
+CUDA library."""
+import pytest
+
+from josefine_b200 import abi
+from oracle.restated import RestatedCluster
+from tests import kat_cases, parity
+from tests.emu.emu import EmuEngine
+
+
+def make_oracle(g, r, **kw):
+    return RestatedCluster.create(g, r, **kw)
+
+
+def make_emu(g, r, **kw):
+    return EmuEngine.create(g, r, **kw)
+
+
+@pytest.mark.parametrize("case", kat_cases.ALL_KATS, ids=lambda f: f.__name__)
+def test_reference_kat_on_device_code(case):
+    case(make_emu)
+
+
+@pytest.mark.parametrize("R", [1, 2, 3, 4, 5, 7])
+def test_cold_start(R):
+    p = parity.Pair(make_oracle, make_emu, 6, R, seed=R)
+    parity.scenario_cold_start(p, steps=45)
+
+
+@pytest.mark.parametrize("R", [3, 5, 7])
+def test_steady_state(R):
+    p = parity.Pair(make_oracle, make_emu, 5, R, seed=1)
+    parity.scenario_steady(p, steps=24)
+
+
+@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("R", [3, 5])
+def test_random_inject(R, seed):
+    p = parity.Pair(make_oracle, make_emu, 3, R, seed=seed, chain_capacity=64)
+    parity.scenario_random_inject(p, seed=seed * 7 + R, steps=50)
+
+
+@pytest.mark.parametrize("R", [3, 5])
+def test_random_inject_strict_commit_key(R):
+    p = parity.Pair(make_oracle, make_emu, 3, R, seed=5, chain_capacity=64,
+                    flags=parity.FULL | abi.F_SLED_COMMIT_KEY_STRICT)
+    parity.scenario_random_inject(p, seed=99 + R, steps=50)
+
+
+def test_run_equals_steps():
+    """jr_run(n) == n x jr_step(DELIVER|TICK|SYNTH), bit for bit (ABI contract)."""
+    a = make_emu(4, 3, seed=3, flags=parity.FULL)
+    b = make_emu(4, 3, seed=3, flags=parity.FULL)
+    a.run(100, 100, 30, 1)
+    for k in range(30):
+        b.step(100 + 100 * k, n_synth=1)
+    parity.compare_states(a, b, chain_ids=40)
+    parity.compare_digests(a, b)

@@ -1,0 +1,136 @@
+"""GPU suite: the CUDA engine, called through the C ABI (libjosefine_b200.so),
+against the C++ restatement oracle -- bit for bit.  Needs a B200."""
+import pytest
+
+from josefine_b200 import abi, RaftEngine
+from oracle.restated import RestatedCluster
+from tests import kat_cases, parity
+
+pytestmark = pytest.mark.gpu
+
+
+def make_oracle(g, r, **kw):
+    return RestatedCluster.create(g, r, n_threads=8 if g >= 1024 else 1, **kw)
+
+
+def make_gpu(g, r, **kw):
+    return RaftEngine.create(g, r, **kw)
+
+
+@pytest.mark.parametrize("case", kat_cases.ALL_KATS, ids=lambda f: f.__name__)
+def test_reference_kat_on_gpu(case):
+    case(make_gpu)
+
+
+@pytest.mark.parametrize("R", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_cold_start(R):
+    p = parity.Pair(make_oracle, make_gpu, 40, R, seed=R, check_states_every=5)
+    parity.scenario_cold_start(p, steps=45)
+
+
+@pytest.mark.parametrize("R", [3, 5, 7])
+def test_steady_state(R):
+    p = parity.Pair(make_oracle, make_gpu, 33, R, seed=1, check_states_every=4)
+    parity.scenario_steady(p, steps=24)
+
+
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("R", [3, 5, 7])
+def test_random_inject(R, seed):
+    p = parity.Pair(make_oracle, make_gpu, 5, R, seed=seed, chain_capacity=64, check_states_every=10)
+    parity.scenario_random_inject(p, seed=seed * 7 + R, steps=50)
+
+
+@pytest.mark.parametrize("R", [3, 5])
+def test_random_inject_strict_commit_key(R):
+    p = parity.Pair(make_oracle, make_gpu, 5, R, seed=5, chain_capacity=64, check_states_every=10,
+                    flags=parity.FULL | abi.F_SLED_COMMIT_KEY_STRICT)
+    parity.scenario_random_inject(p, seed=99 + R, steps=50)
+
+
+def test_run_equals_steps():
+    a = make_gpu(100, 3, seed=3, flags=parity.FULL)
+    b = make_gpu(100, 3, seed=3, flags=parity.FULL)
+    a.run(100, 100, 30, 1)
+    for k in range(30):
+        b.step(100 + 100 * k, n_synth=1)
+    parity.compare_states(a, b, groups=range(0, 100, 7), chain_ids=40)
+    parity.compare_digests(a, b)
+
+
+def _digest_parity(G, R, steps, seed, bootstrap, n_synth=1, sample=16, **kw):
+    """Full-size check through size-independent digests (a checksum of per-replica
+    checksums of every Message / Instruction / state word) plus exact state on a sample."""
+    flags = abi.F_STREAM_DIGEST
+    a = make_oracle(G, R, seed=seed, flags=flags, **kw)
+    b = make_gpu(G, R, seed=seed, flags=flags, **kw)
+    if bootstrap:
+        from josefine_b200 import Command
+        inj = []
+        q = R // 2 + 1
+        for g in range(G):
+            inj.append(Command.timeout(g, 1))
+            for v in range(2, q + 1):
+                inj.append(Command.vote_response(g, 1, 1, v, True))
+        a.step(0, flags=0, inject=inj)
+        b.step(0, flags=0, inject=inj)
+    a.run(100, 100, steps, n_synth)
+    b.run(100, 100, steps, n_synth)
+    parity.compare_digests(a, b, f"[{G}x{R} after {steps} steps]")
+    step = max(G // sample, 1)
+    parity.compare_states(a, b, groups=range(0, G, step), chain_ids=min(steps + 4, 64))
+    assert a.leader_table() == b.leader_table()
+    return a, b
+
+
+def test_config2_1024x3_vote_append():
+    """BASELINE config #2: 1,024 groups x 3 replicas, cold start, elections, then proposals."""
+    a, b = _digest_parity(1024, 3, 256, seed=0, bootstrap=False, chain_capacity=512)
+    leaders = [l for (_, l, _) in b.leader_table()]
+    assert sum(1 for l in leaders if l) > 900  # nearly every group elected someone
+
+
+def test_config3_65536x5_steady_append():
+    """BASELINE config #3 at full size: 65,536 x 5, pre-elected leaders, steady AppendEntries."""
+    a, b = _digest_parity(65536, 5, 48, seed=1, bootstrap=True, chain_capacity=128)
+    assert all(l == 1 for (_, l, _) in b.leader_table()[:100])
+    assert b.fault_count() == 0
+
+
+def test_config5_7_replicas_churn_and_compact():
+    """BASELINE config #5 shape (reduced G): 7 replicas, leader loss, compact()."""
+    G, R = 4096, 7
+    flags = abi.F_STREAM_DIGEST
+    a = make_oracle(G, R, seed=2, flags=flags, chain_capacity=256)
+    b = make_gpu(G, R, seed=2, flags=flags, chain_capacity=256)
+    from josefine_b200 import Command
+    inj = []
+    for g in range(G):
+        inj.append(Command.timeout(g, 1))
+        for v in (2, 3, 4):
+            inj.append(Command.vote_response(g, 1, 1, v, True))
+    for x in (a, b):
+        x.step(0, flags=0, inject=inj)
+    now = 100
+    for rnd in range(3):
+        for x in (a, b):
+            x.run(now, 100, 40, 1)
+        now += 4000
+        ka, kb = a.kill_leaders(rnd, 100), b.kill_leaders(rnd, 100)
+        assert ka == kb
+        for x in (a, b):
+            x.compact()
+        parity.compare_digests(a, b, f"[churn round {rnd}]")
+    parity.compare_states(a, b, groups=range(0, G, 257), chain_ids=64)
+    # followers keep voted_for = dead leader, so killed groups stay leaderless
+    dead = sum(1 for (_, l, _) in b.leader_table() if l == 0)
+    assert dead > 0
+
+
+def test_no_cpu_fallback_symbols():
+    """The product library must be the CUDA one: it reports a device-side digest that
+    only the kernels can produce, and the oracle library is not loaded by the package."""
+    import josefine_b200.raft as r
+    assert r.ENGINE_LIB_PATH.endswith("libjosefine_b200.so")
+    e = make_gpu(8, 3)
+    assert e.state_digest() != 0
