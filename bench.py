@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- Raft-group ticks/sec of the batched Chained-Raft step path.
+
+Metric (BASELINE.json): Raft-group ticks/sec @ 64Ki groups x 5 replicas.
+One group-tick = all R replicas of one group each drain the peer mail of the
+previous step, take the step's client proposal (leader) and apply one
+Command::Tick (the reference defines no such unit -- its
+Tick is a 100 ms wall-clock interval, src/raft/server.rs:25).
+
+Workload (config.workload): BASELINE config #3 -- 65,536 groups x 5 replicas per
+GPU, leaders pre-elected on node 1 by a synthetic vote trace, then steady state:
+one client proposal per group per tick, AppendEntries / AppendResponse /
+Heartbeat / HeartbeatResponse traffic between the co-resident replicas.
+
+A bench "step" = TICKS_PER_STEP consecutive group-ticks of every group (one
+jr_run).  L2 is flushed between timed steps (the per-GPU working set, ~0.1 GB,
+is smaller than the 126 MB L2, so without the flush the state would be served
+from L2 forever); inside a step the ticks run back to back as they do in
+production.  Device time is taken with CUDA events on the engine's stream,
+per step, flush excluded; max over ranks.
+
+Arms:
+  (default)          the CUDA engine.  `value` = device-resident throughput;
+                     `e2e` = the same workload driven tick by tick through the
+                     C-ABI jr_step with HOST buffers: proposals H2D from pinned
+                     memory and the per-group {term, leader, commit} table D2H
+                     every tick.
+  --impl reference   the CPU comparator: the C++ RESTATEMENT of josefine's
+                     src/raft (oracle/; josefine itself is Rust and cannot be
+                     built here) on all host cores, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from josefine_b200 import abi, Command  # noqa: E402
+
+METRIC = "raft_group_ticks_per_sec"
+UNIT = "group-ticks/s"
+GROUPS_PER_GPU = 65536
+REPLICAS = 5
+TICKS_PER_STEP = 64
+DT_MS = 100
+SEED = 1
+L2_FLUSH_BYTES = 256 << 20
+
+
+def bootstrap_inject(G, R, node=1):
+    """Synthetic vote trace: Timeout on `node`, plus quorum-1 granted VoteResponses."""
+    q = 0 if R == 1 else R // 2 + 1
+    voters = [v for v in range(1, R + 1) if v != node][:max(q - 1, 0)]
+    inj = []
+    for g in range(G):
+        inj.append(Command.timeout(g, node))
+        for v in voters:
+            inj.append(Command.vote_response(g, node, 1, v, True))
+    return inj
+
+
+def algorithmic_bytes_per_group_tick(make, R, ticks=64):
+    """Minimum bytes one steady-state group-tick must move with THIS layout
+    (DESIGN.md "Algorithmic bytes"), measured on a small captured run:
+      state   : follower 52 B (P0,P1,P2 + max_key), leader 116 B (+P3, 2 progress planes) -- read AND written
+      mailbox : every 16 B unit written once and read once per addressee (+4 B count, written and read)
+      blocks  : 12 B written per block appended/extended, 12 B read per block shipped or applied, 4 B has() probe
+      fsm     : 16 B per Instruction
+    """
+    G = 32
+    eng = make(G, R, seed=SEED, flags=abi.F_CAPTURE_MESSAGES | abi.F_CAPTURE_FSM, chain_capacity=ticks * 2 + 64,
+               fsm_units=16)
+    eng.step(0, flags=0, inject=bootstrap_inject(G, R))
+    for k in range(16):  # reach the steady regime
+        eng.step((k + 1) * DT_MS, n_synth=1)
+    tot = 0
+    for k in range(16, 16 + ticks):
+        res = eng.step((k + 1) * DT_MS, n_synth=1)
+        b = 0
+        b += G * ((R - 1) * 52 + 116) * 2                    # state read + written
+        b += G * R * 4 * 2 + G * R * (R - 1) * 4             # mailbox counts: reset/written, read by each peer
+        seen_vreq = set()
+        for m in res.messages:
+            readers = (R - 1) if m.to_kind == abi.ADDR_PEERS else 1
+            if m.kind == abi.CMD_VOTE_REQUEST:                # N-1 copies share one unit
+                key = (m.group, m.from_id)
+                if key in seen_vreq:
+                    continue
+                seen_vreq.add(key)
+            units = 1 + (m.n_blocks if m.kind == abi.CMD_APPEND_ENTRIES else 0)
+            b += units * 16 * (1 + readers)
+            if m.kind == abi.CMD_APPEND_ENTRIES:              # leader reads the blocks, follower probes + writes them
+                b += m.n_blocks * (12 + 4 + 12)
+        for f in res.fsm:
+            b += 16
+            b += 12                                           # Notify: block written by append; Apply: block read
+        tot += b
+    return tot / (G * ticks)
+
+
+class ClockSampler:
+    """nvidia-smi clocks during the timed region (profiling recipe's clocks line)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].startswith("Active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, torch copy)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_reference_run(G, R, ticks, threads):
+    """Times the C++ restatement on `threads` host cores: steady state after bootstrap."""
+    from oracle.restated import RestatedCluster
+    c = RestatedCluster.create(G, R, n_threads=threads, seed=SEED, chain_capacity=ticks * 8 + 4096)
+    c.step(0, flags=0, inject=bootstrap_inject(G, R))
+    c.run(DT_MS, DT_MS, 16, 1)
+    return c
+
+
+def run_reference(args):
+    """--impl reference: the C++ restatement of src/raft on the host cores (bounded sample)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    G = max(4096, 64 * cores)
+    R = REPLICAS
+    total_steps = args.warmup + args.steps
+    c = cpu_reference_run(G, R, TICKS_PER_STEP * total_steps + 32, cores)
+    now = DT_MS * 17
+    for _ in range(args.warmup):
+        c.run(now, DT_MS, TICKS_PER_STEP, 1)
+        now += DT_MS * TICKS_PER_STEP
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        c.run(now, DT_MS, TICKS_PER_STEP, 1)
+        now += DT_MS * TICKS_PER_STEP
+    dt = time.perf_counter() - t0
+    value = G * TICKS_PER_STEP * args.steps / dt
+    sample = f"{G} groups x {R} replicas x {TICKS_PER_STEP} ticks per step, {cores} threads (groups partitioned statically)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64/u32 integer",
+        "data": "synthetic",
+        "config": {"workload": "BASELINE config #3 steady-state AppendEntries, bounded sample: " + sample,
+                   "comparator": "C++ restatement of josefine src/raft (oracle/), NOT josefine itself (Rust, unbuildable here)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--groups", type=int, default=GROUPS_PER_GPU, help="groups per GPU")
+    ap.add_argument("--replicas", type=int, default=REPLICAS)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+    from josefine_b200 import RaftEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    G, R = args.groups, args.replicas
+    S = TICKS_PER_STEP
+    total_ticks = S * (args.warmup + args.steps) + 64
+    stream = torch.cuda.Stream()          # explicit non-default stream: handle 0 would mean "engine's own"
+    torch.cuda.set_stream(stream)
+
+    def make(g, r, **kw):
+        kw.setdefault("device", local)
+        return RaftEngine.create(g, r, **kw)
+
+    # ---------------- device-resident arm ----------------
+    eng = make(G, R, seed=SEED, group_offset=rank * G, chain_capacity=total_ticks + 64,
+               flags=abi.F_CAPTURE_FSM, fsm_units=2 * S + 8, mailbox_units=64)
+    eng.set_stream(stream.cuda_stream)
+    eng.step(0, flags=0, inject=bootstrap_inject(G, R))
+    eng.run(DT_MS, DT_MS, 16, 1)
+    now = DT_MS * 17
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+    leaders = torch.empty(G * 16, dtype=torch.uint8, device="cuda")
+    gathered = torch.empty(world * G * 16, dtype=torch.uint8, device="cuda") if world > 1 else None
+
+    def one_step(t_now):
+        eng.run(t_now, DT_MS, S, 1)
+        if world > 1:  # the one cross-shard exchange: leader announce, once per step (every 64 ticks)
+            eng.leader_table_device(leaders.data_ptr())
+            dist.all_gather_into_tensor(gathered, leaders)
+
+    for _ in range(args.warmup):
+        flush.fill_(1)
+        one_step(now)
+        now += DT_MS * S
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = []
+    for _ in range(args.steps):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        one_step(now)
+        b.record(stream)
+        evs.append((a, b))
+        now += DT_MS * S
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    faults = eng.fault_count()
+    value = world * G * S * args.steps / (ms * 1e-3)
+    launches = S * args.steps
+
+    # ---------------- end-to-end arm (host buffers through jr_step) ----------------
+    e2e = None
+    if not args.no_e2e:
+        e2 = make(G, R, seed=SEED, group_offset=rank * G, chain_capacity=total_ticks + 64, mailbox_units=64)
+        e2.set_stream(stream.cuda_stream)
+        e2.step(0, flags=0, inject=bootstrap_inject(G, R))
+        e2.run(DT_MS, DT_MS, 16, 1)
+        prop = torch.zeros(G * 2, dtype=torch.int64).pin_memory()      # jr_proposal[G] = {token, node|reserved}
+        table = torch.zeros(G * 2, dtype=torch.int64).pin_memory()     # jr_leader_entry[G]
+        pv = prop.view(G, 2)
+        pv[:, 1] = 1                                                   # addressed to node 1 (the leader)
+        lib = e2._lib
+        sa = abi.StepArgs()
+        sa.flags = abi.STEP_DELIVER | abi.STEP_TICK
+        sa.proposals = C.cast(prop.data_ptr(), C.POINTER(abi.Proposal))
+        tbl = C.cast(table.data_ptr(), C.POINTER(abi.LeaderEntry))
+        tok = torch.arange(G, dtype=torch.int64)
+        tnow = DT_MS * 17
+
+        def e2e_step(tn, k0):
+            for k in range(S):
+                pv[:, 0] = tok + ((k0 + k + 1) << 32)                  # this tick's payload tokens
+                sa.now_ms = tn + k * DT_MS
+                st = lib.jr_step(e2._h, C.byref(sa))                   # H2D proposals + kernels
+                assert st == 0, st
+                st = lib.jr_leader_table(e2._h, tbl)                   # D2H result + sync
+                assert st == 0, st
+
+        kk = 0
+        for _ in range(args.warmup):
+            e2e_step(tnow, kk)
+            kk += S
+            tnow += DT_MS * S
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step(tnow, kk)
+            kk += S
+            tnow += DT_MS * S
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        commit_ok = int(table.view(G, 2)[0, 1].item() >> 32) > 0
+        e2e = {"value": world * G * S * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": S * G * 16,
+               "d2h_bytes_per_step": S * G * 16, "ms_per_step": dt * 1e3 / args.steps,
+               "api": "jr_step(host jr_proposal[G]) + jr_leader_table(host jr_leader_entry[G]) per tick",
+               "commit_advanced": commit_ok}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline + cpu baseline (rank 0) ----------------
+    abytes = algorithmic_bytes_per_group_tick(make, R)
+    peak, peak_src = measured_peak()
+    avg_launch_s = (ms * 1e-3) / launches
+    achieved = abytes * G / avg_launch_s / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "step_kernel<5>", "algorithmic_bytes_per_group_tick": abytes,
+                "avg_launch_us": avg_launch_s * 1e6, "peak_source": peak_src,
+                "note": "one launch = one group-tick of all groups on this GPU; working set < L2 so DRAM traffic can be "
+                        "far below the algorithmic bytes after the first tick of a step (see profiles/)"}
+    cpu = None
+    if not args.no_cpu:
+        cores = os.cpu_count() or 1
+        cg, ct = max(4096, 64 * cores), 256
+        c = cpu_reference_run(cg, R, ct + 32, cores)
+        t0 = time.perf_counter()
+        c.run(DT_MS * 17, DT_MS, ct, 1)
+        cdt = time.perf_counter() - t0
+        cpu = {"value": cg * ct / cdt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"C++ restatement of josefine src/raft: {cg} groups x {R} replicas x {ct} ticks, {cores} threads"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64/u32 integer", "data": "synthetic",
+        "config": {"workload": f"BASELINE config #3: {G} groups x {R} replicas per GPU, pre-elected leaders, steady-state "
+                               f"AppendEntries, 1 proposal/group/tick",
+                   "groups_per_gpu": G, "replicas": R, "ticks_per_step": S, "tick_ms": DT_MS, "seed": SEED,
+                   "l2": f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write); ticks inside a step run back to back",
+                   "parallelism": f"groups sharded over {world} GPU(s); leader-announce all_gather once per step" if world > 1
+                   else "single GPU", "faulted_replicas": faults},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

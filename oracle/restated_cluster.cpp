@@ -144,6 +144,7 @@ struct StepCtx {
   // inject bucketed per replica: indices into args->inject
   const std::vector<std::vector<uint32_t>>* inject_idx;
   const jr_msg* inject;
+  uint64_t step_index;
 };
 
 void step_group(jro_cluster* c, uint32_t g, const StepCtx& s) {
@@ -177,7 +178,7 @@ void step_group(jro_cluster* c, uint32_t g, const StepCtx& s) {
       for (uint32_t i = 0; i < s.n_synth; ++i) {
         if (n.role() != JR_ROLE_LEADER) break;
         Command cr{JR_CMD_CLIENT_REQUEST};
-        cr.req.id = synth_token(c->step_index, i, gg);
+        cr.req.id = synth_token(s.step_index, i, gg);
         cr.req.address = Address::client();
         n.apply(cr, s.now);
       }
@@ -186,16 +187,24 @@ void step_group(jro_cluster* c, uint32_t g, const StepCtx& s) {
     if (s.flags & JR_STEP_TICK) n.apply(Command{JR_CMD_TICK}, s.now);
   }
   // rotate mailboxes, fold digests
+  const bool digests = (c->cfg.flags & JR_F_STREAM_DIGEST) != 0;
+  const bool keep_fsm = (c->cfg.flags & JR_F_CAPTURE_FSM) != 0;
   for (uint32_t r = 1; r <= R; ++r) {
     Replica& me = c->at(g, r);
     Node& n = *me.node;
-    for (const Message& m : n.rpc) {
-      me.msg_digest = digest_msg(me.msg_digest, to_abi(m, g));
-      ++me.n_msgs;
+    if (digests) {
+      for (const Message& m : n.rpc) {
+        me.msg_digest = digest_msg(me.msg_digest, to_abi(m, g));
+        ++me.n_msgs;
+      }
+      for (; me.fsm_digested < n.fsm.size(); ++me.fsm_digested) {
+        me.fsm_digest = digest_fsm(me.fsm_digest, fsm_to_abi(n.fsm[me.fsm_digested], g, r));
+        ++me.n_fsm;
+      }
     }
-    for (; me.fsm_digested < n.fsm.size(); ++me.fsm_digested) {
-      me.fsm_digest = digest_fsm(me.fsm_digest, fsm_to_abi(n.fsm[me.fsm_digested], g, r));
-      ++me.n_fsm;
+    if (!keep_fsm) {  // fsm_tx with no receiver: drop
+      n.fsm.clear();
+      me.fsm_digested = 0;
     }
     me.prev_out.swap(n.rpc);
     n.rpc.clear();
@@ -287,7 +296,7 @@ jr_status jro_step(jro_cluster* c, jr_step_args* a) {
     for (uint32_t g = 0; g < G; ++g)
       if (a->proposals[g].node > R) return JR_E_UNKNOWN_NODE;
   clear_fsm(c);
-  StepCtx s{a->now_ms, a->flags, a->n_synth, a->proposals, a->n_inject ? &idx : nullptr, a->inject};
+  StepCtx s{a->now_ms, a->flags, a->n_synth, a->proposals, a->n_inject ? &idx : nullptr, a->inject, c->step_index};
   run_step(c, s);
   // capture
   size_t nm = 0, nf = 0;
@@ -316,12 +325,29 @@ jr_status jro_step(jro_cluster* c, jr_step_args* a) {
 jr_status jro_run(jro_cluster* c, uint64_t now0, uint32_t dt, uint32_t n_steps, uint32_t n_synth) {
   if (!c || n_synth > 8) return JR_E_INVAL;
   clear_fsm(c);
-  for (uint32_t k = 0; k < n_steps; ++k) {
-    StepCtx s{now0 + (uint64_t)k * dt,
-              (uint32_t)(JR_STEP_DELIVER | JR_STEP_TICK | (n_synth ? JR_STEP_SYNTH_PROPOSALS : 0)),
-              n_synth, nullptr, nullptr, nullptr};
-    run_step(c, s);
+  // Groups never interact, so each host thread runs ALL n_steps for its own
+  // contiguous slice of groups: no barrier per step, no thread start per step.
+  const uint32_t G = c->cfg.n_groups;
+  const unsigned T = std::min<unsigned>(c->n_threads, G ? G : 1);
+  const uint64_t base = c->step_index;
+  auto work = [=](uint32_t lo, uint32_t hi) {
+    for (uint32_t g = lo; g < hi; ++g)
+      for (uint32_t k = 0; k < n_steps; ++k) {
+        StepCtx s{now0 + (uint64_t)k * dt,
+                  (uint32_t)(JR_STEP_DELIVER | JR_STEP_TICK | (n_synth ? JR_STEP_SYNTH_PROPOSALS : 0)),
+                  n_synth, nullptr, nullptr, nullptr, base + k};
+        step_group(c, g, s);
+      }
+  };
+  if (T <= 1) {
+    work(0, G);
+  } else {
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < T; ++t)
+      th.emplace_back(work, (uint32_t)((uint64_t)G * t / T), (uint32_t)((uint64_t)G * (t + 1) / T));
+    for (auto& x : th) x.join();
   }
+  c->step_index += n_steps;
   return JR_OK;
 }
 
@@ -440,6 +466,7 @@ jr_status jro_state_digest(jro_cluster* c, uint64_t* out) {
 
 jr_status jro_stream_digest(jro_cluster* c, uint64_t* md, uint64_t* fd, uint64_t* nm, uint64_t* nf) {
   if (!c) return JR_E_INVAL;
+  if (!(c->cfg.flags & JR_F_STREAM_DIGEST)) return JR_E_INVAL;
   uint64_t a = 0, b = 0, x = 0, y = 0;
   for (auto& r : c->reps) {
     a += r.msg_digest;
