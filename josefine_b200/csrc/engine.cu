@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -20,29 +21,64 @@ using namespace jr;
 // kernels
 // ============================================================================
 
-// One jr_step phase set for every replica.  CTA = 32 groups x R warps.
+// n_ticks fused schedule steps for every replica.  CTA = 32 groups x R warps; warp w
+// is replica w of those groups.  Replica state lives in registers for the whole
+// launch; the mailboxes of the CTA's groups live in shared memory (double
+// buffered, units beyond Us spill to the global mailbox); block-table reads go
+// through a per-lane shared-memory cache.  Groups never interact, so the only
+// synchronisation between ticks is __syncthreads().
 template <int R>
 __global__ void __launch_bounds__(32 * R) step_kernel(const Dev d, const StepParams p) {
-  const uint32_t r = threadIdx.x >> 5;
-  const uint32_t g = blockIdx.x * GROUPS_PER_CTA + (threadIdx.x & 31u);
-  if (g >= d.G) return;
-  Replica<R> rep(d, r, g);
+  JR_DYN_SMEM(uint4, smem);
+  const uint32_t r = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const uint32_t g = blockIdx.x * GROUPS_PER_CTA + lane;  // padded groups (g >= G) are real, unused replicas
+  const uint32_t box = d.Us * R * 32;
+  Local L;
+  L.in = smem;
+  L.out = smem + box;
+  L.tc = smem + 2 * box;
+  L.cin = reinterpret_cast<uint32_t*>(smem + 2 * box + d.W * R * 32);
+  L.cout = L.cin + R * 32;
+  L.Us = d.Us; L.W = d.W; L.lane = lane;
+  Replica<R> rep(d, L, r, g);
   rep.now = p.now;
   rep.cur = p.cur;
   rep.load(p.phases & PH_RESET_OUT, p.phases & PH_RESET_FSM);
-  rep.run_step(p);
+  rep.tc_prefetch();
+  rep.stage_inbox(p.phases & PH_DRAIN);
+  __syncthreads();
+  StepParams q = p;
+  for (uint32_t t = 0;; ++t) {
+    rep.run_step(q);
+    if (t + 1 == p.n_ticks) break;
+    L.cout[r * 32 + lane] = rep.ocnt;
+    __syncthreads();
+    // next tick: what was written becomes the inbox
+    uint4* tb = L.in; L.in = L.out; L.out = tb;
+    uint32_t* tcn = L.cin; L.cin = L.cout; L.cout = tcn;
+    rep.cur ^= 1;
+    rep.ocnt = 0;
+    rep.ocnt0 = 0;
+    rep.now += p.dt;
+    q.now = rep.now;
+    q.step_index += 1;
+    q.phases = PH_RESET_OUT | PH_DRAIN | PH_PROPOSE | PH_TICK;
+    q.proposals = nullptr;
+  }
   rep.store();
 }
 
 // Host-injected commands: one thread per distinct target replica, commands in
-// array order.  targets[i] = {group, replica index, first, count}.
+// array order.  targets[i] = {group, replica index, first, count}.  No staging.
 template <int R>
 __global__ void inject_kernel(const Dev d, const StepParams p, const jr_msg* msgs, const uint4* targets,
                               uint32_t n_targets) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_targets) return;
   const uint4 t = targets[i];
-  Replica<R> rep(d, t.y, t.x);
+  Local L;
+  L.in = L.out = L.tc = nullptr; L.cin = L.cout = nullptr; L.Us = 0; L.W = 0; L.lane = 0;
+  Replica<R> rep(d, L, t.y, t.x);
   rep.now = p.now;
   rep.cur = p.cur;
   rep.load(false, false);
@@ -52,7 +88,7 @@ __global__ void inject_kernel(const Dev d, const StepParams p, const jr_msg* msg
     c.kind = m->kind; c.flag = m->flag ? 1u : 0u; c.node_id = m->node_id; c.block = (uint32_t)m->block;
     c.nblk = m->n_blocks; c.addr = ((uint32_t)m->client_kind << 16) | (m->client_id & 0xffffu);
     c.term = m->term; c.last_term = m->last_term; c.token = m->token;
-    c.blk_units = nullptr; c.blk_stride = 0; c.host_msg = m;
+    c.blk_s = 0; c.blk_at = 0; c.host_msg = m;
     rep.apply(c);
   }
   rep.store();
@@ -360,9 +396,14 @@ static jr_status dalloc(jr_engine* e, T** p, size_t n) {
     default: { constexpr int RR = 8; CALL; } break; \
   }
 
+static size_t step_smem_bytes(const Dev& d) {
+  return ((size_t)2 * d.Us + d.W) * d.R * 32 * sizeof(uint4) + (size_t)2 * d.R * 32 * sizeof(uint32_t);
+}
+
 static jr_status launch_step(jr_engine* e, const StepParams& p) {
   const uint32_t grid = e->d.Gp / GROUPS_PER_CTA;
-  DISPATCH_R(e->cfg.n_replicas, (JR_LAUNCH(step_kernel<RR>, grid, 32 * RR, e->stream, e->d, p)));
+  const size_t smem = step_smem_bytes(e->d);
+  DISPATCH_R(e->cfg.n_replicas, (JR_LAUNCH_SMEM(step_kernel<RR>, grid, 32 * RR, smem, e->stream, e->d, p)));
   CK(cudaGetLastError());
   return JR_OK;
 }
@@ -422,6 +463,11 @@ jr_status jr_engine_create(const jr_config* cfg, jr_engine** out) {
   d.hb = cfg->heartbeat_ms;
   d.seed = cfg->seed;
   d.goff = cfg->group_offset;
+  // shared-memory staging: Us mailbox units per replica per buffer, W table-cache entries
+  d.Us = std::min<uint32_t>(cfg->mailbox_units, d.R <= 5 ? 16u : 12u);
+  d.W = 8;
+  if (const char* ev = getenv("JR_SMEM_UNITS")) d.Us = std::min<uint32_t>(cfg->mailbox_units, (uint32_t)atoi(ev));
+  if (const char* ev = getenv("JR_TABLE_CACHE")) { uint32_t w = (uint32_t)atoi(ev); d.W = (w & (w - 1)) ? 8 : w; }
   const size_t plane = (size_t)d.R * d.Gp;
   jr_status st = JR_OK;
 #define A(ptr, n) if (st == JR_OK) st = dalloc(e, &(ptr), (n))
@@ -448,6 +494,16 @@ jr_status jr_engine_create(const jr_config* cfg, jr_engine** out) {
     return JR_E_CUDA;
   }
   e->stream = e->own_stream;
+  {
+    const int smem = (int)step_smem_bytes(d);
+    cudaError_t aerr = cudaSuccess;
+    DISPATCH_R(d.R, (aerr = cudaFuncSetAttribute(step_kernel<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)));
+    if (aerr != cudaSuccess) {
+      set_err("step kernel needs %d bytes of shared memory: %s", smem, cudaGetErrorString(aerr));
+      jr_engine_destroy(e);
+      return JR_E_CUDA;
+    }
+  }
   // block tables start empty (all keys absent); pr / qt zero
   cudaMemsetAsync(d.cnext, 0xFF, plane * (size_t)d.cap * sizeof(uint32_t), e->stream);
   cudaMemsetAsync(d.pr, 0, plane * ((d.R + 3) / 4) * sizeof(uint4), e->stream);
@@ -648,6 +704,8 @@ jr_status jr_step(jr_engine* e, jr_step_args* a) {
   p.step_index = e->step_index;
   p.n_synth = (a->flags & JR_STEP_SYNTH_PROPOSALS) ? a->n_synth : 0;
   p.cur = e->cur;
+  p.n_ticks = 1;
+  p.dt = 0;
   p.proposals = nullptr;
   if (a->proposals) {
     CK(cudaMemcpyAsync(e->prop, a->proposals, (size_t)G * sizeof(jr_proposal), cudaMemcpyHostToDevice, e->stream));
@@ -710,19 +768,20 @@ jr_status jr_run(jr_engine* e, uint64_t now0, uint32_t dt, uint32_t n_steps, uin
   if (!e) return JR_E_INVAL;
   if (n_synth > 8) { set_err("n_synth <= 8"); return JR_E_INVAL; }
   CK(cudaSetDevice(e->cfg.device));
-  for (uint32_t k = 0; k < n_steps; ++k) {
-    StepParams p;
-    p.now = now0 + (uint64_t)k * dt;
-    p.step_index = e->step_index;
-    p.n_synth = n_synth;
-    p.cur = e->cur;
-    p.proposals = nullptr;
-    p.phases = PH_RESET_OUT | (k == 0 ? PH_RESET_FSM : 0u) | PH_DRAIN | (n_synth ? PH_PROPOSE : 0u) | PH_TICK;
-    jr_status st = launch_step(e, p);
-    if (st != JR_OK) return st;
-    e->cur ^= 1;
-    e->step_index++;
-  }
+  if (n_steps == 0) return JR_OK;
+  StepParams p;
+  p.now = now0;
+  p.step_index = e->step_index;
+  p.n_synth = n_synth;
+  p.n_ticks = n_steps;
+  p.dt = dt;
+  p.cur = e->cur;
+  p.proposals = nullptr;
+  p.phases = PH_RESET_OUT | PH_RESET_FSM | PH_DRAIN | (n_synth ? PH_PROPOSE : 0u) | PH_TICK;
+  jr_status st = launch_step(e, p);
+  if (st != JR_OK) return st;
+  e->cur ^= (int)(n_steps & 1u);
+  e->step_index += n_steps;
   return JR_OK;
 }
 

@@ -51,16 +51,30 @@ struct Dev {
   uint32_t* fc;
   uint32_t G, Gp, R, cap, U, F, flags;
   uint32_t emin, emax, hb;
+  uint32_t Us, W;                  // shared-memory mailbox units per replica, table-cache entries (power of 2)
   uint64_t seed, goff;
+};
+
+// Per-lane view of the CTA's shared memory.  Us == 0 / W == 0 (sparse inject
+// kernel) means "no staging": every access goes to global memory.
+struct Local {
+  uint4* in;        // mailbox units of the previous tick   [unit][replica][lane]
+  uint4* out;       // mailbox units written this tick
+  uint32_t* cin;    // units used, previous tick            [replica][lane]
+  uint32_t* cout;
+  uint4* tc;        // block-table cache {id, next, token}  [id & (W-1)][replica][lane]
+  uint32_t Us, W, lane;
 };
 
 struct StepParams {
   uint64_t now;
   uint64_t step_index;
-  uint32_t phases;
+  uint32_t phases;               // phases of the FIRST tick; later ticks are RESET_OUT|DRAIN|PROPOSE|TICK
   uint32_t n_synth;
-  int cur;                       // outbox written this step; 1-cur is read
-  const jr_proposal* proposals;  // device, G entries or null
+  uint32_t n_ticks;              // ticks fused in this launch (>= 1)
+  uint32_t dt;                   // ms between fused ticks
+  int cur;                       // outbox written by the first tick; 1-cur is read
+  const jr_proposal* proposals;  // device, G entries or null (first tick only)
 };
 
 __host__ __device__ inline uint64_t mix64(uint64_t x) {
@@ -89,8 +103,7 @@ __host__ __device__ inline uint64_t synth_token(uint64_t step_index, uint32_t i,
 struct Cmd {
   uint32_t kind, flag, node_id, block, nblk, addr;  // addr = client address kind<<16 | id
   uint64_t term, last_term, token;
-  const uint4* blk_units;  // first block unit (mailbox) or null
-  size_t blk_stride;       // in uint4
+  uint32_t blk_s, blk_at;  // mailbox: sender index and slot of the first block unit
   const jr_msg* host_msg;  // injected command or null
 };
 
@@ -154,11 +167,13 @@ __device__ __noinline__ uint64_t digest_fsm_fn(uint64_t h, bool notify, uint32_t
 template <int R>
 struct Replica {
   const Dev& d;
+  const Local& L;
   const uint32_t r, g;   // replica index (node id - 1), local group
   const size_t rg;       // r * Gp + g
   const size_t plane;    // R * Gp
   uint64_t now;
   int cur;
+  uint32_t ocnt0;        // units already in the outbox when this launch started (continuation launches)
   // ---- State (mod.rs:271-287) + role state + Chain scalars (chain.rs:99-104)
   uint64_t term, etime, hbtime;
   uint32_t voted, leader, etimeout, draws, head, commit, idgen, maxkey;
@@ -168,8 +183,8 @@ struct Replica {
   uint32_t ocnt, fcnt, nmsg, nfsm;
   uint64_t mdig, fdig;
 
-  __device__ __forceinline__ Replica(const Dev& dv, uint32_t r_, uint32_t g_)
-      : d(dv), r(r_), g(g_), rg((size_t)r_ * dv.Gp + g_), plane((size_t)R * dv.Gp) {}
+  __device__ __forceinline__ Replica(const Dev& dv, const Local& lv, uint32_t r_, uint32_t g_)
+      : d(dv), L(lv), r(r_), g(g_), rg((size_t)r_ * dv.Gp + g_), plane((size_t)R * dv.Gp) {}
 
   __device__ __forceinline__ uint32_t id() const { return r + 1; }
   __device__ __forceinline__ bool live() const { return !dead && fault == 0; }
@@ -203,6 +218,7 @@ struct Replica {
       }
     }
     ocnt = reset_out ? 0u : d.oc[cur][rg];
+    ocnt0 = ocnt;
     fcnt = reset_fsm ? 0u : d.fc[rg];
     mdig = fdig = 0; nmsg = nfsm = 0;
     if (digest_on()) {
@@ -234,6 +250,10 @@ struct Replica {
         }
       }
     }
+    // the last tick's mailbox lives in shared memory: publish it for the next launch / capture
+    const uint32_t staged = ocnt < L.Us ? ocnt : L.Us;
+    for (uint32_t u = ocnt0; u < staged; ++u)
+      d.ob[cur][((size_t)u * R + r) * d.Gp + g] = L.out[(u * R + r) * 32 + L.lane];
     d.oc[cur][rg] = ocnt;
     d.fc[rg] = fcnt;
     if (digest_on()) {
@@ -244,14 +264,59 @@ struct Replica {
 
   // ------------------------------------------------------------------ block table (chain.rs)
   __device__ __forceinline__ size_t tix(uint32_t bid) const { return (size_t)bid * plane + rg; }
-  __device__ __forceinline__ uint32_t tbl_next(uint32_t bid) const { return d.cnext[tix(bid)]; }
-  __device__ __forceinline__ uint64_t tbl_tok(uint32_t bid) const { return d.ctok[tix(bid)]; }
+  // Block table reads go through a direct-mapped, write-through cache in shared
+  // memory (tag = id).  Only this lane writes its own table, so the cache is
+  // coherent for the whole launch; it is rebuilt at launch start.
+  __device__ __forceinline__ uint4* tc_slot(uint32_t bid) const {
+    return L.tc + (((bid & (L.W - 1)) * R + r) * 32 + L.lane);
+  }
+  __device__ __forceinline__ void tbl_fetch(uint32_t bid, uint32_t& next, uint64_t& tok) const {
+    if (L.W) {
+      const uint4 e = *tc_slot(bid);
+      if (e.x == bid) { next = e.y; tok = (uint64_t)e.z | ((uint64_t)e.w << 32); return; }
+    }
+    next = d.cnext[tix(bid)];   // both loads issue together: one latency
+    tok = d.ctok[tix(bid)];
+    if (L.W) *tc_slot(bid) = make_uint4(bid, next, (uint32_t)tok, (uint32_t)(tok >> 32));
+  }
+  __device__ __forceinline__ uint32_t tbl_next(uint32_t bid) const {
+    uint32_t n; uint64_t t;
+    tbl_fetch(bid, n, t);
+    return n;
+  }
+  __device__ __forceinline__ uint64_t tbl_tok(uint32_t bid) const {
+    uint32_t n; uint64_t t;
+    tbl_fetch(bid, n, t);
+    return t;
+  }
   // chain.rs:155-157
   __device__ __forceinline__ bool has(uint32_t bid) const { return bid < d.cap && tbl_next(bid) != ABSENT; }
   __device__ __forceinline__ void tbl_put(uint32_t bid, uint32_t next, uint64_t tok) {
     d.cnext[tix(bid)] = next;
     d.ctok[tix(bid)] = tok;
+    if (L.W) *tc_slot(bid) = make_uint4(bid, next, (uint32_t)tok, (uint32_t)(tok >> 32));
     if (bid > maxkey) maxkey = bid;
+  }
+  // Launch start: invalidate, then pull the table tail (the blocks the steady state touches).
+  __device__ __forceinline__ void tc_prefetch() const {
+    if (!L.W) return;
+    for (uint32_t k = 0; k < L.W; ++k) L.tc[(k * R + r) * 32 + L.lane] = make_uint4(0xFFFFFFFFu, ABSENT, 0, 0);
+    for (uint32_t k = 0; k < L.W && k <= maxkey; ++k) {
+      const uint32_t bid = maxkey - k;
+      const uint32_t n = d.cnext[tix(bid)];
+      const uint64_t t = d.ctok[tix(bid)];
+      *tc_slot(bid) = make_uint4(bid, n, (uint32_t)t, (uint32_t)(t >> 32));
+    }
+  }
+  // Launch start: copy this lane's own previous-tick outbox into the shared mailbox.
+  __device__ __forceinline__ void stage_inbox(bool deliver) const {
+    if (!L.cin) return;
+    const int prv = 1 - cur;
+    const uint32_t cnt = deliver ? d.oc[prv][rg] : 0u;
+    L.cin[r * 32 + L.lane] = cnt;
+    const uint32_t n = cnt < L.Us ? cnt : L.Us;
+    for (uint32_t u = 0; u < n; ++u)
+      L.in[(u * R + r) * 32 + L.lane] = __ldg(d.ob[prv] + ((size_t)u * R + r) * d.Gp + g);
   }
   // chain.rs:160-175; returns false on fault
   __device__ __forceinline__ bool chain_append(uint64_t tok, uint32_t& out_id) {
@@ -282,8 +347,18 @@ struct Replica {
   // ------------------------------------------------------------------ outputs
   __device__ __forceinline__ bool put_unit(uint32_t slot, uint4 v) {
     if (slot >= d.U) { fault = JR_FAULT_ENGINE_MAILBOX_OVERFLOW; return false; }
-    d.ob[cur][((size_t)slot * R + r) * d.Gp + g] = v;
+    if (slot < L.Us) L.out[(slot * R + r) * 32 + L.lane] = v;
+    else d.ob[cur][((size_t)slot * R + r) * d.Gp + g] = v;
     return true;
+  }
+  __device__ __forceinline__ uint4 own_unit(uint32_t slot) const {  // read back what this lane emitted
+    if (slot < L.Us) return L.out[(slot * R + r) * 32 + L.lane];
+    return d.ob[cur][((size_t)slot * R + r) * d.Gp + g];
+  }
+  // unit `u` of sender `s_` in the previous tick's mailbox
+  __device__ __forceinline__ uint4 inbox_unit(uint32_t s_, uint32_t u) const {
+    if (u < L.Us) return L.in[(u * R + s_) * 32 + L.lane];
+    return __ldcg(d.ob[1 - cur] + ((size_t)u * R + s_) * d.Gp + g);  // spilled unit: L2, never a stale L1 line
   }
 
   // mod.rs:390-400 for every single-unit command.
@@ -416,7 +491,7 @@ struct Replica {
       next = (uint32_t)c.host_msg->blocks[k].next;
       tok = c.host_msg->blocks[k].data;
     } else {
-      uint4 u = c.blk_units[(size_t)k * c.blk_stride];
+      uint4 u = inbox_unit(c.blk_s, c.blk_at + k);
       bid = u.x; next = u.y; tok = (uint64_t)u.z | ((uint64_t)u.w << 32);
     }
   }
@@ -457,8 +532,9 @@ struct Replica {
       uint32_t prev = commit;
       chain_commit(c.block);
       for (uint32_t b = prev; b < c.block; ++b) {  // range(prev..commit), key order
-        uint32_t nx = tbl_next(b);
-        if (nx != ABSENT) { fsm_emit(false, b, nx, tbl_tok(b)); if (fault) return; }
+        uint32_t nx; uint64_t tk;
+        tbl_fetch(b, nx, tk);
+        if (nx != ABSENT) { fsm_emit(false, b, nx, tk); if (fault) return; }
       }
     }
     send(JR_CMD_HEARTBEAT_RESPONSE, ldr, hasc ? 1 : 0, 0, 0, commit);
@@ -521,10 +597,11 @@ struct Replica {
       if (!chain_commit(q)) return;
       bool first = true;
       for (uint32_t b = prev; b <= q; ++b) {  // range(prev..=new).skip(1), key order
-        uint32_t nx = tbl_next(b);
+        uint32_t nx; uint64_t tk;
+        tbl_fetch(b, nx, tk);
         if (nx == ABSENT) continue;
         if (first) { first = false; continue; }
-        fsm_emit(false, b, nx, tbl_tok(b));
+        fsm_emit(false, b, nx, tk);
         if (fault) return;
       }
     }
@@ -538,15 +615,18 @@ struct Replica {
       const uint32_t take = (prmask >> p) & 1u ? JR_MAX_AE_BLOCKS : 1u;
       uint32_t bid = ph[p], pulled = 0, nb = 0;
       while (pulled < 1 + take) {
-        uint32_t nx = ABSENT;
-        while (bid <= maxkey && (nx = tbl_next(bid)) == ABSENT) ++bid;
+        uint32_t nx = ABSENT; uint64_t tok = 0;
+        while (bid <= maxkey) {
+          tbl_fetch(bid, nx, tok);
+          if (nx != ABSENT) break;
+          ++bid;
+        }
         if (bid > maxkey) {
           // sled would now yield the "commit" key and bincode panics (D6)
           if ((d.flags & JR_F_SLED_COMMIT_KEY_STRICT) && ckey) { fault = JR_FAULT_RANGE_COMMIT_KEY; return; }
           break;
         }
         if (pulled >= 1) {
-          uint64_t tok = tbl_tok(bid);
           if (!put_unit(ocnt + 1 + nb, make_uint4(bid, nx, (uint32_t)tok, (uint32_t)(tok >> 32)))) return;
           ++nb;
         }
@@ -560,7 +640,7 @@ struct Replica {
         uint64_t h = digest_message_fn(mdig, JR_CMD_APPEND_ENTRIES, p + 1, 0, nb, id(), term, 0, 0, 0, 0);
         ++nmsg;
         for (uint32_t k = 0; k < nb; ++k) {
-          uint4 u = d.ob[cur][((size_t)(ocnt + 1 + k) * R + r) * d.Gp + g];
+          uint4 u = own_unit(ocnt + 1 + k);
           h = fold(h, u.x);
           h = fold(h, u.y);
           h = fold(h, (uint64_t)u.z | ((uint64_t)u.w << 32));
@@ -666,6 +746,7 @@ struct Replica {
 
   __device__ __forceinline__ bool next_cmd(Cursor& k, Cmd& c, const StepParams& p) {
     const int prv = 1 - cur;
+    (void)prv;
     for (;;) {
       if (k.stage == 0) {
         if (k.reps) { --k.reps; return true; }  // another copy of the same VoteRequest broadcast
@@ -673,22 +754,20 @@ struct Replica {
           ++k.s;
           if (k.s == r) ++k.s;
           if (k.s >= (uint32_t)R) { k.stage = 1; continue; }
-          k.cnt = d.oc[prv][(size_t)k.s * d.Gp + g];
+          k.cnt = L.cin ? L.cin[k.s * 32 + L.lane] : d.oc[prv][(size_t)k.s * d.Gp + g];
           k.u = 0;
           continue;
         }
-        const uint4* base = d.ob[prv] + (size_t)k.s * d.Gp + g;
-        const uint4 h = __ldg(base + (size_t)k.u * plane);
+        const uint4 h = inbox_unit(k.s, k.u);
         const uint32_t kind = h.x & 15u, flag = (h.x >> 4) & 1u, aux = (h.x >> 8) & 255u, to = h.x >> 16;
         const uint32_t at = k.u;
         k.u += 1 + (kind == JR_CMD_APPEND_ENTRIES ? aux : 0u);
         if (to != TO_PEERS && to != id()) continue;
         c.kind = kind; c.flag = flag; c.node_id = k.s + 1; c.block = h.w; c.nblk = 0; c.addr = 0;
         c.term = (uint64_t)h.y | ((uint64_t)h.z << 32); c.last_term = c.term; c.token = 0;
-        c.blk_units = nullptr; c.blk_stride = plane; c.host_msg = nullptr;
+        c.blk_s = k.s; c.blk_at = at + 1; c.host_msg = nullptr;
         if (kind == JR_CMD_APPEND_ENTRIES) {
           c.nblk = aux;
-          c.blk_units = base + (size_t)(at + 1) * plane;
         } else if (kind == JR_CMD_CLIENT_REQUEST || kind == JR_CMD_CLIENT_RESPONSE) {
           c.token = c.term; c.term = 0; c.last_term = 0; c.addr = h.w; c.block = 0;
         } else if (kind == JR_CMD_VOTE_REQUEST) {
@@ -697,10 +776,10 @@ struct Replica {
         return true;
       }
       c.flag = 0; c.node_id = 0; c.block = 0; c.nblk = 0; c.term = c.last_term = 0;
-      c.blk_units = nullptr; c.blk_stride = 0; c.host_msg = nullptr;
+      c.blk_s = 0; c.blk_at = 0; c.host_msg = nullptr;
       if (k.stage == 1) {  // event_loop client arm, server.rs:156-160
         k.stage = 2;
-        if ((p.phases & PH_PROPOSE) && p.proposals) {
+        if ((p.phases & PH_PROPOSE) && p.proposals && g < d.G) {
           const uint4 pr = __ldg(reinterpret_cast<const uint4*>(p.proposals) + g);
           if (pr.z == id()) {
             c.kind = JR_CMD_CLIENT_REQUEST; c.addr = (uint32_t)JR_ADDR_CLIENT << 16;
@@ -735,7 +814,7 @@ struct Replica {
     cursor_init(k, p.phases);
     Cmd c;
     c.kind = JR_CMD_NOOP; c.flag = 0; c.node_id = 0; c.block = 0; c.nblk = 0; c.addr = 0;
-    c.term = c.last_term = c.token = 0; c.blk_units = nullptr; c.blk_stride = 0; c.host_msg = nullptr;
+    c.term = c.last_term = c.token = 0; c.blk_s = 0; c.blk_at = 0; c.host_msg = nullptr;
     while (live() && next_cmd(k, c, p)) apply(c);
   }
 };

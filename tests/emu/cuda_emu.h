@@ -27,33 +27,66 @@ inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return
 #define __launch_bounds__(...)
 #define __shared__ static
 
+#include <pthread.h>
+
+#include <thread>
+#include <vector>
+
 namespace jr_emu {
-inline uint3& tid() { static uint3 v{0, 0, 0}; return v; }
-inline uint3& bid() { static uint3 v{0, 0, 0}; return v; }
-inline uint3& bdim() { static uint3 v{1, 1, 1}; return v; }
-inline uint3& gdim() { static uint3 v{1, 1, 1}; return v; }
+struct Ctx {
+  uint3 tid{0, 0, 0}, bid{0, 0, 0}, bdim{1, 1, 1}, gdim{1, 1, 1};
+  void* smem = nullptr;
+  pthread_barrier_t* bar = nullptr;
+};
+inline Ctx& ctx() { static thread_local Ctx c; return c; }
+// Barrier-free kernels: one thread after another on the calling thread.
 template <class F>
 inline void launch(unsigned grid, unsigned block, F&& body) {
-  gdim().x = grid;
-  bdim().x = block;
+  Ctx& c = ctx();
+  c.gdim.x = grid; c.bdim.x = block; c.smem = nullptr; c.bar = nullptr;
   for (unsigned b = 0; b < grid; ++b)
     for (unsigned t = 0; t < block; ++t) {
-      bid().x = b;
-      tid().x = t;
+      c.bid.x = b; c.tid.x = t;
       body();
     }
 }
+// Kernels that use __syncthreads() / dynamic shared memory: one OS thread per CUDA
+// thread of a CTA and a pthread barrier; CTAs run one after another.
+template <class F>
+inline void launch_coop(unsigned grid, unsigned block, size_t smem_bytes, F&& body) {
+  for (unsigned b = 0; b < grid; ++b) {
+    void* sm = aligned_alloc(64, (smem_bytes + 63) / 64 * 64 + 64);
+    pthread_barrier_t bar;
+    pthread_barrier_init(&bar, nullptr, block);
+    std::vector<std::thread> th;
+    th.reserve(block);
+    for (unsigned t = 0; t < block; ++t)
+      th.emplace_back([&, t]() {
+        Ctx& c = ctx();
+        c.gdim.x = grid; c.bdim.x = block; c.bid.x = b; c.tid.x = t; c.smem = sm; c.bar = &bar;
+        body();
+      });
+    for (auto& x : th) x.join();
+    pthread_barrier_destroy(&bar);
+    free(sm);
+  }
+}
+inline void sync() { if (ctx().bar) pthread_barrier_wait(ctx().bar); }
 }  // namespace jr_emu
-#define threadIdx (jr_emu::tid())
-#define blockIdx (jr_emu::bid())
-#define blockDim (jr_emu::bdim())
-#define gridDim (jr_emu::gdim())
+#define threadIdx (jr_emu::ctx().tid)
+#define blockIdx (jr_emu::ctx().bid)
+#define blockDim (jr_emu::ctx().bdim)
+#define gridDim (jr_emu::ctx().gdim)
 #define JR_LAUNCH(kernel, grid, block, stream, ...) \
   jr_emu::launch((unsigned)(grid), (unsigned)(block), [&]() { kernel(__VA_ARGS__); })
+#define JR_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) \
+  jr_emu::launch_coop((unsigned)(grid), (unsigned)(block), (size_t)(smem), [&]() { kernel(__VA_ARGS__); })
+#define JR_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(jr_emu::ctx().smem)
 
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
-inline void __syncthreads() {}
+inline void __syncthreads() { jr_emu::sync(); }
+template <class T> inline T __ldcg(const T* p) { return *p; }
 template <class T> inline T __shfl_down_sync(unsigned, T v, int) { return v; }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
 inline unsigned atomicMax(unsigned* p, unsigned v) { unsigned o = *p; *p = std::max(o, v); return o; }
@@ -76,4 +109,6 @@ inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <class F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }

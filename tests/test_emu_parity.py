@@ -58,3 +58,21 @@ def test_run_equals_steps():
         b.step(100 + 100 * k, n_synth=1)
     parity.compare_states(a, b, chain_ids=40)
     parity.compare_digests(a, b)
+
+
+@pytest.mark.parametrize("units,cache", [(1, 1), (2, 2), (3, 4), (0, 0)])
+def test_spill_and_cache_paths(monkeypatch, units, cache):
+    """Tiny shared-memory mailbox / table cache: units beyond Us spill to the global
+    mailbox and the direct-mapped cache thrashes -- results must not change."""
+    monkeypatch.setenv("JR_SMEM_UNITS", str(units))
+    monkeypatch.setenv("JR_TABLE_CACHE", str(cache))
+    p = parity.Pair(make_oracle, make_emu, 4, 5, seed=1)
+    parity.scenario_steady(p, steps=20)
+    p = parity.Pair(make_oracle, make_emu, 3, 3, seed=11, chain_capacity=64)
+    parity.scenario_random_inject(p, seed=4242, steps=40)
+    a = make_emu(4, 3, seed=3, flags=parity.FULL, fsm_units=256)
+    b = make_oracle(4, 3, seed=3, flags=parity.FULL, fsm_units=256)
+    a.run(100, 100, 40, 2)
+    b.run(100, 100, 40, 2)
+    parity.compare_states(a, b, chain_ids=90)
+    parity.compare_digests(a, b)
