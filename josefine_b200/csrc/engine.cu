@@ -39,6 +39,8 @@ __global__ void __launch_bounds__(32 * R) step_kernel(const Dev d, const StepPar
   L.tc = smem + 2 * box;
   L.cin = reinterpret_cast<uint32_t*>(smem + 2 * box + d.W * R * 32);
   L.cout = L.cin + R * 32;
+  L.mk_in = L.cout + R * 32;
+  L.mk_out = L.mk_in + R * R * 32;
   L.Us = d.Us; L.W = d.W; L.lane = lane;
   Replica<R> rep(d, L, r, g);
   rep.now = p.now;
@@ -49,6 +51,7 @@ __global__ void __launch_bounds__(32 * R) step_kernel(const Dev d, const StepPar
   __syncthreads();
   StepParams q = p;
   for (uint32_t t = 0;; ++t) {
+    rep.clear_marks();
     rep.run_step(q);
     if (t + 1 == p.n_ticks) break;
     L.cout[r * 32 + lane] = rep.ocnt;
@@ -56,6 +59,7 @@ __global__ void __launch_bounds__(32 * R) step_kernel(const Dev d, const StepPar
     // next tick: what was written becomes the inbox
     uint4* tb = L.in; L.in = L.out; L.out = tb;
     uint32_t* tcn = L.cin; L.cin = L.cout; L.cout = tcn;
+    uint32_t* tmk = L.mk_in; L.mk_in = L.mk_out; L.mk_out = tmk;
     rep.cur ^= 1;
     rep.ocnt = 0;
     rep.ocnt0 = 0;
@@ -77,7 +81,7 @@ __global__ void inject_kernel(const Dev d, const StepParams p, const jr_msg* msg
   if (i >= n_targets) return;
   const uint4 t = targets[i];
   Local L;
-  L.in = L.out = L.tc = nullptr; L.cin = L.cout = nullptr; L.Us = 0; L.W = 0; L.lane = 0;
+  L.in = L.out = L.tc = nullptr; L.cin = L.cout = L.mk_in = L.mk_out = nullptr; L.Us = 0; L.W = 0; L.lane = 0;
   Replica<R> rep(d, L, t.y, t.x);
   rep.now = p.now;
   rep.cur = p.cur;
@@ -397,7 +401,8 @@ static jr_status dalloc(jr_engine* e, T** p, size_t n) {
   }
 
 static size_t step_smem_bytes(const Dev& d) {
-  return ((size_t)2 * d.Us + d.W) * d.R * 32 * sizeof(uint4) + (size_t)2 * d.R * 32 * sizeof(uint32_t);
+  return ((size_t)2 * d.Us + d.W) * d.R * 32 * sizeof(uint4) + (size_t)2 * d.R * 32 * sizeof(uint32_t) +
+         (size_t)2 * d.R * d.R * 32 * sizeof(uint32_t);
 }
 
 static jr_status launch_step(jr_engine* e, const StepParams& p) {
@@ -464,8 +469,8 @@ jr_status jr_engine_create(const jr_config* cfg, jr_engine** out) {
   d.seed = cfg->seed;
   d.goff = cfg->group_offset;
   // shared-memory staging: Us mailbox units per replica per buffer, W table-cache entries
-  d.Us = std::min<uint32_t>(cfg->mailbox_units, d.R <= 5 ? 16u : 12u);
-  d.W = 8;
+  d.Us = std::min<uint32_t>(cfg->mailbox_units, 8u);
+  d.W = 4;
   if (const char* ev = getenv("JR_SMEM_UNITS")) d.Us = std::min<uint32_t>(cfg->mailbox_units, (uint32_t)atoi(ev));
   if (const char* ev = getenv("JR_TABLE_CACHE")) { uint32_t w = (uint32_t)atoi(ev); d.W = (w & (w - 1)) ? 8 : w; }
   const size_t plane = (size_t)d.R * d.Gp;

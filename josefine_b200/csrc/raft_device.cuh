@@ -63,8 +63,14 @@ struct Local {
   uint32_t* cin;    // units used, previous tick            [replica][lane]
   uint32_t* cout;
   uint4* tc;        // block-table cache {id, next, token}  [id & (W-1)][replica][lane]
+  // Delivery index: bit u of mk[receiver][sender][lane] = unit u of the sender's
+  // mailbox is a header addressed to that receiver (or to Peers).  Bit 31 = the
+  // sender emitted a header at slot >= 31: scan its whole mailbox instead.
+  uint32_t* mk_in;
+  uint32_t* mk_out;
   uint32_t Us, W, lane;
 };
+constexpr uint32_t MK_SCAN = 0x80000000u;
 
 struct StepParams {
   uint64_t now;
@@ -317,6 +323,21 @@ struct Replica {
     const uint32_t n = cnt < L.Us ? cnt : L.Us;
     for (uint32_t u = 0; u < n; ++u)
       L.in[(u * R + r) * 32 + L.lane] = __ldg(d.ob[prv] + ((size_t)u * R + r) * d.Gp + g);
+    // the delivery index is derived data: rebuild it from the units just staged
+    uint32_t m[R];
+#pragma unroll
+    for (int t = 0; t < R; ++t) m[t] = 0;
+    for (uint32_t u = 0; u < cnt;) {
+      const uint4 h = u < L.Us ? L.in[(u * R + r) * 32 + L.lane] : __ldg(d.ob[prv] + ((size_t)u * R + r) * d.Gp + g);
+      const uint32_t kind = h.x & 15u, aux = (h.x >> 8) & 255u, to = h.x >> 16;
+      const uint32_t bit = u < 31u ? (1u << u) : MK_SCAN;
+#pragma unroll
+      for (int t = 0; t < R; ++t)
+        if (to == TO_PEERS || to == (uint32_t)t + 1u) m[t] |= bit;
+      u += 1u + (kind == JR_CMD_APPEND_ENTRIES ? aux : 0u);
+    }
+#pragma unroll
+    for (int t = 0; t < R; ++t) L.mk_in[(t * R + r) * 32 + L.lane] = m[t];
   }
   // chain.rs:160-175; returns false on fault
   __device__ __forceinline__ bool chain_append(uint64_t tok, uint32_t& out_id) {
@@ -361,9 +382,27 @@ struct Replica {
     return __ldcg(d.ob[1 - cur] + ((size_t)u * R + s_) * d.Gp + g);  // spilled unit: L2, never a stale L1 line
   }
 
+  __device__ __forceinline__ void mark(uint32_t to, uint32_t slot) {
+    if (!L.mk_out) return;
+    const uint32_t bit = slot < 31u ? (1u << slot) : MK_SCAN;
+    if (to == TO_PEERS) {
+#pragma unroll
+      for (int t = 0; t < R; ++t)
+        if (t != (int)r) L.mk_out[(t * R + r) * 32 + L.lane] |= bit;
+    } else if (to - 1u < (uint32_t)R) {
+      L.mk_out[((to - 1u) * R + r) * 32 + L.lane] |= bit;
+    }
+  }
+  __device__ __forceinline__ void clear_marks() const {
+    if (!L.mk_out) return;
+#pragma unroll
+    for (int t = 0; t < R; ++t) L.mk_out[(t * R + r) * 32 + L.lane] = 0;
+  }
+
   // mod.rs:390-400 for every single-unit command.
   __device__ __forceinline__ void send(uint32_t kind, uint32_t to, uint32_t flag, uint32_t aux, uint64_t t, uint32_t w) {
     if (!put_unit(ocnt, make_uint4(unit_hdr(kind, flag, aux, to), (uint32_t)t, (uint32_t)(t >> 32), w))) return;
+    mark(to, ocnt);
     ++ocnt;
     if (digest_on()) {
       uint32_t n;
@@ -609,33 +648,46 @@ struct Replica {
 
   // leader.rs:124-174.  Probe: range(head..).nth(1); Replicate: range(head..).skip(1).take(5).
   __device__ __forceinline__ void replicate() {
+    // Peers with the same progress head and mode get the same blocks (the steady
+    // state: all of them).  The key-order scan runs once per distinct
+    // (head, mode); repeats copy the block units already sitting in the outbox.
+    uint32_t memo_head = 0xFFFFFFFFu, memo_take = 0, memo_first = 0, memo_nb = 0;
 #pragma unroll
     for (int p = 0; p < R; ++p) {
       if (p == (int)r) continue;  // config.nodes holds peers only
       const uint32_t take = (prmask >> p) & 1u ? JR_MAX_AE_BLOCKS : 1u;
-      uint32_t bid = ph[p], pulled = 0, nb = 0;
-      while (pulled < 1 + take) {
-        uint32_t nx = ABSENT; uint64_t tok = 0;
-        while (bid <= maxkey) {
-          tbl_fetch(bid, nx, tok);
-          if (nx != ABSENT) break;
+      uint32_t nb = 0;
+      if (ph[p] == memo_head && take == memo_take) {
+        for (uint32_t k = 0; k < memo_nb; ++k)
+          if (!put_unit(ocnt + 1 + k, own_unit(memo_first + k))) return;
+        nb = memo_nb;
+      } else {
+        uint32_t bid = ph[p], pulled = 0;
+        while (pulled < 1 + take) {
+          uint32_t nx = ABSENT; uint64_t tok = 0;
+          while (bid <= maxkey) {
+            tbl_fetch(bid, nx, tok);
+            if (nx != ABSENT) break;
+            ++bid;
+          }
+          if (bid > maxkey) {
+            // sled would now yield the "commit" key and bincode panics (D6)
+            if ((d.flags & JR_F_SLED_COMMIT_KEY_STRICT) && ckey) { fault = JR_FAULT_RANGE_COMMIT_KEY; return; }
+            break;
+          }
+          if (pulled >= 1) {
+            if (!put_unit(ocnt + 1 + nb, make_uint4(bid, nx, (uint32_t)tok, (uint32_t)(tok >> 32)))) return;
+            ++nb;
+          }
+          ++pulled;
           ++bid;
         }
-        if (bid > maxkey) {
-          // sled would now yield the "commit" key and bincode panics (D6)
-          if ((d.flags & JR_F_SLED_COMMIT_KEY_STRICT) && ckey) { fault = JR_FAULT_RANGE_COMMIT_KEY; return; }
-          break;
-        }
-        if (pulled >= 1) {
-          if (!put_unit(ocnt + 1 + nb, make_uint4(bid, nx, (uint32_t)tok, (uint32_t)(tok >> 32)))) return;
-          ++nb;
-        }
-        ++pulled;
-        ++bid;
+        memo_head = ph[p]; memo_take = take; memo_first = ocnt + 1; memo_nb = nb;
       }
       if (!put_unit(ocnt, make_uint4(unit_hdr(JR_CMD_APPEND_ENTRIES, 0, nb, p + 1), (uint32_t)term,
                                      (uint32_t)(term >> 32), 0)))
         return;
+      mark(p + 1, ocnt);
       if (digest_on()) {
         uint64_t h = digest_message_fn(mdig, JR_CMD_APPEND_ENTRIES, p + 1, 0, nb, id(), term, 0, 0, 0, 0);
         ++nmsg;
@@ -733,89 +785,72 @@ struct Replica {
   }
 
   // ------------------------------------------------------------------ the step schedule (jr_step_args)
-  // A cursor that yields this replica's commands of one step in order:
-  // peer mail (ascending sender, FIFO) -> dense proposal -> synthetic proposals -> Tick.
-  struct Cursor {
-    uint32_t stage, s, u, cnt, reps, synth_i;
-  };
-
-  __device__ __forceinline__ void cursor_init(Cursor& k, uint32_t phases) const {
-    k.stage = (phases & PH_DRAIN) ? 0u : 1u;
-    k.s = 0xFFFFFFFFu; k.u = 0; k.cnt = 0; k.reps = 0; k.synth_i = 0;
-  }
-
-  __device__ __forceinline__ bool next_cmd(Cursor& k, Cmd& c, const StepParams& p) {
-    const int prv = 1 - cur;
-    (void)prv;
-    for (;;) {
-      if (k.stage == 0) {
-        if (k.reps) { --k.reps; return true; }  // another copy of the same VoteRequest broadcast
-        if (k.u >= k.cnt) {
-          ++k.s;
-          if (k.s == r) ++k.s;
-          if (k.s >= (uint32_t)R) { k.stage = 1; continue; }
-          k.cnt = L.cin ? L.cin[k.s * 32 + L.lane] : d.oc[prv][(size_t)k.s * d.Gp + g];
-          k.u = 0;
-          continue;
-        }
-        const uint4 h = inbox_unit(k.s, k.u);
-        const uint32_t kind = h.x & 15u, flag = (h.x >> 4) & 1u, aux = (h.x >> 8) & 255u, to = h.x >> 16;
-        const uint32_t at = k.u;
-        k.u += 1 + (kind == JR_CMD_APPEND_ENTRIES ? aux : 0u);
-        if (to != TO_PEERS && to != id()) continue;
-        c.kind = kind; c.flag = flag; c.node_id = k.s + 1; c.block = h.w; c.nblk = 0; c.addr = 0;
-        c.term = (uint64_t)h.y | ((uint64_t)h.z << 32); c.last_term = c.term; c.token = 0;
-        c.blk_s = k.s; c.blk_at = at + 1; c.host_msg = nullptr;
-        if (kind == JR_CMD_APPEND_ENTRIES) {
-          c.nblk = aux;
-        } else if (kind == JR_CMD_CLIENT_REQUEST || kind == JR_CMD_CLIENT_RESPONSE) {
-          c.token = c.term; c.term = 0; c.last_term = 0; c.addr = h.w; c.block = 0;
-        } else if (kind == JR_CMD_VOTE_REQUEST) {
-          k.reps = aux ? aux - 1 : 0;  // N-1 identical broadcasts, candidate.rs:30-37
-        }
-        return true;
-      }
-      c.flag = 0; c.node_id = 0; c.block = 0; c.nblk = 0; c.term = c.last_term = 0;
-      c.blk_s = 0; c.blk_at = 0; c.host_msg = nullptr;
-      if (k.stage == 1) {  // event_loop client arm, server.rs:156-160
-        k.stage = 2;
+  // One tick of this replica: peer mail (ascending sender, FIFO per sender) ->
+  // dense proposal -> synthetic proposals -> Tick.  The three trailing sources
+  // are modelled as virtual senders R, R+1, R+2 so the whole schedule is ONE
+  // nested loop with a single `apply` site (the state machine is instantiated
+  // once; keeps the kernel inside the instruction cache).
+  __device__ __forceinline__ void run_step(const StepParams& p) {
+    Cmd c;
+    c.host_msg = nullptr;
+    const uint32_t me = id();
+    const uint32_t s0 = (p.phases & PH_DRAIN) ? 0u : (uint32_t)R;
+    for (uint32_t s = s0; s < (uint32_t)R + 3u && live(); ++s) {
+      uint32_t cnt = 0, idx = MK_SCAN;    // idx: delivery index of sender s for me, or MK_SCAN = walk all units
+      uint4 vh = make_uint4(0, 0, 0, 0);  // header of a virtual unit
+      if (s < (uint32_t)R) {
+        if (s == r) continue;
+        idx = L.mk_in[(r * R + s) * 32 + L.lane];
+        if (idx & MK_SCAN) cnt = L.cin[s * 32 + L.lane];
+      } else if (s == (uint32_t)R) {  // event_loop client arm, server.rs:156-160
         if ((p.phases & PH_PROPOSE) && p.proposals && g < d.G) {
           const uint4 pr = __ldg(reinterpret_cast<const uint4*>(p.proposals) + g);
-          if (pr.z == id()) {
-            c.kind = JR_CMD_CLIENT_REQUEST; c.addr = (uint32_t)JR_ADDR_CLIENT << 16;
-            c.token = (uint64_t)pr.x | ((uint64_t)pr.y << 32);
-            return true;
+          if (pr.z == me) {
+            cnt = 1;
+            vh = make_uint4(unit_hdr(JR_CMD_CLIENT_REQUEST, 0, 0, me), pr.x, pr.y, (uint32_t)JR_ADDR_CLIENT << 16);
           }
         }
-        continue;
+      } else if (s == (uint32_t)R + 1u) {
+        cnt = (p.phases & PH_PROPOSE) ? p.n_synth : 0u;
+      } else {
+        cnt = (p.phases & PH_TICK) ? 1u : 0u;
+        vh = make_uint4(unit_hdr(JR_CMD_TICK, 0, 0, me), 0, 0, 0);
       }
-      if (k.stage == 2) {
-        if ((p.phases & PH_PROPOSE) && k.synth_i < p.n_synth && role == JR_ROLE_LEADER && live()) {
-          c.kind = JR_CMD_CLIENT_REQUEST; c.addr = (uint32_t)JR_ADDR_CLIENT << 16;
-          c.token = synth_token(p.step_index, k.synth_i, d.goff + g);
-          ++k.synth_i;
-          return true;
+      uint32_t u = 0;
+      while (live()) {
+        uint4 h;
+        uint32_t at;
+        if (!(idx & MK_SCAN)) {  // indexed delivery: jump to my next header
+          if (!idx) break;
+          at = (uint32_t)__ffs((int)idx) - 1u;
+          idx &= idx - 1u;
+          h = inbox_unit(s, at);
+        } else {
+          if (u >= cnt) break;
+          at = u;
+          if (s < (uint32_t)R) {
+            h = inbox_unit(s, u);
+          } else if (s == (uint32_t)R + 1u) {
+            if (role != JR_ROLE_LEADER) break;
+            const uint64_t tok = synth_token(p.step_index, u, d.goff + g);
+            h = make_uint4(unit_hdr(JR_CMD_CLIENT_REQUEST, 0, 0, me), (uint32_t)tok, (uint32_t)(tok >> 32),
+                           (uint32_t)JR_ADDR_CLIENT << 16);
+          } else {
+            h = vh;
+          }
+          const uint32_t k0 = h.x & 15u, to = h.x >> 16;
+          u += 1u + (k0 == JR_CMD_APPEND_ENTRIES ? ((h.x >> 8) & 255u) : 0u);
+          if (to != TO_PEERS && to != me) continue;
         }
-        k.stage = 3;
-        continue;
+        const uint32_t kind = h.x & 15u, aux = (h.x >> 8) & 255u;
+        c.kind = kind; c.flag = (h.x >> 4) & 1u; c.node_id = s + 1; c.block = h.w; c.addr = h.w;
+        c.term = (uint64_t)h.y | ((uint64_t)h.z << 32); c.last_term = c.term; c.token = c.term;
+        c.nblk = aux; c.blk_s = s; c.blk_at = at + 1;
+        // N-1 identical VoteRequest broadcasts travel as one unit (candidate.rs:30-37)
+        const uint32_t reps = kind == JR_CMD_VOTE_REQUEST ? aux : 1u;
+        for (uint32_t k = 0; k < reps; ++k) apply(c);
       }
-      if (k.stage == 3) {
-        k.stage = 4;
-        if (p.phases & PH_TICK) { c.kind = JR_CMD_TICK; c.addr = 0; c.token = 0; return true; }
-        continue;
-      }
-      return false;
     }
-  }
-
-  __device__ __forceinline__ void run_step(const StepParams& p) {
-    if (!live()) return;
-    Cursor k;
-    cursor_init(k, p.phases);
-    Cmd c;
-    c.kind = JR_CMD_NOOP; c.flag = 0; c.node_id = 0; c.block = 0; c.nblk = 0; c.addr = 0;
-    c.term = c.last_term = c.token = 0; c.blk_s = 0; c.blk_at = 0; c.host_msg = nullptr;
-    while (live() && next_cmd(k, c, p)) apply(c);
   }
 };
 

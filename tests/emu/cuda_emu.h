@@ -85,6 +85,7 @@ inline void sync() { if (ctx().bar) pthread_barrier_wait(ctx().bar); }
 
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
 inline void __syncthreads() { jr_emu::sync(); }
 template <class T> inline T __ldcg(const T* p) { return *p; }
 template <class T> inline T __shfl_down_sync(unsigned, T v, int) { return v; }

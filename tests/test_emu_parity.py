@@ -76,3 +76,24 @@ def test_spill_and_cache_paths(monkeypatch, units, cache):
     b.run(100, 100, 40, 2)
     parity.compare_states(a, b, chain_ids=90)
     parity.compare_digests(a, b)
+
+
+def test_mailbox_beyond_index_range():
+    """A leader that answers six HeartbeatResponse{!has} with six replicate() rounds
+    emits > 31 units in one step: the delivery index overflows to the scan path and
+    units spill past the shared-memory mailbox."""
+    from josefine_b200 import Command
+    p = parity.Pair(make_oracle, make_emu, 2, 7, seed=9, mailbox_units=128)
+    parity.bootstrap_leaders(p, now=0)
+    for k in range(4):
+        p.step(100 * (k + 1), n_synth=1)
+    inj = [Command.heartbeat_response(g, 1, commit=1, has_committed=False, from_=2 + (i % 6))
+           for g in range(2) for i in range(6)]
+    res = p.step(500, inject=inj, n_synth=1)
+    per_sender = {}
+    for m in res.messages:
+        per_sender[(m.group, m.from_id)] = per_sender.get((m.group, m.from_id), 0) + 1 + m.n_blocks
+    assert max(per_sender.values()) > 40
+    for k in range(6):
+        p.step(600 + 100 * k, n_synth=1)
+    p.finish()
