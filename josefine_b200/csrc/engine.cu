@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(32 * R) step_kernel(const Dev d, const StepPar
     rep.run_step(q);
     if (t + 1 == p.n_ticks) break;
     L.cout[r * 32 + lane] = rep.ocnt;
+    rep.publish_marks();
     __syncthreads();
     // next tick: what was written becomes the inbox
     uint4* tb = L.in; L.in = L.out; L.out = tb;
@@ -469,8 +470,9 @@ jr_status jr_engine_create(const jr_config* cfg, jr_engine** out) {
   d.seed = cfg->seed;
   d.goff = cfg->group_offset;
   // shared-memory staging: Us mailbox units per replica per buffer, W table-cache entries
-  d.Us = std::min<uint32_t>(cfg->mailbox_units, 8u);
+  d.Us = std::min<uint32_t>(cfg->mailbox_units, 6u);
   d.W = 4;
+  d.use_index = getenv("JR_NO_INDEX") ? 0u : 1u;
   if (const char* ev = getenv("JR_SMEM_UNITS")) d.Us = std::min<uint32_t>(cfg->mailbox_units, (uint32_t)atoi(ev));
   if (const char* ev = getenv("JR_TABLE_CACHE")) { uint32_t w = (uint32_t)atoi(ev); d.W = (w & (w - 1)) ? 8 : w; }
   const size_t plane = (size_t)d.R * d.Gp;

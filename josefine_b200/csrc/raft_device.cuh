@@ -52,6 +52,7 @@ struct Dev {
   uint32_t G, Gp, R, cap, U, F, flags;
   uint32_t emin, emax, hb;
   uint32_t Us, W;                  // shared-memory mailbox units per replica, table-cache entries (power of 2)
+  uint32_t use_index;              // receivers use the delivery index (else scan whole mailboxes)
   uint64_t seed, goff;
 };
 
@@ -188,6 +189,7 @@ struct Replica {
   // ---- output cursors
   uint32_t ocnt, fcnt, nmsg, nfsm;
   uint64_t mdig, fdig;
+  uint32_t mko[R];       // delivery index of this tick's outbox, one mask per receiver (see Local::mk_out)
 
   __device__ __forceinline__ Replica(const Dev& dv, const Local& lv, uint32_t r_, uint32_t g_)
       : d(dv), L(lv), r(r_), g(g_), rg((size_t)r_ * dv.Gp + g_), plane((size_t)R * dv.Gp) {}
@@ -383,20 +385,23 @@ struct Replica {
   }
 
   __device__ __forceinline__ void mark(uint32_t to, uint32_t slot) {
-    if (!L.mk_out) return;
     const uint32_t bit = slot < 31u ? (1u << slot) : MK_SCAN;
-    if (to == TO_PEERS) {
 #pragma unroll
-      for (int t = 0; t < R; ++t)
-        if (t != (int)r) L.mk_out[(t * R + r) * 32 + L.lane] |= bit;
-    } else if (to - 1u < (uint32_t)R) {
-      L.mk_out[((to - 1u) * R + r) * 32 + L.lane] |= bit;
-    }
+    for (int t = 0; t < R; ++t)
+      if (to == TO_PEERS || to == (uint32_t)t + 1u) mko[t] |= bit;
   }
-  __device__ __forceinline__ void clear_marks() const {
+  template <int T>
+  __device__ __forceinline__ void mark_peer(uint32_t slot) {  // `to` known at compile time
+    mko[T] |= slot < 31u ? (1u << slot) : MK_SCAN;
+  }
+  __device__ __forceinline__ void clear_marks() {
+#pragma unroll
+    for (int t = 0; t < R; ++t) mko[t] = 0;
+  }
+  __device__ __forceinline__ void publish_marks() const {
     if (!L.mk_out) return;
 #pragma unroll
-    for (int t = 0; t < R; ++t) L.mk_out[(t * R + r) * 32 + L.lane] = 0;
+    for (int t = 0; t < R; ++t) L.mk_out[(t * R + r) * 32 + L.lane] = mko[t];
   }
 
   // mod.rs:390-400 for every single-unit command.
@@ -415,7 +420,7 @@ struct Replica {
   __device__ __forceinline__ void fsm_emit(bool notify, uint32_t bid, uint32_t next_or_addr, uint64_t tok) {
     if (d.flags & JR_F_CAPTURE_FSM) {
       if (fcnt >= d.F) { fault = JR_FAULT_ENGINE_FSM_OVERFLOW; return; }
-      d.fs[((size_t)fcnt * R + r) * d.Gp + g] =
+      d.fs[(size_t)fcnt * plane + rg] =
           make_uint4(bid | (notify ? 0x80000000u : 0u), next_or_addr, (uint32_t)tok, (uint32_t)(tok >> 32));
       ++fcnt;
     }
@@ -630,6 +635,12 @@ struct Replica {
   }
 
   __device__ __forceinline__ void leader_commit() {  // leader.rs:87-99
+    // committed_index() is element [R/2] of the heads sorted descending; it exceeds
+    // `commit` iff at least R/2+1 heads do.  Count first, sort only when it matters.
+    int above = 0;
+#pragma unroll
+    for (int i = 0; i < R; ++i) above += ph[i] > commit ? 1 : 0;
+    if (above < R / 2 + 1) return;
     uint32_t q = committed_index();
     if (q > commit) {
       uint32_t prev = commit;
@@ -687,7 +698,7 @@ struct Replica {
       if (!put_unit(ocnt, make_uint4(unit_hdr(JR_CMD_APPEND_ENTRIES, 0, nb, p + 1), (uint32_t)term,
                                      (uint32_t)(term >> 32), 0)))
         return;
-      mark(p + 1, ocnt);
+      mko[p] |= ocnt < 31u ? (1u << ocnt) : MK_SCAN;
       if (digest_on()) {
         uint64_t h = digest_message_fn(mdig, JR_CMD_APPEND_ENTRIES, p + 1, 0, nb, id(), term, 0, 0, 0, 0);
         ++nmsg;
@@ -800,7 +811,7 @@ struct Replica {
       uint4 vh = make_uint4(0, 0, 0, 0);  // header of a virtual unit
       if (s < (uint32_t)R) {
         if (s == r) continue;
-        idx = L.mk_in[(r * R + s) * 32 + L.lane];
+        idx = d.use_index ? L.mk_in[(r * R + s) * 32 + L.lane] : MK_SCAN;
         if (idx & MK_SCAN) cnt = L.cin[s * 32 + L.lane];
       } else if (s == (uint32_t)R) {  // event_loop client arm, server.rs:156-160
         if ((p.phases & PH_PROPOSE) && p.proposals && g < d.G) {

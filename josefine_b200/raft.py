@@ -314,7 +314,7 @@ class ReplicaHandle:
 
 # ------------------------------------------------------------------------------
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-ENGINE_LIB_PATH = os.path.join(_PKG_DIR, "csrc", "libjosefine_b200.so")
+ENGINE_LIB_PATH = os.environ.get("JR_ENGINE_LIB") or os.path.join(_PKG_DIR, "csrc", "libjosefine_b200.so")
 
 
 def _bind(lib: C.CDLL, p: str):

@@ -87,3 +87,28 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def by_function(rep, so, ksub, src, which=0, unit=1):
+    """Aggregate executed warp-instructions per enclosing __device__ function of `src`."""
+    dis = disasm_lines(so, ksub)
+    hdr, body = ncu_sass(rep, ksub.replace("ILi", "<").split("<")[0], which)
+    col = {h: i for i, h in enumerate(hdr)}
+    fn_at, cur = {}, "?"
+    for i, line in enumerate(open(src), 1):
+        m = re.search(r"__device__\s+(?:__forceinline__|__noinline__|inline)?\s*[\w:<>\*& ]+?\s+(\w+)\s*\(", line)
+        if m and not line.strip().startswith("//"):
+            cur = m.group(1)
+        fn_at[i] = cur
+    base = os.path.basename(src)
+    ex, samp = collections.Counter(), collections.Counter()
+    for i in range(min(len(dis), len(body))):
+        f, ln = dis[i][2]
+        key = fn_at.get(ln, "?") if f == base else f
+        ex[key] += int(body[i][col["Instructions Executed"]] or 0)
+        samp[key] += int(body[i][col["# Samples"]] or 0)
+    tot = sum(ex.values())
+    print(f"{'function':32s} {'executed':>11s} {'%':>6s} {'per unit':>9s} {'samples%':>8s}")
+    ts = sum(samp.values())
+    for k, v in ex.most_common(40):
+        print(f"{k:32s} {v:11d} {100 * v / tot:6.2f} {v / unit:9.1f} {100 * samp[k] / max(ts, 1):8.2f}")
