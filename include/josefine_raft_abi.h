@@ -17,7 +17,7 @@
  *                         Chain::get_head/get_commit      src/raft/chain.rs:230-236
  *   jr_chain_read      <- Chain::range / Chain::has       src/raft/chain.rs:155-157,208-228
  *   jr_compact         <- Chain::compact                  src/raft/chain.rs:239-253
- *   jr_leader_table    <- Leader::write_state             src/raft/leader.rs:101-121
+ *   jr_leader_table*   <- Leader::write_state             src/raft/leader.rs:101-121
  *   jr_set_alive       <- process death (no reference API; a node that stops calling apply)
  *
  * One engine = G independent Raft groups x R replicas, all resident in one GPU's
@@ -311,8 +311,12 @@ jr_status jr_kill_leaders(jr_engine* e, uint64_t salt, uint32_t permille, uint64
 /* ---- leader announce ------------------------------------------------------- */
 /* Writes n_groups entries to DEVICE memory `dev_out` (for a collective) */
 jr_status jr_leader_table_device(jr_engine* e, void* dev_out);
-/* ... or to HOST memory. */
+/* ... or to HOST memory (synchronises the engine stream). */
 jr_status jr_leader_table(jr_engine* e, jr_leader_entry* host_out);
+/* Same, but only ENQUEUES the kernel and the device-to-host copy: `host_out` must be
+ * pinned memory and is valid after the next jr_engine_sync().  Lets a caller pipeline
+ * jr_step (proposals H2D) / kernels / results D2H tick after tick. */
+jr_status jr_leader_table_async(jr_engine* e, jr_leader_entry* host_out);
 
 /* ---- deviation D2, normative ------------------------------------------------
  * draw-th election timeout of (group, node):

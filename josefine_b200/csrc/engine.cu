@@ -923,6 +923,14 @@ jr_status jr_leader_table_device(jr_engine* e, void* dev_out) {
   return JR_OK;
 }
 
+jr_status jr_leader_table_async(jr_engine* e, jr_leader_entry* host_out) {
+  if (!e || !host_out) return JR_E_INVAL;
+  jr_status st = jr_leader_table_device(e, e->leaders);
+  if (st != JR_OK) return st;
+  CK(cudaMemcpyAsync(host_out, e->leaders, (size_t)e->d.G * sizeof(jr_leader_entry), cudaMemcpyDeviceToHost, e->stream));
+  return JR_OK;
+}
+
 jr_status jr_leader_table(jr_engine* e, jr_leader_entry* host_out) {
   if (!e || !host_out) return JR_E_INVAL;
   jr_status st = jr_leader_table_device(e, e->leaders);

@@ -333,9 +333,12 @@ struct Replica {
       const uint4 h = u < L.Us ? L.in[(u * R + r) * 32 + L.lane] : __ldg(d.ob[prv] + ((size_t)u * R + r) * d.Gp + g);
       const uint32_t kind = h.x & 15u, aux = (h.x >> 8) & 255u, to = h.x >> 16;
       const uint32_t bit = u < 31u ? (1u << u) : MK_SCAN;
+      const bool noop = kind == JR_CMD_HEARTBEAT_RESPONSE && (((h.x >> 4) & 1u) || h.w == 0);
+      if (!noop || bit == MK_SCAN) {
 #pragma unroll
-      for (int t = 0; t < R; ++t)
-        if (to == TO_PEERS || to == (uint32_t)t + 1u) m[t] |= bit;
+        for (int t = 0; t < R; ++t)
+          if (to == TO_PEERS || to == (uint32_t)t + 1u) m[t] |= bit;
+      }
       u += 1u + (kind == JR_CMD_APPEND_ENTRIES ? aux : 0u);
     }
 #pragma unroll
@@ -407,7 +410,9 @@ struct Replica {
   // mod.rs:390-400 for every single-unit command.
   __device__ __forceinline__ void send(uint32_t kind, uint32_t to, uint32_t flag, uint32_t aux, uint64_t t, uint32_t w) {
     if (!put_unit(ocnt, make_uint4(unit_hdr(kind, flag, aux, to), (uint32_t)t, (uint32_t)(t >> 32), w))) return;
-    mark(to, ocnt);
+    // HeartbeatResponse{has_committed || commit == 0} changes nothing in any role
+    // (follower.rs:61, candidate.rs:193, leader.rs:227): emitted, but not indexed for dispatch.
+    if (!(kind == JR_CMD_HEARTBEAT_RESPONSE && (flag || w == 0))) mark(to, ocnt);
     ++ocnt;
     if (digest_on()) {
       uint32_t n;
@@ -715,17 +720,18 @@ struct Replica {
   }
 
   // ------------------------------------------------------------------ Apply::apply (mod.rs:471-479)
-  // Single entry for every Command.  The three heavy continuations the
-  // reference reaches from several places are shared tails here so each is
-  // instantiated once:
+  // The state machine is split by role.  A Leader never changes role (leader.rs
+  // has no transition out; a higher term panics, leader.rs:33-35), so once a
+  // replica is Leader the rest of its tick runs in the leader loop; Follower and
+  // Candidate share the other one.  Each handler is instantiated exactly once.
+  // The heavy continuations the reference reaches from several places are shared
+  // tails:
   //   timeout tail   = Raft<Follower>::apply_timeout -> seek_election (follower.rs:248-256, candidate.rs:24-45)
   //   advance tail   = ReplicationProgress::advance + Leader::commit (leader.rs:211-219, also 191-196)
   //   replicate tail = Leader::replicate (leader.rs:124-174, reached from 228 and 242)
-  __device__ __forceinline__ void apply(const Cmd& c) {
-    if (!live()) return;
-    bool t_timeout = false, t_replicate = false, t_advance = false;
-    uint32_t adv_node = 0, adv_block = 0;
-    if (role == JR_ROLE_FOLLOWER) {  // follower.rs:38-63
+  __device__ __forceinline__ void apply_fc(const Cmd& c) {  // follower.rs:38-63, candidate.rs:170-196
+    bool t_timeout = false;
+    if (role == JR_ROLE_FOLLOWER) {
       switch (c.kind) {
         case JR_CMD_TICK: t_timeout = needs_election(); break;  // follower.rs:121-128
         case JR_CMD_TIMEOUT: t_timeout = true; break;
@@ -736,7 +742,7 @@ struct Replica {
         case JR_CMD_CLIENT_RESPONSE: send(JR_CMD_CLIENT_RESPONSE, TO_CLIENT, 0, 0, c.token, 0); break;  // follower.rs:271-282
         default: break;
       }
-    } else if (role == JR_ROLE_CANDIDATE) {  // candidate.rs:170-196
+    } else {
       switch (c.kind) {
         case JR_CMD_TICK:  // candidate.rs:48-68
           if (needs_election()) {
@@ -753,29 +759,6 @@ struct Replica {
         case JR_CMD_CLIENT_REQUEST: queue_push(c.token, c.addr); break;
         default: break;
       }
-    } else {  // leader.rs:248-266
-      switch (c.kind) {
-        case JR_CMD_TICK: {  // leader.rs:234-245
-          uint64_t el = now >= hbtime ? now - hbtime : 0;
-          if (el > (uint64_t)d.hb) {
-            heartbeat();
-            hbtime = now;
-          }
-          t_replicate = true;
-          break;
-        }
-        case JR_CMD_HEARTBEAT_RESPONSE: t_replicate = !c.flag && c.block > 0; break;  // leader.rs:222-231
-        case JR_CMD_APPEND_RESPONSE: t_advance = true; adv_node = c.node_id; adv_block = c.block; break;
-        case JR_CMD_APPEND_ENTRIES: if (c.term > term) set_term(c.term); break;  // leader.rs:200-208
-        case JR_CMD_CLIENT_REQUEST: {  // leader.rs:177-197
-          uint32_t bid;
-          if (!chain_append(c.token, bid)) break;
-          fsm_emit(true, bid, c.addr, c.token);
-          t_advance = true; adv_node = id(); adv_block = head;  // self AppendResponse
-          break;
-        }
-        default: break;
-      }
     }
     if (fault) return;
     if (t_timeout && voted == 0) {  // follower.rs:248-256
@@ -789,77 +772,160 @@ struct Replica {
       if (fault) return;
       candidate_vote_response(id(), true);
     }
+  }
+
+  __device__ __forceinline__ void apply_leader(const Cmd& c) {  // leader.rs:248-266
+    bool t_replicate = false, t_advance = false;
+    uint32_t adv_node = 0, adv_block = 0;
+    switch (c.kind) {
+      case JR_CMD_APPEND_RESPONSE: t_advance = true; adv_node = c.node_id; adv_block = c.block; break;  // leader.rs:211-219
+      case JR_CMD_HEARTBEAT_RESPONSE: t_replicate = !c.flag && c.block > 0; break;                     // leader.rs:222-231
+      case JR_CMD_TICK: {  // leader.rs:234-245
+        uint64_t el = now >= hbtime ? now - hbtime : 0;
+        if (el > (uint64_t)d.hb) {
+          heartbeat();
+          hbtime = now;
+        }
+        t_replicate = true;
+        break;
+      }
+      case JR_CMD_CLIENT_REQUEST: {  // leader.rs:177-197
+        uint32_t bid;
+        if (!chain_append(c.token, bid)) break;
+        fsm_emit(true, bid, c.addr, c.token);
+        t_advance = true; adv_node = id(); adv_block = head;  // self AppendResponse
+        break;
+      }
+      case JR_CMD_APPEND_ENTRIES: if (c.term > term) set_term(c.term); break;  // leader.rs:200-208
+      default: break;
+    }
+    if (fault) return;
     if (t_advance) {
       if (progress_advance(adv_node, adv_block)) leader_commit();
     }
     if (t_replicate && !fault) replicate();
   }
 
+  // Sparse / injected commands (inject kernel): pick the loop by current role.
+  __device__ __forceinline__ void apply(const Cmd& c) {
+    if (!live()) return;
+    if (role == JR_ROLE_LEADER) apply_leader(c);
+    else apply_fc(c);
+  }
+
   // ------------------------------------------------------------------ the step schedule (jr_step_args)
   // One tick of this replica: peer mail (ascending sender, FIFO per sender) ->
   // dense proposal -> synthetic proposals -> Tick.  The three trailing sources
-  // are modelled as virtual senders R, R+1, R+2 so the whole schedule is ONE
-  // nested loop with a single `apply` site (the state machine is instantiated
-  // once; keeps the kernel inside the instruction cache).
+  // are virtual senders R, R+1, R+2.  `Pos` is the resumable position in that
+  // schedule, so the follower/candidate loop can hand over to the leader loop in
+  // the middle of a tick (the moment an election is won).
+  struct Pos {
+    uint32_t pend;   // senders (real 0..R-1, virtual R..R+2) that still have something for me
+    uint32_t s;      // sender being drained
+    uint32_t idx;    // its delivery mask still to visit, or MK_SCAN = walk units u..cnt
+    uint32_t u, cnt;
+    uint32_t reps;   // copies of the current VoteRequest unit still to apply
+    bool open;       // `s` is set up
+  };
+
+  // Which senders have mail for me this tick: one shared-memory read per peer, up front.
+  __device__ __forceinline__ void plan_tick(Pos& k, const StepParams& p) const {
+    k.pend = 0; k.s = 0; k.idx = 0; k.u = 0; k.cnt = 0; k.reps = 0; k.open = false;
+    if (p.phases & PH_DRAIN) {
+#pragma unroll
+      for (int s_ = 0; s_ < R; ++s_) {
+        if (s_ == (int)r) continue;
+        const uint32_t m = d.use_index ? L.mk_in[(r * R + s_) * 32 + L.lane] : L.cin[s_ * 32 + L.lane];
+        if (m) k.pend |= 1u << s_;
+      }
+    }
+    if ((p.phases & PH_PROPOSE) && p.proposals && g < d.G) k.pend |= 1u << R;
+    if ((p.phases & PH_PROPOSE) && p.n_synth) k.pend |= 1u << (R + 1);
+    if (p.phases & PH_TICK) k.pend |= 1u << (R + 2);
+  }
+
+  __device__ __forceinline__ void open_sender(Pos& k, const StepParams& p) const {
+    k.u = 0; k.open = true;
+    if (k.s < (uint32_t)R) {
+      k.idx = d.use_index ? L.mk_in[(r * R + k.s) * 32 + L.lane] : MK_SCAN;
+      k.cnt = (k.idx & MK_SCAN) ? L.cin[k.s * 32 + L.lane] : 0u;
+    } else {
+      k.idx = MK_SCAN;
+      k.cnt = k.s == (uint32_t)R + 1u ? p.n_synth : 1u;
+    }
+  }
+
+  // Next command addressed to this replica, or false when the schedule is exhausted.
+  __device__ __forceinline__ bool next_cmd(Pos& k, const StepParams& p, Cmd& c) {
+    const uint32_t me = id();
+    if (k.reps) { --k.reps; return true; }  // another copy of the same VoteRequest (c unchanged)
+    for (;;) {
+      if (!k.open) {
+        if (!k.pend) return false;
+        k.s = (uint32_t)__ffs((int)k.pend) - 1u;
+        k.pend &= k.pend - 1u;
+        open_sender(k, p);
+      }
+      uint4 h;
+      uint32_t at;
+      if (!(k.idx & MK_SCAN)) {  // indexed delivery: jump to my next header
+        if (!k.idx) { k.open = false; continue; }
+        at = (uint32_t)__ffs((int)k.idx) - 1u;
+        k.idx &= k.idx - 1u;
+        h = inbox_unit(k.s, at);
+      } else {
+        if (k.u >= k.cnt) { k.open = false; continue; }
+        at = k.u;
+        if (k.s < (uint32_t)R) {
+          h = inbox_unit(k.s, k.u);
+          const uint32_t k0 = h.x & 15u, to = h.x >> 16;
+          k.u += 1u + (k0 == JR_CMD_APPEND_ENTRIES ? ((h.x >> 8) & 255u) : 0u);
+          if (to != TO_PEERS && to != me) continue;
+        } else if (k.s == (uint32_t)R) {  // event_loop client arm, server.rs:156-160
+          const uint4 pr = __ldg(reinterpret_cast<const uint4*>(p.proposals) + g);
+          k.u = k.cnt;
+          if (pr.z != me) continue;
+          h = make_uint4(unit_hdr(JR_CMD_CLIENT_REQUEST, 0, 0, me), pr.x, pr.y, (uint32_t)JR_ADDR_CLIENT << 16);
+        } else if (k.s == (uint32_t)R + 1u) {
+          if (role != JR_ROLE_LEADER) { k.open = false; continue; }
+          const uint64_t tok = synth_token(p.step_index, k.u, d.goff + g);
+          h = make_uint4(unit_hdr(JR_CMD_CLIENT_REQUEST, 0, 0, me), (uint32_t)tok, (uint32_t)(tok >> 32),
+                         (uint32_t)JR_ADDR_CLIENT << 16);
+          ++k.u;
+        } else {
+          h = make_uint4(unit_hdr(JR_CMD_TICK, 0, 0, me), 0, 0, 0);
+          ++k.u;
+        }
+      }
+      const uint32_t kind = h.x & 15u, aux = (h.x >> 8) & 255u;
+      c.kind = kind; c.flag = (h.x >> 4) & 1u; c.node_id = k.s + 1; c.block = h.w; c.addr = h.w;
+      c.term = (uint64_t)h.y | ((uint64_t)h.z << 32); c.last_term = c.term; c.token = c.term;
+      c.nblk = aux; c.blk_s = k.s; c.blk_at = at + 1;
+      // N-1 identical VoteRequest broadcasts travel as one unit (candidate.rs:30-37)
+      k.reps = (kind == JR_CMD_VOTE_REQUEST && aux) ? aux - 1u : 0u;
+      return true;
+    }
+  }
+
   __device__ __forceinline__ void run_step(const StepParams& p) {
+    Pos k;
+    plan_tick(k, p);
     Cmd c;
     c.host_msg = nullptr;
-    const uint32_t me = id();
-    const uint32_t s0 = (p.phases & PH_DRAIN) ? 0u : (uint32_t)R;
-    for (uint32_t s = s0; s < (uint32_t)R + 3u && live(); ++s) {
-      uint32_t cnt = 0, idx = MK_SCAN;    // idx: delivery index of sender s for me, or MK_SCAN = walk all units
-      uint4 vh = make_uint4(0, 0, 0, 0);  // header of a virtual unit
-      if (s < (uint32_t)R) {
-        if (s == r) continue;
-        idx = d.use_index ? L.mk_in[(r * R + s) * 32 + L.lane] : MK_SCAN;
-        if (idx & MK_SCAN) cnt = L.cin[s * 32 + L.lane];
-      } else if (s == (uint32_t)R) {  // event_loop client arm, server.rs:156-160
-        if ((p.phases & PH_PROPOSE) && p.proposals && g < d.G) {
-          const uint4 pr = __ldg(reinterpret_cast<const uint4*>(p.proposals) + g);
-          if (pr.z == me) {
-            cnt = 1;
-            vh = make_uint4(unit_hdr(JR_CMD_CLIENT_REQUEST, 0, 0, me), pr.x, pr.y, (uint32_t)JR_ADDR_CLIENT << 16);
-          }
-        }
-      } else if (s == (uint32_t)R + 1u) {
-        cnt = (p.phases & PH_PROPOSE) ? p.n_synth : 0u;
+    c.kind = JR_CMD_NOOP;
+    bool more = live();
+    while (more) {
+      if (role == JR_ROLE_LEADER) {
+        // leader loop: runs to the end of the tick
+        while (live() && next_cmd(k, p, c)) apply_leader(c);
+        more = false;
       } else {
-        cnt = (p.phases & PH_TICK) ? 1u : 0u;
-        vh = make_uint4(unit_hdr(JR_CMD_TICK, 0, 0, me), 0, 0, 0);
-      }
-      uint32_t u = 0;
-      while (live()) {
-        uint4 h;
-        uint32_t at;
-        if (!(idx & MK_SCAN)) {  // indexed delivery: jump to my next header
-          if (!idx) break;
-          at = (uint32_t)__ffs((int)idx) - 1u;
-          idx &= idx - 1u;
-          h = inbox_unit(s, at);
-        } else {
-          if (u >= cnt) break;
-          at = u;
-          if (s < (uint32_t)R) {
-            h = inbox_unit(s, u);
-          } else if (s == (uint32_t)R + 1u) {
-            if (role != JR_ROLE_LEADER) break;
-            const uint64_t tok = synth_token(p.step_index, u, d.goff + g);
-            h = make_uint4(unit_hdr(JR_CMD_CLIENT_REQUEST, 0, 0, me), (uint32_t)tok, (uint32_t)(tok >> 32),
-                           (uint32_t)JR_ADDR_CLIENT << 16);
-          } else {
-            h = vh;
-          }
-          const uint32_t k0 = h.x & 15u, to = h.x >> 16;
-          u += 1u + (k0 == JR_CMD_APPEND_ENTRIES ? ((h.x >> 8) & 255u) : 0u);
-          if (to != TO_PEERS && to != me) continue;
+        // follower / candidate loop: leaves when the replica wins an election
+        more = false;
+        while (live() && next_cmd(k, p, c)) {
+          apply_fc(c);
+          if (role == JR_ROLE_LEADER) { more = live(); break; }
         }
-        const uint32_t kind = h.x & 15u, aux = (h.x >> 8) & 255u;
-        c.kind = kind; c.flag = (h.x >> 4) & 1u; c.node_id = s + 1; c.block = h.w; c.addr = h.w;
-        c.term = (uint64_t)h.y | ((uint64_t)h.z << 32); c.last_term = c.term; c.token = c.term;
-        c.nblk = aux; c.blk_s = s; c.blk_at = at + 1;
-        // N-1 identical VoteRequest broadcasts travel as one unit (candidate.rs:30-37)
-        const uint32_t reps = kind == JR_CMD_VOTE_REQUEST ? aux : 1u;
-        for (uint32_t k = 0; k < reps; ++k) apply(c);
       }
     }
   }

@@ -366,6 +366,8 @@ def load_engine_library() -> C.CDLL:
         lib.jr_engine_sync.restype = C.c_int
         lib.jr_leader_table_device.argtypes = [C.c_void_p, C.c_void_p]
         lib.jr_leader_table_device.restype = C.c_int
+        lib.jr_leader_table_async.argtypes = [C.c_void_p, C.POINTER(abi.LeaderEntry)]
+        lib.jr_leader_table_async.restype = C.c_int
         lib.jr_config_default.argtypes = [C.POINTER(abi.Config), C.c_uint32, C.c_uint32]
         lib.jr_config_default.restype = None
         lib.jr_last_error.restype = C.c_char_p
