@@ -614,8 +614,10 @@ static jr_status capture_messages(jr_engine* e, int buf, std::vector<jr_msg>& ou
       for (uint32_t u = 0; u < cnt[i];) {
         const uint4& h = units[(size_t)u * plane + i];
         const uint32_t kind = h.x & 15u, aux = (h.x >> 8) & 255u;
-        const uint32_t span = 1 + (kind == JR_CMD_APPEND_ENTRIES ? aux : 0u);
-        decode_unit(h, g, r + 1, span > 1 ? &units[(size_t)(u + 1) * plane + i] : nullptr, plane, out);
+        const bool ae = kind == JR_CMD_APPEND_ENTRIES, ref = ae && ((h.x >> 4) & 1u);
+        const uint32_t span = 1 + ((ae && !ref) ? aux : 0u);
+        const uint32_t first = ref ? h.w : u + 1;  // block run: inline, or shared with an earlier AppendEntries
+        decode_unit(h, g, r + 1, (ae && aux) ? &units[(size_t)first * plane + i] : nullptr, plane, out);
         u += span;
       }
     }

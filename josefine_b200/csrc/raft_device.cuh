@@ -32,7 +32,8 @@ enum : uint32_t {
 };
 
 // Mailbox unit (16 B): x = kind[0:4) | flag[4] | aux[8:16) | to[16:32); y,z = term / token; w = block id.
-// AppendEntries: header (aux = n_blocks) followed by n_blocks block units {id, next, token}.
+// AppendEntries: header (aux = n_blocks); its block units {id, next, token} follow inline (flag = 0)
+// or sit at slot w of the same mailbox (flag = 1: an earlier AppendEntries of this tick carried the same run).
 __host__ __device__ inline uint32_t unit_hdr(uint32_t kind, uint32_t flag, uint32_t aux, uint32_t to) {
   return (kind & 15u) | ((flag & 1u) << 4) | ((aux & 255u) << 8) | (to << 16);
 }
@@ -339,7 +340,7 @@ struct Replica {
         for (int t = 0; t < R; ++t)
           if (to == TO_PEERS || to == (uint32_t)t + 1u) m[t] |= bit;
       }
-      u += 1u + (kind == JR_CMD_APPEND_ENTRIES ? aux : 0u);
+      u += 1u + ((kind == JR_CMD_APPEND_ENTRIES && !((h.x >> 4) & 1u)) ? aux : 0u);
     }
 #pragma unroll
     for (int t = 0; t < R; ++t) L.mk_in[(t * R + r) * 32 + L.lane] = m[t];
@@ -672,11 +673,12 @@ struct Replica {
     for (int p = 0; p < R; ++p) {
       if (p == (int)r) continue;  // config.nodes holds peers only
       const uint32_t take = (prmask >> p) & 1u ? JR_MAX_AE_BLOCKS : 1u;
-      uint32_t nb = 0;
+      uint32_t nb = 0, first = ocnt + 1;
+      bool ref = false;
       if (ph[p] == memo_head && take == memo_take) {
-        for (uint32_t k = 0; k < memo_nb; ++k)
-          if (!put_unit(ocnt + 1 + k, own_unit(memo_first + k))) return;
-        nb = memo_nb;
+        nb = memo_nb;       // same blocks as an earlier peer: point at that run
+        first = memo_first;
+        ref = true;
       } else {
         uint32_t bid = ph[p], pulled = 0;
         while (pulled < 1 + take) {
@@ -700,22 +702,22 @@ struct Replica {
         }
         memo_head = ph[p]; memo_take = take; memo_first = ocnt + 1; memo_nb = nb;
       }
-      if (!put_unit(ocnt, make_uint4(unit_hdr(JR_CMD_APPEND_ENTRIES, 0, nb, p + 1), (uint32_t)term,
-                                     (uint32_t)(term >> 32), 0)))
+      if (!put_unit(ocnt, make_uint4(unit_hdr(JR_CMD_APPEND_ENTRIES, ref ? 1u : 0u, nb, p + 1), (uint32_t)term,
+                                     (uint32_t)(term >> 32), first)))
         return;
       mko[p] |= ocnt < 31u ? (1u << ocnt) : MK_SCAN;
       if (digest_on()) {
         uint64_t h = digest_message_fn(mdig, JR_CMD_APPEND_ENTRIES, p + 1, 0, nb, id(), term, 0, 0, 0, 0);
         ++nmsg;
         for (uint32_t k = 0; k < nb; ++k) {
-          uint4 u = own_unit(ocnt + 1 + k);
+          uint4 u = own_unit(first + k);
           h = fold(h, u.x);
           h = fold(h, u.y);
           h = fold(h, (uint64_t)u.z | ((uint64_t)u.w << 32));
         }
         mdig = h;
       }
-      ocnt += 1 + nb;
+      ocnt += ref ? 1u : 1u + nb;
     }
   }
 
@@ -822,64 +824,46 @@ struct Replica {
   struct Pos {
     uint32_t pend;   // senders (real 0..R-1, virtual R..R+2) that still have something for me
     uint32_t s;      // sender being drained
-    uint32_t idx;    // its delivery mask still to visit, or MK_SCAN = walk units u..cnt
-    uint32_t u, cnt;
+    uint32_t idx;    // indexed delivery: my headers of sender s still to visit (0 = none)
+    uint32_t u, cnt; // scan delivery (index overflow, or a virtual sender): units u..cnt of sender s
     uint32_t reps;   // copies of the current VoteRequest unit still to apply
-    bool open;       // `s` is set up
   };
 
   // Which senders have mail for me this tick: one shared-memory read per peer, up front.
   __device__ __forceinline__ void plan_tick(Pos& k, const StepParams& p) const {
-    k.pend = 0; k.s = 0; k.idx = 0; k.u = 0; k.cnt = 0; k.reps = 0; k.open = false;
+    k.pend = 0; k.s = 0; k.idx = 0; k.u = 0; k.cnt = 0; k.reps = 0;
     if (p.phases & PH_DRAIN) {
+      // delivery masks mk_in[me][s] and mailbox counts cin[s] have the same stride over s
+      const uint32_t* src = d.use_index ? L.mk_in + (r * R) * 32 + L.lane : L.cin + L.lane;
 #pragma unroll
-      for (int s_ = 0; s_ < R; ++s_) {
-        if (s_ == (int)r) continue;
-        const uint32_t m = d.use_index ? L.mk_in[(r * R + s_) * 32 + L.lane] : L.cin[s_ * 32 + L.lane];
-        if (m) k.pend |= 1u << s_;
-      }
+      for (int s_ = 0; s_ < R; ++s_)
+        if (src[s_ * 32]) k.pend |= 1u << s_;
+      k.pend &= ~(1u << r);  // never my own mailbox
     }
     if ((p.phases & PH_PROPOSE) && p.proposals && g < d.G) k.pend |= 1u << R;
     if ((p.phases & PH_PROPOSE) && p.n_synth) k.pend |= 1u << (R + 1);
     if (p.phases & PH_TICK) k.pend |= 1u << (R + 2);
   }
 
-  __device__ __forceinline__ void open_sender(Pos& k, const StepParams& p) const {
-    k.u = 0; k.open = true;
-    if (k.s < (uint32_t)R) {
-      k.idx = d.use_index ? L.mk_in[(r * R + k.s) * 32 + L.lane] : MK_SCAN;
-      k.cnt = (k.idx & MK_SCAN) ? L.cin[k.s * 32 + L.lane] : 0u;
-    } else {
-      k.idx = MK_SCAN;
-      k.cnt = k.s == (uint32_t)R + 1u ? p.n_synth : 1u;
-    }
-  }
-
   // Next command addressed to this replica, or false when the schedule is exhausted.
   __device__ __forceinline__ bool next_cmd(Pos& k, const StepParams& p, Cmd& c) {
     const uint32_t me = id();
     if (k.reps) { --k.reps; return true; }  // another copy of the same VoteRequest (c unchanged)
+    uint4 h;
+    uint32_t at = 0;
     for (;;) {
-      if (!k.open) {
-        if (!k.pend) return false;
-        k.s = (uint32_t)__ffs((int)k.pend) - 1u;
-        k.pend &= k.pend - 1u;
-        open_sender(k, p);
-      }
-      uint4 h;
-      uint32_t at;
-      if (!(k.idx & MK_SCAN)) {  // indexed delivery: jump to my next header
-        if (!k.idx) { k.open = false; continue; }
+      if (k.idx) {  // indexed delivery: jump to my next header of sender s
         at = (uint32_t)__ffs((int)k.idx) - 1u;
         k.idx &= k.idx - 1u;
         h = inbox_unit(k.s, at);
-      } else {
-        if (k.u >= k.cnt) { k.open = false; continue; }
+        break;
+      }
+      if (k.u < k.cnt) {  // scan delivery
         at = k.u;
         if (k.s < (uint32_t)R) {
           h = inbox_unit(k.s, k.u);
           const uint32_t k0 = h.x & 15u, to = h.x >> 16;
-          k.u += 1u + (k0 == JR_CMD_APPEND_ENTRIES ? ((h.x >> 8) & 255u) : 0u);
+          k.u += 1u + ((k0 == JR_CMD_APPEND_ENTRIES && !((h.x >> 4) & 1u)) ? ((h.x >> 8) & 255u) : 0u);
           if (to != TO_PEERS && to != me) continue;
         } else if (k.s == (uint32_t)R) {  // event_loop client arm, server.rs:156-160
           const uint4 pr = __ldg(reinterpret_cast<const uint4*>(p.proposals) + g);
@@ -887,7 +871,7 @@ struct Replica {
           if (pr.z != me) continue;
           h = make_uint4(unit_hdr(JR_CMD_CLIENT_REQUEST, 0, 0, me), pr.x, pr.y, (uint32_t)JR_ADDR_CLIENT << 16);
         } else if (k.s == (uint32_t)R + 1u) {
-          if (role != JR_ROLE_LEADER) { k.open = false; continue; }
+          if (role != JR_ROLE_LEADER) { k.u = k.cnt; continue; }
           const uint64_t tok = synth_token(p.step_index, k.u, d.goff + g);
           h = make_uint4(unit_hdr(JR_CMD_CLIENT_REQUEST, 0, 0, me), (uint32_t)tok, (uint32_t)(tok >> 32),
                          (uint32_t)JR_ADDR_CLIENT << 16);
@@ -896,15 +880,28 @@ struct Replica {
           h = make_uint4(unit_hdr(JR_CMD_TICK, 0, 0, me), 0, 0, 0);
           ++k.u;
         }
+        break;
       }
-      const uint32_t kind = h.x & 15u, aux = (h.x >> 8) & 255u;
-      c.kind = kind; c.flag = (h.x >> 4) & 1u; c.node_id = k.s + 1; c.block = h.w; c.addr = h.w;
-      c.term = (uint64_t)h.y | ((uint64_t)h.z << 32); c.last_term = c.term; c.token = c.term;
-      c.nblk = aux; c.blk_s = k.s; c.blk_at = at + 1;
-      // N-1 identical VoteRequest broadcasts travel as one unit (candidate.rs:30-37)
-      k.reps = (kind == JR_CMD_VOTE_REQUEST && aux) ? aux - 1u : 0u;
-      return true;
+      if (!k.pend) return false;  // next sender with something for me
+      k.s = (uint32_t)__ffs((int)k.pend) - 1u;
+      k.pend &= k.pend - 1u;
+      k.u = 0; k.cnt = 0;
+      if (k.s < (uint32_t)R) {
+        const uint32_t m = d.use_index ? L.mk_in[(r * R + k.s) * 32 + L.lane] : MK_SCAN;
+        if (m & MK_SCAN) k.cnt = L.cin[k.s * 32 + L.lane];
+        else k.idx = m;
+      } else {
+        k.cnt = k.s == (uint32_t)R + 1u ? p.n_synth : 1u;
+      }
     }
+    const uint32_t kind = h.x & 15u, aux = (h.x >> 8) & 255u;
+    c.kind = kind; c.flag = (h.x >> 4) & 1u; c.node_id = k.s + 1; c.block = h.w; c.addr = h.w;
+    c.term = (uint64_t)h.y | ((uint64_t)h.z << 32); c.last_term = c.term; c.token = c.term;
+    c.nblk = aux; c.blk_s = k.s;
+    c.blk_at = (kind == JR_CMD_APPEND_ENTRIES && c.flag) ? h.w : at + 1;
+    // N-1 identical VoteRequest broadcasts travel as one unit (candidate.rs:30-37)
+    k.reps = (kind == JR_CMD_VOTE_REQUEST && aux) ? aux - 1u : 0u;
+    return true;
   }
 
   __device__ __forceinline__ void run_step(const StepParams& p) {
