@@ -73,7 +73,8 @@ def algorithmic_bytes_per_group_tick(make, R, ticks=64):
     """Minimum bytes one steady-state group-tick must move with THIS layout
     (DESIGN.md "Algorithmic bytes"), measured on a small captured run:
       state   : follower 52 B (P0,P1,P2 + max_key), leader 116 B (+P3, 2 progress planes) -- read AND written
-      mailbox : every 16 B unit written once and read once per addressee (+4 B count, written and read)
+      mailbox : every 16 B unit written once and read once per addressee (+4 B count, written and read);
+                AppendEntries of one sender that carry the same block run share the block units
       blocks  : 12 B written per block appended/extended, 12 B read per block shipped or applied, 4 B has() probe
       fsm     : 16 B per Instruction
     """
@@ -89,7 +90,7 @@ def algorithmic_bytes_per_group_tick(make, R, ticks=64):
         b = 0
         b += G * ((R - 1) * 52 + 116) * 2                    # state read + written
         b += G * R * 4 * 2 + G * R * (R - 1) * 4             # mailbox counts: reset/written, read by each peer
-        seen_vreq = set()
+        seen_vreq, seen_runs = set(), set()
         for m in res.messages:
             readers = (R - 1) if m.to_kind == abi.ADDR_PEERS else 1
             if m.kind == abi.CMD_VOTE_REQUEST:                # N-1 copies share one unit
@@ -97,10 +98,13 @@ def algorithmic_bytes_per_group_tick(make, R, ticks=64):
                 if key in seen_vreq:
                     continue
                 seen_vreq.add(key)
-            units = 1 + (m.n_blocks if m.kind == abi.CMD_APPEND_ENTRIES else 0)
-            b += units * 16 * (1 + readers)
-            if m.kind == abi.CMD_APPEND_ENTRIES:              # leader reads the blocks, follower probes + writes them
-                b += m.n_blocks * (12 + 4 + 12)
+            b += 16 * (1 + readers)                           # header unit: written once, read per addressee
+            if m.kind == abi.CMD_APPEND_ENTRIES and m.n_blocks:
+                run = (m.group, m.from_id, tuple(m.blocks[i].id for i in range(m.n_blocks)))
+                if run not in seen_runs:                      # identical block runs of one sender are emitted once
+                    seen_runs.add(run)
+                    b += m.n_blocks * (12 + 16)               # leader reads the table entries, writes the block units
+                b += m.n_blocks * (16 + 4 + 12)               # each follower reads the units, probes has(next), writes its table
         for f in res.fsm:
             b += 16
             b += 12                                           # Notify: block written by append; Apply: block read
@@ -280,7 +284,7 @@ def main():
     ms = float(t.item())
     faults = eng.fault_count()
     value = world * G * S * args.steps / (ms * 1e-3)
-    launches = S * args.steps
+    launches = args.steps * (2 if world > 1 else 1)   # one fused step_kernel launch per step (+ leader_table_kernel)
 
     # ---------------- end-to-end arm (host buffers through jr_step) ----------------
     # Every tick: jr_step copies that tick's jr_proposal[G] from PINNED host memory
@@ -348,13 +352,21 @@ def main():
     # ---------------- roofline + cpu baseline (rank 0) ----------------
     abytes = algorithmic_bytes_per_group_tick(make, R)
     peak, peak_src = measured_peak()
-    avg_launch_s = (ms * 1e-3) / launches
-    achieved = abytes * G / avg_launch_s / 1e9
+    avg_launch_s = (ms * 1e-3) / args.steps            # one step_kernel launch = S fused ticks of all G groups
+    achieved = abytes * G * S / avg_launch_s / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "step_kernel_latest.json")
+    if os.path.exists(prof):   # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this
+        pj = json.load(open(prof))           # command, per launch (one launch = TICKS_PER_STEP ticks)
+        if pj.get("ticks_per_launch") == S and pj.get("groups") == G:
+            traffic = pj["dram_bytes_per_launch"]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "step_kernel<5>", "algorithmic_bytes_per_group_tick": abytes,
+                "traffic": traffic, "kernel": "step_kernel<5>", "algorithmic_bytes_per_group_tick": abytes,
                 "avg_launch_us": avg_launch_s * 1e6, "peak_source": peak_src,
-                "note": "one launch = one group-tick of all groups on this GPU; working set < L2 so DRAM traffic can be "
-                        "far below the algorithmic bytes after the first tick of a step (see profiles/)"}
+                "algorithmic_bytes_per_launch": abytes * G * S,
+                "note": f"one launch = {S} fused group-ticks of all {G} groups; replica state stays in registers and the "
+                        "mailboxes in shared memory across those ticks, so DRAM traffic is far below the algorithmic "
+                        "bytes (which count every tick's state + mailbox movement); see profiles/"}
     cpu = None
     if not args.no_cpu:
         cores = os.cpu_count() or 1

@@ -10,6 +10,9 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 
 #include "restated_raft.hpp"
@@ -122,9 +125,69 @@ struct Replica {
 
 }  // namespace
 
+// Persistent workers: thread t always owns the same contiguous slice of groups, so
+// its nodes' allocations stay in its own malloc arena (spawning threads per call
+// made 128-core hosts slower than 8-core ones).
+class Pool {
+ public:
+  explicit Pool(unsigned n) : n_(n) {
+    for (unsigned t = 0; t < n_; ++t) th_.emplace_back([this, t] { loop(t); });
+  }
+  ~Pool() {
+    {
+      std::lock_guard<std::mutex> l(m_);
+      stop_ = true;
+      ++gen_;
+    }
+    cv_.notify_all();
+    for (auto& x : th_) x.join();
+  }
+  void run(const std::function<void(unsigned)>& f) {
+    {
+      std::lock_guard<std::mutex> l(m_);
+      job_ = &f;
+      left_ = n_;
+      ++gen_;
+    }
+    cv_.notify_all();
+    std::unique_lock<std::mutex> l(m_);
+    done_.wait(l, [this] { return left_ == 0; });
+  }
+  unsigned size() const { return n_; }
+
+ private:
+  void loop(unsigned t) {
+    uint64_t seen = 0;
+    for (;;) {
+      const std::function<void(unsigned)>* f;
+      {
+        std::unique_lock<std::mutex> l(m_);
+        cv_.wait(l, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+        f = job_;
+      }
+      (*f)(t);
+      {
+        std::lock_guard<std::mutex> l(m_);
+        if (--left_ == 0) done_.notify_all();
+      }
+    }
+  }
+  unsigned n_;
+  std::vector<std::thread> th_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  const std::function<void(unsigned)>* job_ = nullptr;
+  unsigned left_ = 0;
+  uint64_t gen_ = 0;
+  bool stop_ = false;
+};
+
 struct jro_cluster {
   jr_config cfg;
   unsigned n_threads = 1;
+  std::unique_ptr<Pool> pool;
   uint64_t step_index = 0;
   std::vector<Replica> reps;  // [g * R + (node-1)]
   Replica& at(uint32_t g, uint32_t node) { return reps[(size_t)g * cfg.n_replicas + (node - 1)]; }
@@ -211,21 +274,20 @@ void step_group(jro_cluster* c, uint32_t g, const StepCtx& s) {
   }
 }
 
-void run_step(jro_cluster* c, const StepCtx& s) {
+void for_groups(jro_cluster* c, const std::function<void(uint32_t, uint32_t)>& body) {
   const uint32_t G = c->cfg.n_groups;
-  unsigned T = std::min<unsigned>(c->n_threads, G ? G : 1);
-  if (T <= 1) {
-    for (uint32_t g = 0; g < G; ++g) step_group(c, g, s);
-  } else {
-    std::vector<std::thread> th;
-    for (unsigned t = 0; t < T; ++t) {
-      th.emplace_back([=]() {
-        uint32_t lo = (uint64_t)G * t / T, hi = (uint64_t)G * (t + 1) / T;
-        for (uint32_t g = lo; g < hi; ++g) step_group(c, g, s);
-      });
-    }
-    for (auto& x : th) x.join();
+  if (!c->pool) {
+    body(0, G);
+    return;
   }
+  const unsigned T = c->pool->size();
+  c->pool->run([&](unsigned t) { body((uint32_t)((uint64_t)G * t / T), (uint32_t)((uint64_t)G * (t + 1) / T)); });
+}
+
+void run_step(jro_cluster* c, const StepCtx& s) {
+  for_groups(c, [&](uint32_t lo, uint32_t hi) {
+    for (uint32_t g = lo; g < hi; ++g) step_group(c, g, s);
+  });
   c->step_index++;
 }
 
@@ -248,10 +310,13 @@ jr_status jro_create(const jr_config* cfg, unsigned n_threads, jro_cluster** out
   if (cfg->chain_capacity < 2) return JR_E_INVAL;
   auto* c = new jro_cluster();
   c->cfg = *cfg;
-  c->n_threads = n_threads ? n_threads : 1;
+  c->n_threads = std::max(1u, std::min<unsigned>(n_threads ? n_threads : 1, cfg->n_groups));
+  if (c->n_threads > 1) c->pool = std::make_unique<Pool>(c->n_threads);
   const uint32_t R = cfg->n_replicas;
   c->reps.resize((size_t)cfg->n_groups * R);
-  for (uint32_t g = 0; g < cfg->n_groups; ++g) {
+  // nodes are built by the worker that will step them (allocation locality)
+  for_groups(c, [&](uint32_t glo, uint32_t ghi) {
+  for (uint32_t g = glo; g < ghi; ++g) {
     for (uint32_t r = 1; r <= R; ++r) {
       NodeConfig nc;
       nc.id = r;
@@ -269,6 +334,7 @@ jr_status jro_create(const jr_config* cfg, unsigned n_threads, jro_cluster** out
       rep.msg_digest = rep.fsm_digest = mix64(((cfg->group_offset + g) << 8) | r);
     }
   }
+  });
   *out = c;
   return JR_OK;
 }
@@ -327,10 +393,8 @@ jr_status jro_run(jro_cluster* c, uint64_t now0, uint32_t dt, uint32_t n_steps, 
   clear_fsm(c);
   // Groups never interact, so each host thread runs ALL n_steps for its own
   // contiguous slice of groups: no barrier per step, no thread start per step.
-  const uint32_t G = c->cfg.n_groups;
-  const unsigned T = std::min<unsigned>(c->n_threads, G ? G : 1);
   const uint64_t base = c->step_index;
-  auto work = [=](uint32_t lo, uint32_t hi) {
+  for_groups(c, [&](uint32_t lo, uint32_t hi) {
     for (uint32_t g = lo; g < hi; ++g)
       for (uint32_t k = 0; k < n_steps; ++k) {
         StepCtx s{now0 + (uint64_t)k * dt,
@@ -338,15 +402,7 @@ jr_status jro_run(jro_cluster* c, uint64_t now0, uint32_t dt, uint32_t n_steps, 
                   n_synth, nullptr, nullptr, nullptr, base + k};
         step_group(c, g, s);
       }
-  };
-  if (T <= 1) {
-    work(0, G);
-  } else {
-    std::vector<std::thread> th;
-    for (unsigned t = 0; t < T; ++t)
-      th.emplace_back(work, (uint32_t)((uint64_t)G * t / T), (uint32_t)((uint64_t)G * (t + 1) / T));
-    for (auto& x : th) x.join();
-  }
+  });
   c->step_index += n_steps;
   return JR_OK;
 }
