@@ -55,6 +55,7 @@ TICKS_PER_STEP = 64
 DT_MS = 100
 SEED = 1
 L2_FLUSH_BYTES = 256 << 20
+CHAIN_CAP_MAX = 6144        # block-table ids per replica (12 B x 327,680 replicas each = 3.9 MB per id, 24 GB total)
 
 
 def bootstrap_inject(G, R, node=1):
@@ -125,7 +126,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -205,17 +206,27 @@ def run_reference(args):
     R = REPLICAS
     cores = best_cpu_threads(R, effective_cores())
     G = max(4096, 64 * cores)
-    total_steps = args.warmup + args.steps
-    c = cpu_reference_run(G, R, TICKS_PER_STEP * total_steps + 32, cores)
-    now = DT_MS * 17
+    span = 16 * TICKS_PER_STEP            # ticks one cluster lives before it is rebuilt (bounds the std::map chains)
+    st = {"c": None, "left": 0, "now": 0}
+
+    def step():
+        if st["left"] < TICKS_PER_STEP:   # untimed rebuild, like the GPU arm's rebase
+            st["c"] = cpu_reference_run(G, R, span + 64, cores)
+            st["left"], st["now"] = span, DT_MS * 17
+            return 0.0
+        t0 = time.perf_counter()
+        st["c"].run(st["now"], DT_MS, TICKS_PER_STEP, 1)
+        st["now"] += DT_MS * TICKS_PER_STEP
+        st["left"] -= TICKS_PER_STEP
+        return time.perf_counter() - t0
+
+    def timed_step():
+        d = step()
+        return d if d > 0.0 else step()
+
     for _ in range(args.warmup):
-        c.run(now, DT_MS, TICKS_PER_STEP, 1)
-        now += DT_MS * TICKS_PER_STEP
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        c.run(now, DT_MS, TICKS_PER_STEP, 1)
-        now += DT_MS * TICKS_PER_STEP
-    dt = time.perf_counter() - t0
+        timed_step()
+    dt = sum(timed_step() for _ in range(args.steps))
     value = G * TICKS_PER_STEP * args.steps / dt
     sample = (f"{G} groups x {R} replicas x {TICKS_PER_STEP} ticks per step, {cores} threads (fastest of a probe over "
               f"1..{effective_cores()} usable host threads; groups partitioned statically)")
@@ -236,7 +247,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--groups", type=int, default=GROUPS_PER_GPU, help="groups per GPU")
@@ -272,26 +283,57 @@ def main():
         return RaftEngine.create(g, r, **kw)
 
     # ---------------- device-resident arm ----------------
-    eng = make(G, R, seed=SEED, group_offset=rank * G, chain_capacity=total_ticks + 64,
+    # The block table grows by one id per tick (12 B x R x G each), so the engine is sized for
+    # at most CHAIN_CAP_MAX ids and REBASED (jr_engine_reset + the bootstrap trace + 16 warm ticks)
+    # between timed steps when it runs low -- never inside a timed event pair.
+    cap = min(total_ticks + 64, CHAIN_CAP_MAX)
+    eng = make(G, R, seed=SEED, group_offset=rank * G, chain_capacity=cap,
                flags=abi.F_CAPTURE_FSM, fsm_units=2 * S + 8, mailbox_units=64)
     eng.set_stream(stream.cuda_stream)
-    eng.step(0, flags=0, inject=bootstrap_inject(G, R))
-    eng.run(DT_MS, DT_MS, 16, 1)
-    now = DT_MS * 17
+    boot = bootstrap_inject(G, R)
+    state = {"ticks_left": 0, "now": 0}
+
+    def rebase(e):
+        e.reset()
+        e.step(0, flags=0, inject=boot)
+        e.run(DT_MS, DT_MS, 16, 1)
+        state["ticks_left"] = cap - 32 - 16
+        state["now"] = DT_MS * 17
+
+    rebase(eng)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
     leaders = torch.empty(G * 16, dtype=torch.uint8, device="cuda")
     gathered = torch.empty(world * G * 16, dtype=torch.uint8, device="cuda") if world > 1 else None
+    side = torch.cuda.Stream() if world > 1 else None
+    announce_done = [None]
 
-    def one_step(t_now):
-        eng.run(t_now, DT_MS, S, 1)
-        if world > 1:  # the one cross-shard exchange: leader announce, once per step (every 64 ticks)
+    def one_step():
+        eng.run(state["now"], DT_MS, S, 1)
+        state["now"] += DT_MS * S
+        state["ticks_left"] -= S
+        if world > 1:
+            # the one cross-shard exchange: leader announce, once per step (every 64 ticks).  The table is packed on
+            # the engine stream; the NCCL all-gather runs on a side stream and overlaps the next step's kernel.
+            if announce_done[0] is not None:
+                stream.wait_event(announce_done[0])            # previous announce must be over before `leaders` is rewritten
             eng.leader_table_device(leaders.data_ptr())
-            dist.all_gather_into_tensor(gathered, leaders)
+            packed = torch.cuda.Event()
+            packed.record(stream)
+            with torch.cuda.stream(side):
+                side.wait_event(packed)
+                dist.all_gather_into_tensor(gathered, leaders)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            announce_done[0] = ev
+
+    def between_steps():
+        flush.fill_(1)
+        if state["ticks_left"] < S:
+            rebase(eng)
 
     for _ in range(args.warmup):
-        flush.fill_(1)
-        one_step(now)
-        now += DT_MS * S
+        between_steps()
+        one_step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -299,14 +341,15 @@ def main():
     if rank == 0:
         sampler.start()
     evs = []
-    for _ in range(args.steps):
-        flush.fill_(1)
+    for i in range(args.steps):
+        between_steps()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
-        one_step(now)
+        one_step()
+        if world > 1 and i == args.steps - 1:
+            stream.wait_event(announce_done[0])                # the last announce is not hidden by a next step: time it
         b.record(stream)
         evs.append((a, b))
-        now += DT_MS * S
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -330,10 +373,9 @@ def main():
     if not args.no_e2e:
         del eng
         torch.cuda.empty_cache()
-        e2 = make(G, R, seed=SEED, group_offset=rank * G, chain_capacity=total_ticks + 64, mailbox_units=64)
+        e2 = make(G, R, seed=SEED, group_offset=rank * G, chain_capacity=cap, mailbox_units=64)
         e2.set_stream(stream.cuda_stream)
-        e2.step(0, flags=0, inject=bootstrap_inject(G, R))
-        e2.run(DT_MS, DT_MS, 16, 1)
+        rebase(e2)
         prop = torch.zeros(S, G, 2, dtype=torch.int64).pin_memory()    # jr_proposal[S][G] = {token, node|reserved}
         table = torch.zeros(S, G, 2, dtype=torch.int64).pin_memory()   # jr_leader_entry[S][G]
         prop[:, :, 1] = 1                                              # addressed to node 1 (the leader)
@@ -342,9 +384,13 @@ def main():
         sa = abi.StepArgs()
         sa.flags = abi.STEP_DELIVER | abi.STEP_TICK
         pstride, tstride = G * 16, G * 16
-        tnow = DT_MS * 17
 
-        def e2e_step(tn):
+        def e2e_step():
+            if state["ticks_left"] < S:
+                rebase(e2)
+            tn = state["now"]
+            state["now"] += DT_MS * S
+            state["ticks_left"] -= S
             for k in range(S):
                 sa.now_ms = tn + k * DT_MS
                 sa.proposals = C.cast(prop.data_ptr() + k * pstride, C.POINTER(abi.Proposal))
@@ -356,17 +402,17 @@ def main():
             e2.sync()
 
         for _ in range(args.warmup):
-            e2e_step(tnow)
-            tnow += DT_MS * S
+            e2e_step()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        t0 = time.perf_counter()
+        dt = 0.0
         for _ in range(args.steps):
-            e2e_step(tnow)
-            tnow += DT_MS * S
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+            if state["ticks_left"] < S:
+                rebase(e2)                                             # untimed, like the device-resident arm
+            t0 = time.perf_counter()
+            e2e_step()
+            dt += time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -376,7 +422,8 @@ def main():
                "d2h_bytes_per_step": S * G * 16, "ms_per_step": dt * 1e3 / args.steps,
                "api": "per tick: jr_step(pinned jr_proposal[G]) + jr_leader_table_async(pinned jr_leader_entry[G]); "
                       "jr_engine_sync once per step",
-               "commit_min": int(commits.min().item()), "faulted_replicas": e2.fault_count()}
+               "commit_min": int(commits.min().item()), "faulted_replicas": e2.fault_count(),
+               "timing": "host wall clock around each step incl. the jr_engine_sync, max over ranks"}
 
     if rank != 0:
         if world > 1:

@@ -272,6 +272,10 @@ typedef struct jr_engine jr_engine;
 /* ---- lifecycle ------------------------------------------------------------- */
 jr_status jr_engine_create(const jr_config* cfg, jr_engine** out);
 void      jr_engine_destroy(jr_engine* e);
+/* Back to the state right after jr_engine_create (every replica a fresh Follower with
+ * an empty chain), keeping all allocations.  Reference: dropping the RaftHandle and
+ * calling RaftHandle::new again on an empty data directory. */
+jr_status jr_engine_reset(jr_engine* e);
 /* Run all engine work on `cuda_stream` (a cudaStream_t); NULL = the engine's own. */
 jr_status jr_engine_set_stream(jr_engine* e, void* cuda_stream);
 jr_status jr_engine_sync(jr_engine* e);

@@ -511,18 +511,28 @@ jr_status jr_engine_create(const jr_config* cfg, jr_engine** out) {
       return JR_E_CUDA;
     }
   }
-  // block tables start empty (all keys absent); pr / qt zero
-  cudaMemsetAsync(d.cnext, 0xFF, plane * (size_t)d.cap * sizeof(uint32_t), e->stream);
-  cudaMemsetAsync(d.pr, 0, plane * ((d.R + 3) / 4) * sizeof(uint4), e->stream);
-  cudaMemsetAsync(d.qt, 0, plane * JR_CLIENT_QUEUE_CAP * sizeof(uint4), e->stream);
-  JR_LAUNCH(init_kernel, (unsigned)((plane + 255) / 256), 256, e->stream, d);
-  cudaError_t err = cudaStreamSynchronize(e->stream);
-  if (err != cudaSuccess) {
-    set_err("engine init: %s", cudaGetErrorString(err));
+  if (jr_engine_reset(e) != JR_OK) {
     jr_engine_destroy(e);
     return JR_E_CUDA;
   }
   *out = e;
+  return JR_OK;
+}
+
+jr_status jr_engine_reset(jr_engine* e) {
+  if (!e) return JR_E_INVAL;
+  CK(cudaSetDevice(e->cfg.device));
+  const Dev& d = e->d;
+  const size_t plane = (size_t)d.R * d.Gp;
+  // block tables start empty (all keys absent); pr / qt zero
+  CK(cudaMemsetAsync(d.cnext, 0xFF, plane * (size_t)d.cap * sizeof(uint32_t), e->stream));
+  CK(cudaMemsetAsync(d.pr, 0, plane * ((d.R + 3) / 4) * sizeof(uint4), e->stream));
+  CK(cudaMemsetAsync(d.qt, 0, plane * JR_CLIENT_QUEUE_CAP * sizeof(uint4), e->stream));
+  JR_LAUNCH(init_kernel, (unsigned)((plane + 255) / 256), 256, e->stream, d);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(e->stream));
+  e->cur = 0;
+  e->step_index = 0;
   return JR_OK;
 }
 

@@ -360,6 +360,8 @@ def load_engine_library() -> C.CDLL:
         lib.jr_engine_create.restype = C.c_int
         lib.jr_engine_destroy.argtypes = [C.c_void_p]
         lib.jr_engine_destroy.restype = None
+        lib.jr_engine_reset.argtypes = [C.c_void_p]
+        lib.jr_engine_reset.restype = C.c_int
         lib.jr_engine_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         lib.jr_engine_set_stream.restype = C.c_int
         lib.jr_engine_sync.argtypes = [C.c_void_p]
@@ -389,6 +391,10 @@ class RaftEngine(RaftApi):
     @classmethod
     def create(cls, n_groups: int, n_replicas: int, **kw) -> "RaftEngine":
         return cls(abi.default_config(n_groups, n_replicas, **kw))
+
+    def reset(self):
+        """Every replica back to a fresh Follower with an empty chain (allocations kept)."""
+        self._check(self._lib.jr_engine_reset(self._h), "engine_reset")
 
     def set_stream(self, cuda_stream: int):
         self._check(self._lib.jr_engine_set_stream(self._h, C.c_void_p(cuda_stream)), "engine_set_stream")

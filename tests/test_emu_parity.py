@@ -97,3 +97,17 @@ def test_mailbox_beyond_index_range():
     for k in range(6):
         p.step(600 + 100 * k, n_synth=1)
     p.finish()
+
+
+def test_engine_reset_is_a_fresh_engine():
+    """jr_engine_reset == drop the handle and RaftHandle::new again (mod.rs:428-435)."""
+    a = make_emu(5, 3, seed=8, flags=parity.FULL)
+    a.run(100, 100, 25, 1)
+    first = (a.state_digest(), a.leader_table())
+    a.apply_reset = getattr(a, "_lib").jr_engine_reset
+    a.apply_reset.argtypes = [__import__("ctypes").c_void_p]
+    assert a.apply_reset(a._h) == 0
+    fresh = make_emu(5, 3, seed=8, flags=parity.FULL)
+    parity.compare_states(a, fresh, chain_ids=30)
+    a.run(100, 100, 25, 1)
+    assert (a.state_digest(), a.leader_table()) == first
