@@ -382,7 +382,7 @@ def main():
         prop[:, :, 0] = (torch.arange(S, dtype=torch.int64).view(S, 1) + 1 << 32) + torch.arange(G, dtype=torch.int64)
         lib = e2._lib
         sa = abi.StepArgs()
-        sa.flags = abi.STEP_DELIVER | abi.STEP_TICK
+        sa.flags = abi.STEP_DELIVER | abi.STEP_TICK | abi.STEP_TRUSTED_PROPOSALS
         pstride, tstride = G * 16, G * 16
 
         def e2e_step():

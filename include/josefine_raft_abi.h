@@ -207,7 +207,8 @@ typedef struct jr_proposal {
 enum {
   JR_STEP_DELIVER = 1u << 0,  /* apply peer mail emitted in the previous step        */
   JR_STEP_TICK = 1u << 1,     /* then apply Command::Tick on every replica           */
-  JR_STEP_SYNTH_PROPOSALS = 1u << 2 /* every current Leader receives n_synth ClientRequests */
+  JR_STEP_SYNTH_PROPOSALS = 1u << 2, /* every current Leader receives n_synth ClientRequests */
+  JR_STEP_TRUSTED_PROPOSALS = 1u << 3 /* caller guarantees proposals[g].node <= R: skip the O(G) host check */
 };
 
 /*

@@ -54,6 +54,7 @@ F_STREAM_DIGEST = 1 << 3
 STEP_DELIVER = 1 << 0
 STEP_TICK = 1 << 1
 STEP_SYNTH_PROPOSALS = 1 << 2
+STEP_TRUSTED_PROPOSALS = 1 << 3
 
 FSM_APPLY, FSM_NOTIFY = 0, 1
 

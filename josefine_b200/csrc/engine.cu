@@ -369,8 +369,19 @@ struct jr_engine {
   jr_msg* inj_msgs = nullptr;             // device, grows
   uint4* inj_targets = nullptr;
   size_t inj_cap = 0;
-  jr_proposal* prop = nullptr;            // device, G entries
-  jr_leader_entry* leaders = nullptr;     // device, G entries
+  // Copy/compute overlap for the host-buffer path: proposals are staged H2D on `h2d`,
+  // leader tables leave D2H on `d2h`, both double buffered and fenced with events, so the
+  // copy-in of tick k+1, the kernels of tick k and the copy-out of tick k-1 run concurrently.
+  static constexpr int NBUF = 2;
+  jr_proposal* prop[NBUF] = {nullptr, nullptr};         // device, G entries each
+  jr_leader_entry* leaders[NBUF] = {nullptr, nullptr};  // device, G entries each
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+  cudaEvent_t prop_ready[NBUF] = {nullptr, nullptr};    // H2D of prop[i] finished
+  cudaEvent_t prop_free[NBUF] = {nullptr, nullptr};     // the kernel that read prop[i] finished
+  cudaEvent_t tab_ready[NBUF] = {nullptr, nullptr};     // leader_table_kernel into leaders[i] finished
+  cudaEvent_t tab_free[NBUF] = {nullptr, nullptr};      // D2H of leaders[i] finished
+  bool prop_used[NBUF] = {false, false}, tab_used[NBUF] = {false, false};
+  int prop_i = 0, tab_i = 0;
   jr_block* cr_blocks = nullptr;          // device scratch for chain_read
   uint8_t* cr_present = nullptr;
   uint32_t cr_cap = 0;
@@ -491,8 +502,7 @@ jr_status jr_engine_create(const jr_config* cfg, jr_engine** out) {
   A(d.fc, plane);
   A(e->scratch, 8);
   A(e->q_state, 1);
-  A(e->prop, d.G);
-  A(e->leaders, d.G);
+  for (int i = 0; i < jr_engine::NBUF; ++i) { A(e->prop[i], d.G); A(e->leaders[i], d.G); }
 #undef A
   if (st != JR_OK) { jr_engine_destroy(e); return st; }
   if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -501,6 +511,20 @@ jr_status jr_engine_create(const jr_config* cfg, jr_engine** out) {
     return JR_E_CUDA;
   }
   e->stream = e->own_stream;
+  {
+    bool ok = cudaStreamCreateWithFlags(&e->h2d, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&e->d2h, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i < jr_engine::NBUF; ++i)
+      ok = cudaEventCreateWithFlags(&e->prop_ready[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&e->prop_free[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&e->tab_ready[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&e->tab_free[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+      set_err("copy streams / events could not be created");
+      jr_engine_destroy(e);
+      return JR_E_CUDA;
+    }
+  }
   {
     const int smem = (int)step_smem_bytes(d);
     cudaError_t aerr = cudaSuccess;
@@ -545,6 +569,14 @@ void jr_engine_destroy(jr_engine* e) {
   if (e->inj_targets) cudaFree(e->inj_targets);
   if (e->cr_blocks) cudaFree(e->cr_blocks);
   if (e->cr_present) cudaFree(e->cr_present);
+  if (e->h2d) { cudaStreamSynchronize(e->h2d); cudaStreamDestroy(e->h2d); }
+  if (e->d2h) { cudaStreamSynchronize(e->d2h); cudaStreamDestroy(e->d2h); }
+  for (int i = 0; i < jr_engine::NBUF; ++i) {
+    if (e->prop_ready[i]) cudaEventDestroy(e->prop_ready[i]);
+    if (e->prop_free[i]) cudaEventDestroy(e->prop_free[i]);
+    if (e->tab_ready[i]) cudaEventDestroy(e->tab_ready[i]);
+    if (e->tab_free[i]) cudaEventDestroy(e->tab_free[i]);
+  }
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   delete e;
 }
@@ -558,7 +590,9 @@ jr_status jr_engine_set_stream(jr_engine* e, void* s) {
 
 jr_status jr_engine_sync(jr_engine* e) {
   if (!e) return JR_E_INVAL;
+  CK(cudaStreamSynchronize(e->h2d));
   CK(cudaStreamSynchronize(e->stream));
+  CK(cudaStreamSynchronize(e->d2h));
   return JR_OK;
 }
 
@@ -714,7 +748,7 @@ jr_status jr_step(jr_engine* e, jr_step_args* a) {
       sorted.push_back(m);
     }
   }
-  if (a->proposals)
+  if (a->proposals && !(a->flags & JR_STEP_TRUSTED_PROPOSALS))
     for (uint32_t g = 0; g < G; ++g)
       if (a->proposals[g].node > R) return JR_E_UNKNOWN_NODE;
 
@@ -726,9 +760,16 @@ jr_status jr_step(jr_engine* e, jr_step_args* a) {
   p.n_ticks = 1;
   p.dt = 0;
   p.proposals = nullptr;
+  int staged = -1;
   if (a->proposals) {
-    CK(cudaMemcpyAsync(e->prop, a->proposals, (size_t)G * sizeof(jr_proposal), cudaMemcpyHostToDevice, e->stream));
-    p.proposals = e->prop;
+    const int b = e->prop_i;
+    e->prop_i = (b + 1) % jr_engine::NBUF;
+    if (e->prop_used[b]) CK(cudaStreamWaitEvent(e->h2d, e->prop_free[b], 0));  // its last reader is done
+    CK(cudaMemcpyAsync(e->prop[b], a->proposals, (size_t)G * sizeof(jr_proposal), cudaMemcpyHostToDevice, e->h2d));
+    CK(cudaEventRecord(e->prop_ready[b], e->h2d));
+    CK(cudaStreamWaitEvent(e->stream, e->prop_ready[b], 0));
+    p.proposals = e->prop[b];
+    staged = b;
   }
   const uint32_t ph_first = PH_RESET_OUT | PH_RESET_FSM | ((a->flags & JR_STEP_DELIVER) ? PH_DRAIN : 0u);
   const uint32_t ph_last = ((p.proposals || p.n_synth) ? PH_PROPOSE : 0u) | ((a->flags & JR_STEP_TICK) ? PH_TICK : 0u);
@@ -757,6 +798,10 @@ jr_status jr_step(jr_engine* e, jr_step_args* a) {
       if ((st = launch_step(e, p)) != JR_OK) return st;
     }
     CK(cudaStreamSynchronize(e->stream));  // `sorted` / `targets` are stack-owned host buffers
+  }
+  if (staged >= 0) {  // proposals buffer may be refilled once the kernels of this step are done
+    CK(cudaEventRecord(e->prop_free[staged], e->stream));
+    e->prop_used[staged] = true;
   }
   const int written = e->cur;
   e->cur ^= 1;
@@ -937,18 +982,23 @@ jr_status jr_leader_table_device(jr_engine* e, void* dev_out) {
 
 jr_status jr_leader_table_async(jr_engine* e, jr_leader_entry* host_out) {
   if (!e || !host_out) return JR_E_INVAL;
-  jr_status st = jr_leader_table_device(e, e->leaders);
+  const int b = e->tab_i;
+  e->tab_i = (b + 1) % jr_engine::NBUF;
+  if (e->tab_used[b]) CK(cudaStreamWaitEvent(e->stream, e->tab_free[b], 0));  // its last copy-out is done
+  jr_status st = jr_leader_table_device(e, e->leaders[b]);
   if (st != JR_OK) return st;
-  CK(cudaMemcpyAsync(host_out, e->leaders, (size_t)e->d.G * sizeof(jr_leader_entry), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaEventRecord(e->tab_ready[b], e->stream));
+  CK(cudaStreamWaitEvent(e->d2h, e->tab_ready[b], 0));
+  CK(cudaMemcpyAsync(host_out, e->leaders[b], (size_t)e->d.G * sizeof(jr_leader_entry), cudaMemcpyDeviceToHost, e->d2h));
+  CK(cudaEventRecord(e->tab_free[b], e->d2h));
+  e->tab_used[b] = true;
   return JR_OK;
 }
 
 jr_status jr_leader_table(jr_engine* e, jr_leader_entry* host_out) {
-  if (!e || !host_out) return JR_E_INVAL;
-  jr_status st = jr_leader_table_device(e, e->leaders);
+  jr_status st = jr_leader_table_async(e, host_out);
   if (st != JR_OK) return st;
-  CK(cudaMemcpyAsync(host_out, e->leaders, (size_t)e->d.G * sizeof(jr_leader_entry), cudaMemcpyDeviceToHost, e->stream));
-  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaStreamSynchronize(e->d2h));
   return JR_OK;
 }
 

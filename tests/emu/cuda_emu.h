@@ -107,6 +107,12 @@ inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { mem
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, int) { *s = (void*)1; return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
+typedef void* cudaEvent_t;
+enum { cudaEventDisableTiming = 2 };
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, int) { *e = (void*)1; return cudaSuccess; }
+inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, int) { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
