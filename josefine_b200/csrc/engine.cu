@@ -48,15 +48,24 @@ __global__ void __launch_bounds__(32 * R) step_kernel(const Dev d, const StepPar
   rep.load(p.phases & PH_RESET_OUT, p.phases & PH_RESET_FSM);
   rep.tc_prefetch();
   rep.stage_inbox(p.phases & PH_DRAIN);
+#ifdef JR_PROFILE
+  for (uint32_t i = threadIdx.x; i < 8 * 3 * 16 * 2; i += blockDim.x) jr_prof_smem()[i] = 0;
+#endif
   __syncthreads();
   StepParams q = p;
   for (uint32_t t = 0;; ++t) {
+    JR_PROF_T0(tt);
+    const uint32_t prole = rep.role == JR_ROLE_LEADER ? JR_ROLE_LEADER : JR_ROLE_FOLLOWER;
+    (void)prole;
     rep.clear_marks();
     rep.run_step(q);
+    JR_PROF_ADD(prole, 12, tt);
     if (t + 1 == p.n_ticks) break;
     L.cout[r * 32 + lane] = rep.ocnt;
     rep.publish_marks();
+    JR_PROF_ADD(prole, 15, tt);
     __syncthreads();
+    JR_PROF_ADD(prole, 13, tt);
     // next tick: what was written becomes the inbox
     uint4* tb = L.in; L.in = L.out; L.out = tb;
     uint32_t* tcn = L.cin; L.cin = L.cout; L.cout = tcn;
@@ -71,6 +80,14 @@ __global__ void __launch_bounds__(32 * R) step_kernel(const Dev d, const StepPar
     q.proposals = nullptr;
   }
   rep.store();
+#ifdef JR_PROFILE
+  __syncthreads();
+  if (d.prof)
+    for (uint32_t i = threadIdx.x; i < R * 3 * 16 * 2; i += blockDim.x) {
+      const unsigned long long v = jr_prof_smem()[i];
+      if (v) atomicAdd(d.prof + (i % (3 * 16 * 2)), v);
+    }
+#endif
 }
 
 // Host-injected commands: one thread per distinct target replica, commands in
@@ -91,8 +108,11 @@ __global__ void inject_kernel(const Dev d, const StepParams p, const jr_msg* msg
     const jr_msg* m = msgs + t.z + k;
     Cmd c;
     c.kind = m->kind; c.flag = m->flag ? 1u : 0u; c.node_id = m->node_id; c.block = (uint32_t)m->block;
-    c.nblk = m->n_blocks; c.addr = ((uint32_t)m->client_kind << 16) | (m->client_id & 0xffffu);
-    c.term = m->term; c.last_term = m->last_term; c.token = m->token;
+    c.nblk = m->n_blocks; c.term = m->term; c.last_term = m->last_term;
+    if (m->kind == JR_CMD_CLIENT_REQUEST || m->kind == JR_CMD_CLIENT_RESPONSE) {  // Cmd aliases, see raft_device.cuh
+      c.term = m->token;
+      c.block = ((uint32_t)m->client_kind << 16) | (m->client_id & 0xffffu);
+    }
     c.blk_s = 0; c.blk_at = 0; c.host_msg = m;
     rep.apply(c);
   }
@@ -501,6 +521,9 @@ jr_status jr_engine_create(const jr_config* cfg, jr_engine** out) {
   A(d.fs, plane * (size_t)((d.flags & JR_F_CAPTURE_FSM) ? d.F : 1));
   A(d.fc, plane);
   A(e->scratch, 8);
+#ifdef JR_PROFILE
+  A(d.prof, 3 * 16 * 2);
+#endif
   A(e->q_state, 1);
   for (int i = 0; i < jr_engine::NBUF; ++i) { A(e->prop[i], d.G); A(e->leaders[i], d.G); }
 #undef A
@@ -543,6 +566,18 @@ jr_status jr_engine_create(const jr_config* cfg, jr_engine** out) {
   return JR_OK;
 }
 
+#ifdef JR_PROFILE
+// Profiling builds only (not part of the ABI): read and clear the phase counters.
+jr_status jr_profile_read(jr_engine* e, unsigned long long* out96) {
+  if (!e || !out96) return JR_E_INVAL;
+  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaMemcpyAsync(out96, e->d.prof, 96 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemsetAsync(e->d.prof, 0, 96 * sizeof(unsigned long long), e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return JR_OK;
+}
+#endif
+
 jr_status jr_engine_reset(jr_engine* e) {
   if (!e) return JR_E_INVAL;
   CK(cudaSetDevice(e->cfg.device));
@@ -557,6 +592,9 @@ jr_status jr_engine_reset(jr_engine* e) {
   CK(cudaStreamSynchronize(e->stream));
   e->cur = 0;
   e->step_index = 0;
+#ifdef JR_PROFILE
+  CK(cudaMemsetAsync(e->d.prof, 0, 96 * sizeof(unsigned long long), e->stream));
+#endif
   return JR_OK;
 }
 

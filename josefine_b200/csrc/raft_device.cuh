@@ -54,6 +54,7 @@ struct Dev {
   uint32_t emin, emax, hb;
   uint32_t Us, W;                  // shared-memory mailbox units per replica, table-cache entries (power of 2)
   uint32_t use_index;              // receivers use the delivery index (else scan whole mailboxes)
+  unsigned long long* prof;        // JR_PROFILE builds: cycle counters [role 3][slot 16] x {cycles, count}
   uint64_t seed, goff;
 };
 
@@ -109,10 +110,12 @@ __host__ __device__ inline uint64_t synth_token(uint64_t step_index, uint32_t i,
 // A decoded command as the handlers see it.  Blocks come either from mailbox
 // units (strided) or from a host jr_msg copied to the device.
 struct Cmd {
-  uint32_t kind, flag, node_id, block, nblk, addr;  // addr = client address kind<<16 | id
-  uint64_t term, last_term, token;
+  uint32_t kind, flag, node_id, nblk;
+  uint32_t block;          // head / commit / block id; for ClientRequest: client address (kind<<16 | id)
+  uint64_t term;           // term; for ClientRequest / ClientResponse: the request token (D5)
+  uint64_t last_term;      // VoteRequest only
   uint32_t blk_s, blk_at;  // mailbox: sender index and slot of the first block unit
-  const jr_msg* host_msg;  // injected command or null
+  const jr_msg* host_msg;  // injected command (blocks are read from it) or null
 };
 
 #ifdef JR_DEVICE_CODE
@@ -171,6 +174,22 @@ __device__ __noinline__ uint64_t digest_fsm_fn(uint64_t h, bool notify, uint32_t
   }
   return fold(h, tok);
 }
+
+#ifdef JR_PROFILE
+// Phase profiler (tools/phase_profile.py): lane 0 of a warp attributes clock64() deltas
+// to (role, slot).  Slots 0..11 = time inside apply for that Command kind, 12 = whole
+// tick, 13 = waiting at the per-tick barrier, 14 = fetch (next_cmd), 15 = tick bookkeeping.
+// per-warp accumulators live in static shared memory and are flushed once per launch
+__device__ __forceinline__ unsigned long long* jr_prof_smem() {
+  __shared__ unsigned long long acc[8 * 3 * 16 * 2];
+  return acc;
+}
+#define JR_PROF_T0(var) long long var = clock64()
+#define JR_PROF_ADD(role, slot, var) do { long long _n = clock64(); if ((threadIdx.x & 31u) == 0) { unsigned long long* _p = jr_prof_smem() + (((threadIdx.x >> 5) * 3 + (role)) * 16 + (slot)) * 2; _p[0] += (unsigned long long)(_n - var); _p[1] += 1ull; } var = clock64(); } while (0)
+#else
+#define JR_PROF_T0(var) do { } while (0)
+#define JR_PROF_ADD(role, slot, var) do { } while (0)
+#endif
 
 template <int R>
 struct Replica {
@@ -740,8 +759,8 @@ struct Replica {
         case JR_CMD_APPEND_ENTRIES: follower_append_entries(c); break;
         case JR_CMD_HEARTBEAT: follower_heartbeat(c); break;
         case JR_CMD_VOTE_REQUEST: follower_vote_request(c); break;
-        case JR_CMD_CLIENT_REQUEST: follower_client_request(c.token); break;
-        case JR_CMD_CLIENT_RESPONSE: send(JR_CMD_CLIENT_RESPONSE, TO_CLIENT, 0, 0, c.token, 0); break;  // follower.rs:271-282
+        case JR_CMD_CLIENT_REQUEST: follower_client_request(c.term); break;
+        case JR_CMD_CLIENT_RESPONSE: send(JR_CMD_CLIENT_RESPONSE, TO_CLIENT, 0, 0, c.term, 0); break;  // follower.rs:271-282
         default: break;
       }
     } else {
@@ -758,7 +777,7 @@ struct Replica {
         case JR_CMD_VOTE_RESPONSE: candidate_vote_response(c.node_id, c.flag != 0); break;
         case JR_CMD_APPEND_ENTRIES: if (c.term >= term) candidate_to_follower(); break;  // candidate.rs:116-134
         case JR_CMD_HEARTBEAT: candidate_heartbeat(c); break;
-        case JR_CMD_CLIENT_REQUEST: queue_push(c.token, c.addr); break;
+        case JR_CMD_CLIENT_REQUEST: queue_push(c.term, c.block); break;
         default: break;
       }
     }
@@ -793,8 +812,8 @@ struct Replica {
       }
       case JR_CMD_CLIENT_REQUEST: {  // leader.rs:177-197
         uint32_t bid;
-        if (!chain_append(c.token, bid)) break;
-        fsm_emit(true, bid, c.addr, c.token);
+        if (!chain_append(c.term, bid)) break;
+        fsm_emit(true, bid, c.block, c.term);
         t_advance = true; adv_node = id(); adv_block = head;  // self AppendResponse
         break;
       }
@@ -826,12 +845,13 @@ struct Replica {
     uint32_t s;      // sender being drained
     uint32_t idx;    // indexed delivery: my headers of sender s still to visit (0 = none)
     uint32_t u, cnt; // scan delivery (index overflow, or a virtual sender): units u..cnt of sender s
-    uint32_t reps;   // copies of the current VoteRequest unit still to apply
+    uint32_t reps;   // copies of the current VoteRequest unit still to apply ...
+    uint32_t rep_at; // ... and its slot (the unit is re-read, so no Cmd has to stay alive)
   };
 
   // Which senders have mail for me this tick: one shared-memory read per peer, up front.
   __device__ __forceinline__ void plan_tick(Pos& k, const StepParams& p) const {
-    k.pend = 0; k.s = 0; k.idx = 0; k.u = 0; k.cnt = 0; k.reps = 0;
+    k.pend = 0; k.s = 0; k.idx = 0; k.u = 0; k.cnt = 0; k.reps = 0; k.rep_at = 0;
     if (p.phases & PH_DRAIN) {
       // delivery masks mk_in[me][s] and mailbox counts cin[s] have the same stride over s
       const uint32_t* src = d.use_index ? L.mk_in + (r * R) * 32 + L.lane : L.cin + L.lane;
@@ -848,10 +868,17 @@ struct Replica {
   // Next command addressed to this replica, or false when the schedule is exhausted.
   __device__ __forceinline__ bool next_cmd(Pos& k, const StepParams& p, Cmd& c) {
     const uint32_t me = id();
-    if (k.reps) { --k.reps; return true; }  // another copy of the same VoteRequest (c unchanged)
     uint4 h;
     uint32_t at = 0;
+    bool again = false;
     for (;;) {
+      if (k.reps) {  // another copy of the same VoteRequest broadcast: re-read the unit
+        --k.reps;
+        at = k.rep_at;
+        h = inbox_unit(k.s, at);
+        again = true;
+        break;
+      }
       if (k.idx) {  // indexed delivery: jump to my next header of sender s
         at = (uint32_t)__ffs((int)k.idx) - 1u;
         k.idx &= k.idx - 1u;
@@ -895,12 +922,12 @@ struct Replica {
       }
     }
     const uint32_t kind = h.x & 15u, aux = (h.x >> 8) & 255u;
-    c.kind = kind; c.flag = (h.x >> 4) & 1u; c.node_id = k.s + 1; c.block = h.w; c.addr = h.w;
-    c.term = (uint64_t)h.y | ((uint64_t)h.z << 32); c.last_term = c.term; c.token = c.term;
-    c.nblk = aux; c.blk_s = k.s;
+    c.kind = kind; c.flag = (h.x >> 4) & 1u; c.node_id = k.s + 1; c.nblk = aux; c.block = h.w;
+    c.term = (uint64_t)h.y | ((uint64_t)h.z << 32); c.last_term = c.term;
+    c.blk_s = k.s;
     c.blk_at = (kind == JR_CMD_APPEND_ENTRIES && c.flag) ? h.w : at + 1;
     // N-1 identical VoteRequest broadcasts travel as one unit (candidate.rs:30-37)
-    k.reps = (kind == JR_CMD_VOTE_REQUEST && aux) ? aux - 1u : 0u;
+    if (!again && kind == JR_CMD_VOTE_REQUEST && aux > 1u) { k.reps = aux - 1u; k.rep_at = at; }
     return true;
   }
 
@@ -909,18 +936,74 @@ struct Replica {
     plan_tick(k, p);
     Cmd c;
     c.host_msg = nullptr;
-    c.kind = JR_CMD_NOOP;
     bool more = live();
     while (more) {
+      JR_PROF_T0(tp);
       if (role == JR_ROLE_LEADER) {
+        // Steady-state fast drain: a peer whose only dispatchable mail is ONE AppendResponse
+        // (its HeartbeatResponse{has} is a no-op and not indexed).  Same effect as the generic
+        // path below -- ReplicationProgress::advance + Leader::commit, leader.rs:211-219 --
+        // without the generic fetch/dispatch.  Senders are taken in ascending order and the
+        // drain stops at the first one that does not fit, so delivery order is unchanged.
+        if (d.use_index && k.idx == 0 && k.u >= k.cnt && k.reps == 0) {
+          const uint32_t real = k.pend & ((1u << R) - 1u);
+          // all peers' delivery masks, then all candidate units: independent loads, one latency each
+          uint32_t m[R], w[R];
+#pragma unroll
+          for (int s_ = 0; s_ < R; ++s_) m[s_] = ((real >> s_) & 1u) ? L.mk_in[(r * R + s_) * 32 + L.lane] : 0u;
+          uint32_t okm = 0;
+#pragma unroll
+          for (int s_ = 0; s_ < R; ++s_) {
+            const bool single = m[s_] != 0u && !(m[s_] & MK_SCAN) && !(m[s_] & (m[s_] - 1u));
+            uint4 h = make_uint4(0, 0, 0, 0);
+            if (single) h = inbox_unit(s_, (uint32_t)__ffs((int)m[s_]) - 1u);
+            w[s_] = h.w;
+            if (single && (h.x & 15u) == JR_CMD_APPEND_RESPONSE) okm |= 1u << s_;
+          }
+          // ascending sender order: only the senders below the first one that does not fit
+          const uint32_t bad = real & ~okm;
+          uint32_t elig = bad ? (okm & ((bad & (0u - bad)) - 1u)) : okm;
+          int above = 0;
+#pragma unroll
+          for (int i = 0; i < R; ++i) above += ph[i] > commit ? 1 : 0;
+          while (elig && live()) {
+            bool trig = false;
+#pragma unroll
+            for (int s_ = 0; s_ < R; ++s_) {
+              if (!trig && ((elig >> s_) & 1u)) {  // ReplicationProgress::advance, progress.rs:42-46,76-94,133-140
+                const uint32_t v = w[s_];
+                const bool inc = ph[s_] < v;
+                if (inc && ph[s_] <= commit && v > commit) ++above;
+                if (inc) ph[s_] = v;
+                prmask = inc ? (prmask | (1u << s_)) : (prmask & ~(1u << s_));
+                elig &= ~(1u << s_);
+                k.pend &= ~(1u << s_);
+                trig = above >= R / 2 + 1;  // committed_index() > commit: Leader::commit acts (leader.rs:87-99)
+              }
+            }
+            if (trig) {
+              leader_commit();
+              above = 0;
+#pragma unroll
+              for (int i = 0; i < R; ++i) above += ph[i] > commit ? 1 : 0;
+            }
+          }
+          JR_PROF_ADD(JR_ROLE_LEADER, 11, tp);
+        }
         // leader loop: runs to the end of the tick
-        while (live() && next_cmd(k, p, c)) apply_leader(c);
+        while (live() && next_cmd(k, p, c)) {
+          JR_PROF_ADD(JR_ROLE_LEADER, 14, tp);
+          apply_leader(c);
+          JR_PROF_ADD(JR_ROLE_LEADER, c.kind, tp);
+        }
         more = false;
       } else {
         // follower / candidate loop: leaves when the replica wins an election
         more = false;
         while (live() && next_cmd(k, p, c)) {
+          JR_PROF_ADD(JR_ROLE_FOLLOWER, 14, tp);
           apply_fc(c);
+          JR_PROF_ADD(JR_ROLE_FOLLOWER, c.kind, tp);
           if (role == JR_ROLE_LEADER) { more = live(); break; }
         }
       }
