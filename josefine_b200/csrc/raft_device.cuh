@@ -961,6 +961,7 @@ struct Replica {
             if (single && (h.x & 15u) == JR_CMD_APPEND_RESPONSE) okm |= 1u << s_;
           }
           // ascending sender order: only the senders below the first one that does not fit
+          JR_PROF_ADD(JR_ROLE_LEADER, 8, tp);   // profile: drain loads
           const uint32_t bad = real & ~okm;
           uint32_t elig = bad ? (okm & ((bad & (0u - bad)) - 1u)) : okm;
           int above = 0;
@@ -982,7 +983,9 @@ struct Replica {
               }
             }
             if (trig) {
+              JR_PROF_ADD(JR_ROLE_LEADER, 9, tp);  // profile: drain advances
               leader_commit();
+              JR_PROF_ADD(JR_ROLE_LEADER, 1, tp);  // profile: Leader::commit
               above = 0;
 #pragma unroll
               for (int i = 0; i < R; ++i) above += ph[i] > commit ? 1 : 0;

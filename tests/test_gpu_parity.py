@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 
 def make_oracle(g, r, **kw):
-    return RestatedCluster.create(g, r, n_threads=8 if g >= 1024 else 1, **kw)
+    return RestatedCluster.create(g, r, n_threads=16 if g >= 1024 else 1, **kw)
 
 
 def make_gpu(g, r, **kw):
@@ -134,3 +134,40 @@ def test_no_cpu_fallback_symbols():
     assert r.ENGINE_LIB_PATH.endswith("libjosefine_b200.so")
     e = make_gpu(8, 3)
     assert e.state_digest() != 0
+
+
+def test_config4_per_gpu_shard_131072x5():
+    """BASELINE config #4's per-GPU share (1,048,576 / 8 = 131,072 groups x 5), as the shard of
+    rank 3: group_offset keeps the D2 timeouts keyed by GLOBAL group id."""
+    G = 131072
+    a, b = _digest_parity(G, 5, 24, seed=1, bootstrap=True, chain_capacity=64, group_offset=3 * G)
+    assert b.fault_count() == 0
+
+
+def test_config5_full_size_65536x7_churn_compact():
+    """BASELINE config #5 at full size: 65,536 x 7, leaders silenced in 10% of the groups, compact()."""
+    G, R = 65536, 7
+    flags = abi.F_STREAM_DIGEST
+    a = make_oracle(G, R, seed=2, flags=flags, chain_capacity=96)
+    b = make_gpu(G, R, seed=2, flags=flags, chain_capacity=96)
+    from josefine_b200 import Command
+    inj = []
+    for g in range(G):
+        inj.append(Command.timeout(g, 1))
+        for v in (2, 3, 4):
+            inj.append(Command.vote_response(g, 1, 1, v, True))
+    for x in (a, b):
+        x.step(0, flags=0, inject=inj)
+    now = 100
+    for rnd in range(2):
+        for x in (a, b):
+            x.run(now, 100, 20, 1)
+        now += 2000
+        assert a.kill_leaders(rnd, 100) == b.kill_leaders(rnd, 100)
+        for x in (a, b):
+            x.compact()
+    parity.compare_digests(a, b, "[65536x7 churn]")
+    parity.compare_states(a, b, groups=range(0, G, 4099), chain_ids=48)
+    table = b.leader_table()
+    assert table == a.leader_table()
+    assert 0.05 < sum(1 for (_, l, _) in table if l == 0) / G < 0.30
