@@ -841,12 +841,13 @@ struct Replica {
   // schedule, so the follower/candidate loop can hand over to the leader loop in
   // the middle of a tick (the moment an election is won).
   struct Pos {
-    uint32_t pend;   // senders (real 0..R-1, virtual R..R+2) that still have something for me
+    uint32_t pend;   // peers (0..R-1) that still have something for me
     uint32_t s;      // sender being drained
     uint32_t idx;    // indexed delivery: my headers of sender s still to visit (0 = none)
     uint32_t u, cnt; // scan delivery (index overflow, or a virtual sender): units u..cnt of sender s
     uint32_t reps;   // copies of the current VoteRequest unit still to apply ...
     uint32_t rep_at; // ... and its slot (the unit is re-read, so no Cmd has to stay alive)
+    uint32_t tail, tail_i;  // trailing schedule entries: see next_tail
   };
 
   // Which senders have mail for me this tick: one shared-memory read per peer, up front.
@@ -860,9 +861,40 @@ struct Replica {
         if (src[s_ * 32]) k.pend |= 1u << s_;
       k.pend &= ~(1u << r);  // never my own mailbox
     }
-    if ((p.phases & PH_PROPOSE) && p.proposals && g < d.G) k.pend |= 1u << R;
-    if ((p.phases & PH_PROPOSE) && p.n_synth) k.pend |= 1u << (R + 1);
-    if (p.phases & PH_TICK) k.pend |= 1u << (R + 2);
+    k.tail = 0;
+  }
+
+  // The trailing schedule entries need no mailbox: dense proposal (stage 0), synthetic
+  // proposals to a Leader (stage 1, `tail_i` counts them), Tick (stage 2).
+  __device__ __forceinline__ bool next_tail(Pos& k, const StepParams& p, Cmd& c) const {
+    const uint32_t me = id();
+    c.flag = 0; c.node_id = 0; c.nblk = 0; c.last_term = 0; c.blk_s = 0; c.blk_at = 0;
+    if (k.tail == 0) {  // event_loop client arm, server.rs:156-160
+      k.tail = 1;
+      k.tail_i = 0;
+      if ((p.phases & PH_PROPOSE) && p.proposals && g < d.G) {
+        const uint4 pr = __ldg(reinterpret_cast<const uint4*>(p.proposals) + g);
+        if (pr.z == me) {
+          c.kind = JR_CMD_CLIENT_REQUEST; c.block = (uint32_t)JR_ADDR_CLIENT << 16;
+          c.term = (uint64_t)pr.x | ((uint64_t)pr.y << 32);
+          return true;
+        }
+      }
+    }
+    if (k.tail == 1) {
+      if ((p.phases & PH_PROPOSE) && k.tail_i < p.n_synth && role == JR_ROLE_LEADER) {
+        c.kind = JR_CMD_CLIENT_REQUEST; c.block = (uint32_t)JR_ADDR_CLIENT << 16;
+        c.term = synth_token(p.step_index, k.tail_i, d.goff + g);
+        ++k.tail_i;
+        return true;
+      }
+      k.tail = 2;
+    }
+    if (k.tail == 2) {
+      k.tail = 3;
+      if (p.phases & PH_TICK) { c.kind = JR_CMD_TICK; c.block = 0; c.term = 0; return true; }
+    }
+    return false;
   }
 
   // Next command addressed to this replica, or false when the schedule is exhausted.
@@ -885,41 +917,21 @@ struct Replica {
         h = inbox_unit(k.s, at);
         break;
       }
-      if (k.u < k.cnt) {  // scan delivery
+      if (k.u < k.cnt) {  // scan delivery (the sender's index overflowed)
         at = k.u;
-        if (k.s < (uint32_t)R) {
-          h = inbox_unit(k.s, k.u);
-          const uint32_t k0 = h.x & 15u, to = h.x >> 16;
-          k.u += 1u + ((k0 == JR_CMD_APPEND_ENTRIES && !((h.x >> 4) & 1u)) ? ((h.x >> 8) & 255u) : 0u);
-          if (to != TO_PEERS && to != me) continue;
-        } else if (k.s == (uint32_t)R) {  // event_loop client arm, server.rs:156-160
-          const uint4 pr = __ldg(reinterpret_cast<const uint4*>(p.proposals) + g);
-          k.u = k.cnt;
-          if (pr.z != me) continue;
-          h = make_uint4(unit_hdr(JR_CMD_CLIENT_REQUEST, 0, 0, me), pr.x, pr.y, (uint32_t)JR_ADDR_CLIENT << 16);
-        } else if (k.s == (uint32_t)R + 1u) {
-          if (role != JR_ROLE_LEADER) { k.u = k.cnt; continue; }
-          const uint64_t tok = synth_token(p.step_index, k.u, d.goff + g);
-          h = make_uint4(unit_hdr(JR_CMD_CLIENT_REQUEST, 0, 0, me), (uint32_t)tok, (uint32_t)(tok >> 32),
-                         (uint32_t)JR_ADDR_CLIENT << 16);
-          ++k.u;
-        } else {
-          h = make_uint4(unit_hdr(JR_CMD_TICK, 0, 0, me), 0, 0, 0);
-          ++k.u;
-        }
+        h = inbox_unit(k.s, k.u);
+        const uint32_t k0 = h.x & 15u, to = h.x >> 16;
+        k.u += 1u + ((k0 == JR_CMD_APPEND_ENTRIES && !((h.x >> 4) & 1u)) ? ((h.x >> 8) & 255u) : 0u);
+        if (to != TO_PEERS && to != me) continue;
         break;
       }
-      if (!k.pend) return false;  // next sender with something for me
+      if (!k.pend) return next_tail(k, p, c);  // peers exhausted: proposals, then Tick
       k.s = (uint32_t)__ffs((int)k.pend) - 1u;
       k.pend &= k.pend - 1u;
       k.u = 0; k.cnt = 0;
-      if (k.s < (uint32_t)R) {
-        const uint32_t m = d.use_index ? L.mk_in[(r * R + k.s) * 32 + L.lane] : MK_SCAN;
-        if (m & MK_SCAN) k.cnt = L.cin[k.s * 32 + L.lane];
-        else k.idx = m;
-      } else {
-        k.cnt = k.s == (uint32_t)R + 1u ? p.n_synth : 1u;
-      }
+      const uint32_t m = d.use_index ? L.mk_in[(r * R + k.s) * 32 + L.lane] : MK_SCAN;
+      if (m & MK_SCAN) k.cnt = L.cin[k.s * 32 + L.lane];
+      else k.idx = m;
     }
     const uint32_t kind = h.x & 15u, aux = (h.x >> 8) & 255u;
     c.kind = kind; c.flag = (h.x >> 4) & 1u; c.node_id = k.s + 1; c.nblk = aux; c.block = h.w;
