@@ -114,11 +114,14 @@ def algorithmic_bytes_per_group_tick(make, R, ticks=64):
 
 
 class ClockSampler:
-    """nvidia-smi clocks during the timed region (profiling recipe's clocks line)."""
+    """nvidia-smi clocks and throttle reasons (profiling recipe's clocks line).  Started before
+    the warm-up so nvidia-smi's start-up latency is absorbed; `window()` then keeps the samples
+    that arrived inside the timed region (or, if the region was shorter than the sampling
+    period, the ones closest to it -- the GPU is under the same load during warm-up)."""
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
+        self.rows = []      # (arrival time, fields)
         self.proc = None
 
     def start(self):
@@ -134,19 +137,26 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def window(self, t0, t1):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        time.sleep(0.15)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0}
+        time.sleep(0.1)
         self.proc.terminate()
-        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        good = [(t, r) for t, r in self.rows if len(r) >= 6 and r[0].isdigit()]
+        inside = [r for t, r in good if t0 <= t <= t1 + 0.03]
+        where = "timed region"
+        if not inside and good:   # region shorter than the sampling period: nearest samples under the same load
+            good.sort(key=lambda tr: min(abs(tr[0] - t0), abs(tr[0] - t1)))
+            inside = [r for _, r in good[:5]]
+            where = "nearest to the timed region (region shorter than the 20 ms sampling period)"
+        sm = [int(r[0]) for r in inside]
+        mx = [int(r[1]) for r in inside if r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].startswith("Active")})
+        reasons = sorted({names[i] for r in inside for i in range(4) if r[2 + i].startswith("Active")})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "sampled": where}
 
 
 def measured_peak():
@@ -331,15 +341,16 @@ def main():
         if state["ticks_left"] < S:
             rebase(eng)
 
-    for _ in range(args.warmup):
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for _ in range(max(args.warmup, 20)):   # >= 20 untimed steps: also covers nvidia-smi's start-up
         between_steps()
         one_step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    t_region0 = time.time()
     evs = []
     for i in range(args.steps):
         between_steps()
@@ -353,7 +364,7 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.window(t_region0, time.time()) if rank == 0 else None
     ms = sum(a.elapsed_time(b) for a, b in evs)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -469,7 +480,8 @@ def main():
                    "groups_per_gpu": G, "replicas": R, "ticks_per_step": S, "tick_ms": DT_MS, "seed": SEED,
                    "l2": f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write); ticks inside a step run back to back",
                    "parallelism": f"groups sharded over {world} GPU(s); leader-announce all_gather once per step" if world > 1
-                   else "single GPU", "faulted_replicas": faults},
+                   else "single GPU", "faulted_replicas": faults,
+                   "untimed_steps_before_timing": max(args.warmup, 20)},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
     }
     print(json.dumps(line))

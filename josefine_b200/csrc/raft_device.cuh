@@ -688,9 +688,15 @@ struct Replica {
     // state: all of them).  The key-order scan runs once per distinct
     // (head, mode); repeats copy the block units already sitting in the outbox.
     uint32_t memo_head = 0xFFFFFFFFu, memo_take = 0, memo_first = 0, memo_nb = 0;
+    JR_PROF_T0(tr);
+    bool first_done = false;
+    (void)first_done;
 #pragma unroll
     for (int p = 0; p < R; ++p) {
       if (p == (int)r) continue;  // config.nodes holds peers only
+#ifdef JR_PROFILE
+      if (first_done) { JR_PROF_ADD(JR_ROLE_LEADER, 2, tr); first_done = false; }
+#endif
       const uint32_t take = (prmask >> p) & 1u ? JR_MAX_AE_BLOCKS : 1u;
       uint32_t nb = 0, first = ocnt + 1;
       bool ref = false;
@@ -720,6 +726,9 @@ struct Replica {
           ++bid;
         }
         memo_head = ph[p]; memo_take = take; memo_first = ocnt + 1; memo_nb = nb;
+#ifdef JR_PROFILE
+        first_done = true;
+#endif
       }
       if (!put_unit(ocnt, make_uint4(unit_hdr(JR_CMD_APPEND_ENTRIES, ref ? 1u : 0u, nb, p + 1), (uint32_t)term,
                                      (uint32_t)(term >> 32), first)))
@@ -738,6 +747,7 @@ struct Replica {
       }
       ocnt += ref ? 1u : 1u + nb;
     }
+    JR_PROF_ADD(JR_ROLE_LEADER, 3, tr);
   }
 
   // ------------------------------------------------------------------ Apply::apply (mod.rs:471-479)

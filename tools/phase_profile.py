@@ -24,13 +24,13 @@ for _ in range(5):
     e.run(now, 100, S, 1)
     now += 100 * S
 e._lib.jr_profile_read(e._h, buf)
-names = {1: "  drain: Leader::commit", 8: "  drain: mask+unit loads", 9: "  drain: advances", 0: "Tick", 2: "VoteRequest", 3: "VoteResponse", 4: "AppendEntries", 5: "AppendResponse", 6: "Heartbeat",
+names = {1: "  drain: Leader::commit", 8: "  drain: mask+unit loads", 9: "  drain: advances", 0: "Tick", 2: "  replicate: first peer (scan)", 3: "  replicate: other peers (refs)", 4: "AppendEntries", 5: "AppendResponse", 6: "Heartbeat",
          7: "HeartbeatResponse", 10: "ClientRequest", 11: "fast AResp drain", 12: "WHOLE TICK", 13: "barrier wait", 14: "fetch (next_cmd)",
          15: "publish marks/counts"}
 for role, rn in ((2, "LEADER warp"), (0, "FOLLOWER warp")):
     tick_n = buf[(role * 16 + 12) * 2 + 1] or 1
     print(f"== {rn}: cycles per warp-tick (count = events per warp-tick)")
-    for slot in (12, 14, 8, 9, 1, 11, 0, 4, 5, 6, 7, 10, 2, 3, 15, 13):
+    for slot in (12, 14, 8, 9, 1, 11, 2, 3, 0, 4, 5, 6, 7, 10, 2, 3, 15, 13):
         cyc, n = buf[(role * 16 + slot) * 2], buf[(role * 16 + slot) * 2 + 1]
         if n:
             print(f"  {names[slot]:22s} {cyc / tick_n:9.0f} cycles   x{n / tick_n:5.2f}   ({cyc / n:7.0f} per event)")
