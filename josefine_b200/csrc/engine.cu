@@ -277,16 +277,25 @@ __global__ void leader_table_kernel(const Dev d, jr_leader_entry* out) {
 
 __global__ void kill_leaders_kernel(const Dev d, uint64_t base, uint32_t permille, unsigned long long* n_killed) {
   const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= d.G) return;
-  if (mix64(base + d.goff + g) % 1000 >= permille) return;
+  const bool pick = g < d.G && mix64(base + d.goff + g) % 1000 < permille;
+  uint32_t killed = 0;
   for (uint32_t r = 0; r < d.R; ++r) {
-    const size_t i = (size_t)r * d.Gp + g;
-    const uint32_t m = d.p2[i].w;
-    if ((m & 255u) == JR_ROLE_LEADER && ((m >> 8) & 255u) == 0 && ((m >> 27) & 1u) == 0) {
-      d.p2[i].w = m | (1u << 27);
-      atomicAdd(n_killed, 1ull);
+    bool hit = false;
+    if (pick) {
+      const size_t i = (size_t)r * d.Gp + g;
+      const uint32_t m = d.p2[i].w;
+      hit = (m & 255u) == JR_ROLE_LEADER && ((m >> 8) & 255u) == 0 && ((m >> 27) & 1u) == 0;
+      if (hit) d.p2[i].w = m | (1u << 27);
     }
+#ifdef JR_EMU
+    killed += hit ? 1u : 0u;
+#else
+    // warp-aggregated count: one vote per lane, popcount of the ballot, one atomic per warp
+    const uint32_t votes = __ballot_sync(0xffffffffu, hit);
+    if ((threadIdx.x & 31u) == 0) killed += (uint32_t)__popc(votes);
+#endif
   }
+  if (killed) atomicAdd(n_killed, (unsigned long long)killed);
 }
 
 __global__ void set_alive_kernel(const Dev d, uint32_t g, uint32_t r, int alive) {
