@@ -4,6 +4,9 @@
 // replicas; warp w holds replica index w of those 32 groups, so every state
 // plane [replica][group] is read with one coalesced 128-bit load per lane and a
 // warp normally executes ONE role's code path (all leaders or all followers).
+// A launch fuses n ticks: replica state stays in registers, the CTA's mailboxes
+// and a block-table cache live in shared memory (struct Local), ticks are
+// separated by __syncthreads() only (groups never interact).
 //
 // Behaviour follows josefine src/raft (file:line cited per function, paths
 // relative to the reference).  Data layout and control structure are ours.
@@ -27,8 +30,7 @@ enum : uint32_t {
   PH_RESET_FSM = 1u << 1,  // start a new Instruction FIFO
   PH_DRAIN = 1u << 2,      // apply peer mail of the previous step
   PH_PROPOSE = 1u << 3,    // dense + synthetic proposals
-  PH_TICK = 1u << 4,       // Command::Tick
-  PH_DROP_PREV = 1u << 5   // previous outbox is discarded (no DELIVER)
+  PH_TICK = 1u << 4        // Command::Tick
 };
 
 // Mailbox unit (16 B): x = kind[0:4) | flag[4] | aux[8:16) | to[16:32); y,z = term / token; w = block id.
@@ -207,8 +209,9 @@ struct Replica {
   uint32_t role, fault, prmask, nq, dead, ckey, seen, granted;
   uint32_t ph[R];
   // ---- output cursors
-  uint32_t ocnt, fcnt, nmsg, nfsm;
-  uint64_t mdig, fdig;
+  uint32_t ocnt, fcnt;
+  // (the running stream digests live in global memory, d.dg / d.cn, and are updated in place:
+  //  they are only touched with JR_F_STREAM_DIGEST and must not cost registers otherwise)
   uint32_t mko[R];       // delivery index of this tick's outbox, one mask per receiver (see Local::mk_out)
 
   __device__ __forceinline__ Replica(const Dev& dv, const Local& lv, uint32_t r_, uint32_t g_)
@@ -248,14 +251,6 @@ struct Replica {
     ocnt = reset_out ? 0u : d.oc[cur][rg];
     ocnt0 = ocnt;
     fcnt = reset_fsm ? 0u : d.fc[rg];
-    mdig = fdig = 0; nmsg = nfsm = 0;
-    if (digest_on()) {
-      uint4 v = d.dg[rg];
-      mdig = (uint64_t)v.x | ((uint64_t)v.y << 32);
-      fdig = (uint64_t)v.z | ((uint64_t)v.w << 32);
-      uint2 n = d.cn[rg];
-      nmsg = n.x; nfsm = n.y;
-    }
   }
 
   __device__ __forceinline__ void store() {
@@ -284,10 +279,6 @@ struct Replica {
       d.ob[cur][((size_t)u * R + r) * d.Gp + g] = L.out[(u * R + r) * 32 + L.lane];
     d.oc[cur][rg] = ocnt;
     d.fc[rg] = fcnt;
-    if (digest_on()) {
-      d.dg[rg] = make_uint4((uint32_t)mdig, (uint32_t)(mdig >> 32), (uint32_t)fdig, (uint32_t)(fdig >> 32));
-      d.cn[rg] = make_uint2(nmsg, nfsm);
-    }
   }
 
   // ------------------------------------------------------------------ block table (chain.rs)
@@ -413,10 +404,6 @@ struct Replica {
     for (int t = 0; t < R; ++t)
       if (to == TO_PEERS || to == (uint32_t)t + 1u) mko[t] |= bit;
   }
-  template <int T>
-  __device__ __forceinline__ void mark_peer(uint32_t slot) {  // `to` known at compile time
-    mko[T] |= slot < 31u ? (1u << slot) : MK_SCAN;
-  }
   __device__ __forceinline__ void clear_marks() {
 #pragma unroll
     for (int t = 0; t < R; ++t) mko[t] = 0;
@@ -436,8 +423,10 @@ struct Replica {
     ++ocnt;
     if (digest_on()) {
       uint32_t n;
-      mdig = digest_send_fn(mdig, id(), kind, to, flag, aux, t, w, &n);
-      nmsg += n;
+      const uint4 dv = d.dg[rg];
+      const uint64_t md = digest_send_fn((uint64_t)dv.x | ((uint64_t)dv.y << 32), id(), kind, to, flag, aux, t, w, &n);
+      d.dg[rg] = make_uint4((uint32_t)md, (uint32_t)(md >> 32), dv.z, dv.w);
+      d.cn[rg].x += n;
     }
   }
 
@@ -450,8 +439,10 @@ struct Replica {
       ++fcnt;
     }
     if (digest_on()) {
-      fdig = digest_fsm_fn(fdig, notify, bid, next_or_addr, tok);
-      ++nfsm;
+      const uint4 dv = d.dg[rg];
+      const uint64_t fd = digest_fsm_fn((uint64_t)dv.z | ((uint64_t)dv.w << 32), notify, bid, next_or_addr, tok);
+      d.dg[rg] = make_uint4(dv.x, dv.y, (uint32_t)fd, (uint32_t)(fd >> 32));
+      d.cn[rg].y += 1;
     }
   }
 
@@ -735,15 +726,17 @@ struct Replica {
         return;
       mko[p] |= ocnt < 31u ? (1u << ocnt) : MK_SCAN;
       if (digest_on()) {
-        uint64_t h = digest_message_fn(mdig, JR_CMD_APPEND_ENTRIES, p + 1, 0, nb, id(), term, 0, 0, 0, 0);
-        ++nmsg;
+        const uint4 dv = d.dg[rg];
+        uint64_t h = digest_message_fn((uint64_t)dv.x | ((uint64_t)dv.y << 32), JR_CMD_APPEND_ENTRIES, p + 1, 0, nb,
+                                       id(), term, 0, 0, 0, 0);
+        d.cn[rg].x += 1;
         for (uint32_t k = 0; k < nb; ++k) {
           uint4 u = own_unit(first + k);
           h = fold(h, u.x);
           h = fold(h, u.y);
           h = fold(h, (uint64_t)u.z | ((uint64_t)u.w << 32));
         }
-        mdig = h;
+        d.dg[rg] = make_uint4((uint32_t)h, (uint32_t)(h >> 32), dv.z, dv.w);
       }
       ocnt += ref ? 1u : 1u + nb;
     }
