@@ -139,7 +139,11 @@ typedef struct jr_config {
   uint32_t mailbox_units;      /* 16-byte units one replica may emit per step            */
   uint32_t fsm_units;          /* Instructions one replica may emit per launch           */
   uint32_t flags;              /* JR_F_*                                                 */
-  uint32_t reserved;
+  uint32_t resident_mask;      /* bit (id-1): node id is hosted by this engine; 0 = all R.
+                                * A josefine process hosts ONE node per group (RaftConfig::id,
+                                * config.rs:23) and reaches the others over TCP: non-resident
+                                * nodes are never stepped, and mail addressed to them is only
+                                * returned through out_msgs for the host to forward.           */
 } jr_config;
 
 /* Block (src/raft/chain.rs:86-91); `data` is the payload token (D5). */

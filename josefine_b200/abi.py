@@ -66,7 +66,7 @@ class Config(C.Structure):
         ("election_min_ms", C.c_uint32), ("election_max_ms", C.c_uint32),
         ("heartbeat_ms", C.c_uint32), ("chain_capacity", C.c_uint32),
         ("mailbox_units", C.c_uint32), ("fsm_units", C.c_uint32),
-        ("flags", C.c_uint32), ("reserved", C.c_uint32),
+        ("flags", C.c_uint32), ("resident_mask", C.c_uint32),
     ]
 
 

@@ -128,7 +128,8 @@ __global__ void init_kernel(const Dev d) {
   const uint32_t timeout = election_timeout_draw(d.seed, d.goff + g, r + 1, 0, d.emin, d.emax);
   d.p0[i] = make_uint4(0, 0, 0, 0);
   d.p1[i] = make_uint4(0, 0, timeout, 1);                 // init(): first draw, election_time = 0
-  d.p2[i] = make_uint4(0, 0, 1, JR_ROLE_FOLLOWER);        // head 0, commit 0, id_gen 1
+  // head 0, commit 0, id_gen 1; a node this engine does not host is inert (the `dead` bit)
+  d.p2[i] = make_uint4(0, 0, 1, JR_ROLE_FOLLOWER | (((d.resident >> r) & 1u) ? 0u : (1u << 27)));
   d.p3[i] = make_uint4(0, 0, 0, 0);
   d.mk[i] = 0;
   d.cnext[i] = 0;                                         // genesis block 0 -> 0 (chain.rs:139-153)
@@ -513,6 +514,7 @@ jr_status jr_engine_create(const jr_config* cfg, jr_engine** out) {
   d.Us = std::min<uint32_t>(cfg->mailbox_units, 6u);
   d.W = 4;
   d.use_index = getenv("JR_NO_INDEX") ? 0u : 1u;
+  d.resident = cfg->resident_mask ? cfg->resident_mask : 0xffu;
   if (const char* ev = getenv("JR_SMEM_UNITS")) d.Us = std::min<uint32_t>(cfg->mailbox_units, (uint32_t)atoi(ev));
   if (const char* ev = getenv("JR_TABLE_CACHE")) { uint32_t w = (uint32_t)atoi(ev); d.W = (w & (w - 1)) ? 8 : w; }
   const size_t plane = (size_t)d.R * d.Gp;

@@ -56,6 +56,7 @@ struct Dev {
   uint32_t emin, emax, hb;
   uint32_t Us, W;                  // shared-memory mailbox units per replica, table-cache entries (power of 2)
   uint32_t use_index;              // receivers use the delivery index (else scan whole mailboxes)
+  uint32_t resident;               // bit r: replica index r is hosted here (others are inert, see jr_config)
   unsigned long long* prof;        // JR_PROFILE builds: cycle counters [role 3][slot 16] x {cycles, count}
   uint64_t seed, goff;
 };

@@ -331,6 +331,7 @@ jr_status jro_create(const jr_config* cfg, unsigned n_threads, jro_cluster** out
       nc.strict_commit_key = (cfg->flags & JR_F_SLED_COMMIT_KEY_STRICT) != 0;
       Replica& rep = c->at(g, r);
       rep.node = std::make_unique<Node>(nc);
+      if (cfg->resident_mask && !((cfg->resident_mask >> (r - 1)) & 1u)) rep.node->alive = false;  // hosted elsewhere
       rep.msg_digest = rep.fsm_digest = mix64(((cfg->group_offset + g) << 8) | r);
     }
   }

@@ -401,7 +401,7 @@ class PyNode:
         self.s.set_election_timeout()                 # follower.rs:93-95
         self.h = Follower(self.s)
         self.fault = 0
-        self.alive = True
+        self.alive = not cfg.resident_mask or bool((cfg.resident_mask >> (node - 1)) & 1)
         self.prev_out: List[tuple] = []
 
     def apply(self, c, now):

@@ -191,3 +191,34 @@ def kat_chain_compact(make):
 
 
 ALL_KATS = [v for k, v in sorted(globals().items()) if k.startswith("kat_")]
+
+
+# ---- the drop-in shape: ONE resident node per group, peers remote (RaftConfig::id + nodes) --------
+def kat_single_resident_node_with_remote_peers(make):
+    """What event_loop (server.rs:103-165) does for one josefine process: node 1 of a 3-node group is
+    hosted here, nodes 2 and 3 are remote.  Their mail arrives as injected commands (tcp_rx arm,
+    server.rs:127-137) and everything node 1 sends comes back through out_msgs (tcp_tx)."""
+    api = make(1, 3, flags=CAPTURE, resident_mask=0b001)
+    timeout = api.query(0, 1).election_timeout_ms
+    res = api.step(timeout + 1)                                     # Tick: election timer fires
+    assert api.handle(0, 1).is_candidate()
+    vreq = [m for m in res.messages if m.kind == abi.CMD_VOTE_REQUEST]
+    assert len(vreq) == 2 and all(m.to_kind == abi.ADDR_PEERS and m.from_id == 1 for m in vreq)   # N-1 broadcasts
+    assert not [m for m in res.messages if m.from_id != 1]          # nodes 2 and 3 are not simulated
+    res = api.step(timeout + 101, inject=[Command.vote_response(0, 1, term=0, from_=2, granted=True)])
+    assert api.handle(0, 1).is_leader()
+    hb = [m for m in res.messages if m.kind == abi.CMD_HEARTBEAT]
+    assert hb and hb[0].term == 1
+    res = api.step(timeout + 201, inject=[Command.client_request(0, 1, token=55)])
+    ae = [m for m in res.messages if m.kind == abi.CMD_APPEND_ENTRIES]
+    assert sorted(m.to_id for m in ae) == [2, 3]                    # replicate() to both remote peers
+    assert all(m.n_blocks == 1 and m.blocks[0].data == 55 for m in ae)
+    assert [f.kind for f in res.fsm] == [abi.FSM_NOTIFY]            # not committed yet: quorum needs a peer
+    res = api.step(timeout + 301, inject=[Command.append_response(0, 1, node_id=2, term=1, head=1)])
+    assert [(f.kind, f.block.id, f.block.data) for f in res.fsm] == [(abi.FSM_APPLY, 1, 55)]
+    st = api.query(0, 1)
+    assert (st.commit, st.progress_head[1], st.progress_replicate & 0b010) == (1, 1, 0b010)
+    assert api.query(0, 2).alive == 0 and api.query(0, 3).alive == 0
+
+
+ALL_KATS = [v for k, v in sorted(globals().items()) if k.startswith("kat_")]
