@@ -374,12 +374,12 @@ def main():
     value = world * G * S * args.steps / (ms * 1e-3)
     launches = args.steps * (2 if world > 1 else 1)   # one fused step_kernel launch per step (+ leader_table_kernel)
 
-    # ---------------- end-to-end arm (host buffers through jr_step) ----------------
-    # Every tick: jr_step copies that tick's jr_proposal[G] from PINNED host memory
-    # (H2D) and runs the step; jr_leader_table_async copies the per-group
-    # {term, leader, commit} result back (D2H).  The ring of TICKS_PER_STEP pinned
-    # buffers lets copies and kernels of consecutive ticks pipeline on the stream;
-    # the host synchronises once per step.
+    # ---------------- end-to-end arm (host buffers through the C ABI) ----------------
+    # Every step: jr_run_proposals copies that step's jr_proposal[S][G] from PINNED host memory
+    # (H2D, on the engine's copy stream) and runs the S ticks fused; jr_leader_table_async copies
+    # the per-group {term, leader, commit} result back (D2H).  Two steps are in flight: the host
+    # submits step k+1, then waits for and reads step k's result -- copy-in, kernels and copy-out
+    # of neighbouring steps overlap.
     e2e = None
     if not args.no_e2e:
         del eng
@@ -387,54 +387,60 @@ def main():
         e2 = make(G, R, seed=SEED, group_offset=rank * G, chain_capacity=cap, mailbox_units=64)
         e2.set_stream(stream.cuda_stream)
         rebase(e2)
-        prop = torch.zeros(S, G, 2, dtype=torch.int64).pin_memory()    # jr_proposal[S][G] = {token, node|reserved}
-        table = torch.zeros(S, G, 2, dtype=torch.int64).pin_memory()   # jr_leader_entry[S][G]
-        prop[:, :, 1] = 1                                              # addressed to node 1 (the leader)
-        prop[:, :, 0] = (torch.arange(S, dtype=torch.int64).view(S, 1) + 1 << 32) + torch.arange(G, dtype=torch.int64)
+        NB = 2
+        prop = torch.zeros(NB, S, G, 2, dtype=torch.int64).pin_memory()   # jr_proposal[NB][S][G] = {token, node|reserved}
+        table = torch.zeros(NB, G, 2, dtype=torch.int64).pin_memory()     # jr_leader_entry[NB][G]
+        prop[..., 1] = 1                                                  # addressed to node 1 (the leader)
+        prop[..., 0] = ((torch.arange(NB * S, dtype=torch.int64).view(NB, S, 1) + 1) << 32) + torch.arange(G, dtype=torch.int64)
         lib = e2._lib
-        sa = abi.StepArgs()
-        sa.flags = abi.STEP_DELIVER | abi.STEP_TICK | abi.STEP_TRUSTED_PROPOSALS
-        pstride, tstride = G * 16, G * 16
+        pstride, tstride = S * G * 16, G * 16
+        checks = []
 
-        def e2e_step():
+        def submit(i):
             if state["ticks_left"] < S:
+                e2.sync()
                 rebase(e2)
             tn = state["now"]
             state["now"] += DT_MS * S
             state["ticks_left"] -= S
-            for k in range(S):
-                sa.now_ms = tn + k * DT_MS
-                sa.proposals = C.cast(prop.data_ptr() + k * pstride, C.POINTER(abi.Proposal))
-                st = lib.jr_step(e2._h, C.byref(sa))                   # H2D proposals + step kernel
-                assert st == 0, st
-                st = lib.jr_leader_table_async(e2._h, C.cast(table.data_ptr() + k * tstride,
-                                                             C.POINTER(abi.LeaderEntry)))   # result D2H
-                assert st == 0, st
-            e2.sync()
+            st = lib.jr_run_proposals(e2._h, C.c_uint64(tn), C.c_uint32(DT_MS), C.c_uint32(S),
+                                      C.cast(prop.data_ptr() + (i % NB) * pstride, C.POINTER(abi.Proposal)),
+                                      C.c_uint32(abi.STEP_TRUSTED_PROPOSALS))          # H2D + fused kernel
+            assert st == 0, st
+            st = lib.jr_leader_table_async(e2._h, C.cast(table.data_ptr() + (i % NB) * tstride,
+                                                         C.POINTER(abi.LeaderEntry)))   # result D2H
+            assert st == 0, st
 
-        for _ in range(args.warmup):
-            e2e_step()
-        torch.cuda.synchronize()
+        def consume(i):
+            st = lib.jr_leader_table_wait(e2._h)
+            assert st == 0, st
+            checks.append(int(table[i % NB, 0, 1].item() >> 32))        # read the step's result: commit of group 0
+
+        def e2e_steps(n):
+            submit(0)
+            for i in range(n):
+                if i + 1 < n:
+                    submit(i + 1)
+                consume(i)
+
+        e2e_steps(max(args.warmup, 2))
+        e2.sync()
         if world > 1:
             dist.barrier()
-        dt = 0.0
-        for _ in range(args.steps):
-            if state["ticks_left"] < S:
-                rebase(e2)                                             # untimed, like the device-resident arm
-            t0 = time.perf_counter()
-            e2e_step()
-            dt += time.perf_counter() - t0
+        t0 = time.perf_counter()
+        e2e_steps(args.steps)
+        e2.sync()
+        dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
-        commits = table[S - 1, :, 1] >> 32                             # jr_leader_entry.commit of the last tick
         e2e = {"value": world * G * S * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": S * G * 16,
-               "d2h_bytes_per_step": S * G * 16, "ms_per_step": dt * 1e3 / args.steps,
-               "api": "per tick: jr_step(pinned jr_proposal[G]) + jr_leader_table_async(pinned jr_leader_entry[G]); "
-                      "jr_engine_sync once per step",
-               "commit_min": int(commits.min().item()), "faulted_replicas": e2.fault_count(),
-               "timing": "host wall clock around each step incl. the jr_engine_sync, max over ranks"}
+               "d2h_bytes_per_step": G * 16, "ms_per_step": dt * 1e3 / args.steps,
+               "api": "per step: jr_run_proposals(pinned jr_proposal[64][G]) + jr_leader_table_async(pinned jr_leader_entry[G]) "
+                      "+ jr_leader_table_wait; two steps in flight",
+               "commit_last": checks[-1], "faulted_replicas": e2.fault_count(),
+               "timing": "host wall clock around all timed steps incl. the final sync, max over ranks"}
 
     if rank != 0:
         if world > 1:

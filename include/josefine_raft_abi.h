@@ -13,6 +13,7 @@
  *   jr_step outputs    <- rpc_tx.send(Message)            src/raft/mod.rs:390-400
  *                         fsm_tx.send(Instruction)        src/raft/leader.rs:94,184; follower.rs:205
  *   jr_run             <- N consecutive event_loop turns with no host traffic (Tick + peer mail)
+ *   jr_run_proposals   <- N consecutive event_loop turns incl. the client arm (server.rs:156-160)
  *   jr_query           <- pub fields id/state/role/chain  src/raft/mod.rs:326-341,437-447;
  *                         Chain::get_head/get_commit      src/raft/chain.rs:230-236
  *   jr_chain_read      <- Chain::range / Chain::has       src/raft/chain.rs:155-157,208-228
@@ -296,6 +297,15 @@ jr_status jr_step(jr_engine* e, jr_step_args* args);
  * engine stream.  Equivalent to n_steps jr_step calls, bit for bit.
  */
 jr_status jr_run(jr_engine* e, uint64_t now0_ms, uint32_t dt_ms, uint32_t n_steps, uint32_t n_synth);
+/*
+ * jr_run with client input: `proposals` is HOST memory holding n_steps consecutive dense
+ * arrays of n_groups entries (tick k uses proposals[k*n_groups ..]); equivalent to n_steps
+ * jr_step calls with flags DELIVER|TICK and that tick's array, bit for bit, but one fused
+ * launch and one host-to-device copy (staged on the engine's copy stream: pass pinned memory
+ * and the call is asynchronous).  `flags` may carry JR_STEP_TRUSTED_PROPOSALS.
+ */
+jr_status jr_run_proposals(jr_engine* e, uint64_t now0_ms, uint32_t dt_ms, uint32_t n_steps,
+                           const jr_proposal* proposals, uint32_t flags);
 /* Drop and return the Instructions accumulated by jr_run (same order as jr_step). */
 jr_status jr_drain_fsm(jr_engine* e, jr_fsm_instr* out, size_t cap, size_t* n);
 
@@ -326,6 +336,9 @@ jr_status jr_leader_table(jr_engine* e, jr_leader_entry* host_out);
  * pinned memory and is valid after the next jr_engine_sync().  Lets a caller pipeline
  * jr_step (proposals H2D) / kernels / results D2H tick after tick. */
 jr_status jr_leader_table_async(jr_engine* e, jr_leader_entry* host_out);
+/* Block until the OLDEST outstanding jr_leader_table_async copy has landed (FIFO; at most two are
+ * in flight).  Lets the host consume tick/step k's result while k+1 is already running. */
+jr_status jr_leader_table_wait(jr_engine* e);
 
 /* ---- deviation D2, normative ------------------------------------------------
  * draw-th election timeout of (group, node):

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(32 * R) step_kernel(const Dev d, const StepPar
     q.now = rep.now;
     q.step_index += 1;
     q.phases = PH_RESET_OUT | PH_DRAIN | PH_PROPOSE | PH_TICK;
-    q.proposals = nullptr;
+    q.proposals = (p.proposals && p.prop_stride) ? p.proposals + (size_t)(t + 1) * p.prop_stride : nullptr;
   }
   rep.store();
 #ifdef JR_PROFILE
@@ -411,6 +411,13 @@ struct jr_engine {
   cudaEvent_t tab_ready[NBUF] = {nullptr, nullptr};     // leader_table_kernel into leaders[i] finished
   cudaEvent_t tab_free[NBUF] = {nullptr, nullptr};      // D2H of leaders[i] finished
   bool prop_used[NBUF] = {false, false}, tab_used[NBUF] = {false, false};
+  jr_proposal* batch[NBUF] = {nullptr, nullptr};        // device, batch_cap entries each (jr_run_proposals)
+  size_t batch_cap[NBUF] = {0, 0};
+  cudaEvent_t batch_ready[NBUF] = {nullptr, nullptr}, batch_free[NBUF] = {nullptr, nullptr};
+  bool batch_used[NBUF] = {false, false};
+  int batch_i = 0;
+  int tab_pending[NBUF] = {0, 0};  // FIFO of leaders[] buffers whose copy-out has not been waited for
+  int tab_npending = 0;
   int prop_i = 0, tab_i = 0;
   jr_block* cr_blocks = nullptr;          // device scratch for chain_read
   uint8_t* cr_present = nullptr;
@@ -552,7 +559,9 @@ jr_status jr_engine_create(const jr_config* cfg, jr_engine** out) {
       ok = cudaEventCreateWithFlags(&e->prop_ready[i], cudaEventDisableTiming) == cudaSuccess &&
            cudaEventCreateWithFlags(&e->prop_free[i], cudaEventDisableTiming) == cudaSuccess &&
            cudaEventCreateWithFlags(&e->tab_ready[i], cudaEventDisableTiming) == cudaSuccess &&
-           cudaEventCreateWithFlags(&e->tab_free[i], cudaEventDisableTiming) == cudaSuccess;
+           cudaEventCreateWithFlags(&e->tab_free[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&e->batch_ready[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&e->batch_free[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
       set_err("copy streams / events could not be created");
       jr_engine_destroy(e);
@@ -625,6 +634,9 @@ void jr_engine_destroy(jr_engine* e) {
     if (e->prop_free[i]) cudaEventDestroy(e->prop_free[i]);
     if (e->tab_ready[i]) cudaEventDestroy(e->tab_ready[i]);
     if (e->tab_free[i]) cudaEventDestroy(e->tab_free[i]);
+    if (e->batch_ready[i]) cudaEventDestroy(e->batch_ready[i]);
+    if (e->batch_free[i]) cudaEventDestroy(e->batch_free[i]);
+    if (e->batch[i]) cudaFree(e->batch[i]);
   }
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   delete e;
@@ -808,6 +820,7 @@ jr_status jr_step(jr_engine* e, jr_step_args* a) {
   p.cur = e->cur;
   p.n_ticks = 1;
   p.dt = 0;
+  p.prop_stride = 0;
   p.proposals = nullptr;
   int staged = -1;
   if (a->proposals) {
@@ -890,9 +903,53 @@ jr_status jr_run(jr_engine* e, uint64_t now0, uint32_t dt, uint32_t n_steps, uin
   p.dt = dt;
   p.cur = e->cur;
   p.proposals = nullptr;
+  p.prop_stride = 0;
   p.phases = PH_RESET_OUT | PH_RESET_FSM | PH_DRAIN | (n_synth ? PH_PROPOSE : 0u) | PH_TICK;
   jr_status st = launch_step(e, p);
   if (st != JR_OK) return st;
+  e->cur ^= (int)(n_steps & 1u);
+  e->step_index += n_steps;
+  return JR_OK;
+}
+
+jr_status jr_run_proposals(jr_engine* e, uint64_t now0, uint32_t dt, uint32_t n_steps, const jr_proposal* proposals,
+                           uint32_t flags) {
+  if (!e || !proposals) return JR_E_INVAL;
+  if (n_steps == 0) return JR_OK;
+  CK(cudaSetDevice(e->cfg.device));
+  const uint32_t G = e->d.G, R = e->d.R;
+  const size_t n = (size_t)n_steps * G;
+  if (!(flags & JR_STEP_TRUSTED_PROPOSALS))
+    for (size_t i = 0; i < n; ++i)
+      if (proposals[i].node > R) return JR_E_UNKNOWN_NODE;
+  const int b = e->batch_i;
+  e->batch_i = (b + 1) % jr_engine::NBUF;
+  if (e->batch_used[b]) CK(cudaStreamWaitEvent(e->h2d, e->batch_free[b], 0));  // its last reader is done
+  if (n > e->batch_cap[b]) {
+    if (e->batch_used[b]) CK(cudaStreamSynchronize(e->h2d));
+    if (e->batch[b]) cudaFree(e->batch[b]);
+    e->batch[b] = nullptr;
+    e->batch_cap[b] = 0;
+    CK(cudaMalloc(&e->batch[b], n * sizeof(jr_proposal)));
+    e->batch_cap[b] = n;
+  }
+  CK(cudaMemcpyAsync(e->batch[b], proposals, n * sizeof(jr_proposal), cudaMemcpyHostToDevice, e->h2d));
+  CK(cudaEventRecord(e->batch_ready[b], e->h2d));
+  CK(cudaStreamWaitEvent(e->stream, e->batch_ready[b], 0));
+  StepParams p;
+  p.now = now0;
+  p.step_index = e->step_index;
+  p.n_synth = 0;
+  p.n_ticks = n_steps;
+  p.dt = dt;
+  p.cur = e->cur;
+  p.proposals = e->batch[b];
+  p.prop_stride = G;
+  p.phases = PH_RESET_OUT | PH_RESET_FSM | PH_DRAIN | PH_PROPOSE | PH_TICK;
+  jr_status st = launch_step(e, p);
+  if (st != JR_OK) return st;
+  CK(cudaEventRecord(e->batch_free[b], e->stream));
+  e->batch_used[b] = true;
   e->cur ^= (int)(n_steps & 1u);
   e->step_index += n_steps;
   return JR_OK;
@@ -1041,6 +1098,21 @@ jr_status jr_leader_table_async(jr_engine* e, jr_leader_entry* host_out) {
   CK(cudaMemcpyAsync(host_out, e->leaders[b], (size_t)e->d.G * sizeof(jr_leader_entry), cudaMemcpyDeviceToHost, e->d2h));
   CK(cudaEventRecord(e->tab_free[b], e->d2h));
   e->tab_used[b] = true;
+  if (e->tab_npending == jr_engine::NBUF) {  // the oldest one is about to be overwritten anyway
+    e->tab_pending[0] = e->tab_pending[1];
+    e->tab_npending = 1;
+  }
+  e->tab_pending[e->tab_npending++] = b;
+  return JR_OK;
+}
+
+jr_status jr_leader_table_wait(jr_engine* e) {
+  if (!e) return JR_E_INVAL;
+  if (e->tab_npending == 0) return JR_OK;
+  const int b = e->tab_pending[0];
+  e->tab_pending[0] = e->tab_pending[1];
+  --e->tab_npending;
+  CK(cudaEventSynchronize(e->tab_free[b]));
   return JR_OK;
 }
 
@@ -1048,6 +1120,7 @@ jr_status jr_leader_table(jr_engine* e, jr_leader_entry* host_out) {
   jr_status st = jr_leader_table_async(e, host_out);
   if (st != JR_OK) return st;
   CK(cudaStreamSynchronize(e->d2h));
+  e->tab_npending = 0;
   return JR_OK;
 }
 

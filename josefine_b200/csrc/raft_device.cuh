@@ -86,7 +86,8 @@ struct StepParams {
   uint32_t n_ticks;              // ticks fused in this launch (>= 1)
   uint32_t dt;                   // ms between fused ticks
   int cur;                       // outbox written by the first tick; 1-cur is read
-  const jr_proposal* proposals;  // device, G entries or null (first tick only)
+  const jr_proposal* proposals;  // device, G entries for the first tick, or null
+  uint32_t prop_stride;          // entries from one tick's proposals to the next (0: first tick only)
 };
 
 __host__ __device__ inline uint64_t mix64(uint64_t x) {

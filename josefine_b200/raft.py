@@ -227,6 +227,20 @@ class RaftApi:
         self._check(self._fn("run")(self._h, C.c_uint64(now0_ms), C.c_uint32(dt_ms), C.c_uint32(n_steps),
                                     C.c_uint32(n_synth)), "run")
 
+    def run_proposals(self, now0_ms: int, dt_ms: int, proposals: Sequence[Sequence[Tuple[int, int]]], flags: int = 0):
+        """Fused ticks with client input: proposals[k][g] = (node, token) for tick k (node 0 = none)."""
+        n = len(proposals)
+        arr = (abi.Proposal * (n * self.n_groups))()
+        for k, tick in enumerate(proposals):
+            if len(tick) != self.n_groups:
+                raise ValueError("every tick needs one proposal entry per group")
+            for g, (node, token) in enumerate(tick):
+                arr[k * self.n_groups + g].node, arr[k * self.n_groups + g].token = node, token
+        self._check(self._fn("run_proposals")(self._h, C.c_uint64(now0_ms), C.c_uint32(dt_ms), C.c_uint32(n), arr,
+                                              C.c_uint32(flags)), "run_proposals")
+        if self._p == "jr_":
+            self._check(self._lib.jr_engine_sync(self._h), "engine_sync")   # `arr` is pageable and about to be freed
+
     def drain_fsm(self) -> List[abi.FsmInstr]:
         n = C.c_size_t(0)
         cap = self.n_groups * self.n_replicas * self.cfg.fsm_units
@@ -323,6 +337,7 @@ def _bind(lib: C.CDLL, p: str):
     sig = {
         "step": [vp, C.POINTER(abi.StepArgs)],
         "run": [vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32],
+        "run_proposals": [vp, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(abi.Proposal), C.c_uint32],
         "drain_fsm": [vp, C.POINTER(abi.FsmInstr), C.c_size_t, C.POINTER(C.c_size_t)],
         "query": [vp, C.c_uint32, C.c_uint32, C.POINTER(abi.ReplicaState)],
         "chain_read": [vp, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.POINTER(abi.Block),
@@ -370,6 +385,8 @@ def load_engine_library() -> C.CDLL:
         lib.jr_leader_table_device.restype = C.c_int
         lib.jr_leader_table_async.argtypes = [C.c_void_p, C.POINTER(abi.LeaderEntry)]
         lib.jr_leader_table_async.restype = C.c_int
+        lib.jr_leader_table_wait.argtypes = [C.c_void_p]
+        lib.jr_leader_table_wait.restype = C.c_int
         lib.jr_config_default.argtypes = [C.POINTER(abi.Config), C.c_uint32, C.c_uint32]
         lib.jr_config_default.restype = None
         lib.jr_last_error.restype = C.c_char_p

@@ -408,6 +408,28 @@ jr_status jro_run(jro_cluster* c, uint64_t now0, uint32_t dt, uint32_t n_steps, 
   return JR_OK;
 }
 
+jr_status jro_run_proposals(jro_cluster* c, uint64_t now0, uint32_t dt, uint32_t n_steps, const jr_proposal* props,
+                            uint32_t flags) {
+  (void)flags;
+  if (!c || !props) return JR_E_INVAL;
+  const uint32_t G = c->cfg.n_groups;
+  for (size_t i = 0; i < (size_t)n_steps * G; ++i)
+    if (props[i].node > c->cfg.n_replicas) return JR_E_UNKNOWN_NODE;
+  clear_fsm(c);
+  const uint64_t base = c->step_index;
+  for_groups(c, [&](uint32_t lo, uint32_t hi) {
+    for (uint32_t g = lo; g < hi; ++g)
+      for (uint32_t k = 0; k < n_steps; ++k) {
+        // step_group indexes proposals by group: point it at tick k's array
+        StepCtx s{now0 + (uint64_t)k * dt, (uint32_t)(JR_STEP_DELIVER | JR_STEP_TICK), 0, props + (size_t)k * G,
+                  nullptr, nullptr, base + k};
+        step_group(c, g, s);
+      }
+  });
+  c->step_index += n_steps;
+  return JR_OK;
+}
+
 jr_status jro_drain_fsm(jro_cluster* c, jr_fsm_instr* out, size_t cap, size_t* n) {
   if (!c || !n) return JR_E_INVAL;
   size_t k = 0;

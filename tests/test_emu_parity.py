@@ -111,3 +111,26 @@ def test_engine_reset_is_a_fresh_engine():
     parity.compare_states(a, fresh, chain_ids=30)
     a.run(100, 100, 25, 1)
     assert (a.state_digest(), a.leader_table()) == first
+
+
+def test_run_proposals_equals_steps_with_proposals():
+    """jr_run_proposals(n) == n x jr_step(DELIVER|TICK, proposals[k]) (ABI contract), on the device
+    code and on the oracle -- proposals aimed at leaders, followers (proxied) and nobody."""
+    import random
+    rng = random.Random(5)
+    G, R, N = 6, 3, 36
+    props = [[(rng.choice([0, 1, 2, 3]), 1000 * k + g + 1) for g in range(G)] for k in range(N)]
+    a = make_emu(G, R, seed=4, flags=parity.FULL, fsm_units=256)
+    b = make_emu(G, R, seed=4, flags=parity.FULL, fsm_units=256)
+    o = make_oracle(G, R, seed=4, flags=parity.FULL, fsm_units=256)
+    for eng in (a, o):
+        eng.run(100, 100, 20, 0)                         # elect leaders first
+        eng.run_proposals(2100, 100, props)
+    b.run(100, 100, 20, 0)
+    for k in range(N):
+        b.step(2100 + 100 * k, proposals=props[k])
+    parity.compare_states(a, b, chain_ids=60)
+    parity.compare_digests(a, b)
+    parity.compare_states(a, o, chain_ids=60)
+    parity.compare_digests(a, o)
+    assert max(c for (_, _, c) in a.leader_table()) > 5
