@@ -211,9 +211,8 @@ struct Replica {
   uint32_t role, fault, prmask, nq, dead, ckey, seen, granted;
   uint32_t ph[R];
   // ---- output cursors
-  uint32_t ocnt, fcnt;
-  // (the running stream digests live in global memory, d.dg / d.cn, and are updated in place:
-  //  they are only touched with JR_F_STREAM_DIGEST and must not cost registers otherwise)
+  uint32_t ocnt, fcnt, nmsg, nfsm;
+  uint64_t mdig, fdig;
   uint32_t mko[R];       // delivery index of this tick's outbox, one mask per receiver (see Local::mk_out)
 
   __device__ __forceinline__ Replica(const Dev& dv, const Local& lv, uint32_t r_, uint32_t g_)
@@ -253,6 +252,14 @@ struct Replica {
     ocnt = reset_out ? 0u : d.oc[cur][rg];
     ocnt0 = ocnt;
     fcnt = reset_fsm ? 0u : d.fc[rg];
+    mdig = fdig = 0; nmsg = nfsm = 0;
+    if (digest_on()) {
+      uint4 v = d.dg[rg];
+      mdig = (uint64_t)v.x | ((uint64_t)v.y << 32);
+      fdig = (uint64_t)v.z | ((uint64_t)v.w << 32);
+      uint2 n = d.cn[rg];
+      nmsg = n.x; nfsm = n.y;
+    }
   }
 
   __device__ __forceinline__ void store() {
@@ -281,6 +288,10 @@ struct Replica {
       d.ob[cur][((size_t)u * R + r) * d.Gp + g] = L.out[(u * R + r) * 32 + L.lane];
     d.oc[cur][rg] = ocnt;
     d.fc[rg] = fcnt;
+    if (digest_on()) {
+      d.dg[rg] = make_uint4((uint32_t)mdig, (uint32_t)(mdig >> 32), (uint32_t)fdig, (uint32_t)(fdig >> 32));
+      d.cn[rg] = make_uint2(nmsg, nfsm);
+    }
   }
 
   // ------------------------------------------------------------------ block table (chain.rs)
@@ -425,10 +436,8 @@ struct Replica {
     ++ocnt;
     if (digest_on()) {
       uint32_t n;
-      const uint4 dv = d.dg[rg];
-      const uint64_t md = digest_send_fn((uint64_t)dv.x | ((uint64_t)dv.y << 32), id(), kind, to, flag, aux, t, w, &n);
-      d.dg[rg] = make_uint4((uint32_t)md, (uint32_t)(md >> 32), dv.z, dv.w);
-      d.cn[rg].x += n;
+      mdig = digest_send_fn(mdig, id(), kind, to, flag, aux, t, w, &n);
+      nmsg += n;
     }
   }
 
@@ -441,10 +450,8 @@ struct Replica {
       ++fcnt;
     }
     if (digest_on()) {
-      const uint4 dv = d.dg[rg];
-      const uint64_t fd = digest_fsm_fn((uint64_t)dv.z | ((uint64_t)dv.w << 32), notify, bid, next_or_addr, tok);
-      d.dg[rg] = make_uint4(dv.x, dv.y, (uint32_t)fd, (uint32_t)(fd >> 32));
-      d.cn[rg].y += 1;
+      fdig = digest_fsm_fn(fdig, notify, bid, next_or_addr, tok);
+      ++nfsm;
     }
   }
 
@@ -728,17 +735,15 @@ struct Replica {
         return;
       mko[p] |= ocnt < 31u ? (1u << ocnt) : MK_SCAN;
       if (digest_on()) {
-        const uint4 dv = d.dg[rg];
-        uint64_t h = digest_message_fn((uint64_t)dv.x | ((uint64_t)dv.y << 32), JR_CMD_APPEND_ENTRIES, p + 1, 0, nb,
-                                       id(), term, 0, 0, 0, 0);
-        d.cn[rg].x += 1;
+        uint64_t h = digest_message_fn(mdig, JR_CMD_APPEND_ENTRIES, p + 1, 0, nb, id(), term, 0, 0, 0, 0);
+        ++nmsg;
         for (uint32_t k = 0; k < nb; ++k) {
           uint4 u = own_unit(first + k);
           h = fold(h, u.x);
           h = fold(h, u.y);
           h = fold(h, (uint64_t)u.z | ((uint64_t)u.w << 32));
         }
-        d.dg[rg] = make_uint4((uint32_t)h, (uint32_t)(h >> 32), dv.z, dv.w);
+        mdig = h;
       }
       ocnt += ref ? 1u : 1u + nb;
     }

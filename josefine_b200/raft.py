@@ -351,6 +351,8 @@ def _bind(lib: C.CDLL, p: str):
         "leader_table": [vp, C.POINTER(abi.LeaderEntry)],
     }
     for name, args in sig.items():
+        if not hasattr(lib, p + name):   # an older A/B build (JR_ENGINE_LIB): the call site will fail loudly
+            continue
         fn = getattr(lib, p + name)
         fn.argtypes = args
         fn.restype = C.c_int
@@ -385,8 +387,9 @@ def load_engine_library() -> C.CDLL:
         lib.jr_leader_table_device.restype = C.c_int
         lib.jr_leader_table_async.argtypes = [C.c_void_p, C.POINTER(abi.LeaderEntry)]
         lib.jr_leader_table_async.restype = C.c_int
-        lib.jr_leader_table_wait.argtypes = [C.c_void_p]
-        lib.jr_leader_table_wait.restype = C.c_int
+        if hasattr(lib, "jr_leader_table_wait"):
+            lib.jr_leader_table_wait.argtypes = [C.c_void_p]
+            lib.jr_leader_table_wait.restype = C.c_int
         lib.jr_config_default.argtypes = [C.POINTER(abi.Config), C.c_uint32, C.c_uint32]
         lib.jr_config_default.restype = None
         lib.jr_last_error.restype = C.c_char_p
