@@ -337,9 +337,12 @@ def main():
             announce_done[0] = ev
 
     def between_steps():
-        flush.fill_(1)
         if state["ticks_left"] < S:
             rebase(eng)
+            if world > 1:      # the rebase is untimed host work of uneven length: re-align the ranks before timing again
+                torch.cuda.synchronize()
+                dist.barrier()
+        flush.fill_(1)
 
     sampler = ClockSampler(local)
     if rank == 0:
