@@ -1,0 +1,400 @@
+//! josefine_gpu_shim.rs -- Rust side of the drop-in boundary.
+//!
+//! **UNTESTED SOURCE.**  The build environment of this repository has no `cargo` / `rustc`, so
+//! this file has never been compiled.  It shows, concretely, what a josefine maintainer would
+//! add to `src/raft/` to drive `libjosefine_b200.so` through `include/josefine_raft_abi.h`:
+//! `#[repr(C)]` mirrors of the POD structs, the `extern "C"` block, `Command <-> jr_msg`
+//! conversion, and an `event_loop` whose five `raft.apply(..)` sites (src/raft/server.rs:125,
+//! 133,135,143,159) become one `jr_step` per tick.  The Python binding in
+//! `josefine_b200/raft.py` is the one the tests exercise; field order and sizes here follow the
+//! same header and are checked on the C side by `tests/test_abi.py`.
+//!
+//! Mapping (reference item -> here):
+//!   RaftHandle::new                   mod.rs:428-435     -> GpuRaft::new (jr_engine_create, resident_mask = this node)
+//!   Apply::apply(Command::Tick)       server.rs:125      -> GpuRaft::tick (jr_step DELIVER|TICK)
+//!   apply(msg.command) from tcp_rx    server.rs:127-137  -> GpuRaft::on_peer_message (queued, injected at the next tick)
+//!   apply(ClientRequest)              server.rs:156-160  -> GpuRaft::propose
+//!   rpc_tx.send(Message)              mod.rs:390-400     -> StepOutput::messages
+//!   fsm_tx.send(Instruction)          leader.rs:94,184   -> StepOutput::instructions
+//!   panic!/Err in the state machine   (see JR_FAULT_*)   -> StepOutput::fault -> event_loop returns Err
+
+#![allow(dead_code)]
+
+use std::collections::HashMap;
+use std::os::raw::{c_char, c_int, c_void};
+
+use crate::raft::chain::{Block, BlockId};
+use crate::raft::fsm::Instruction;
+use crate::raft::rpc::{Address, Message, Proposal};
+use crate::raft::{ClientRequest, ClientRequestId, Command, NodeId};
+
+// ---- POD mirrors of include/josefine_raft_abi.h ------------------------------------------------
+
+pub const JR_ABI_VERSION: u32 = 1;
+pub const JR_MAX_AE_BLOCKS: usize = 5;
+pub const JR_F_CAPTURE_MESSAGES: u32 = 1 << 1;
+pub const JR_F_CAPTURE_FSM: u32 = 1 << 2;
+pub const JR_STEP_DELIVER: u32 = 1 << 0;
+pub const JR_STEP_TICK: u32 = 1 << 1;
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct JrConfig {
+    pub abi_version: u32,
+    pub n_groups: u32,
+    pub n_replicas: u32,
+    pub device: i32,
+    pub seed: u64,
+    pub group_offset: u64,
+    pub election_min_ms: u32,
+    pub election_max_ms: u32,
+    pub heartbeat_ms: u32,
+    pub chain_capacity: u32,
+    pub mailbox_units: u32,
+    pub fsm_units: u32,
+    pub flags: u32,
+    pub resident_mask: u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct JrBlock {
+    pub id: u64,
+    pub next: u64,
+    pub data: u64, // payload token (deviation D5)
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct JrMsg {
+    pub group: u32,
+    pub from_kind: u8,
+    pub to_kind: u8,
+    pub kind: u8,
+    pub flag: u8,
+    pub from_id: u32,
+    pub to_id: u32,
+    pub node_id: u32,
+    pub n_blocks: u8,
+    pub client_kind: u8,
+    pub reserved: u16,
+    pub client_id: u32,
+    pub reserved2: u32,
+    pub term: u64,
+    pub last_term: u64,
+    pub block: u64,
+    pub token: u64,
+    pub blocks: [JrBlock; JR_MAX_AE_BLOCKS],
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct JrFsmInstr {
+    pub group: u32,
+    pub node: u32,
+    pub kind: u8, // 0 Apply, 1 Notify
+    pub client_kind: u8,
+    pub reserved: u16,
+    pub client_id: u32,
+    pub block: JrBlock,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct JrProposal {
+    pub token: u64,
+    pub node: u32,
+    pub reserved: u32,
+}
+
+#[repr(C)]
+pub struct JrStepArgs {
+    pub now_ms: u64,
+    pub flags: u32,
+    pub n_synth: u32,
+    pub inject: *const JrMsg,
+    pub n_inject: usize,
+    pub proposals: *const JrProposal,
+    pub out_msgs: *mut JrMsg,
+    pub cap_msgs: usize,
+    pub n_msgs: usize,
+    pub out_fsm: *mut JrFsmInstr,
+    pub cap_fsm: usize,
+    pub n_fsm: usize,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct JrReplicaState {
+    pub current_term: u64,
+    pub voted_for: u32,
+    pub leader_id: u32,
+    pub election_time_ms: u64,
+    pub election_timeout_ms: u32,
+    pub rng_draws: u32,
+    pub head: u64,
+    pub commit: u64,
+    pub id_gen: u64,
+    pub max_key: u64,
+    pub heartbeat_time_ms: u64,
+    pub votes_seen: u32,
+    pub votes_granted: u32,
+    pub progress_head: [u64; 8],
+    pub progress_replicate: u32,
+    pub role: u8,
+    pub fault: u8,
+    pub alive: u8,
+    pub n_queued: u8,
+}
+
+#[link(name = "josefine_b200")]
+extern "C" {
+    fn jr_config_default(cfg: *mut JrConfig, n_groups: u32, n_replicas: u32);
+    fn jr_engine_create(cfg: *const JrConfig, out: *mut *mut c_void) -> c_int;
+    fn jr_engine_destroy(e: *mut c_void);
+    fn jr_step(e: *mut c_void, args: *mut JrStepArgs) -> c_int;
+    fn jr_query(e: *mut c_void, group: u32, node: u32, out: *mut JrReplicaState) -> c_int;
+    fn jr_last_error() -> *const c_char;
+}
+
+// Command discriminants, in the order of `enum Command` (src/raft/mod.rs:160-227)
+const K_TICK: u8 = 0;
+const K_VOTE_REQUEST: u8 = 2;
+const K_VOTE_RESPONSE: u8 = 3;
+const K_APPEND_ENTRIES: u8 = 4;
+const K_APPEND_RESPONSE: u8 = 5;
+const K_HEARTBEAT: u8 = 6;
+const K_HEARTBEAT_RESPONSE: u8 = 7;
+const K_CLIENT_REQUEST: u8 = 10;
+const K_CLIENT_RESPONSE: u8 = 11;
+// Address kinds (src/raft/rpc.rs:5-14)
+const A_PEERS: u8 = 0;
+const A_PEER: u8 = 1;
+const A_LOCAL: u8 = 2;
+const A_CLIENT: u8 = 3;
+
+fn block_id(b: &BlockId) -> u64 {
+    // BlockId is 8 big-endian bytes (chain.rs:63-66)
+    let mut a = [0u8; 8];
+    a.copy_from_slice(b.as_ref());
+    u64::from_be_bytes(a)
+}
+
+/// Payload bytes and request ids never cross the FFI: blocks and requests carry 64-bit tokens.
+#[derive(Default)]
+pub struct Tokens {
+    next: u64,
+    payload: HashMap<u64, Vec<u8>>,
+    request: HashMap<u64, (ClientRequestId, Address)>,
+}
+
+impl Tokens {
+    fn intern(&mut self, data: Vec<u8>) -> u64 {
+        self.next += 1;
+        self.payload.insert(self.next, data);
+        self.next
+    }
+}
+
+fn addr(kind: u8, id: u32) -> Address {
+    match kind {
+        A_PEERS => Address::Peers,
+        A_PEER => Address::Peer(id),
+        A_LOCAL => Address::Local,
+        _ => Address::Client,
+    }
+}
+
+/// `Message` of the reference -> `jr_msg` to inject (the tcp_rx arm, server.rs:127-137).
+fn encode(group: u32, me: NodeId, msg: &Message, tokens: &mut Tokens) -> JrMsg {
+    let mut m = JrMsg { group, to_kind: A_PEER, to_id: me, ..Default::default() };
+    if let Address::Peer(p) = msg.from {
+        m.from_kind = A_PEER;
+        m.from_id = p;
+    }
+    match &msg.command {
+        Command::VoteRequest { term, candidate_id, last_term, head } => {
+            m.kind = K_VOTE_REQUEST;
+            m.term = *term;
+            m.node_id = *candidate_id;
+            m.last_term = *last_term;
+            m.block = block_id(head);
+        }
+        Command::VoteResponse { term, from, granted } => {
+            m.kind = K_VOTE_RESPONSE;
+            m.term = *term;
+            m.node_id = *from;
+            m.flag = *granted as u8;
+        }
+        Command::AppendEntries { term, leader_id, blocks } => {
+            m.kind = K_APPEND_ENTRIES;
+            m.term = *term;
+            m.node_id = *leader_id;
+            m.n_blocks = blocks.len().min(JR_MAX_AE_BLOCKS) as u8; // MAX_INFLIGHT = 5, progress.rs:117
+            for (i, b) in blocks.iter().take(JR_MAX_AE_BLOCKS).enumerate() {
+                m.blocks[i] = JrBlock { id: block_id(&b.id), next: block_id(&b.next), data: tokens.intern(b.data.clone()) };
+            }
+        }
+        Command::AppendResponse { node_id, term, head, success } => {
+            m.kind = K_APPEND_RESPONSE;
+            m.node_id = *node_id;
+            m.term = *term;
+            m.block = block_id(head);
+            m.flag = *success as u8;
+        }
+        Command::Heartbeat { term, commit, leader_id } => {
+            m.kind = K_HEARTBEAT;
+            m.term = *term;
+            m.block = block_id(commit);
+            m.node_id = *leader_id;
+        }
+        Command::HeartbeatResponse { commit, has_committed } => {
+            m.kind = K_HEARTBEAT_RESPONSE;
+            m.block = block_id(commit);
+            m.flag = *has_committed as u8;
+        }
+        _ => { /* Tick / Timeout / Noop never arrive over TCP; ClientRequest: see propose() */ }
+    }
+    m
+}
+
+/// `jr_msg` returned by the engine -> `Message` for tcp_tx (server.rs:141-142).
+fn decode(me: NodeId, m: &JrMsg, tokens: &Tokens) -> Message {
+    let id = |v: u64| BlockId::new(v);
+    let command = match m.kind {
+        K_VOTE_REQUEST => Command::VoteRequest { term: m.term, candidate_id: m.node_id, last_term: m.last_term, head: id(m.block) },
+        K_VOTE_RESPONSE => Command::VoteResponse { term: m.term, from: m.node_id, granted: m.flag != 0 },
+        K_APPEND_ENTRIES => Command::AppendEntries {
+            term: m.term,
+            leader_id: m.node_id,
+            blocks: m.blocks[..m.n_blocks as usize]
+                .iter()
+                .map(|b| Block { id: id(b.id), next: id(b.next), data: tokens.payload.get(&b.data).cloned().unwrap_or_default() })
+                .collect(),
+        },
+        K_APPEND_RESPONSE => Command::AppendResponse { node_id: m.node_id, term: m.term, head: id(m.block), success: m.flag != 0 },
+        K_HEARTBEAT => Command::Heartbeat { term: m.term, commit: id(m.block), leader_id: m.node_id },
+        K_HEARTBEAT_RESPONSE => Command::HeartbeatResponse { commit: id(m.block), has_committed: m.flag != 0 },
+        _ => Command::Noop,
+    };
+    Message::new(Address::Peer(me), addr(m.to_kind, m.to_id), command)
+}
+
+pub struct StepOutput {
+    pub messages: Vec<Message>,
+    pub instructions: Vec<Instruction>,
+    pub fault: u8,
+}
+
+/// One hosted node (this process) of ONE Raft group on the GPU engine.  A multi-raft broker
+/// would keep one engine for all its groups and index them by `group`.
+pub struct GpuRaft {
+    engine: *mut c_void,
+    me: NodeId,
+    group: u32,
+    pending: Vec<JrMsg>,
+    proposal: Option<JrProposal>,
+    tokens: Tokens,
+    out_msgs: Vec<JrMsg>,
+    out_fsm: Vec<JrFsmInstr>,
+}
+
+impl GpuRaft {
+    pub fn new(me: NodeId, n_nodes: u32, seed: u64) -> anyhow::Result<Self> {
+        let mut cfg = JrConfig::default();
+        unsafe { jr_config_default(&mut cfg, 1, n_nodes) };
+        cfg.seed = seed;
+        cfg.flags = JR_F_CAPTURE_MESSAGES | JR_F_CAPTURE_FSM;
+        cfg.resident_mask = 1 << (me - 1); // this process hosts only `me` (RaftConfig::id, config.rs:23)
+        let mut engine = std::ptr::null_mut();
+        let st = unsafe { jr_engine_create(&cfg, &mut engine) };
+        anyhow::ensure!(st == 0, "jr_engine_create failed: status {}", st);
+        Ok(GpuRaft {
+            engine,
+            me,
+            group: 0,
+            pending: Vec::new(),
+            proposal: None,
+            tokens: Tokens::default(),
+            out_msgs: vec![JrMsg::default(); 256],
+            out_fsm: vec![JrFsmInstr::default(); 256],
+        })
+    }
+
+    /// tcp_rx arm (server.rs:127-137)
+    pub fn on_peer_message(&mut self, msg: &Message) {
+        let m = encode(self.group, self.me, msg, &mut self.tokens);
+        self.pending.push(m);
+    }
+
+    /// client arm (server.rs:156-160)
+    pub fn propose(&mut self, id: ClientRequestId, proposal: Proposal) {
+        let token = self.tokens.intern(proposal.get());
+        self.tokens.request.insert(token, (id, Address::Client));
+        self.proposal = Some(JrProposal { token, node: self.me, reserved: 0 });
+    }
+
+    /// tick arm (server.rs:125): everything queued since the last tick, then Command::Tick.
+    pub fn tick(&mut self, now_ms: u64) -> anyhow::Result<StepOutput> {
+        let prop = self.proposal.take();
+        let mut args = JrStepArgs {
+            now_ms,
+            flags: JR_STEP_DELIVER | JR_STEP_TICK,
+            n_synth: 0,
+            inject: self.pending.as_ptr(),
+            n_inject: self.pending.len(),
+            proposals: prop.as_ref().map_or(std::ptr::null(), |p| p as *const JrProposal),
+            out_msgs: self.out_msgs.as_mut_ptr(),
+            cap_msgs: self.out_msgs.len(),
+            n_msgs: 0,
+            out_fsm: self.out_fsm.as_mut_ptr(),
+            cap_fsm: self.out_fsm.len(),
+            n_fsm: 0,
+        };
+        let st = unsafe { jr_step(self.engine, &mut args) };
+        self.pending.clear();
+        anyhow::ensure!(st == 0, "jr_step failed: status {}", st);
+        let messages = self.out_msgs[..args.n_msgs].iter().map(|m| decode(self.me, m, &self.tokens)).collect();
+        let instructions = self.out_fsm[..args.n_fsm]
+            .iter()
+            .map(|f| {
+                if f.kind == 0 {
+                    Instruction::Apply {
+                        block: Block {
+                            id: BlockId::new(f.block.id),
+                            next: BlockId::new(f.block.next),
+                            data: self.tokens.payload.get(&f.block.data).cloned().unwrap_or_default(),
+                        },
+                    }
+                } else {
+                    let (id, _) = self.tokens.request[&f.block.data];
+                    Instruction::Notify { id, client_address: addr(f.client_kind, f.client_id), block_id: BlockId::new(f.block.id) }
+                }
+            })
+            .collect();
+        let mut st8 = std::mem::MaybeUninit::<JrReplicaState>::uninit();
+        unsafe { jr_query(self.engine, self.group, self.me, st8.as_mut_ptr()) };
+        let fault = unsafe { st8.assume_init() }.fault;
+        Ok(StepOutput { messages, instructions, fault })
+    }
+}
+
+impl Drop for GpuRaft {
+    fn drop(&mut self) {
+        unsafe { jr_engine_destroy(self.engine) }
+    }
+}
+
+// event_loop (src/raft/server.rs:103-165) with the engine in place of RaftHandle:
+//
+//   loop { tokio::select! {
+//       _ = shutdown.wait()              => break,
+//       _ = step_interval.tick()         => {
+//           let out = raft.tick(start.elapsed().as_millis() as u64)?;
+//           if out.fault != 0 { return Err(anyhow!("raft fault {}", out.fault)); }   // the reference's `?` / panic
+//           for m in out.messages     { tcp_tx.send(m)?; }
+//           for i in out.instructions { fsm_tx.send(i)?; }
+//       }
+//       Some(msg) = tcp_rx.recv()        => raft.on_peer_message(&msg),
+//       Some((proposal, res)) = client_rx.recv() => { let id = Uuid::new_v4(); requests.insert(id, res); raft.propose(id, proposal); }
+//   } }
