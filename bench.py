@@ -58,15 +58,16 @@ L2_FLUSH_BYTES = 256 << 20
 CHAIN_CAP_MAX = 6144        # block-table ids per replica (12 B x 327,680 replicas each = 3.9 MB per id, 24 GB total)
 
 
-def bootstrap_inject(G, R, node=1):
-    """Synthetic vote trace: Timeout on `node`, plus quorum-1 granted VoteResponses."""
+def bootstrap_inject(G, R, node=1, scattered=False):
+    """Synthetic vote trace: Timeout on `node` (or on node g % R + 1 with `scattered`), plus
+    quorum-1 granted VoteResponses."""
     q = 0 if R == 1 else R // 2 + 1
-    voters = [v for v in range(1, R + 1) if v != node][:max(q - 1, 0)]
     inj = []
     for g in range(G):
-        inj.append(Command.timeout(g, node))
-        for v in voters:
-            inj.append(Command.vote_response(g, node, 1, v, True))
+        n = (g % R) + 1 if scattered else node
+        inj.append(Command.timeout(g, n))
+        for v in [v for v in range(1, R + 1) if v != n][:max(q - 1, 0)]:
+            inj.append(Command.vote_response(g, n, 1, v, True))
     return inj
 
 
@@ -262,6 +263,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--groups", type=int, default=GROUPS_PER_GPU, help="groups per GPU")
     ap.add_argument("--replicas", type=int, default=REPLICAS)
+    ap.add_argument("--scattered-leaders", action="store_true",
+                    help="diagnostic: leader of group g on node g %% R + 1 instead of node 1 (not the BASELINE workload)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -300,7 +303,7 @@ def main():
     eng = make(G, R, seed=SEED, group_offset=rank * G, chain_capacity=cap,
                flags=abi.F_CAPTURE_FSM, fsm_units=2 * S + 8, mailbox_units=64)
     eng.set_stream(stream.cuda_stream)
-    boot = bootstrap_inject(G, R)
+    boot = bootstrap_inject(G, R, scattered=args.scattered_leaders)
     state = {"ticks_left": 0, "now": 0}
 
     def rebase(e):
