@@ -9,6 +9,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 os.environ["JR_ENGINE_LIB"] = os.path.join(ROOT, "josefine_b200", "csrc", "ab", "lib_prof.so")
+if not os.path.exists(os.environ["JR_ENGINE_LIB"]):
+    raise SystemExit("build it first (here, no GPU needed): python __graft_entry__.py --profile-build")
 import bench  # noqa: E402
 from josefine_b200 import abi, RaftEngine  # noqa: E402
 
