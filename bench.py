@@ -287,7 +287,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     G, R = args.groups, args.replicas
     S = TICKS_PER_STEP
-    total_ticks = S * (args.warmup + args.steps) + 64
+    total_ticks = S * (max(args.warmup, 20) + args.steps) + 64
     stream = torch.cuda.Stream()          # explicit non-default stream: handle 0 would mean "engine's own"
     torch.cuda.set_stream(stream)
 

@@ -27,11 +27,26 @@ using namespace jr;
 // buffered, units beyond Us spill to the global mailbox); block-table reads go
 // through a per-lane shared-memory cache.  Groups never interact, so the only
 // synchronisation between ticks is __syncthreads().
-template <int R>
+template <int R, bool SORTED>
 __global__ void __launch_bounds__(32 * R) step_kernel(const Dev d, const StepParams p) {
   JR_DYN_SMEM(uint4, smem);
-  const uint32_t r = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31u;
   const uint32_t g = blockIdx.x * GROUPS_PER_CTA + lane;  // padded groups (g >= G) are real, unused replicas
+  // Which replica of group g this thread steps.  Plain variant: replica index = warp index, so a
+  // warp runs one role's code when the CTA's leaders share a replica index (and every branch on
+  // `r` is provably warp-uniform).  SORTED variant, picked by the host when a previous launch saw
+  // leaders on several indices: the group's live leader goes to warp 0, the others follow in
+  // index order.  Pure scheduling -- state planes and mailboxes are indexed by replica.
+  uint32_t r = w;
+  if constexpr (SORTED) {
+    uint32_t lead = R;
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) {
+      const uint32_t m = d.p2[(size_t)rr * d.Gp + g].w;
+      if (lead == (uint32_t)R && (m & 255u) == JR_ROLE_LEADER && ((m >> 8) & 255u) == 0 && !((m >> 27) & 1u)) lead = rr;
+    }
+    if (lead != (uint32_t)R) r = w == 0 ? lead : (w <= lead ? w - 1 : w);
+  }
   const uint32_t box = d.Us * R * 32;
   Local L;
   L.in = smem;
@@ -42,7 +57,7 @@ __global__ void __launch_bounds__(32 * R) step_kernel(const Dev d, const StepPar
   L.mk_in = L.cout + R * 32;
   L.mk_out = L.mk_in + R * R * 32;
   L.Us = d.Us; L.W = d.W; L.lane = lane;
-  Replica<R> rep(d, L, r, g);
+  Replica<R, SORTED> rep(d, L, r, g);
   rep.now = p.now;
   rep.cur = p.cur;
   rep.load(p.phases & PH_RESET_OUT, p.phases & PH_RESET_FSM);
@@ -80,6 +95,15 @@ __global__ void __launch_bounds__(32 * R) step_kernel(const Dev d, const StepPar
     q.proposals = (p.proposals && p.prop_stride) ? p.proposals + (size_t)(t + 1) * p.prop_stride : nullptr;
   }
   rep.store();
+  {  // tell the host whether the next launch should sort: leaders on >= 2 replica indices in this CTA?
+    uint32_t* lmask = reinterpret_cast<uint32_t*>(L.tc);  // the table cache is dead now; reuse one word of it
+    __syncthreads();
+    if (threadIdx.x == 0) *lmask = 0;
+    __syncthreads();
+    if (rep.role == JR_ROLE_LEADER && rep.live()) atomicOr(lmask, 1u << r);
+    __syncthreads();
+    if (threadIdx.x == 0 && (*lmask & (*lmask - 1u))) atomicOr(d.scatter, 1u);
+  }
 #ifdef JR_PROFILE
   __syncthreads();
   if (d.prof)
@@ -390,6 +414,9 @@ struct jr_engine {
   Dev d;
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
+  volatile uint32_t* h_scatter = nullptr;  // pinned: last scatter flag copied back (may lag one launch)
+  int force_sorted = 0;      // JR_STEP_VARIANT=sorted|plain pins the kernel variant (tests, A/B)
+  uint64_t launches_sorted = 0, launches_total = 0;
   int cur = 0;               // outbox index the NEXT step writes
   uint64_t step_index = 0;
   std::vector<void*> allocs;
@@ -449,6 +476,19 @@ static jr_status dalloc(jr_engine* e, T** p, size_t n) {
     default: { constexpr int RR = 8; CALL; } break; \
   }
 
+template <int R>
+static void launch_step_r(jr_engine* e, const StepParams& p, bool sorted, uint32_t grid, size_t smem) {
+  auto kfn = sorted ? step_kernel<R, true> : step_kernel<R, false>;
+  JR_LAUNCH_SMEM(kfn, grid, 32 * R, smem, e->stream, e->d, p);
+}
+
+template <int R>
+static cudaError_t step_smem_attr_r(int smem) {
+  cudaError_t a = cudaFuncSetAttribute(step_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (a != cudaSuccess) return a;
+  return cudaFuncSetAttribute(step_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+
 static size_t step_smem_bytes(const Dev& d) {
   return ((size_t)2 * d.Us + d.W) * d.R * 32 * sizeof(uint4) + (size_t)2 * d.R * 32 * sizeof(uint32_t) +
          (size_t)2 * d.R * d.R * 32 * sizeof(uint32_t);
@@ -457,8 +497,14 @@ static size_t step_smem_bytes(const Dev& d) {
 static jr_status launch_step(jr_engine* e, const StepParams& p) {
   const uint32_t grid = e->d.Gp / GROUPS_PER_CTA;
   const size_t smem = step_smem_bytes(e->d);
-  DISPATCH_R(e->cfg.n_replicas, (JR_LAUNCH_SMEM(step_kernel<RR>, grid, 32 * RR, smem, e->stream, e->d, p)));
+  // Variant choice from the (possibly one launch stale) scatter flag: it only affects speed.
+  const bool sorted = e->force_sorted > 0 || (e->force_sorted == 0 && e->h_scatter && *e->h_scatter != 0);
+  CK(cudaMemsetAsync(e->d.scatter, 0, sizeof(uint32_t), e->stream));
+  DISPATCH_R(e->cfg.n_replicas, (launch_step_r<RR>(e, p, sorted, grid, smem)));
   CK(cudaGetLastError());
+  CK(cudaMemcpyAsync((void*)e->h_scatter, e->d.scatter, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+  e->launches_sorted += sorted ? 1 : 0;
+  e->launches_total += 1;
   return JR_OK;
 }
 
@@ -539,6 +585,7 @@ jr_status jr_engine_create(const jr_config* cfg, jr_engine** out) {
   A(d.fs, plane * (size_t)((d.flags & JR_F_CAPTURE_FSM) ? d.F : 1));
   A(d.fc, plane);
   A(e->scratch, 8);
+  A(d.scatter, 1);
 #ifdef JR_PROFILE
   A(d.prof, 3 * 16 * 2);
 #endif
@@ -571,7 +618,10 @@ jr_status jr_engine_create(const jr_config* cfg, jr_engine** out) {
   {
     const int smem = (int)step_smem_bytes(d);
     cudaError_t aerr = cudaSuccess;
-    DISPATCH_R(d.R, (aerr = cudaFuncSetAttribute(step_kernel<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)));
+    DISPATCH_R(d.R, (aerr = step_smem_attr_r<RR>(smem)));
+    if (aerr == cudaSuccess) aerr = cudaHostAlloc((void**)&e->h_scatter, sizeof(uint32_t), 0);
+    if (aerr == cudaSuccess) *e->h_scatter = 0;
+    if (const char* ev = getenv("JR_STEP_VARIANT")) e->force_sorted = !strcmp(ev, "sorted") ? 1 : (!strcmp(ev, "plain") ? -1 : 0);
     if (aerr != cudaSuccess) {
       set_err("step kernel needs %d bytes of shared memory: %s", smem, cudaGetErrorString(aerr));
       jr_engine_destroy(e);
@@ -612,6 +662,7 @@ jr_status jr_engine_reset(jr_engine* e) {
   CK(cudaStreamSynchronize(e->stream));
   e->cur = 0;
   e->step_index = 0;
+  // (h_scatter keeps its last value: advisory only, and a reset is usually followed by the same workload)
 #ifdef JR_PROFILE
   CK(cudaMemsetAsync(e->d.prof, 0, 96 * sizeof(unsigned long long), e->stream));
 #endif
@@ -620,6 +671,9 @@ jr_status jr_engine_reset(jr_engine* e) {
 
 void jr_engine_destroy(jr_engine* e) {
   if (!e) return;
+  if (getenv("JR_DEBUG_VARIANT"))
+    fprintf(stderr, "[jr] engine %p: %llu step launches, %llu role-sorted\n", (void*)e, (unsigned long long)e->launches_total,
+            (unsigned long long)e->launches_sorted);
   cudaSetDevice(e->cfg.device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (void* p : e->allocs) cudaFree(p);
@@ -638,6 +692,7 @@ void jr_engine_destroy(jr_engine* e) {
     if (e->batch_free[i]) cudaEventDestroy(e->batch_free[i]);
     if (e->batch[i]) cudaFree(e->batch[i]);
   }
+  if (e->h_scatter) cudaFreeHost((void*)e->h_scatter);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   delete e;
 }

@@ -57,6 +57,7 @@ struct Dev {
   uint32_t Us, W;                  // shared-memory mailbox units per replica, table-cache entries (power of 2)
   uint32_t use_index;              // receivers use the delivery index (else scan whole mailboxes)
   uint32_t resident;               // bit r: replica index r is hosted here (others are inert, see jr_config)
+  uint32_t* scatter;               // set by a launch when some CTA has leaders on >= 2 replica indices
   unsigned long long* prof;        // JR_PROFILE builds: cycle counters [role 3][slot 16] x {cycles, count}
   uint64_t seed, goff;
 };
@@ -195,7 +196,7 @@ __device__ __forceinline__ unsigned long long* jr_prof_smem() {
 #define JR_PROF_ADD(role, slot, var) do { } while (0)
 #endif
 
-template <int R>
+template <int R, bool SORTED = false>
 struct Replica {
   const Dev& d;
   const Local& L;
@@ -691,6 +692,38 @@ struct Replica {
     JR_PROF_T0(tr);
     bool first_done = false;
     (void)first_done;
+    uint32_t first_peer = 0xFFFFFFFFu;  // SORTED: the peer whose block run was scanned up front
+    if constexpr (SORTED) {
+      // Role-sorted warps hold leaders with DIFFERENT replica indices, so "the first peer" differs
+      // per lane (index 1 for replica 0, else 0).  Scan its block run here, for all lanes at once;
+      // the loop below then only writes headers.  Mailbox layout is identical to the plain path:
+      // the first peer's header goes to slot ocnt, its blocks follow inline.
+      if (R > 1) {
+        first_peer = r == 0 ? 1u : 0u;
+        const uint32_t take = (prmask >> first_peer) & 1u ? JR_MAX_AE_BLOCKS : 1u;
+        const uint32_t head0 = get_ph(first_peer);
+        uint32_t bid = head0, pulled = 0, nb = 0;
+        while (pulled < 1 + take) {
+          uint32_t nx = ABSENT; uint64_t tok = 0;
+          while (bid <= maxkey) {
+            tbl_fetch(bid, nx, tok);
+            if (nx != ABSENT) break;
+            ++bid;
+          }
+          if (bid > maxkey) {
+            if ((d.flags & JR_F_SLED_COMMIT_KEY_STRICT) && ckey) { fault = JR_FAULT_RANGE_COMMIT_KEY; return; }
+            break;
+          }
+          if (pulled >= 1) {
+            if (!put_unit(ocnt + 1 + nb, make_uint4(bid, nx, (uint32_t)tok, (uint32_t)(tok >> 32)))) return;
+            ++nb;
+          }
+          ++pulled;
+          ++bid;
+        }
+        memo_head = head0; memo_take = take; memo_first = ocnt + 1; memo_nb = nb;
+      }
+    }
 #pragma unroll
     for (int p = 0; p < R; ++p) {
       if (p == (int)r) continue;  // config.nodes holds peers only
@@ -703,7 +736,7 @@ struct Replica {
       if (ph[p] == memo_head && take == memo_take) {
         nb = memo_nb;       // same blocks as an earlier peer: point at that run
         first = memo_first;
-        ref = true;
+        ref = (uint32_t)p != first_peer;  // (the peer scanned up front owns the inline run)
       } else {
         uint32_t bid = ph[p], pulled = 0;
         while (pulled < 1 + take) {

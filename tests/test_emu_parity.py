@@ -134,3 +134,27 @@ def test_run_proposals_equals_steps_with_proposals():
     parity.compare_states(a, o, chain_ids=60)
     parity.compare_digests(a, o)
     assert max(c for (_, _, c) in a.leader_table()) > 5
+
+
+@pytest.mark.parametrize("variant", ["plain", "sorted"])
+def test_both_kernel_variants_match_the_oracle(monkeypatch, variant):
+    """The role-sorted variant (leader -> warp 0; chosen when leaders sit on several replica
+    indices) is pure scheduling: same results as the plain one, on scattered and on uniform leaders."""
+    monkeypatch.setenv("JR_STEP_VARIANT", variant)
+    from josefine_b200 import Command
+    for R in (3, 5, 7):
+        p = parity.Pair(make_oracle, make_emu, 7, R, seed=R)
+        inj = []
+        q = R // 2 + 1
+        for g in range(7):                      # leader of group g on node g % R + 1
+            n = g % R + 1
+            inj.append(Command.timeout(g, n))
+            for v in [v for v in range(1, R + 1) if v != n][:q - 1]:
+                inj.append(Command.vote_response(g, n, 1, v, True))
+        p.step(0, flags=0, inject=inj)
+        for k in range(14):
+            p.step(100 * (k + 1), n_synth=1)
+        p.run(1500, 100, 12, 1)
+        p.finish()
+    p = parity.Pair(make_oracle, make_emu, 4, 3, seed=21, chain_capacity=64)
+    parity.scenario_random_inject(p, seed=77, steps=40)

@@ -171,3 +171,28 @@ def test_config5_full_size_65536x7_churn_compact():
     table = b.leader_table()
     assert table == a.leader_table()
     assert 0.05 < sum(1 for (_, l, _) in table if l == 0) / G < 0.30
+
+
+@pytest.mark.parametrize("variant", ["plain", "sorted"])
+def test_kernel_variants_scattered_leaders(monkeypatch, variant):
+    """Leaders spread over all replica indices (what real elections produce): the plain and the
+    role-sorted kernel variant both match the oracle at 8,192 x 5."""
+    monkeypatch.setenv("JR_STEP_VARIANT", variant)
+    from josefine_b200 import Command
+    G, R = 8192, 5
+    flags = abi.F_STREAM_DIGEST
+    a = make_oracle(G, R, seed=6, flags=flags, chain_capacity=128)
+    b = make_gpu(G, R, seed=6, flags=flags, chain_capacity=128)
+    inj = []
+    for g in range(G):
+        n = g % R + 1
+        inj.append(Command.timeout(g, n))
+        for v in [v for v in range(1, R + 1) if v != n][:2]:
+            inj.append(Command.vote_response(g, n, 1, v, True))
+    for x in (a, b):
+        x.step(0, flags=0, inject=inj)
+        x.run(100, 100, 40, 1)
+        x.run(4100, 100, 9, 2)
+    parity.compare_digests(a, b, f"[scattered leaders, {variant}]")
+    parity.compare_states(a, b, groups=range(0, G, 331), chain_ids=64)
+    assert sorted({l for (_, l, _) in b.leader_table()}) == [1, 2, 3, 4, 5]
