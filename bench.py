@@ -47,7 +47,7 @@ if ROOT not in sys.path:
 
 from josefine_b200 import abi, Command  # noqa: E402
 
-METRIC = "raft_group_ticks_per_sec"
+METRIC = "Raft-group ticks/sec @ 64Ki groups x 5 replicas"   # BASELINE.json `metric`
 UNIT = "group-ticks/s"
 GROUPS_PER_GPU = 65536
 REPLICAS = 5

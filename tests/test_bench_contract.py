@@ -17,7 +17,7 @@ def test_reference_arm_prints_the_contract_line():
     for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
                 "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in d, key
-    assert d["impl"] == "reference" and d["metric"] == "raft_group_ticks_per_sec" and d["unit"] == "group-ticks/s"
+    assert d["impl"] == "reference" and d["metric"].startswith("Raft-group ticks/sec") and d["unit"] == "group-ticks/s"
     assert d["value"] > 1e4 and d["higher_is_better"] is True and d["vs_baseline"] is None
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
