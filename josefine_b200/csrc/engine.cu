@@ -510,6 +510,11 @@ static jr_status launch_step(jr_engine* e, const StepParams& p) {
 
 extern "C" {
 
+#ifdef JR_EMU
+// Marker of the TEST-ONLY host build (tests/emu): the package loader refuses a library that has it.
+int jr_is_emulation(void) { return 1; }
+#endif
+
 const char* jr_last_error(void) { return g_err; }
 
 void jr_config_default(jr_config* cfg, uint32_t n_groups, uint32_t n_replicas) {

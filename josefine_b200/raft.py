@@ -372,6 +372,9 @@ def load_engine_library() -> C.CDLL:
             raise RaftError(abi.E_NO_DEVICE, "load_engine_library",
                             f"{ENGINE_LIB_PATH} not built; run `python -c 'import __graft_entry__ as g; g.build()'`")
         lib = C.CDLL(ENGINE_LIB_PATH)
+        if hasattr(lib, "jr_is_emulation"):   # tests/emu's host build of the device code: never a product path
+            raise RaftError(abi.E_NO_DEVICE, "load_engine_library",
+                            f"{ENGINE_LIB_PATH} is the test-only CPU emulation build; there is no CPU fallback")
         _bind(lib, "jr_")
         lib.jr_engine_create.argtypes = [C.POINTER(abi.Config), C.POINTER(C.c_void_p)]
         lib.jr_engine_create.restype = C.c_int

@@ -74,3 +74,21 @@ def test_create_without_gpu_fails_loudly(engine_lib):
     st = engine_lib.jr_engine_create(C.byref(cfg), C.byref(h))
     assert st in (abi.E_NO_DEVICE, abi.E_CUDA)
     assert not h.value
+
+
+def test_package_refuses_the_emulation_library(monkeypatch):
+    """The CPU emulation of the device code (tests/emu) is test infrastructure; pointing the
+    package at it must fail loudly rather than become a CPU fallback."""
+    import importlib
+    from tests.emu import emu
+    emu.load()
+    monkeypatch.setenv("JR_ENGINE_LIB", emu.LIB_PATH)
+    import josefine_b200.raft as r
+    r2 = importlib.reload(r)
+    try:
+        with pytest.raises(r2.RaftError) as e:
+            r2.load_engine_library()
+        assert "no CPU fallback" in str(e.value)
+    finally:
+        monkeypatch.delenv("JR_ENGINE_LIB")
+        importlib.reload(r)
