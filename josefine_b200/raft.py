@@ -364,6 +364,14 @@ def _bind(lib: C.CDLL, p: str):
 _engine_lib: Optional[C.CDLL] = None
 
 
+def _open_engine_library(path: str) -> C.CDLL:
+    lib = C.CDLL(path)
+    if hasattr(lib, "jr_is_emulation"):   # tests/emu's host build of the device code: never a product path
+        raise RaftError(abi.E_NO_DEVICE, "load_engine_library",
+                        f"{path} is the test-only CPU emulation build; there is no CPU fallback")
+    return lib
+
+
 def load_engine_library() -> C.CDLL:
     """Load the CUDA engine.  There is no CPU fallback: a missing library is an error."""
     global _engine_lib
@@ -371,10 +379,7 @@ def load_engine_library() -> C.CDLL:
         if not os.path.exists(ENGINE_LIB_PATH):
             raise RaftError(abi.E_NO_DEVICE, "load_engine_library",
                             f"{ENGINE_LIB_PATH} not built; run `python -c 'import __graft_entry__ as g; g.build()'`")
-        lib = C.CDLL(ENGINE_LIB_PATH)
-        if hasattr(lib, "jr_is_emulation"):   # tests/emu's host build of the device code: never a product path
-            raise RaftError(abi.E_NO_DEVICE, "load_engine_library",
-                            f"{ENGINE_LIB_PATH} is the test-only CPU emulation build; there is no CPU fallback")
+        lib = _open_engine_library(ENGINE_LIB_PATH)
         _bind(lib, "jr_")
         lib.jr_engine_create.argtypes = [C.POINTER(abi.Config), C.POINTER(C.c_void_p)]
         lib.jr_engine_create.restype = C.c_int

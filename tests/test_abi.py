@@ -76,19 +76,12 @@ def test_create_without_gpu_fails_loudly(engine_lib):
     assert not h.value
 
 
-def test_package_refuses_the_emulation_library(monkeypatch):
+def test_package_refuses_the_emulation_library():
     """The CPU emulation of the device code (tests/emu) is test infrastructure; pointing the
     package at it must fail loudly rather than become a CPU fallback."""
-    import importlib
+    from josefine_b200.raft import RaftError, _open_engine_library
     from tests.emu import emu
     emu.load()
-    monkeypatch.setenv("JR_ENGINE_LIB", emu.LIB_PATH)
-    import josefine_b200.raft as r
-    r2 = importlib.reload(r)
-    try:
-        with pytest.raises(r2.RaftError) as e:
-            r2.load_engine_library()
-        assert "no CPU fallback" in str(e.value)
-    finally:
-        monkeypatch.delenv("JR_ENGINE_LIB")
-        importlib.reload(r)
+    with pytest.raises(RaftError) as e:
+        _open_engine_library(emu.LIB_PATH)
+    assert "no CPU fallback" in str(e.value)
