@@ -196,3 +196,45 @@ def test_kernel_variants_scattered_leaders(monkeypatch, variant):
     parity.compare_digests(a, b, f"[scattered leaders, {variant}]")
     parity.compare_states(a, b, groups=range(0, G, 331), chain_ids=64)
     assert sorted({l for (_, l, _) in b.leader_table()}) == [1, 2, 3, 4, 5]
+
+
+def test_config3_soak_256_ticks():
+    """Config #3 at full size for 256 ticks in four fused launches (the bench's launch shape)."""
+    G, R = 65536, 5
+    flags = abi.F_STREAM_DIGEST
+    a = make_oracle(G, R, seed=1, flags=flags, chain_capacity=320)
+    b = make_gpu(G, R, seed=1, flags=flags, chain_capacity=320)
+    from josefine_b200 import Command
+    inj = []
+    for g in range(G):
+        inj.append(Command.timeout(g, 1))
+        for v in (2, 3):
+            inj.append(Command.vote_response(g, 1, 1, v, True))
+    for x in (a, b):
+        x.step(0, flags=0, inject=inj)
+    now = 100
+    for chunk in range(4):
+        for x in (a, b):
+            x.run(now, 100, 64, 1)
+        now += 6400
+    parity.compare_digests(a, b, "[65536x5, 256 ticks]")
+    parity.compare_states(a, b, groups=range(0, G, 5003), chain_ids=64)
+    assert b.fault_count() == 0 and min(c for (_, _, c) in b.leader_table()) > 240
+
+
+def test_long_run_1024_ticks_with_two_proposals_per_tick():
+    G, R = 2048, 5
+    flags = abi.F_STREAM_DIGEST
+    a = make_oracle(G, R, seed=12, flags=flags, chain_capacity=2200)
+    b = make_gpu(G, R, seed=12, flags=flags, chain_capacity=2200)
+    from josefine_b200 import Command
+    inj = []
+    for g in range(G):
+        inj.append(Command.timeout(g, 2))
+        for v in (1, 3):
+            inj.append(Command.vote_response(g, 2, 1, v, True))
+    for x in (a, b):
+        x.step(0, flags=0, inject=inj)
+        x.run(100, 100, 1024, 2)
+    parity.compare_digests(a, b, "[2048x5, 1024 ticks, 2 proposals/tick]")
+    assert b.fault_count() == 0 and max(c for (_, _, c) in b.leader_table()) > 2000
