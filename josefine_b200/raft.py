@@ -149,6 +149,9 @@ def fsm_tuple(f: abi.FsmInstr) -> tuple:
     return (f.group, f.node, f.kind, f.client_kind, f.client_id, f.block.id, f.block.next, f.block.data)
 
 
+DEFAULT_CAPTURE_CAP = 1 << 18
+
+
 @dataclass
 class StepResult:
     messages: List[abi.Msg]
@@ -206,15 +209,23 @@ class RaftApi:
                 parr[g].node, parr[g].token = node, token
             a.proposals = parr
         cap_m = cap_f = 0
+        # default capture buffers: the worst case, but never more than DEFAULT_CAPTURE_CAP entries
+        # (capture is a debugging / small-deployment feature; pass cap_msgs / cap_fsm to go beyond)
         if self.cfg.flags & abi.F_CAPTURE_MESSAGES:
-            cap_m = cap_msgs if cap_msgs is not None else self.n_groups * self.n_replicas * self.cfg.mailbox_units
+            cap_m = cap_msgs if cap_msgs is not None else min(
+                self.n_groups * self.n_replicas * self.cfg.mailbox_units, DEFAULT_CAPTURE_CAP)
             mbuf = (abi.Msg * max(cap_m, 1))()
             a.out_msgs, a.cap_msgs = mbuf, cap_m
         if self.cfg.flags & abi.F_CAPTURE_FSM:
-            cap_f = cap_fsm if cap_fsm is not None else self.n_groups * self.n_replicas * self.cfg.fsm_units
+            cap_f = cap_fsm if cap_fsm is not None else min(
+                self.n_groups * self.n_replicas * self.cfg.fsm_units, DEFAULT_CAPTURE_CAP)
             fbuf = (abi.FsmInstr * max(cap_f, 1))()
             a.out_fsm, a.cap_fsm = fbuf, cap_f
-        self._check(self._fn("step")(self._h, C.byref(a)), "step")
+        st = self._fn("step")(self._h, C.byref(a))
+        if st == abi.E_CAPACITY:
+            raise RaftError(st, self._p + "step", f"the step emitted {a.n_msgs} messages / {a.n_fsm} instructions but the "
+                            f"capture buffers hold {cap_m} / {cap_f}; the step HAS been applied -- pass cap_msgs / cap_fsm")
+        self._check(st, "step")
         msgs = [mbuf[i] for i in range(a.n_msgs)] if cap_m else []
         fsm = [fbuf[i] for i in range(a.n_fsm)] if cap_f else []
         return StepResult(msgs, fsm)
