@@ -252,9 +252,10 @@ class RaftApi:
         if self._p == "jr_":
             self._check(self._lib.jr_engine_sync(self._h), "engine_sync")   # `arr` is pageable and about to be freed
 
-    def drain_fsm(self) -> List[abi.FsmInstr]:
+    def drain_fsm(self, cap: Optional[int] = None) -> List[abi.FsmInstr]:
         n = C.c_size_t(0)
-        cap = self.n_groups * self.n_replicas * self.cfg.fsm_units
+        if cap is None:
+            cap = min(self.n_groups * self.n_replicas * self.cfg.fsm_units, 4 * DEFAULT_CAPTURE_CAP)
         buf = (abi.FsmInstr * max(cap, 1))()
         self._check(self._fn("drain_fsm")(self._h, buf, C.c_size_t(cap), C.byref(n)), "drain_fsm")
         return [buf[i] for i in range(n.value)]
