@@ -158,3 +158,9 @@ def test_both_kernel_variants_match_the_oracle(monkeypatch, variant):
         p.finish()
     p = parity.Pair(make_oracle, make_emu, 4, 3, seed=21, chain_capacity=64)
     parity.scenario_random_inject(p, seed=77, steps=40)
+
+
+def test_three_single_node_engines_over_the_wire_match_resident_cluster():
+    from tests.wire_cluster import run_networked_vs_resident
+    frames, _ = run_networked_vs_resident(make_emu)
+    assert frames > 100

@@ -238,3 +238,11 @@ def test_long_run_1024_ticks_with_two_proposals_per_tick():
         x.run(100, 100, 1024, 2)
     parity.compare_digests(a, b, "[2048x5, 1024 ticks, 2 proposals/tick]")
     assert b.fault_count() == 0 and max(c for (_, _, c) in b.leader_table()) > 2000
+
+
+def test_three_single_node_engines_over_the_wire_match_resident_cluster():
+    """INTEGRATION.md section 1 arrangement: one hosted node per engine (resident_mask), peers reached through
+    josefine's TCP framing (josefine_b200/wire.py; tcp.rs:39-51,143-156) -- must equal the co-resident group."""
+    from tests.wire_cluster import run_networked_vs_resident
+    frames, nbytes = run_networked_vs_resident(make_gpu)
+    assert frames > 100 and nbytes > frames * 60
