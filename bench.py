@@ -381,8 +381,9 @@ def main():
     launches = args.steps * (2 if world > 1 else 1)   # one fused step_kernel launch per step (+ leader_table_kernel)
 
     # ---------------- end-to-end arm (host buffers through the C ABI) ----------------
-    # Every step: jr_run_proposals copies that step's jr_proposal[S][G] from PINNED host memory
-    # (H2D, on the engine's copy stream) and runs the S ticks fused; jr_leader_table_async copies
+    # Every step: jr_run_tokens copies that step's 64-bit payload tokens [S][G] from PINNED host memory
+    # (H2D, on the engine's copy stream), addresses each to the leader the previous step's
+    # jr_leader_table_async announced, and runs the S ticks fused; jr_leader_table_async copies
     # the per-group {term, leader, commit} result back (D2H).  Two steps are in flight: the host
     # submits step k+1, then waits for and reads step k's result -- copy-in, kernels and copy-out
     # of neighbouring steps overlap.
@@ -394,12 +395,12 @@ def main():
         e2.set_stream(stream.cuda_stream)
         rebase(e2)
         NB = 2
-        prop = torch.zeros(NB, S, G, 2, dtype=torch.int64).pin_memory()   # jr_proposal[NB][S][G] = {token, node|reserved}
+        prop = torch.zeros(NB, S, G, dtype=torch.int64).pin_memory()      # tokens[NB][S][G], one proposal per group-tick
         table = torch.zeros(NB, G, 2, dtype=torch.int64).pin_memory()     # jr_leader_entry[NB][G]
-        prop[..., 1] = 1                                                  # addressed to node 1 (the leader)
-        prop[..., 0] = ((torch.arange(NB * S, dtype=torch.int64).view(NB, S, 1) + 1) << 32) + torch.arange(G, dtype=torch.int64)
+        prop[...] = ((torch.arange(NB * S, dtype=torch.int64).view(NB, S, 1) + 1) << 32) + torch.arange(G, dtype=torch.int64)
         lib = e2._lib
-        pstride, tstride = S * G * 16, G * 16
+        pstride, tstride = S * G * 8, G * 16
+        e2.leader_table()                                                 # first announce: where the tokens go
         checks = []
 
         excluded = [0.0]
@@ -409,13 +410,13 @@ def main():
                 e2.sync()
                 tp = time.perf_counter()
                 rebase(e2)
+                e2.leader_table()
                 excluded[0] += time.perf_counter() - tp
             tn = state["now"]
             state["now"] += DT_MS * S
             state["ticks_left"] -= S
-            st = lib.jr_run_proposals(e2._h, C.c_uint64(tn), C.c_uint32(DT_MS), C.c_uint32(S),
-                                      C.cast(prop.data_ptr() + (i % NB) * pstride, C.POINTER(abi.Proposal)),
-                                      C.c_uint32(abi.STEP_TRUSTED_PROPOSALS))          # H2D + fused kernel
+            st = lib.jr_run_tokens(e2._h, C.c_uint64(tn), C.c_uint32(DT_MS), C.c_uint32(S),
+                                   C.cast(prop.data_ptr() + (i % NB) * pstride, C.POINTER(C.c_uint64)))   # H2D + route + fused kernel
             assert st == 0, st
             st = lib.jr_leader_table_async(e2._h, C.cast(table.data_ptr() + (i % NB) * tstride,
                                                          C.POINTER(abi.LeaderEntry)))   # result D2H
@@ -446,9 +447,9 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
-        e2e = {"value": world * G * S * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": S * G * 16,
+        e2e = {"value": world * G * S * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": S * G * 8,
                "d2h_bytes_per_step": G * 16, "ms_per_step": dt * 1e3 / args.steps,
-               "api": "per step: jr_run_proposals(pinned jr_proposal[64][G]) + jr_leader_table_async(pinned jr_leader_entry[G]) "
+               "api": "per step: jr_run_tokens(pinned u64 tokens[64][G], routed to the last announced leader) + jr_leader_table_async(pinned jr_leader_entry[G]) "
                       "+ jr_leader_table_wait; two steps in flight",
                "commit_last": checks[-1], "faulted_replicas": e2.fault_count(),
                "timing": "host wall clock around all timed steps incl. the final sync, max over ranks"}

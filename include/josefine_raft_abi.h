@@ -14,6 +14,7 @@
  *                         fsm_tx.send(Instruction)        src/raft/leader.rs:94,184; follower.rs:205
  *   jr_run             <- N consecutive event_loop turns with no host traffic (Tick + peer mail)
  *   jr_run_proposals   <- N consecutive event_loop turns incl. the client arm (server.rs:156-160)
+ *   jr_run_tokens      <- the same, with proposals addressed to the last announced leader
  *   jr_query           <- pub fields id/state/role/chain  src/raft/mod.rs:326-341,437-447;
  *                         Chain::get_head/get_commit      src/raft/chain.rs:230-236
  *   jr_chain_read      <- Chain::range / Chain::has       src/raft/chain.rs:155-157,208-228
@@ -306,6 +307,20 @@ jr_status jr_run(jr_engine* e, uint64_t now0_ms, uint32_t dt_ms, uint32_t n_step
  */
 jr_status jr_run_proposals(jr_engine* e, uint64_t now0_ms, uint32_t dt_ms, uint32_t n_steps,
                            const jr_proposal* proposals, uint32_t flags);
+/*
+ * jr_run_proposals with leader-routed input: `tokens` is HOST memory holding n_steps consecutive
+ * arrays of n_groups 64-bit payload tokens (0 = no proposal; tick k uses tokens[k*n_groups ..]).
+ * Each token is proposed at the node the most recent jr_leader_table / _device / _async call on this
+ * engine announced as its group's leader -- the routing a josefine client does with the leader it
+ * last learnt (Leader::write_state, leader.rs:101-121) before RaftClient::propose (client.rs:35-37)
+ * reaches apply_client_request (leader.rs:177-194).  A group with no announced leader (also: no
+ * announce since create / reset) drops its tokens, like a request sent nowhere: no Notify follows.
+ * A stale route lands on a follower, which proxies or queues it (follower.rs:258-270).
+ * Bit for bit equal to jr_run_proposals with proposals[k*G+g] = {tokens[k*G+g], route[g]}, at half
+ * the host-to-device bytes (8 instead of 16 per group-tick).  Same asynchrony rules.
+ */
+jr_status jr_run_tokens(jr_engine* e, uint64_t now0_ms, uint32_t dt_ms, uint32_t n_steps,
+                        const uint64_t* tokens);
 /* Drop and return the Instructions accumulated by jr_run (same order as jr_step). */
 jr_status jr_drain_fsm(jr_engine* e, jr_fsm_instr* out, size_t cap, size_t* n);
 

@@ -140,7 +140,7 @@ EXPECTED_SIZES = {
 # every symbol include/josefine_raft_abi.h declares
 ENGINE_SYMBOLS = [
     "jr_engine_create", "jr_engine_destroy", "jr_engine_reset", "jr_engine_set_stream", "jr_engine_sync",
-    "jr_last_error", "jr_config_default", "jr_step", "jr_run", "jr_run_proposals", "jr_drain_fsm", "jr_query",
+    "jr_last_error", "jr_config_default", "jr_step", "jr_run", "jr_run_proposals", "jr_run_tokens", "jr_drain_fsm", "jr_query",
     "jr_chain_read", "jr_state_digest", "jr_stream_digest", "jr_fault_count", "jr_compact",
     "jr_set_alive", "jr_kill_leaders", "jr_leader_table_device", "jr_leader_table", "jr_leader_table_async", "jr_leader_table_wait",
     "jr_election_timeout",

@@ -280,7 +280,7 @@ __global__ void stream_digest_kernel(const Dev d, unsigned long long* out) {
 
 // Leader::write_state (leader.rs:101-121) for every group: the live leader with
 // the highest (term, id).  One thread per group.
-__global__ void leader_table_kernel(const Dev d, jr_leader_entry* out) {
+__global__ void leader_table_kernel(const Dev d, jr_leader_entry* out, uint32_t* route) {
   const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= d.G) return;
   jr_leader_entry e{0, 0, 0};
@@ -298,6 +298,22 @@ __global__ void leader_table_kernel(const Dev d, jr_leader_entry* out) {
     }
   }
   out[g] = e;
+  route[g] = e.leader_id;  // where jr_run_tokens sends this group's proposals until the next announce
+}
+
+// jr_run_tokens: tokens[k*G + g] -> jr_proposal{token, node = last announced leader of g}.  Pure streaming
+// (8 B in, 16 B out per group-tick); the step kernel then reads the same dense layout jr_run_proposals stages.
+__global__ void route_tokens_kernel(const unsigned long long* __restrict__ tokens, const uint32_t* __restrict__ route,
+                                    jr_proposal* __restrict__ out, uint32_t G, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const unsigned long long t = tokens[i];
+    jr_proposal p;
+    p.token = t;
+    p.node = t ? route[i % G] : 0u;
+    p.reserved = 0;
+    out[i] = p;
+  }
 }
 
 __global__ void kill_leaders_kernel(const Dev d, uint64_t base, uint32_t permille, unsigned long long* n_killed) {
@@ -443,6 +459,9 @@ struct jr_engine {
   cudaEvent_t batch_ready[NBUF] = {nullptr, nullptr}, batch_free[NBUF] = {nullptr, nullptr};
   bool batch_used[NBUF] = {false, false};
   int batch_i = 0;
+  unsigned long long* tokbuf[NBUF] = {nullptr, nullptr};  // device staging of jr_run_tokens input, tok_cap entries each
+  size_t tok_cap[NBUF] = {0, 0};
+  uint32_t* route = nullptr;              // device, G entries: leader_id of the last leader-table call (0 = none)
   int tab_pending[NBUF] = {0, 0};  // FIFO of leaders[] buffers whose copy-out has not been waited for
   int tab_npending = 0;
   int prop_i = 0, tab_i = 0;
@@ -596,6 +615,7 @@ jr_status jr_engine_create(const jr_config* cfg, jr_engine** out) {
 #endif
   A(e->q_state, 1);
   for (int i = 0; i < jr_engine::NBUF; ++i) { A(e->prop[i], d.G); A(e->leaders[i], d.G); }
+  A(e->route, d.G);
 #undef A
   if (st != JR_OK) { jr_engine_destroy(e); return st; }
   if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -662,6 +682,7 @@ jr_status jr_engine_reset(jr_engine* e) {
   CK(cudaMemsetAsync(d.cnext, 0xFF, plane * (size_t)d.cap * sizeof(uint32_t), e->stream));
   CK(cudaMemsetAsync(d.pr, 0, plane * ((d.R + 3) / 4) * sizeof(uint4), e->stream));
   CK(cudaMemsetAsync(d.qt, 0, plane * JR_CLIENT_QUEUE_CAP * sizeof(uint4), e->stream));
+  CK(cudaMemsetAsync(e->route, 0, (size_t)d.G * sizeof(uint32_t), e->stream));  // no leader announced yet
   JR_LAUNCH(init_kernel, (unsigned)((plane + 255) / 256), 256, e->stream, d);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(e->stream));
@@ -696,6 +717,7 @@ void jr_engine_destroy(jr_engine* e) {
     if (e->batch_ready[i]) cudaEventDestroy(e->batch_ready[i]);
     if (e->batch_free[i]) cudaEventDestroy(e->batch_free[i]);
     if (e->batch[i]) cudaFree(e->batch[i]);
+    if (e->tokbuf[i]) cudaFree(e->tokbuf[i]);
   }
   if (e->h_scatter) cudaFreeHost((void*)e->h_scatter);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -972,6 +994,41 @@ jr_status jr_run(jr_engine* e, uint64_t now0, uint32_t dt, uint32_t n_steps, uin
   return JR_OK;
 }
 
+// Grow batch[b] to n entries once its last reader is done; returns with the h2d stream fenced on that reader.
+static jr_status batch_reserve(jr_engine* e, int b, size_t n) {
+  if (e->batch_used[b]) CK(cudaStreamWaitEvent(e->h2d, e->batch_free[b], 0));  // its last reader is done
+  if (n > e->batch_cap[b]) {
+    if (e->batch_used[b]) CK(cudaEventSynchronize(e->batch_free[b]));
+    if (e->batch[b]) cudaFree(e->batch[b]);
+    e->batch[b] = nullptr;
+    e->batch_cap[b] = 0;
+    CK(cudaMalloc(&e->batch[b], n * sizeof(jr_proposal)));
+    e->batch_cap[b] = n;
+  }
+  return JR_OK;
+}
+
+// The fused launch over batch[b] (already ordered after whatever filled it on e->stream).
+static jr_status batch_launch(jr_engine* e, int b, uint64_t now0, uint32_t dt, uint32_t n_steps) {
+  StepParams p;
+  p.now = now0;
+  p.step_index = e->step_index;
+  p.n_synth = 0;
+  p.n_ticks = n_steps;
+  p.dt = dt;
+  p.cur = e->cur;
+  p.proposals = e->batch[b];
+  p.prop_stride = e->d.G;
+  p.phases = PH_RESET_OUT | PH_RESET_FSM | PH_DRAIN | PH_PROPOSE | PH_TICK;
+  jr_status st = launch_step(e, p);
+  if (st != JR_OK) return st;
+  CK(cudaEventRecord(e->batch_free[b], e->stream));
+  e->batch_used[b] = true;
+  e->cur ^= (int)(n_steps & 1u);
+  e->step_index += n_steps;
+  return JR_OK;
+}
+
 jr_status jr_run_proposals(jr_engine* e, uint64_t now0, uint32_t dt, uint32_t n_steps, const jr_proposal* proposals,
                            uint32_t flags) {
   if (!e || !proposals) return JR_E_INVAL;
@@ -984,35 +1041,40 @@ jr_status jr_run_proposals(jr_engine* e, uint64_t now0, uint32_t dt, uint32_t n_
       if (proposals[i].node > R) return JR_E_UNKNOWN_NODE;
   const int b = e->batch_i;
   e->batch_i = (b + 1) % jr_engine::NBUF;
-  if (e->batch_used[b]) CK(cudaStreamWaitEvent(e->h2d, e->batch_free[b], 0));  // its last reader is done
-  if (n > e->batch_cap[b]) {
-    if (e->batch_used[b]) CK(cudaStreamSynchronize(e->h2d));
-    if (e->batch[b]) cudaFree(e->batch[b]);
-    e->batch[b] = nullptr;
-    e->batch_cap[b] = 0;
-    CK(cudaMalloc(&e->batch[b], n * sizeof(jr_proposal)));
-    e->batch_cap[b] = n;
-  }
+  jr_status st = batch_reserve(e, b, n);
+  if (st != JR_OK) return st;
   CK(cudaMemcpyAsync(e->batch[b], proposals, n * sizeof(jr_proposal), cudaMemcpyHostToDevice, e->h2d));
   CK(cudaEventRecord(e->batch_ready[b], e->h2d));
   CK(cudaStreamWaitEvent(e->stream, e->batch_ready[b], 0));
-  StepParams p;
-  p.now = now0;
-  p.step_index = e->step_index;
-  p.n_synth = 0;
-  p.n_ticks = n_steps;
-  p.dt = dt;
-  p.cur = e->cur;
-  p.proposals = e->batch[b];
-  p.prop_stride = G;
-  p.phases = PH_RESET_OUT | PH_RESET_FSM | PH_DRAIN | PH_PROPOSE | PH_TICK;
-  jr_status st = launch_step(e, p);
+  return batch_launch(e, b, now0, dt, n_steps);
+}
+
+jr_status jr_run_tokens(jr_engine* e, uint64_t now0, uint32_t dt, uint32_t n_steps, const uint64_t* tokens) {
+  if (!e || !tokens) return JR_E_INVAL;
+  if (n_steps == 0) return JR_OK;
+  CK(cudaSetDevice(e->cfg.device));
+  const uint32_t G = e->d.G;
+  const size_t n = (size_t)n_steps * G;
+  const int b = e->batch_i;
+  e->batch_i = (b + 1) % jr_engine::NBUF;
+  jr_status st = batch_reserve(e, b, n);  // batch_free[b] also covers tokbuf[b]: the routing kernel precedes the step
   if (st != JR_OK) return st;
-  CK(cudaEventRecord(e->batch_free[b], e->stream));
-  e->batch_used[b] = true;
-  e->cur ^= (int)(n_steps & 1u);
-  e->step_index += n_steps;
-  return JR_OK;
+  if (n > e->tok_cap[b]) {
+    if (e->batch_used[b]) CK(cudaEventSynchronize(e->batch_free[b]));
+    if (e->tokbuf[b]) cudaFree(e->tokbuf[b]);
+    e->tokbuf[b] = nullptr;
+    e->tok_cap[b] = 0;
+    CK(cudaMalloc(&e->tokbuf[b], n * sizeof(unsigned long long)));
+    e->tok_cap[b] = n;
+  }
+  CK(cudaMemcpyAsync(e->tokbuf[b], tokens, n * sizeof(unsigned long long), cudaMemcpyHostToDevice, e->h2d));
+  CK(cudaEventRecord(e->batch_ready[b], e->h2d));
+  CK(cudaStreamWaitEvent(e->stream, e->batch_ready[b], 0));
+  // on the engine stream: ordered after the leader_table_kernel that last wrote `route`
+  const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)148 * 16);
+  JR_LAUNCH(route_tokens_kernel, blocks, 256, e->stream, e->tokbuf[b], e->route, e->batch[b], G, n);
+  CK(cudaGetLastError());
+  return batch_launch(e, b, now0, dt, n_steps);
 }
 
 jr_status jr_drain_fsm(jr_engine* e, jr_fsm_instr* out, size_t cap, size_t* n) {
@@ -1141,7 +1203,7 @@ jr_status jr_kill_leaders(jr_engine* e, uint64_t salt, uint32_t permille, uint64
 jr_status jr_leader_table_device(jr_engine* e, void* dev_out) {
   if (!e || !dev_out) return JR_E_INVAL;
   CK(cudaSetDevice(e->cfg.device));
-  JR_LAUNCH(leader_table_kernel, (e->d.G + 127) / 128, 128, e->stream, e->d, (jr_leader_entry*)dev_out);
+  JR_LAUNCH(leader_table_kernel, (e->d.G + 127) / 128, 128, e->stream, e->d, (jr_leader_entry*)dev_out, e->route);
   CK(cudaGetLastError());
   return JR_OK;
 }

@@ -252,6 +252,19 @@ class RaftApi:
         if self._p == "jr_":
             self._check(self._lib.jr_engine_sync(self._h), "engine_sync")   # `arr` is pageable and about to be freed
 
+    def run_tokens(self, now0_ms: int, dt_ms: int, tokens: Sequence[Sequence[int]]):
+        """Fused ticks with leader-routed client input: tokens[k][g] (0 = none) is proposed at the node the last
+        leader_table() call announced as group g's leader."""
+        n = len(tokens)
+        arr = (C.c_uint64 * max(n * self.n_groups, 1))()
+        for k, tick in enumerate(tokens):
+            if len(tick) != self.n_groups:
+                raise ValueError("every tick needs one token per group")
+            arr[k * self.n_groups:(k + 1) * self.n_groups] = list(tick)
+        self._check(self._fn("run_tokens")(self._h, C.c_uint64(now0_ms), C.c_uint32(dt_ms), C.c_uint32(n), arr), "run_tokens")
+        if self._p == "jr_":
+            self._check(self._lib.jr_engine_sync(self._h), "engine_sync")   # `arr` is pageable and about to be freed
+
     def drain_fsm(self, cap: Optional[int] = None) -> List[abi.FsmInstr]:
         n = C.c_size_t(0)
         if cap is None:
@@ -350,6 +363,7 @@ def _bind(lib: C.CDLL, p: str):
         "step": [vp, C.POINTER(abi.StepArgs)],
         "run": [vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32],
         "run_proposals": [vp, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(abi.Proposal), C.c_uint32],
+        "run_tokens": [vp, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)],
         "drain_fsm": [vp, C.POINTER(abi.FsmInstr), C.c_size_t, C.POINTER(C.c_size_t)],
         "query": [vp, C.c_uint32, C.c_uint32, C.POINTER(abi.ReplicaState)],
         "chain_read": [vp, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.POINTER(abi.Block),

@@ -190,6 +190,7 @@ struct jro_cluster {
   std::unique_ptr<Pool> pool;
   uint64_t step_index = 0;
   std::vector<Replica> reps;  // [g * R + (node-1)]
+  std::vector<uint32_t> route;  // [g]: leader_id of the last jro_leader_table call (0 = none), for jro_run_tokens
   Replica& at(uint32_t g, uint32_t node) { return reps[(size_t)g * cfg.n_replicas + (node - 1)]; }
 };
 
@@ -314,6 +315,7 @@ jr_status jro_create(const jr_config* cfg, unsigned n_threads, jro_cluster** out
   if (c->n_threads > 1) c->pool = std::make_unique<Pool>(c->n_threads);
   const uint32_t R = cfg->n_replicas;
   c->reps.resize((size_t)cfg->n_groups * R);
+  c->route.assign(cfg->n_groups, 0u);
   // nodes are built by the worker that will step them (allocation locality)
   for_groups(c, [&](uint32_t glo, uint32_t ghi) {
   for (uint32_t g = glo; g < ghi; ++g) {
@@ -428,6 +430,19 @@ jr_status jro_run_proposals(jro_cluster* c, uint64_t now0, uint32_t dt, uint32_t
   });
   c->step_index += n_steps;
   return JR_OK;
+}
+
+// include/josefine_raft_abi.h jr_run_tokens: tokens routed to the leader the last jro_leader_table call announced.
+jr_status jro_run_tokens(jro_cluster* c, uint64_t now0, uint32_t dt, uint32_t n_steps, const uint64_t* tokens) {
+  if (!c || !tokens) return JR_E_INVAL;
+  const uint32_t G = c->cfg.n_groups;
+  std::vector<jr_proposal> props((size_t)n_steps * G);
+  for (size_t i = 0; i < props.size(); ++i) {
+    props[i].token = tokens[i];
+    props[i].node = tokens[i] ? c->route[i % G] : 0u;
+    props[i].reserved = 0;
+  }
+  return jro_run_proposals(c, now0, dt, n_steps, props.data(), 0);
 }
 
 jr_status jro_drain_fsm(jro_cluster* c, jr_fsm_instr* out, size_t cap, size_t* n) {
@@ -613,6 +628,7 @@ jr_status jro_leader_table(jro_cluster* c, jr_leader_entry* out) {
       }
     }
     out[g] = e;
+    c->route[g] = e.leader_id;
   }
   return JR_OK;
 }

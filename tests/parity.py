@@ -168,3 +168,57 @@ def scenario_random_inject(p: Pair, seed=0, steps=60, dt=100, per_step=3, max_no
             g, n = rng.randrange(G), rng.randint(1, R)
             p.both("set_alive", g, n, False)
     p.finish()
+
+
+def scenario_leader_routed_tokens(make_a, make_b, G=12, R=3, seed=6):
+    """jr_run_tokens on both implementations: routes before any announce (dropped), fresh routes, routes gone
+    stale after a leader is silenced (token lands on a dead node / a follower), re-announce after failover."""
+    cfg = dict(seed=seed, flags=FULL, fsm_units=256)
+    a, b = make_a(G, R, **cfg), make_b(G, R, **cfg)
+    now = [0]
+
+    def both(name, *args):
+        ra, rb = getattr(a, name)(*args), getattr(b, name)(*args)
+        assert ra == rb, name
+        return ra
+
+    def tokens(n, salt):
+        return [[0 if (g + k) % 5 == 0 else (salt << 32) | (k << 16) | (g + 1) for g in range(G)] for k in range(n)]
+
+    def run_tokens(n, salt):
+        t = tokens(n, salt)
+        a.run_tokens(now[0] + 100, 100, t)
+        b.run_tokens(now[0] + 100, 100, t)
+        now[0] += 100 * n
+        fa, fb = [fsm_tuple(f) for f in a.drain_fsm()], [fsm_tuple(f) for f in b.drain_fsm()]
+        assert fa == fb
+        compare_states(a, b, chain_ids=64, where=f"[tokens salt={salt}]")
+        return fa
+
+    both("run", 100, 100, 20, 0)                      # elections
+    now[0] = 2000
+    assert run_tokens(4, 1) == []                     # no announce yet: every token is dropped
+    table = both("leader_table")
+    assert sum(1 for (_, lid, _) in table if lid) * 10 >= 8 * G      # (a split vote can leave a group leaderless)
+    fsm = run_tokens(8, 2)
+    assert any(f[2] == abi.FSM_NOTIFY for f in fsm) and any(f[2] == abi.FSM_APPLY for f in fsm)
+    commit0 = max(c for (_, _, c) in both("leader_table"))
+    assert commit0 > 0
+    killed = both("kill_leaders", 77, 500)            # routes to those leaders are now stale
+    assert 0 < killed < G
+    run_tokens(6, 3)
+    both("leader_table")                              # groups without a live leader announce 0 -> dropped again
+    run_tokens(6, 4)
+    # equivalence with explicit proposals (the ABI's definition), on implementation a
+    c = make_a(G, R, **cfg)
+    c.run(100, 100, 20, 0)
+    route = [lid for (_, lid, _) in c.leader_table()]
+    t = tokens(8, 2)
+    c.run_proposals(2500, 100, [[(route[g] if tok else 0, tok) for g, tok in enumerate(tick)] for tick in t])
+    d = make_a(G, R, **cfg)
+    d.run(100, 100, 20, 0)
+    d.leader_table()
+    d.run_tokens(2500, 100, t)
+    compare_states(c, d, chain_ids=64, where="[tokens == proposals]")
+    compare_digests(c, d, "[tokens == proposals]")
+    compare_digests(a, b, "[final]")

@@ -164,3 +164,7 @@ def test_three_single_node_engines_over_the_wire_match_resident_cluster():
     from tests.wire_cluster import run_networked_vs_resident
     frames, _ = run_networked_vs_resident(make_emu)
     assert frames > 100
+
+
+def test_leader_routed_tokens():
+    parity.scenario_leader_routed_tokens(make_emu, make_oracle)

@@ -246,3 +246,11 @@ def test_three_single_node_engines_over_the_wire_match_resident_cluster():
     from tests.wire_cluster import run_networked_vs_resident
     frames, nbytes = run_networked_vs_resident(make_gpu)
     assert frames > 100 and nbytes > frames * 60
+
+
+def test_leader_routed_tokens():
+    parity.scenario_leader_routed_tokens(make_gpu, make_oracle)
+
+
+def test_leader_routed_tokens_many_groups():
+    parity.scenario_leader_routed_tokens(make_gpu, make_oracle, G=3000, R=3, seed=2)
