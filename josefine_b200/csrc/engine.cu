@@ -27,11 +27,56 @@ using namespace jr;
 // buffered, units beyond Us spill to the global mailbox); block-table reads go
 // through a per-lane shared-memory cache.  Groups never interact, so the only
 // synchronisation between ticks is __syncthreads().
+// A split launch (p0.n_parts > 1) runs every block's ticks as n_parts consecutive tasks.  Tasks are taken by
+// ticket, in launch order, so all part k-1 tasks are running or done before any part k task starts; a part k
+// task waits for its block's part k-1 (release/acquire on d.done[block]) and then continues from the state
+// and mailboxes that task stored -- exactly what the next launch would do.  The point is the last wave:
+// 2048 equal tasks on 592 CTA slots take 4 rounds, 4096 half-length tasks take 7 half-rounds.
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+#ifdef JR_EMU
+  return *reinterpret_cast<const volatile uint32_t*>(p);
+#else
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+#endif
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
+#ifdef JR_EMU
+  *reinterpret_cast<volatile uint32_t*>(p) = v;
+#else
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
+}
+
 template <int R, bool SORTED>
-__global__ void __launch_bounds__(32 * R) step_kernel(const Dev d, const StepParams p) {
+__global__ void __launch_bounds__(32 * R) step_kernel(const Dev d, const StepParams p0) {
   JR_DYN_SMEM(uint4, smem);
   const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-  const uint32_t g = blockIdx.x * GROUPS_PER_CTA + lane;  // padded groups (g >= G) are real, unused replicas
+  StepParams p = p0;
+  uint32_t blk = blockIdx.x, part = 0;
+  if (p0.n_parts > 1) {
+    uint32_t* s_ticket = reinterpret_cast<uint32_t*>(smem);  // free until stage_inbox: fenced by the two barriers
+    if (threadIdx.x == 0) *s_ticket = atomicAdd(d.scatter + 1, 1u);
+    __syncthreads();
+    const uint32_t ticket = *s_ticket;
+    __syncthreads();
+    part = ticket / p0.n_blocks;
+    blk = ticket - part * p0.n_blocks;
+    const uint32_t t0 = part * p0.part_ticks;  // host: (n_parts - 1) * part_ticks < n_ticks
+    p.n_ticks = min(p0.part_ticks, p0.n_ticks - t0);
+    p.now += (uint64_t)t0 * p0.dt;
+    p.step_index += t0;
+    p.cur ^= (int)(t0 & 1u);
+    if (p.proposals) p.proposals += (size_t)t0 * p0.prop_stride;
+    if (part) {
+      p.phases = PH_RESET_OUT | PH_DRAIN | PH_PROPOSE | PH_TICK;
+      if (threadIdx.x == 0)
+        while (ld_acquire_u32(d.done + blk) != p0.epoch + part) {}
+      __syncthreads();
+    }
+  }
+  const uint32_t g = blk * GROUPS_PER_CTA + lane;  // padded groups (g >= G) are real, unused replicas
   // Which replica of group g this thread steps.  Plain variant: replica index = warp index, so a
   // warp runs one role's code when the CTA's leaders share a replica index (and every branch on
   // `r` is provably warp-uniform).  SORTED variant, picked by the host when a previous launch saw
@@ -103,6 +148,11 @@ __global__ void __launch_bounds__(32 * R) step_kernel(const Dev d, const StepPar
     if (rep.role == JR_ROLE_LEADER && rep.live()) atomicOr(lmask, 1u << r);
     __syncthreads();
     if (threadIdx.x == 0 && (*lmask & (*lmask - 1u))) atomicOr(d.scatter, 1u);
+  }
+  if (p0.n_parts > 1 && part + 1 < p0.n_parts) {  // hand the block over to its next part
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_u32(d.done + blk, p0.epoch + part + 1);
   }
 #ifdef JR_PROFILE
   __syncthreads();
@@ -432,7 +482,9 @@ struct jr_engine {
   cudaStream_t own_stream = nullptr;
   volatile uint32_t* h_scatter = nullptr;  // pinned: last scatter flag copied back (may lag one launch)
   int force_sorted = 0;      // JR_STEP_VARIANT=sorted|plain pins the kernel variant (tests, A/B)
-  uint64_t launches_sorted = 0, launches_total = 0;
+  uint64_t launches_sorted = 0, launches_total = 0, launches_split = 0;
+  uint32_t slots = 0;        // CTAs of the step kernel the device holds at once (occupancy x SMs)
+  uint32_t force_parts = 0;  // JR_PARTS=n pins the split (tests, A/B); 0 = choose_parts
   int cur = 0;               // outbox index the NEXT step writes
   uint64_t step_index = 0;
   std::vector<void*> allocs;
@@ -508,21 +560,53 @@ static cudaError_t step_smem_attr_r(int smem) {
   return cudaFuncSetAttribute(step_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
+#ifndef JR_EMU
+template <int R>
+static cudaError_t step_occupancy_r(int* per_sm, int smem) {
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, step_kernel<R, false>, 32 * R, (size_t)smem);
+}
+#endif
+
 static size_t step_smem_bytes(const Dev& d) {
   return ((size_t)2 * d.Us + d.W) * d.R * 32 * sizeof(uint4) + (size_t)2 * d.R * 32 * sizeof(uint32_t) +
          (size_t)2 * d.R * d.R * 32 * sizeof(uint32_t);
 }
 
-static jr_status launch_step(jr_engine* e, const StepParams& p) {
-  const uint32_t grid = e->d.Gp / GROUPS_PER_CTA;
+// How many consecutive tasks to cut each block's ticks into: the fewest that minimise the number of
+// rounds the CTA slots need, in units of a whole-launch task.  1 when the grid fits the slots anyway,
+// when the launch is short, or when its first tick is not a whole tick (jr_step's split phases).
+static uint32_t choose_parts(const jr_engine* e, const StepParams& p, uint32_t n_blocks) {
+  const uint32_t whole = PH_RESET_OUT | PH_DRAIN | PH_TICK;
+  if ((p.phases & whole) != whole || p.n_ticks < 2) return 1;
+  if (e->force_parts) return std::min<uint32_t>(e->force_parts, p.n_ticks);
+  if (!e->slots || n_blocks <= e->slots) return 1;
+  uint32_t best = 1;
+  double best_rounds = (double)((n_blocks + e->slots - 1) / e->slots);
+  for (uint32_t n = 2; n <= 8 && p.n_ticks / n >= 8; n *= 2) {
+    const double rounds = (double)(((size_t)n_blocks * n + e->slots - 1) / e->slots) / n;
+    if (rounds < best_rounds * 0.97) { best = n; best_rounds = rounds; }
+  }
+  return best;
+}
+
+static jr_status launch_step(jr_engine* e, const StepParams& p_in) {
+  const uint32_t n_blocks = e->d.Gp / GROUPS_PER_CTA;
   const size_t smem = step_smem_bytes(e->d);
+  StepParams p = p_in;
+  p.n_parts = choose_parts(e, p, n_blocks);
+  p.part_ticks = (p.n_ticks + p.n_parts - 1) / p.n_parts;
+  p.n_parts = (p.n_ticks + p.part_ticks - 1) / p.part_ticks;  // no empty trailing part
+  p.n_blocks = n_blocks;
+  p.epoch = (uint32_t)(e->launches_total + 1) * 8u;
+  const uint32_t grid = n_blocks * p.n_parts;
   // Variant choice from the (possibly one launch stale) scatter flag: it only affects speed.
   const bool sorted = e->force_sorted > 0 || (e->force_sorted == 0 && e->h_scatter && *e->h_scatter != 0);
-  CK(cudaMemsetAsync(e->d.scatter, 0, sizeof(uint32_t), e->stream));
+  CK(cudaMemsetAsync(e->d.scatter, 0, 2 * sizeof(uint32_t), e->stream));  // scatter flag + ticket counter
   DISPATCH_R(e->cfg.n_replicas, (launch_step_r<RR>(e, p, sorted, grid, smem)));
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync((void*)e->h_scatter, e->d.scatter, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
   e->launches_sorted += sorted ? 1 : 0;
+  e->launches_split += p.n_parts > 1 ? 1 : 0;
   e->launches_total += 1;
   return JR_OK;
 }
@@ -609,7 +693,8 @@ jr_status jr_engine_create(const jr_config* cfg, jr_engine** out) {
   A(d.fs, plane * (size_t)((d.flags & JR_F_CAPTURE_FSM) ? d.F : 1));
   A(d.fc, plane);
   A(e->scratch, 8);
-  A(d.scatter, 1);
+  A(d.scatter, 2);
+  A(d.done, d.Gp / GROUPS_PER_CTA);
 #ifdef JR_PROFILE
   A(d.prof, 3 * 16 * 2);
 #endif
@@ -646,6 +731,15 @@ jr_status jr_engine_create(const jr_config* cfg, jr_engine** out) {
     DISPATCH_R(d.R, (aerr = step_smem_attr_r<RR>(smem)));
     if (aerr == cudaSuccess) aerr = cudaHostAlloc((void**)&e->h_scatter, sizeof(uint32_t), 0);
     if (aerr == cudaSuccess) *e->h_scatter = 0;
+    if (const char* ev = getenv("JR_PARTS")) e->force_parts = (uint32_t)std::min(std::max(atoi(ev), 0), 8);
+#ifndef JR_EMU
+    if (aerr == cudaSuccess) {
+      int per_sm = 0, sms = 0;
+      DISPATCH_R(d.R, (aerr = step_occupancy_r<RR>(&per_sm, smem)));
+      if (aerr == cudaSuccess) aerr = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+      e->slots = (uint32_t)(per_sm * sms);
+    }
+#endif
     if (const char* ev = getenv("JR_STEP_VARIANT")) e->force_sorted = !strcmp(ev, "sorted") ? 1 : (!strcmp(ev, "plain") ? -1 : 0);
     if (aerr != cudaSuccess) {
       set_err("step kernel needs %d bytes of shared memory: %s", smem, cudaGetErrorString(aerr));
@@ -683,6 +777,7 @@ jr_status jr_engine_reset(jr_engine* e) {
   CK(cudaMemsetAsync(d.pr, 0, plane * ((d.R + 3) / 4) * sizeof(uint4), e->stream));
   CK(cudaMemsetAsync(d.qt, 0, plane * JR_CLIENT_QUEUE_CAP * sizeof(uint4), e->stream));
   CK(cudaMemsetAsync(e->route, 0, (size_t)d.G * sizeof(uint32_t), e->stream));  // no leader announced yet
+  CK(cudaMemsetAsync(d.done, 0, (size_t)(d.Gp / GROUPS_PER_CTA) * sizeof(uint32_t), e->stream));
   JR_LAUNCH(init_kernel, (unsigned)((plane + 255) / 256), 256, e->stream, d);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(e->stream));
@@ -698,8 +793,9 @@ jr_status jr_engine_reset(jr_engine* e) {
 void jr_engine_destroy(jr_engine* e) {
   if (!e) return;
   if (getenv("JR_DEBUG_VARIANT"))
-    fprintf(stderr, "[jr] engine %p: %llu step launches, %llu role-sorted\n", (void*)e, (unsigned long long)e->launches_total,
-            (unsigned long long)e->launches_sorted);
+    fprintf(stderr, "[jr] engine %p: %llu step launches, %llu role-sorted, %llu split; %u CTA slots\n", (void*)e,
+            (unsigned long long)e->launches_total, (unsigned long long)e->launches_sorted,
+            (unsigned long long)e->launches_split, e->slots);
   cudaSetDevice(e->cfg.device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (void* p : e->allocs) cudaFree(p);

@@ -57,7 +57,9 @@ struct Dev {
   uint32_t Us, W;                  // shared-memory mailbox units per replica, table-cache entries (power of 2)
   uint32_t use_index;              // receivers use the delivery index (else scan whole mailboxes)
   uint32_t resident;               // bit r: replica index r is hosted here (others are inert, see jr_config)
-  uint32_t* scatter;               // set by a launch when some CTA has leaders on >= 2 replica indices
+  uint32_t* scatter;               // [0] set by a launch when some CTA has leaders on >= 2 replica indices;
+                                   // [1] task ticket counter of the running step launch (both zeroed per launch)
+  uint32_t* done;                  // [CTA-sized group block]: epoch + parts finished (split launches, see step_kernel)
   unsigned long long* prof;        // JR_PROFILE builds: cycle counters [role 3][slot 16] x {cycles, count}
   uint64_t seed, goff;
 };
@@ -89,6 +91,9 @@ struct StepParams {
   int cur;                       // outbox written by the first tick; 1-cur is read
   const jr_proposal* proposals;  // device, G entries for the first tick, or null
   uint32_t prop_stride;          // entries from one tick's proposals to the next (0: first tick only)
+  // Split launch: the n_ticks of every 32-group block are cut into n_parts consecutive runs, one CTA each
+  // (grid = n_blocks * n_parts).  Finer tasks fill the last wave of CTAs; see step_kernel.
+  uint32_t n_parts = 1, part_ticks = 0, n_blocks = 0, epoch = 0;
 };
 
 __host__ __device__ inline uint64_t mix64(uint64_t x) {
@@ -331,14 +336,24 @@ struct Replica {
     if (bid > maxkey) maxkey = bid;
   }
   // Launch start: invalidate, then pull the table tail (the blocks the steady state touches).
+  // The loads of a batch are independent and issued together: this runs once per task, in front of
+  // every tick, and a task is short when a launch is split (step_kernel).
   __device__ __forceinline__ void tc_prefetch() const {
     if (!L.W) return;
     for (uint32_t k = 0; k < L.W; ++k) L.tc[(k * R + r) * 32 + L.lane] = make_uint4(0xFFFFFFFFu, ABSENT, 0, 0);
-    for (uint32_t k = 0; k < L.W && k <= maxkey; ++k) {
-      const uint32_t bid = maxkey - k;
-      const uint32_t n = d.cnext[tix(bid)];
-      const uint64_t t = d.ctok[tix(bid)];
-      *tc_slot(bid) = make_uint4(bid, n, (uint32_t)t, (uint32_t)(t >> 32));
+    for (uint32_t k0 = 0; k0 < L.W && k0 <= maxkey; k0 += 4) {
+      uint32_t n[4];
+      uint64_t t[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (k0 + j < L.W && k0 + j <= maxkey) {
+          n[j] = d.cnext[tix(maxkey - k0 - j)];
+          t[j] = d.ctok[tix(maxkey - k0 - j)];
+        }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (k0 + j < L.W && k0 + j <= maxkey)
+          *tc_slot(maxkey - k0 - j) = make_uint4(maxkey - k0 - j, n[j], (uint32_t)t[j], (uint32_t)(t[j] >> 32));
     }
   }
   // Launch start: copy this lane's own previous-tick outbox into the shared mailbox.
@@ -348,14 +363,21 @@ struct Replica {
     const uint32_t cnt = deliver ? d.oc[prv][rg] : 0u;
     L.cin[r * 32 + L.lane] = cnt;
     const uint32_t n = cnt < L.Us ? cnt : L.Us;
-    for (uint32_t u = 0; u < n; ++u)
-      L.in[(u * R + r) * 32 + L.lane] = __ldg(d.ob[prv] + ((size_t)u * R + r) * d.Gp + g);
+    for (uint32_t u0 = 0; u0 < n; u0 += 4) {  // coherent loads: a split launch hands mailboxes over inside a kernel
+      uint4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (u0 + j < n) v[j] = __ldcg(d.ob[prv] + ((size_t)(u0 + j) * R + r) * d.Gp + g);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (u0 + j < n) L.in[((u0 + j) * R + r) * 32 + L.lane] = v[j];
+    }
     // the delivery index is derived data: rebuild it from the units just staged
     uint32_t m[R];
 #pragma unroll
     for (int t = 0; t < R; ++t) m[t] = 0;
     for (uint32_t u = 0; u < cnt;) {
-      const uint4 h = u < L.Us ? L.in[(u * R + r) * 32 + L.lane] : __ldg(d.ob[prv] + ((size_t)u * R + r) * d.Gp + g);
+      const uint4 h = u < L.Us ? L.in[(u * R + r) * 32 + L.lane] : __ldcg(d.ob[prv] + ((size_t)u * R + r) * d.Gp + g);
       const uint32_t kind = h.x & 15u, aux = (h.x >> 8) & 255u, to = h.x >> 16;
       const uint32_t bit = u < 31u ? (1u << u) : MK_SCAN;
       const bool noop = kind == JR_CMD_HEARTBEAT_RESPONSE && (((h.x >> 4) & 1u) || h.w == 0);

@@ -90,6 +90,8 @@ inline void __syncthreads() { jr_emu::sync(); }
 template <class T> inline T __ldcg(const T* p) { return *p; }
 template <class T> inline T __shfl_down_sync(unsigned, T v, int) { return v; }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p += v; return o; }  // CTAs run one after another
+inline void __threadfence() {}
 inline unsigned atomicOr(unsigned* p, unsigned v) { static pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER; pthread_mutex_lock(&mu); unsigned o = *p; *p |= v; pthread_mutex_unlock(&mu); return o; }
 inline unsigned atomicMax(unsigned* p, unsigned v) { unsigned o = *p; *p = std::max(o, v); return o; }
 using std::max;
