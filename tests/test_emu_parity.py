@@ -168,3 +168,29 @@ def test_three_single_node_engines_over_the_wire_match_resident_cluster():
 
 def test_leader_routed_tokens():
     parity.scenario_leader_routed_tokens(make_emu, make_oracle)
+
+
+@pytest.mark.parametrize("parts", [2, 3, 8])
+def test_split_launches_are_bit_identical(monkeypatch, parts):
+    """launch_step may cut a block's fused ticks into consecutive tasks handed over through global memory
+    ("Split launches"); any split must give the results of the unsplit launch."""
+    import random
+    monkeypatch.setenv("JR_PARTS", str(parts))
+    split = make_emu(40, 3, seed=9, flags=parity.FULL, fsm_units=512)
+    monkeypatch.setenv("JR_PARTS", "1")
+    whole = make_emu(40, 3, seed=9, flags=parity.FULL, fsm_units=512)
+    o = make_oracle(40, 3, seed=9, flags=parity.FULL, fsm_units=512)
+    rng = random.Random(parts)
+    props = [[(rng.choice([0, 1, 2, 3]), 7000 * k + g + 1) for g in range(40)] for k in range(19)]
+    for eng in (split, whole, o):
+        eng.run(100, 100, 23, 0)                      # odd tick counts: parts of unequal length, both mailbox parities
+        eng.run(2400, 100, 17, 2)
+        eng.run_proposals(4100, 100, props)
+        eng.leader_table()
+        eng.run_tokens(6000, 100, [[(k << 20) | (g + 1) for g in range(40)] for k in range(9)])
+    fa, fb, fo = ([parity.fsm_tuple(f) for f in e.drain_fsm()] for e in (split, whole, o))
+    assert fa == fb == fo
+    parity.compare_states(split, whole, chain_ids=80)
+    parity.compare_digests(split, whole)
+    parity.compare_states(split, o, chain_ids=80)
+    parity.compare_digests(split, o)

@@ -254,3 +254,24 @@ def test_leader_routed_tokens():
 
 def test_leader_routed_tokens_many_groups():
     parity.scenario_leader_routed_tokens(make_gpu, make_oracle, G=3000, R=3, seed=2)
+
+
+@pytest.mark.parametrize("parts", [2, 3, 8])
+def test_split_launches_are_bit_identical(monkeypatch, parts):
+    """A launch cut into ticket-ordered tasks ("Split launches") -- here forced, at a size where
+    the tasks of one block really run on different SMs at different times -- equals the unsplit launch and the oracle."""
+    G, R = 8192, 3
+    monkeypatch.setenv("JR_PARTS", str(parts))
+    split = make_gpu(G, R, seed=9, flags=abi.F_STREAM_DIGEST)
+    monkeypatch.setenv("JR_PARTS", "1")
+    whole = make_gpu(G, R, seed=9, flags=abi.F_STREAM_DIGEST)
+    o = make_oracle(G, R, seed=9, flags=abi.F_STREAM_DIGEST)
+    for eng in (split, whole, o):
+        eng.run(100, 100, 23, 0)
+        eng.run(2400, 100, 37, 2)
+        eng.leader_table()
+        eng.run_tokens(6100, 100, [[(k << 20) | (g + 1) for g in range(G)] for k in range(9)])
+    assert split.state_digest() == whole.state_digest() == o.state_digest()
+    assert split.stream_digest() == whole.stream_digest() == o.stream_digest()
+    assert split.leader_table() == whole.leader_table() == o.leader_table()
+    assert split.fault_count() == o.fault_count()
