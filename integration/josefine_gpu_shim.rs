@@ -153,6 +153,9 @@ extern "C" {
     fn jr_engine_create(cfg: *const JrConfig, out: *mut *mut c_void) -> c_int;
     fn jr_engine_destroy(e: *mut c_void);
     fn jr_step(e: *mut c_void, args: *mut JrStepArgs) -> c_int;
+    /// n_steps fused ticks; tokens[k * n_groups + g] (0 = none) goes to the leader the last jr_leader_table* call announced.
+    #[allow(dead_code)]
+    fn jr_run_tokens(e: *mut c_void, now0_ms: u64, dt_ms: u32, n_steps: u32, tokens: *const u64) -> c_int;
     fn jr_query(e: *mut c_void, group: u32, node: u32, out: *mut JrReplicaState) -> c_int;
     fn jr_last_error() -> *const c_char;
 }
