@@ -32,9 +32,18 @@ using namespace jr;
 // task waits for its block's part k-1 (release/acquire on d.done[block]) and then continues from the state
 // and mailboxes that task stored -- exactly what the next launch would do.  The point is the last wave:
 // 2048 equal tasks on 592 CTA slots take 4 rounds, 4096 half-length tasks take 7 half-rounds.
+#ifdef JR_EMU
+#ifdef JR_EMU_BREAK_HANDOFF  // negative control of tests/emu/tsan_split.cpp: the race detector must notice this
+#define JR_EMU_HANDOFF_ACQUIRE __ATOMIC_RELAXED
+#define JR_EMU_HANDOFF_RELEASE __ATOMIC_RELAXED
+#else
+#define JR_EMU_HANDOFF_ACQUIRE __ATOMIC_ACQUIRE
+#define JR_EMU_HANDOFF_RELEASE __ATOMIC_RELEASE
+#endif
+#endif
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
 #ifdef JR_EMU
-  return *reinterpret_cast<const volatile uint32_t*>(p);
+  return __atomic_load_n(p, JR_EMU_HANDOFF_ACQUIRE);
 #else
   uint32_t v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -43,7 +52,7 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
 }
 __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
 #ifdef JR_EMU
-  *reinterpret_cast<volatile uint32_t*>(p) = v;
+  __atomic_store_n(p, v, JR_EMU_HANDOFF_RELEASE);
 #else
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 #endif

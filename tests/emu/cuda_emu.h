@@ -51,24 +51,40 @@ inline void launch(unsigned grid, unsigned block, F&& body) {
     }
 }
 // Kernels that use __syncthreads() / dynamic shared memory: one OS thread per CUDA
-// thread of a CTA and a pthread barrier; CTAs run one after another.
+// thread of a CTA and a pthread barrier.  CTAs run one after another by default;
+// JR_EMU_CTAS=k runs them k at a time (each with its own shared memory and barrier),
+// which is what the ThreadSanitizer harness (tsan_split.cpp) uses to check the
+// split-launch hand-over between CTAs.
+inline unsigned concurrent_ctas() {
+  const char* v = getenv("JR_EMU_CTAS");
+  const int k = v ? atoi(v) : 1;
+  return (unsigned)(k < 1 ? 1 : (k > 16 ? 16 : k));
+}
 template <class F>
 inline void launch_coop(unsigned grid, unsigned block, size_t smem_bytes, F&& body) {
-  for (unsigned b = 0; b < grid; ++b) {
-    void* sm = aligned_alloc(64, (smem_bytes + 63) / 64 * 64 + 64);
-    pthread_barrier_t bar;
-    pthread_barrier_init(&bar, nullptr, block);
+  const unsigned K = concurrent_ctas();
+  for (unsigned b0 = 0; b0 < grid; b0 += K) {
+    const unsigned nb = std::min(K, grid - b0);
+    std::vector<void*> sm(nb);
+    std::vector<pthread_barrier_t> bar(nb);
+    for (unsigned i = 0; i < nb; ++i) {
+      sm[i] = aligned_alloc(64, (smem_bytes + 63) / 64 * 64 + 64);
+      pthread_barrier_init(&bar[i], nullptr, block);
+    }
     std::vector<std::thread> th;
-    th.reserve(block);
-    for (unsigned t = 0; t < block; ++t)
-      th.emplace_back([&, t]() {
-        Ctx& c = ctx();
-        c.gdim.x = grid; c.bdim.x = block; c.bid.x = b; c.tid.x = t; c.smem = sm; c.bar = &bar;
-        body();
-      });
+    th.reserve((size_t)nb * block);
+    for (unsigned i = 0; i < nb; ++i)
+      for (unsigned t = 0; t < block; ++t)
+        th.emplace_back([&, i, t]() {
+          Ctx& c = ctx();
+          c.gdim.x = grid; c.bdim.x = block; c.bid.x = b0 + i; c.tid.x = t; c.smem = sm[i]; c.bar = &bar[i];
+          body();
+        });
     for (auto& x : th) x.join();
-    pthread_barrier_destroy(&bar);
-    free(sm);
+    for (unsigned i = 0; i < nb; ++i) {
+      pthread_barrier_destroy(&bar[i]);
+      free(sm[i]);
+    }
   }
 }
 inline void sync() { if (ctx().bar) pthread_barrier_wait(ctx().bar); }
@@ -89,11 +105,15 @@ inline int __ffs(int v) { return __builtin_ffs(v); }
 inline void __syncthreads() { jr_emu::sync(); }
 template <class T> inline T __ldcg(const T* p) { return *p; }
 template <class T> inline T __shfl_down_sync(unsigned, T v, int) { return v; }
-inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
-inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p += v; return o; }  // CTAs run one after another
-inline void __threadfence() {}
-inline unsigned atomicOr(unsigned* p, unsigned v) { static pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER; pthread_mutex_lock(&mu); unsigned o = *p; *p |= v; pthread_mutex_unlock(&mu); return o; }
-inline unsigned atomicMax(unsigned* p, unsigned v) { unsigned o = *p; *p = std::max(o, v); return o; }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+#ifdef __SANITIZE_THREAD__
+inline void __threadfence() {}  // TSAN does not model fences; the hand-over's release store carries the ordering here
+#else
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+#endif
+inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+inline unsigned atomicMax(unsigned* p, unsigned v) { unsigned o = *p; *p = std::max(o, v); return o; }  // barrier-free kernels only
 using std::max;
 using std::min;
 
