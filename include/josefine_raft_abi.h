@@ -277,6 +277,9 @@ typedef struct jr_leader_entry {
 typedef struct jr_engine jr_engine;
 
 /* ---- lifecycle ------------------------------------------------------------- */
+/* JR_E_INVAL for a configuration RaftConfig::validate (config.rs:60-84) rejects where the field exists here
+ * (heartbeat_ms < 5, election_min_ms < 5), for an empty election range (follower.rs:103-108 gen_range would
+ * panic) and for sizes outside the engine's limits. */
 jr_status jr_engine_create(const jr_config* cfg, jr_engine** out);
 void      jr_engine_destroy(jr_engine* e);
 /* Back to the state right after jr_engine_create (every replica a fresh Follower with

@@ -654,6 +654,9 @@ jr_status jr_engine_create(const jr_config* cfg, jr_engine** out) {
   if (cfg->abi_version != JR_ABI_VERSION) { set_err("abi_version mismatch"); return JR_E_INVAL; }
   if (cfg->n_replicas < 1 || cfg->n_replicas > JR_MAX_REPLICAS || cfg->n_groups < 1) { set_err("bad G/R"); return JR_E_INVAL; }
   if (cfg->election_max_ms <= cfg->election_min_ms) { set_err("empty election timeout range"); return JR_E_INVAL; }
+  // RaftConfig::validate, config.rs:70-75 (the rules that have a counterpart here)
+  if (cfg->heartbeat_ms < 5) { set_err("heartbeat timeout is too low"); return JR_E_INVAL; }
+  if (cfg->election_min_ms < 5) { set_err("election timeout is too low"); return JR_E_INVAL; }
   if (cfg->chain_capacity < 2 || cfg->chain_capacity > 0x7fffffffu) { set_err("chain_capacity out of range"); return JR_E_INVAL; }
   if (cfg->mailbox_units < 8 || cfg->fsm_units < 1) { set_err("mailbox_units >= 8, fsm_units >= 1"); return JR_E_INVAL; }
   int ndev = 0;

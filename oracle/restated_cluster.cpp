@@ -308,6 +308,7 @@ jr_status jro_create(const jr_config* cfg, unsigned n_threads, jro_cluster** out
   if (cfg->abi_version != JR_ABI_VERSION) return JR_E_INVAL;
   if (cfg->n_replicas < 1 || cfg->n_replicas > JR_MAX_REPLICAS || cfg->n_groups < 1) return JR_E_INVAL;
   if (cfg->election_max_ms <= cfg->election_min_ms) return JR_E_INVAL;
+  if (cfg->heartbeat_ms < 5 || cfg->election_min_ms < 5) return JR_E_INVAL;  // RaftConfig::validate, config.rs:70-75
   if (cfg->chain_capacity < 2) return JR_E_INVAL;
   auto* c = new jro_cluster();
   c->cfg = *cfg;

@@ -190,6 +190,40 @@ def kat_chain_compact(make):
     assert present == [True, True, True, True, False, True, True]
 
 
+def kat_follower_apply_append_entries(make):
+    """follower.rs:416-425 `apply_append_entries`: despite its name the reference test is the election of a
+    lone node after the timeout (same body as apply_tick, follower.rs:405-414)."""
+    api = make(1, 1, flags=CAPTURE)
+    timeout = api.query(0, 1).election_timeout_ms
+    api.step(1)
+    assert api.handle(0, 1).is_follower()
+    api.step(timeout + 1)
+    assert api.handle(0, 1).is_leader()
+
+
+def kat_mod_send_all(make):
+    """mod.rs:533-552 `send_all`: a broadcast is Message{from: Peer(id), to: Peers, command} (mod.rs:396-400).
+    `send_all(Noop)` itself has no caller; the candidate's VoteRequest broadcast goes through the same function."""
+    api = make(1, 3, flags=CAPTURE)
+    res = api.apply(Command.timeout(0, 2))
+    assert res.messages and all(m.kind == abi.CMD_VOTE_REQUEST for m in res.messages)
+    for m in res.messages:
+        assert (m.from_kind, m.from_id, m.to_kind) == (abi.ADDR_PEER, 2, abi.ADDR_PEERS)
+
+
+def kat_config_validation(make):
+    """config.rs:128-156: `default()` builds, `validation()` rejects heartbeat_timeout = 1 ms."""
+    from josefine_b200 import RaftError
+    make(1, 3)                                                   # defaults: 100 ms heartbeat, 500..1000 ms election
+    for bad in (dict(heartbeat_ms=1), dict(election_min_ms=4, election_max_ms=9)):
+        try:
+            make(1, 3, **bad)
+        except RaftError as e:
+            assert e.status == abi.E_INVAL
+        else:
+            raise AssertionError(f"{bad} must be rejected")
+
+
 ALL_KATS = [v for k, v in sorted(globals().items()) if k.startswith("kat_")]
 
 
@@ -219,6 +253,40 @@ def kat_single_resident_node_with_remote_peers(make):
     st = api.query(0, 1)
     assert (st.commit, st.progress_head[1], st.progress_replicate & 0b010) == (1, 1, 0b010)
     assert api.query(0, 2).alive == 0 and api.query(0, 3).alive == 0
+
+
+def kat_follower_apply_append_entries(make):
+    """follower.rs:416-425 `apply_append_entries`: despite its name the reference test is the election of a
+    lone node after the timeout (same body as apply_tick, follower.rs:405-414)."""
+    api = make(1, 1, flags=CAPTURE)
+    timeout = api.query(0, 1).election_timeout_ms
+    api.step(1)
+    assert api.handle(0, 1).is_follower()
+    api.step(timeout + 1)
+    assert api.handle(0, 1).is_leader()
+
+
+def kat_mod_send_all(make):
+    """mod.rs:533-552 `send_all`: a broadcast is Message{from: Peer(id), to: Peers, command} (mod.rs:396-400).
+    `send_all(Noop)` itself has no caller; the candidate's VoteRequest broadcast goes through the same function."""
+    api = make(1, 3, flags=CAPTURE)
+    res = api.apply(Command.timeout(0, 2))
+    assert res.messages and all(m.kind == abi.CMD_VOTE_REQUEST for m in res.messages)
+    for m in res.messages:
+        assert (m.from_kind, m.from_id, m.to_kind) == (abi.ADDR_PEER, 2, abi.ADDR_PEERS)
+
+
+def kat_config_validation(make):
+    """config.rs:128-156: `default()` builds, `validation()` rejects heartbeat_timeout = 1 ms."""
+    from josefine_b200 import RaftError
+    make(1, 3)                                                   # defaults: 100 ms heartbeat, 500..1000 ms election
+    for bad in (dict(heartbeat_ms=1), dict(election_min_ms=4, election_max_ms=9)):
+        try:
+            make(1, 3, **bad)
+        except RaftError as e:
+            assert e.status == abi.E_INVAL
+        else:
+            raise AssertionError(f"{bad} must be rejected")
 
 
 ALL_KATS = [v for k, v in sorted(globals().items()) if k.startswith("kat_")]

@@ -25,6 +25,13 @@ def test_block_record_bytes():
             persist.decode_block(bad)
 
 
+def test_reference_block_id_serde():
+    # chain.rs:345-350: bincode round trip of BlockId::new(0)
+    rec = persist.encode_block(0, 0, b"")
+    assert rec[:16].hex() == "0800000000000000" + "00" * 8          # bincode(BlockId(0)): u64 length 8 + the 8 id bytes
+    assert persist.decode_block(rec)[0] == 0
+
+
 def test_commit_key_sorts_inside_the_block_keyspace():
     # D6: b"commit" = 63 6f 6d 6d 69 74 lies between block ids 0x636f6d6d6973ffff.. and 0x636f6d6d69740000..
     assert persist.block_key(1) < persist.COMMIT_KEY < persist.block_key(0x64 << 56)

@@ -98,6 +98,17 @@ def test_client_request_and_response_bytes():
     assert '"res":{"Err":{}}' in body(c.encode_frame(rp))
 
 
+def test_reference_tcp_tests_frame():
+    # tcp.rs:171-194 `read_message` and tcp.rs:198-229 `send_message` both move
+    # Message::new(Address::Peer(1), Address::Peer(2), Command::Tick) as serde_json::to_string in one frame
+    c = Codec()
+    m = peer_msg(Command.tick(0, 2), 1, 2)
+    frame = c.encode_frame(m)
+    assert body(frame) == '{"from":{"Peer":1},"to":{"Peer":2},"command":"Tick"}'
+    back, rest = c.decode_frame(frame)
+    assert rest == b"" and msg_tuple(back) == msg_tuple(m)
+
+
 def all_kinds(c: Codec):
     t = c.intern_payload(b"abc")
     q = c.intern_request(b"req")
