@@ -418,6 +418,10 @@ class PyCluster:
     """Same surface as RaftApi (the parts the differential test uses)."""
 
     def __init__(self, cfg: abi.Config):
+        # RaftConfig::validate, config.rs:70-75 (heartbeat / election timeout floors); empty gen_range, follower.rs:103-108
+        if cfg.heartbeat_ms < 5 or cfg.election_min_ms < 5 or cfg.election_max_ms <= cfg.election_min_ms:
+            from josefine_b200.raft import RaftError
+            raise RaftError(abi.E_INVAL, "PyCluster", "configuration does not validate")
         self.cfg = cfg
         self.n_groups, self.n_replicas = cfg.n_groups, cfg.n_replicas
         self.nodes = [[PyNode(cfg, g, n) for n in range(1, cfg.n_replicas + 1)] for g in range(cfg.n_groups)]
