@@ -476,7 +476,9 @@ def main():
                 "algorithmic_bytes_per_launch": abytes * G * S,
                 "note": f"one launch = {S} fused group-ticks of all {G} groups; replica state stays in registers and the "
                         "mailboxes in shared memory across those ticks, so DRAM traffic is far below the algorithmic "
-                        "bytes (which count every tick's state + mailbox movement); see profiles/"}
+                        "bytes (which count every tick's state + mailbox movement); the engine runs a block's ticks as "
+                        "two ticket-ordered tasks when that fills the last wave of CTAs (DESIGN.md, Split launches); "
+                        "see profiles/"}
     cpu = None
     if not args.no_cpu:
         cores = best_cpu_threads(R, effective_cores())
