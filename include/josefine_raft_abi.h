@@ -21,6 +21,15 @@
  *   jr_compact         <- Chain::compact                  src/raft/chain.rs:239-253
  *   jr_leader_table*   <- Leader::write_state             src/raft/leader.rs:101-121
  *   jr_set_alive       <- process death (no reference API; a node that stops calling apply)
+ *   jr_fsm_records_*   <- the receiving end of fsm_tx         src/raft/fsm.rs:52-56 (Driver::run's rx.recv loop),
+ *                         fed by leader.rs:87-99,177-197 and follower.rs:198-207; compact form, see jr_fsm_record
+ *   jr_fsm_expand      <- Instruction::{Apply,Notify}         src/raft/fsm.rs:19-29, one per record element
+ *   jr_node_restart    <- RaftHandle::new over an existing data directory: Chain::new reopening a
+ *                         persisted chain                     src/raft/chain.rs:117-137
+ *   jr_query_many / jr_chain_read_many <- the same pub fields, for many replicas in one call
+ *   jr_engine_save / jr_engine_restore <- checkpoint of the whole engine (no reference API: sled persistence of
+ *                         every node at once, chain.rs:119-123,198, plus the volatile State the reference loses)
+ *   jr_truncate        <- no reference API (deviation D7)
  *
  * One engine = G independent Raft groups x R replicas, all resident in one GPU's
  * HBM.  The reference is one group, one node per process; the group dimension is
@@ -44,6 +53,13 @@
  *       block hits it and panics in bincode (chain.rs:222-226).  That is
  *       reproduced only when JR_F_SLED_COMMIT_KEY_STRICT is set; by default the
  *       block map holds blocks only.
+ *   D7  log truncation (opt-in, only through jr_truncate): the reference never removes a block
+ *       except in Chain::compact (chain.rs:239-253, never called outside its test), so its sled
+ *       tree grows forever.  jr_truncate drops, per group, every block below
+ *       floor = min(commit of the live replicas) - margin from ALL replicas of the group; block ids
+ *       must then lie in [floor, floor + chain_capacity).  Removed keys read as absent, exactly as
+ *       if sled had lost them (has() false, range() skips them).  An engine that never calls
+ *       jr_truncate behaves as before (floor 0).
  *
  * All structs are plain data, little endian, naturally aligned.  No callbacks.
  * Buffers passed to jr_step are HOST memory owned by the caller.
@@ -58,7 +74,7 @@
 extern "C" {
 #endif
 
-#define JR_ABI_VERSION 1u
+#define JR_ABI_VERSION 2u
 
 /* ---- limits ------------------------------------------------------------ */
 #define JR_MAX_REPLICAS 8u        /* R <= 8 (reference configs use 3, 5, 7)         */
@@ -112,10 +128,14 @@ enum {
   JR_FAULT_CANDIDATE_TICK_ELECTED = 7,/* panic!("this should never happen"), candidate.rs:63 */
   JR_FAULT_RANGE_COMMIT_KEY = 8,      /* bincode panic on the "commit" key, chain.rs:222-226 (D6) */
   /* 64..: engine limits, not reference behaviour */
-  JR_FAULT_ENGINE_CHAIN_CAPACITY = 64,   /* block id >= chain_capacity                       */
+  JR_FAULT_ENGINE_CHAIN_CAPACITY = 64,   /* block id outside [floor, floor + chain_capacity) (D4, D7) */
   JR_FAULT_ENGINE_MAILBOX_OVERFLOW = 65, /* a replica emitted more than mailbox_units units  */
-  JR_FAULT_ENGINE_FSM_OVERFLOW = 66,     /* more than fsm_units instructions in one launch   */
-  JR_FAULT_ENGINE_QUEUE_OVERFLOW = 67    /* more than JR_CLIENT_QUEUE_CAP queued requests    */
+  JR_FAULT_ENGINE_FSM_OVERFLOW = 66,     /* retired in ABI 2: a full Instruction FIFO drops records and the drain
+                                          * returns JR_E_CAPACITY; observing a node never changes consensus     */
+  JR_FAULT_ENGINE_QUEUE_OVERFLOW = 67    /* more than JR_CLIENT_QUEUE_CAP queued requests: the reference's
+                                          * queued_reqs is an unbounded Vec (follower.rs:23); this engine bounds it,
+                                          * so the (JR_CLIENT_QUEUE_CAP+1)-th ClientRequest a leaderless follower or
+                                          * a candidate receives stops that replica                              */
 };
 
 /* ---- engine flags ---------------------------------------------------------- */
@@ -137,15 +157,19 @@ typedef struct jr_config {
   uint32_t election_min_ms;    /* State::min_election_timeout, mod.rs:318 (500)          */
   uint32_t election_max_ms;    /* State::max_election_timeout, mod.rs:319 (1000)         */
   uint32_t heartbeat_ms;       /* RaftConfig::heartbeat_timeout, config.rs:104 (100)     */
-  uint32_t chain_capacity;     /* blocks per replica block table (D4)                    */
+  uint32_t chain_capacity;     /* block ids one replica's table may span above the floor (D4, D7) */
   uint32_t mailbox_units;      /* 16-byte units one replica may emit per step            */
-  uint32_t fsm_units;          /* Instructions one replica may emit per launch           */
+  uint32_t fsm_units;          /* jr_fsm_record slots per replica between two drains      */
   uint32_t flags;              /* JR_F_*                                                 */
   uint32_t resident_mask;      /* bit (id-1): node id is hosted by this engine; 0 = all R.
                                 * A josefine process hosts ONE node per group (RaftConfig::id,
                                 * config.rs:23) and reaches the others over TCP: non-resident
                                 * nodes are never stepped, and mail addressed to them is only
                                 * returned through out_msgs for the host to forward.           */
+  uint32_t fsm_host_records;   /* records one jr_fsm_records_async batch may hold (pinned host memory, two
+                                * buffers of this size); 0 = max(2 * n_groups * n_replicas + 1024,
+                                * min(n_groups * n_replicas * fsm_units, 65536))                            */
+  uint32_t reserved0;
 } jr_config;
 
 /* Block (src/raft/chain.rs:86-91); `data` is the payload token (D5). */
@@ -200,6 +224,42 @@ typedef struct jr_fsm_instr {
   uint32_t client_id;
   jr_block block;       /* Apply: the Block; Notify: block.id = block_id, block.data = request token */
 } jr_fsm_instr;
+
+/*
+ * Compact form of a replica's Instruction stream (fsm_tx; fsm.rs:19-29).  One record = a run:
+ *   JR_FSMR_APPLY    `count` Apply instructions of blocks id0, id0+1, ...; element i carries
+ *                    Block{id0+i, next_i, tok0 + i*stride} with next_i = id0+i-1.  count == 1 is the
+ *                    general case: any block, next = (uint32_t)stride, data = tok0.
+ *   JR_FSMR_NOTIFY   `count` Notify instructions for block ids id0, id0+1, ..., all with client address
+ *                    (addr >> 16, addr & 0xffff); element i carries request token tok0 + i*stride.
+ *   JR_FSMR_PATTERN  interleaving: bit b (0 <= b < count <= 64) of tok0 set = the (id0+b)-th Instruction this
+ *                    replica emitted since the last drain is a Notify.  Positions no PATTERN record marks are
+ *                    Apply.  Applies and Notifies each appear in record order, so the records of one replica
+ *                    reproduce its stream exactly (jr_fsm_expand does).
+ * A steady-state follower needs one APPLY record per drain, a leader one APPLY + one NOTIFY + one PATTERN per
+ * 64 Instructions, whatever the number of fused ticks -- when tokens advance by a constant stride.
+ */
+enum { JR_FSMR_APPLY = 0, JR_FSMR_NOTIFY = 1, JR_FSMR_PATTERN = 2 };
+typedef struct jr_fsm_record {
+  uint32_t group;
+  uint32_t hdr;      /* bits 0-1 JR_FSMR_*, bits 2-4 node id - 1, bits 8-31 count */
+  uint32_t id0;
+  uint32_t addr;
+  uint64_t tok0;
+  uint64_t stride;
+} jr_fsm_record;
+#define JR_FSMR_KIND(hdr) ((hdr) & 3u)
+#define JR_FSMR_NODE(hdr) ((((hdr) >> 2) & 7u) + 1u)
+#define JR_FSMR_COUNT(hdr) ((hdr) >> 8)
+
+/* What one jr_fsm_records_async batch holds. */
+typedef struct jr_fsm_batch {
+  uint64_t n_records;                          /* records in the batch, sorted by (node, group), FIFO per replica */
+  uint64_t n_dropped;                          /* records lost to a full per-replica FIFO or a full batch buffer  */
+  uint64_t n_instructions;                     /* Instructions the records stand for                              */
+  uint32_t node_offset[JR_MAX_REPLICAS + 1];   /* records of node n are [node_offset[n-1], node_offset[n])        */
+  uint32_t reserved;
+} jr_fsm_batch;
 
 /* One dense client proposal per group: ClientRequest applied to `node` (0 = none).
  * Reference: event_loop client arm, src/raft/server.rs:156-160. */
@@ -265,6 +325,7 @@ typedef struct jr_replica_state {
   uint8_t  fault;             /* JR_FAULT_*                                */
   uint8_t  alive;
   uint8_t  n_queued;          /* queued_reqs.len()                         */
+  uint64_t chain_floor;       /* D7: ids below this were truncated (0 = never) */
 } jr_replica_state;
 
 /* Leader::write_state record (leader.rs:103-107), one per group. */
@@ -298,7 +359,11 @@ jr_status jr_step(jr_engine* e, jr_step_args* args);
 /*
  * n_steps fused steps with no host traffic: step k uses now = now0 + k*dt_ms and
  * flags DELIVER|TICK (+SYNTH_PROPOSALS when n_synth > 0).  Asynchronous on the
- * engine stream.  Equivalent to n_steps jr_step calls, bit for bit.
+ * engine stream.  Replica state, block tables, mailboxes and digests are bit for bit
+ * those of n_steps jr_step calls.  Instructions are not returned here: with
+ * JR_F_CAPTURE_FSM they accumulate, run-length encoded, in a per-replica FIFO of
+ * fsm_units records until jr_fsm_records_async / jr_drain_fsm takes them (a jr_step
+ * call starts its own FIFO and returns its Instructions itself).
  */
 jr_status jr_run(jr_engine* e, uint64_t now0_ms, uint32_t dt_ms, uint32_t n_steps, uint32_t n_synth);
 /*
@@ -318,20 +383,49 @@ jr_status jr_run_proposals(jr_engine* e, uint64_t now0_ms, uint32_t dt_ms, uint3
  * last learnt (Leader::write_state, leader.rs:101-121) before RaftClient::propose (client.rs:35-37)
  * reaches apply_client_request (leader.rs:177-194).  A group with no announced leader (also: no
  * announce since create / reset) drops its tokens, like a request sent nowhere: no Notify follows.
- * A stale route lands on a follower, which proxies or queues it (follower.rs:258-270).
+ * A stale route lands on a follower, which proxies it to its leader or, leaderless, queues it
+ * (follower.rs:258-270) -- at most JR_CLIENT_QUEUE_CAP requests, see JR_FAULT_ENGINE_QUEUE_OVERFLOW.
  * Bit for bit equal to jr_run_proposals with proposals[k*G+g] = {tokens[k*G+g], route[g]}, at half
  * the host-to-device bytes (8 instead of 16 per group-tick).  Same asynchrony rules.
  */
 jr_status jr_run_tokens(jr_engine* e, uint64_t now0_ms, uint32_t dt_ms, uint32_t n_steps,
                         const uint64_t* tokens);
-/* Drop and return the Instructions accumulated by jr_run (same order as jr_step). */
+/* Take the Instructions accumulated by jr_run* since the last drain, expanded: group-major, node ascending,
+ * FIFO per node (the order jr_step returns).  *n = Instructions there were; JR_E_CAPACITY if `out` is too
+ * small or records were dropped (fsm_units / fsm_host_records too small).  Synchronous; the FIFOs are empty
+ * afterwards.  Small deployments and tests -- the batched path below is the fast one. */
 jr_status jr_drain_fsm(jr_engine* e, jr_fsm_instr* out, size_t cap, size_t* n);
+/*
+ * The batched output path.  jr_fsm_records_async ENQUEUES, after everything submitted so far: pack all records
+ * accumulated since the last drain into one dense array sorted by (node, group) and write it to the engine's
+ * next pinned host buffer (two buffers; the kernel writes host memory directly, no staging copy).  The FIFOs are
+ * empty afterwards.  jr_fsm_records_wait blocks until the OLDEST outstanding batch has landed and returns it:
+ * `*records` points into the engine's buffer and stays valid until the second jr_fsm_records_async call after
+ * this one.  JR_E_CAPACITY (batch still returned) if records were dropped.  At most two batches may be
+ * outstanding.  Requires JR_F_CAPTURE_FSM.
+ */
+jr_status jr_fsm_records_async(jr_engine* e);
+jr_status jr_fsm_records_wait(jr_engine* e, const jr_fsm_record** records, jr_fsm_batch* batch);
+/*
+ * Pure host function (no device, no engine): records (any order across replicas, FIFO per replica) ->
+ * Instructions, group-major, node ascending, FIFO per node.  out may be NULL to size the buffer.
+ * JR_E_CAPACITY if cap is too small (*n_out = needed), JR_E_INVAL for a malformed record set.
+ */
+jr_status jr_fsm_expand(const jr_fsm_record* records, size_t n_records, uint32_t n_groups, uint32_t n_replicas,
+                        jr_fsm_instr* out, size_t cap, size_t* n_out);
 
 /* ---- introspection --------------------------------------------------------- */
 jr_status jr_query(jr_engine* e, uint32_t group, uint32_t node, jr_replica_state* out);
 /* blocks with first_id <= id < first_id+n of one replica; present[i]=0 if absent. */
 jr_status jr_chain_read(jr_engine* e, uint32_t group, uint32_t node, uint64_t first_id,
                         uint32_t n, jr_block* out, uint8_t* present);
+/* The same for n replicas in ONE kernel + ONE copy: replica i is (groups[i], nodes[i]). */
+jr_status jr_query_many(jr_engine* e, const uint32_t* groups, const uint32_t* nodes, size_t n,
+                        jr_replica_state* out);
+/* n block-table reads in one kernel + one copy: request i reads ids [first_id[i], first_id[i] + count[i]) of
+ * replica (groups[i], nodes[i]); results are concatenated in request order. */
+jr_status jr_chain_read_many(jr_engine* e, const uint32_t* groups, const uint32_t* nodes, const uint64_t* first_id,
+                             const uint32_t* count, size_t n, jr_block* out, uint8_t* present);
 /* order-independent digest of all replica state + block tables, computed on the device */
 jr_status jr_state_digest(jr_engine* e, uint64_t* out);
 /* cumulative digests of every Message / Instruction emitted so far (order sensitive per replica) */
@@ -342,6 +436,26 @@ jr_status jr_fault_count(jr_engine* e, uint64_t* n_faulted);
 /* ---- maintenance ----------------------------------------------------------- */
 jr_status jr_compact(jr_engine* e);                                    /* every replica */
 jr_status jr_set_alive(jr_engine* e, uint32_t group, uint32_t node, int alive);
+/* D7: per group, floor = max(old floor, min(commit of the live, unfaulted replicas) - margin); every block
+ * below it is dropped from all replicas of the group.  Groups without a live replica keep their floor.
+ * Asynchronous on the engine stream. */
+jr_status jr_truncate(jr_engine* e, uint32_t margin);
+/*
+ * Node restart: replica (group, node) becomes what RaftHandle::new builds over an existing data directory
+ * (mod.rs:428-435 -> follower.rs:68-95 -> Chain::new, chain.rs:117-137): a Follower with State::default
+ * (term 0, voted_for None -- the reference does not persist them), election timer started at now_ms,
+ * the block table = `blocks`, commit = head = id_gen = `commit` (so the first append of a restarted
+ * leader-to-be asserts id > head and faults, SURVEY note N2).  commit == 0 runs Chain::init (genesis
+ * block 0 -> 0 is (re)written, id_gen = 1).  `commit_key` = the sled "commit" key exists (D6).
+ * The replica's mailbox and client queue are emptied; it is alive and unfaulted afterwards.
+ */
+jr_status jr_node_restart(jr_engine* e, uint32_t group, uint32_t node, uint64_t now_ms, const jr_block* blocks,
+                          size_t n_blocks, uint64_t commit, int commit_key);
+/* Checkpoint: everything the engine holds (state planes, block tables, mailboxes, FIFOs, routing, counters).
+ * jr_engine_save_size -> bytes needed; restore needs an engine created with the same jr_config. */
+jr_status jr_engine_save_size(jr_engine* e, size_t* bytes);
+jr_status jr_engine_save(jr_engine* e, void* buf, size_t cap);
+jr_status jr_engine_restore(jr_engine* e, const void* buf, size_t bytes);
 /* Silence the current leader of every group g with hash(seed,g,salt) % 1000 < permille. */
 jr_status jr_kill_leaders(jr_engine* e, uint64_t salt, uint32_t permille, uint64_t* n_killed);
 

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_REPLICAS = 8
 MAX_AE_BLOCKS = 5
 MAX_NODE_ID = 65534
@@ -67,6 +67,7 @@ class Config(C.Structure):
         ("heartbeat_ms", C.c_uint32), ("chain_capacity", C.c_uint32),
         ("mailbox_units", C.c_uint32), ("fsm_units", C.c_uint32),
         ("flags", C.c_uint32), ("resident_mask", C.c_uint32),
+        ("fsm_host_records", C.c_uint32), ("reserved0", C.c_uint32),
     ]
 
 
@@ -117,6 +118,7 @@ class ReplicaState(C.Structure):
         ("heartbeat_time_ms", C.c_uint64), ("votes_seen", C.c_uint32), ("votes_granted", C.c_uint32),
         ("progress_head", C.c_uint64 * MAX_REPLICAS), ("progress_replicate", C.c_uint32),
         ("role", C.c_uint8), ("fault", C.c_uint8), ("alive", C.c_uint8), ("n_queued", C.c_uint8),
+        ("chain_floor", C.c_uint64),
     ]
 
     def as_dict(self) -> dict:
@@ -127,14 +129,41 @@ class ReplicaState(C.Structure):
         return d
 
 
+FSMR_APPLY, FSMR_NOTIFY, FSMR_PATTERN = 0, 1, 2
+
+
+class FsmRecord(C.Structure):
+    """jr_fsm_record: one run of a replica's Instruction stream (layout normative in the header)."""
+    _fields_ = [("group", C.c_uint32), ("hdr", C.c_uint32), ("id0", C.c_uint32), ("addr", C.c_uint32),
+                ("tok0", C.c_uint64), ("stride", C.c_uint64)]
+
+    @property
+    def kind(self) -> int:
+        return self.hdr & 3
+
+    @property
+    def node(self) -> int:
+        return ((self.hdr >> 2) & 7) + 1
+
+    @property
+    def count(self) -> int:
+        return self.hdr >> 8
+
+
+class FsmBatch(C.Structure):
+    _fields_ = [("n_records", C.c_uint64), ("n_dropped", C.c_uint64), ("n_instructions", C.c_uint64),
+                ("node_offset", C.c_uint32 * (MAX_REPLICAS + 1)), ("reserved", C.c_uint32)]
+
+
 class LeaderEntry(C.Structure):
     _fields_ = [("term", C.c_uint64), ("leader_id", C.c_uint32), ("commit", C.c_uint32)]
 
 
 # sizes the header implies (checked in tests/test_abi.py against offsetof-free arithmetic)
 EXPECTED_SIZES = {
-    "Config": 64, "Block": 24, "Msg": 64 + 24 * MAX_AE_BLOCKS, "FsmInstr": 16 + 24,
-    "Proposal": 16, "LeaderEntry": 16,
+    "Config": 72, "Block": 24, "Msg": 64 + 24 * MAX_AE_BLOCKS, "FsmInstr": 16 + 24,
+    "Proposal": 16, "LeaderEntry": 16, "FsmRecord": 32, "FsmBatch": 24 + 4 * (MAX_REPLICAS + 1) + 4,
+    "ReplicaState": 160,
 }
 
 # every symbol include/josefine_raft_abi.h declares
@@ -143,7 +172,8 @@ ENGINE_SYMBOLS = [
     "jr_last_error", "jr_config_default", "jr_step", "jr_run", "jr_run_proposals", "jr_run_tokens", "jr_drain_fsm", "jr_query",
     "jr_chain_read", "jr_state_digest", "jr_stream_digest", "jr_fault_count", "jr_compact",
     "jr_set_alive", "jr_kill_leaders", "jr_leader_table_device", "jr_leader_table", "jr_leader_table_async", "jr_leader_table_wait",
-    "jr_election_timeout",
+    "jr_election_timeout", "jr_fsm_records_async", "jr_fsm_records_wait", "jr_fsm_expand", "jr_query_many",
+    "jr_chain_read_many", "jr_truncate", "jr_node_restart", "jr_engine_save_size", "jr_engine_save", "jr_engine_restore",
 ]
 
 
@@ -163,6 +193,7 @@ def default_config(n_groups: int, n_replicas: int, **kw) -> Config:
     cfg.mailbox_units = 64
     cfg.fsm_units = 64
     cfg.flags = 0
+    cfg.fsm_host_records = 0
     for k, v in kw.items():
         if not hasattr(cfg, k):
             raise AttributeError(k)

@@ -58,8 +58,13 @@ __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
 #endif
 }
 
+// Resident CTAs the register allocation must allow (the kernel is latency bound: occupancy is throughput).
+// R = 5 (160 threads) holds 4 CTAs per SM at 96 registers, what ptxas picked on its own before the stream encoder
+// was added; the other sizes keep their natural allocation.
+constexpr int step_min_ctas(int R) { return (R == 4 || R == 5) ? 4 : 1; }
+
 template <int R, bool SORTED>
-__global__ void __launch_bounds__(32 * R) step_kernel(const Dev d, const StepParams p0) {
+__global__ void __launch_bounds__(32 * R, step_min_ctas(R)) step_kernel(const Dev d, const StepParams p0) {
   JR_DYN_SMEM(uint4, smem);
   const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31u;
   StepParams p = p0;
@@ -108,8 +113,10 @@ __global__ void __launch_bounds__(32 * R) step_kernel(const Dev d, const StepPar
   L.tc = smem + 2 * box;
   L.cin = reinterpret_cast<uint32_t*>(smem + 2 * box + d.W * R * 32);
   L.cout = L.cin + R * 32;
-  L.mk_in = L.cout + R * 32;
+  L.mk_in = reinterpret_cast<uint16_t*>(L.cout + R * 32);
   L.mk_out = L.mk_in + R * R * 32;
+  L.fsm = reinterpret_cast<uint32_t*>(L.mk_out + R * R * 32);   // only there (and only touched) with JR_F_CAPTURE_FSM
+  L.nt = 32 * R; L.tid = threadIdx.x;
   L.Us = d.Us; L.W = d.W; L.lane = lane;
   Replica<R, SORTED> rep(d, L, r, g);
   rep.now = p.now;
@@ -138,7 +145,7 @@ __global__ void __launch_bounds__(32 * R) step_kernel(const Dev d, const StepPar
     // next tick: what was written becomes the inbox
     uint4* tb = L.in; L.in = L.out; L.out = tb;
     uint32_t* tcn = L.cin; L.cin = L.cout; L.cout = tcn;
-    uint32_t* tmk = L.mk_in; L.mk_in = L.mk_out; L.mk_out = tmk;
+    uint16_t* tmk = L.mk_in; L.mk_in = L.mk_out; L.mk_out = tmk;
     rep.cur ^= 1;
     rep.ocnt = 0;
     rep.ocnt0 = 0;
@@ -179,10 +186,12 @@ template <int R>
 __global__ void inject_kernel(const Dev d, const StepParams p, const jr_msg* msgs, const uint4* targets,
                               uint32_t n_targets) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ uint32_t fsm_state[FS_WORDS * 64];   // launched with 64 threads per CTA
+  Local L;
+  L.in = L.out = L.tc = nullptr; L.cin = L.cout = nullptr; L.mk_in = L.mk_out = nullptr; L.Us = 0; L.W = 0; L.lane = 0;
+  L.fsm = fsm_state; L.nt = 64; L.tid = threadIdx.x;
   if (i >= n_targets) return;
   const uint4 t = targets[i];
-  Local L;
-  L.in = L.out = L.tc = nullptr; L.cin = L.cout = L.mk_in = L.mk_out = nullptr; L.Us = 0; L.W = 0; L.lane = 0;
   Replica<R> rep(d, L, t.y, t.x);
   rep.now = p.now;
   rep.cur = p.cur;
@@ -219,7 +228,8 @@ __global__ void init_kernel(const Dev d) {
   d.ctok[i] = 0;
   d.oc[0][i] = 0;
   d.oc[1][i] = 0;
-  d.fc[i] = 0;
+  d.fc[i] = make_uint2(0, 0);
+  if (r == 0) d.tb[g] = 0;
   const uint64_t tag = mix64(((d.goff + g) << 8) | (r + 1));
   d.dg[i] = make_uint4((uint32_t)tag, (uint32_t)(tag >> 32), (uint32_t)tag, (uint32_t)(tag >> 32));
   d.cn[i] = make_uint2(0, 0);
@@ -235,10 +245,12 @@ __global__ void compact_kernel(const Dev d) {
   if (((meta >> 8) & 255u) != 0 || ((meta >> 27) & 1u)) return;  // faulted or dead
   bool have = false;
   uint32_t expect = 0;
-  for (uint32_t b = c.y; b-- > 0;) {  // ids in [0, commit), descending
-    const uint32_t nx = d.cnext[(size_t)b * plane + i];
+  const uint32_t floor = d.tb[i % d.Gp];
+  for (uint32_t b = c.y; b-- > floor;) {  // ids in [0, commit), descending; nothing is left below the floor (D7)
+    if (b - floor >= d.cap) continue;    // (a commit past the window cannot exist: chain_commit needs the block)
+    const uint32_t nx = d.cnext[(size_t)(b & d.capm) * plane + i];
     if (nx == ABSENT) continue;
-    if (have && b != expect) d.cnext[(size_t)b * plane + i] = ABSENT;
+    if (have && b != expect) d.cnext[(size_t)(b & d.capm) * plane + i] = ABSENT;
     expect = nx;  // even for a removed block
     have = true;
   }
@@ -303,11 +315,11 @@ __global__ void state_digest_kernel(const Dev d, unsigned long long* out) {
       h = fold(h, (uint64_t)(e.z >> 16) | ((uint64_t)(e.z & 0xffffu) << 8));
     }
     uint64_t chain = 0;
-    const uint32_t mk = d.mk[i];
-    for (uint32_t bid = 0; bid <= mk; ++bid) {
-      const uint32_t nx = d.cnext[(size_t)bid * plane + i];
+    const uint32_t mk = d.mk[i], floor = d.tb[g];
+    for (uint32_t bid = floor; bid <= mk && bid - floor < d.cap; ++bid) {
+      const uint32_t nx = d.cnext[(size_t)(bid & d.capm) * plane + i];
       if (nx == ABSENT) continue;
-      const uint64_t tok = d.ctok[(size_t)bid * plane + i];
+      const uint64_t tok = d.ctok[(size_t)(bid & d.capm) * plane + i];
       chain += mix64(mix64((uint64_t)bid + 0x13198a2e03707344ull) ^ ((uint64_t)nx * 0xa4093822299f31d1ull) ^ tok);
     }
     h = fold(h, chain);
@@ -404,7 +416,12 @@ __global__ void set_alive_kernel(const Dev d, uint32_t g, uint32_t r, int alive)
   d.p2[i].w = alive ? (m & ~(1u << 27)) : (m | (1u << 27));
 }
 
-__global__ void query_kernel(const Dev d, uint32_t g, uint32_t r, jr_replica_state* o) {
+// jr_query_many: thread k reads replica (groups[k], nodes[k] - 1)
+__global__ void query_kernel(const Dev d, const uint32_t* groups, const uint32_t* nodes, uint32_t n, jr_replica_state* out) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t g = groups[k], r = nodes[k] - 1u;
+  jr_replica_state* o = out + k;
   const size_t plane = (size_t)d.R * d.Gp;
   const size_t i = (size_t)r * d.Gp + g;
   const uint4 a = d.p0[i], b = d.p1[i], c = d.p2[i], e = d.p3[i];
@@ -436,20 +453,167 @@ __global__ void query_kernel(const Dev d, uint32_t g, uint32_t r, jr_replica_sta
     s.votes_seen = e.z;
     s.votes_granted = e.w;
   }
+  s.chain_floor = d.tb[g];
   *o = s;
 }
 
-__global__ void chain_read_kernel(const Dev d, uint32_t g, uint32_t r, uint32_t first, uint32_t n, jr_block* out,
-                                  uint8_t* present) {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
+// jr_chain_read_many: request q = {group, node - 1, first id, output offset}; one CTA per request
+__global__ void chain_read_kernel(const Dev d, const uint4* reqs, const uint32_t* counts, jr_block* out, uint8_t* present) {
+  const uint32_t q = blockIdx.x;
+  const uint4 rq = reqs[q];
+  const uint32_t n = counts[q];
+  const size_t plane = (size_t)d.R * d.Gp;
+  const size_t i = (size_t)rq.y * d.Gp + rq.x;
+  const uint32_t floor = d.tb[rq.x];
+  for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+    const uint64_t bid = (uint64_t)rq.z + k;
+    uint32_t nx = ABSENT;
+    if (bid >= floor && bid - floor < d.cap) nx = d.cnext[(size_t)((uint32_t)bid & d.capm) * plane + i];
+    present[rq.w + k] = nx != ABSENT;
+    out[rq.w + k] = jr_block{bid, nx != ABSENT ? nx : 0ull,
+                             nx != ABSENT ? d.ctok[(size_t)((uint32_t)bid & d.capm) * plane + i] : 0ull};
+  }
+}
+
+// jr_truncate (deviation D7).  One thread per group: new floor = min(commit over live replicas) - margin, never
+// below the old one; every block below it leaves the table of EVERY replica of the group (rows are reused by
+// the ids one window further up, so they must read as absent).
+__global__ void truncate_kernel(const Dev d, uint32_t margin) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= d.Gp) return;
+  const size_t plane = (size_t)d.R * d.Gp;
+  const uint32_t old = d.tb[g];
+  uint32_t lo = 0xFFFFFFFFu;
+  for (uint32_t r = 0; r < d.R; ++r) {
+    const uint4 c = d.p2[(size_t)r * d.Gp + g];
+    if (((c.w >> 8) & 255u) != 0 || ((c.w >> 27) & 1u)) continue;  // faulted or silenced: not waited for
+    lo = min(lo, c.y);
+  }
+  if (lo == 0xFFFFFFFFu) return;
+  const uint32_t floor = lo > margin ? lo - margin : 0u;
+  if (floor <= old) return;
+  for (uint32_t b = old; b < floor && b - old < d.cap; ++b)
+    for (uint32_t r = 0; r < d.R; ++r) d.cnext[(size_t)(b & d.capm) * plane + (size_t)r * d.Gp + g] = ABSENT;
+  d.tb[g] = floor;
+}
+
+// jr_node_restart: Chain::new over persisted blocks (chain.rs:117-137) + Raft::<Follower>::new (follower.rs:68-95)
+// for one replica.  Single thread; `blocks` is device memory.
+__global__ void node_restart_kernel(const Dev d, uint32_t g, uint32_t r, uint64_t now, const jr_block* blocks, uint32_t n,
+                                    uint32_t commit, uint32_t ckey) {
   const size_t plane = (size_t)d.R * d.Gp;
   const size_t i = (size_t)r * d.Gp + g;
-  const uint64_t bid = (uint64_t)first + k;
-  uint32_t nx = ABSENT;
-  if (bid < d.cap) nx = d.cnext[(size_t)bid * plane + i];
-  present[k] = nx != ABSENT;
-  out[k] = jr_block{bid, nx != ABSENT ? nx : 0ull, nx != ABSENT ? d.ctok[(size_t)bid * plane + i] : 0ull};
+  const uint32_t floor = d.tb[g];
+  for (uint32_t b = 0; b < d.cap; ++b) d.cnext[(size_t)((floor + b) & d.capm) * plane + i] = ABSENT;  // an empty sled tree
+  uint32_t mk = 0;
+  for (uint32_t k = 0; k < n; ++k) {   // host-validated: floor <= id < floor + cap
+    const uint32_t bid = (uint32_t)blocks[k].id;
+    d.cnext[(size_t)(bid & d.capm) * plane + i] = (uint32_t)blocks[k].next;
+    d.ctok[(size_t)(bid & d.capm) * plane + i] = blocks[k].data;
+    mk = max(mk, bid);
+  }
+  uint32_t idgen = commit;             // IdGenerator::new(commit), chain.rs:126
+  if (commit == 0) {                   // chain.init(), chain.rs:139-153: id_gen.next() == 0, block 0 -> 0 inserted
+    if (floor == 0) { d.cnext[i] = 0; d.ctok[i] = 0; }
+    idgen = 1;
+  }
+  const uint32_t timeout = election_timeout_draw(d.seed, d.goff + g, r + 1, 0, d.emin, d.emax);
+  d.p0[i] = make_uint4(0, 0, 0, 0);
+  d.p1[i] = make_uint4((uint32_t)now, (uint32_t)(now >> 32), timeout, 1);
+  d.p2[i] = make_uint4(commit, commit, idgen, JR_ROLE_FOLLOWER | ((ckey ? 1u : 0u) << 28));
+  d.p3[i] = make_uint4(0, 0, 0, 0);
+  d.mk[i] = mk;
+  d.oc[0][i] = 0;
+  d.oc[1][i] = 0;
+}
+
+// ---- Instruction-stream drain -----------------------------------------------------------------
+// Records sit in per-replica FIFOs ([2*rec + half][replica][group]).  The drain packs them into one dense
+// array in thread order i = replica * Gp + group -- sorted by (node, group), FIFO per replica -- with an exclusive
+// scan over the per-replica counts, then writes them (to device memory, or straight into mapped pinned host
+// memory) and empties the FIFOs.
+constexpr uint32_t SCAN_THREADS = 1024;
+struct FsmHeader {          // written by fsm_pack_kernel next to the records
+  unsigned long long n_records, n_dropped, n_instructions;
+  uint32_t node_offset[JR_MAX_REPLICAS + 1];
+  uint32_t ready;           // epoch of the batch, written last
+};
+
+// One CTA of T <= SCAN_THREADS threads (the CPU emulation runs it with T = 1).  offs[i] = records of replicas
+// before i; hdr totals.  Padded groups (g >= G) contribute nothing.
+__global__ void fsm_scan_kernel(const Dev d, uint32_t* offs, FsmHeader* hdr, uint32_t cap_records) {
+  __shared__ unsigned long long s_rec[SCAN_THREADS], s_drop[SCAN_THREADS], s_ins[SCAN_THREADS];
+  const size_t plane = (size_t)d.R * d.Gp;
+  const uint32_t t = threadIdx.x, T = blockDim.x;
+  const size_t per = (plane + T - 1) / T;
+  const size_t lo = min(plane, per * t), hi = min(plane, per * (t + 1));
+  unsigned long long rec = 0, drop = 0, ins = 0;
+  for (size_t i = lo; i < hi; ++i) {
+    if ((uint32_t)(i % d.Gp) >= d.G) continue;
+    const uint2 c = d.fc[i];
+    rec += min(c.x, d.F);
+    drop += c.x > d.F ? c.x - d.F : 0u;
+    ins += c.y;
+  }
+  s_rec[t] = rec; s_drop[t] = drop; s_ins[t] = ins;
+  __syncthreads();
+  if (t == 0) {
+    unsigned long long run = 0, dr = 0, in = 0;
+    for (uint32_t k = 0; k < T; ++k) {
+      const unsigned long long v = s_rec[k];
+      s_rec[k] = run;
+      run += v;
+      dr += s_drop[k];
+      in += s_ins[k];
+    }
+    hdr->n_records = min(run, (unsigned long long)cap_records);
+    hdr->n_dropped = dr + (run > cap_records ? run - cap_records : 0ull);
+    hdr->n_instructions = in;
+  }
+  __syncthreads();
+  unsigned long long at = s_rec[t];
+  for (size_t i = lo; i < hi; ++i) {
+    offs[i] = (uint32_t)min(at, 0xFFFFFFFFull);
+    if ((uint32_t)(i % d.Gp) < d.G) at += min(d.fc[i].x, d.F);
+    if (i % d.Gp == 0) hdr->node_offset[i / d.Gp] = (uint32_t)min((unsigned long long)offs[i], (unsigned long long)cap_records);
+  }
+  if (t == T - 1) hdr->node_offset[d.R] = (uint32_t)min(at, (unsigned long long)cap_records);
+}
+
+// Thread i moves its replica's records to out[offs[i] ..] and empties the FIFO.  `out` / `hdr_out` may be mapped host memory.
+__global__ void fsm_pack_kernel(const Dev d, const uint32_t* offs, const FsmHeader* hdr, uint4* out, FsmHeader* hdr_out,
+                                uint32_t cap_records, uint32_t epoch) {
+  const size_t plane = (size_t)d.R * d.Gp;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < plane) {
+    if ((uint32_t)(i % d.Gp) < d.G) {
+      const uint32_t n = min(d.fc[i].x, d.F);
+      const uint32_t at = offs[i];
+      for (uint32_t k = 0; k < n && at + k < cap_records; ++k) {
+        out[(size_t)2 * (at + k)] = d.fs[(size_t)(2 * k) * plane + i];
+        out[(size_t)2 * (at + k) + 1] = d.fs[(size_t)(2 * k + 1) * plane + i];
+      }
+    }
+    d.fc[i] = make_uint2(0, 0);
+  }
+  if (i == 0 && hdr_out) {
+    FsmHeader h = *hdr;
+    h.ready = epoch;
+    *hdr_out = h;
+  }
+}
+
+// Packed batch (device) -> the engine's pinned host buffer, by the SMs: the size is only known on the device, so
+// a cudaMemcpyAsync would need a host round trip first.  Runs on the copy-out stream next to the following step.
+__global__ void fsm_copy_kernel(const uint4* __restrict__ src, const FsmHeader* __restrict__ hdr, uint4* __restrict__ dst,
+                                FsmHeader* hdr_dst, uint32_t epoch) {
+  const size_t n = (size_t)hdr->n_records * 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    FsmHeader h = *hdr;
+    h.ready = epoch;
+    *hdr_dst = h;
+  }
 }
 
 __global__ void max_u32_kernel(const uint32_t* v, size_t n, uint32_t* out) {
@@ -499,7 +663,6 @@ struct jr_engine {
   std::vector<void*> allocs;
   // scratch
   unsigned long long* scratch = nullptr;  // 8 x u64 (device)
-  jr_replica_state* q_state = nullptr;    // device
   jr_msg* inj_msgs = nullptr;             // device, grows
   uint4* inj_targets = nullptr;
   size_t inj_cap = 0;
@@ -526,9 +689,22 @@ struct jr_engine {
   int tab_pending[NBUF] = {0, 0};  // FIFO of leaders[] buffers whose copy-out has not been waited for
   int tab_npending = 0;
   int prop_i = 0, tab_i = 0;
-  jr_block* cr_blocks = nullptr;          // device scratch for chain_read
-  uint8_t* cr_present = nullptr;
-  uint32_t cr_cap = 0;
+  // scratch of the *_many introspection calls (device, grows)
+  void* many_buf = nullptr;
+  size_t many_cap = 0;
+  // Instruction-stream drain (JR_F_CAPTURE_FSM): scan -> pack into stage[b] on the engine stream, then
+  // fsm_copy_kernel moves stage[b] into the pinned host buffer host[b] on the d2h stream.
+  uint32_t* fsm_offs = nullptr;                               // device, plane entries
+  uint32_t fsm_cap = 0;                                       // records per batch
+  uint4* fsm_stage[NBUF] = {nullptr, nullptr};                // device, 2 * fsm_cap uint4 each
+  FsmHeader* fsm_stage_hdr[NBUF] = {nullptr, nullptr};        // device
+  uint4* fsm_host[NBUF] = {nullptr, nullptr};                 // pinned + mapped host
+  FsmHeader* fsm_host_hdr[NBUF] = {nullptr, nullptr};         // pinned + mapped host
+  cudaEvent_t fsm_packed[NBUF] = {nullptr, nullptr};          // pack into stage[b] finished (engine stream)
+  cudaEvent_t fsm_landed[NBUF] = {nullptr, nullptr};          // copy into host[b] finished (d2h stream)
+  bool fsm_used[NBUF] = {false, false};
+  int fsm_i = 0, fsm_pending[NBUF] = {0, 0}, fsm_npending = 0;
+  uint32_t fsm_epoch = 0;
 };
 
 template <typename T>
@@ -578,7 +754,8 @@ static cudaError_t step_occupancy_r(int* per_sm, int smem) {
 
 static size_t step_smem_bytes(const Dev& d) {
   return ((size_t)2 * d.Us + d.W) * d.R * 32 * sizeof(uint4) + (size_t)2 * d.R * 32 * sizeof(uint32_t) +
-         (size_t)2 * d.R * d.R * 32 * sizeof(uint32_t);
+         (size_t)2 * d.R * d.R * 32 * sizeof(uint16_t) +
+         ((d.flags & JR_F_CAPTURE_FSM) ? (size_t)FS_WORDS * d.R * 32 * sizeof(uint32_t) : 0);
 }
 
 // How many consecutive tasks to cut each block's ticks into: the fewest that minimise the number of
@@ -659,6 +836,7 @@ jr_status jr_engine_create(const jr_config* cfg, jr_engine** out) {
   if (cfg->election_min_ms < 5) { set_err("election timeout is too low"); return JR_E_INVAL; }
   if (cfg->chain_capacity < 2 || cfg->chain_capacity > 0x7fffffffu) { set_err("chain_capacity out of range"); return JR_E_INVAL; }
   if (cfg->mailbox_units < 8 || cfg->fsm_units < 1) { set_err("mailbox_units >= 8, fsm_units >= 1"); return JR_E_INVAL; }
+  if (cfg->fsm_units > (1u << 20)) { set_err("fsm_units <= 2^20"); return JR_E_INVAL; }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     set_err("no CUDA device; this library has no CPU fallback");
@@ -675,6 +853,9 @@ jr_status jr_engine_create(const jr_config* cfg, jr_engine** out) {
   d.Gp = (cfg->n_groups + GROUPS_PER_CTA - 1) / GROUPS_PER_CTA * GROUPS_PER_CTA;
   d.R = cfg->n_replicas;
   d.cap = cfg->chain_capacity;
+  d.capm = 1;
+  while (d.capm < d.cap) d.capm <<= 1;   // table rows: the power of two >= cap, so row = id & capm
+  d.capm -= 1;
   d.U = cfg->mailbox_units;
   d.F = cfg->fsm_units;
   d.flags = cfg->flags;
@@ -698,19 +879,27 @@ jr_status jr_engine_create(const jr_config* cfg, jr_engine** out) {
   A(d.mk, plane);
   A(d.qt, plane * JR_CLIENT_QUEUE_CAP);
   A(d.dg, plane); A(d.cn, plane);
-  A(d.cnext, plane * (size_t)d.cap);
-  A(d.ctok, plane * (size_t)d.cap);
+  A(d.cnext, plane * ((size_t)d.capm + 1));
+  A(d.ctok, plane * ((size_t)d.capm + 1));
   A(d.ob[0], plane * (size_t)d.U); A(d.ob[1], plane * (size_t)d.U);
   A(d.oc[0], plane); A(d.oc[1], plane);
-  A(d.fs, plane * (size_t)((d.flags & JR_F_CAPTURE_FSM) ? d.F : 1));
+  A(d.fs, plane * (size_t)((d.flags & JR_F_CAPTURE_FSM) ? 2 * (size_t)d.F : 1));
   A(d.fc, plane);
+  A(d.tb, d.Gp);
+  if (d.flags & JR_F_CAPTURE_FSM) {
+    const size_t reps = (size_t)cfg->n_groups * cfg->n_replicas;   // default: 2 per replica, but never less than a small engine's whole FIFO space
+    const size_t want = cfg->fsm_host_records ? cfg->fsm_host_records
+                                              : std::max(2 * reps + 1024, std::min<size_t>(reps * cfg->fsm_units, 1u << 16));
+    e->fsm_cap = (uint32_t)std::min<size_t>(want, 0x7fffffffu);
+    A(e->fsm_offs, plane);
+    for (int i = 0; i < jr_engine::NBUF; ++i) { A(e->fsm_stage[i], 2 * (size_t)e->fsm_cap); A(e->fsm_stage_hdr[i], 1); }
+  }
   A(e->scratch, 8);
   A(d.scatter, 2);
   A(d.done, d.Gp / GROUPS_PER_CTA);
 #ifdef JR_PROFILE
   A(d.prof, 3 * 16 * 2);
 #endif
-  A(e->q_state, 1);
   for (int i = 0; i < jr_engine::NBUF; ++i) { A(e->prop[i], d.G); A(e->leaders[i], d.G); }
   A(e->route, d.G);
 #undef A
@@ -730,7 +919,12 @@ jr_status jr_engine_create(const jr_config* cfg, jr_engine** out) {
            cudaEventCreateWithFlags(&e->tab_ready[i], cudaEventDisableTiming) == cudaSuccess &&
            cudaEventCreateWithFlags(&e->tab_free[i], cudaEventDisableTiming) == cudaSuccess &&
            cudaEventCreateWithFlags(&e->batch_ready[i], cudaEventDisableTiming) == cudaSuccess &&
-           cudaEventCreateWithFlags(&e->batch_free[i], cudaEventDisableTiming) == cudaSuccess;
+           cudaEventCreateWithFlags(&e->batch_free[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&e->fsm_packed[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&e->fsm_landed[i], cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; ok && e->fsm_cap && i < jr_engine::NBUF; ++i)   // the drain's landing buffers: pinned, device-visible
+      ok = cudaHostAlloc((void**)&e->fsm_host[i], (size_t)e->fsm_cap * sizeof(jr_fsm_record), cudaHostAllocMapped) == cudaSuccess &&
+           cudaHostAlloc((void**)&e->fsm_host_hdr[i], sizeof(FsmHeader), cudaHostAllocMapped) == cudaSuccess;
     if (!ok) {
       set_err("copy streams / events could not be created");
       jr_engine_destroy(e);
@@ -785,7 +979,7 @@ jr_status jr_engine_reset(jr_engine* e) {
   const Dev& d = e->d;
   const size_t plane = (size_t)d.R * d.Gp;
   // block tables start empty (all keys absent); pr / qt zero
-  CK(cudaMemsetAsync(d.cnext, 0xFF, plane * (size_t)d.cap * sizeof(uint32_t), e->stream));
+  CK(cudaMemsetAsync(d.cnext, 0xFF, plane * ((size_t)d.capm + 1) * sizeof(uint32_t), e->stream));
   CK(cudaMemsetAsync(d.pr, 0, plane * ((d.R + 3) / 4) * sizeof(uint4), e->stream));
   CK(cudaMemsetAsync(d.qt, 0, plane * JR_CLIENT_QUEUE_CAP * sizeof(uint4), e->stream));
   CK(cudaMemsetAsync(e->route, 0, (size_t)d.G * sizeof(uint32_t), e->stream));  // no leader announced yet
@@ -813,8 +1007,7 @@ void jr_engine_destroy(jr_engine* e) {
   for (void* p : e->allocs) cudaFree(p);
   if (e->inj_msgs) cudaFree(e->inj_msgs);
   if (e->inj_targets) cudaFree(e->inj_targets);
-  if (e->cr_blocks) cudaFree(e->cr_blocks);
-  if (e->cr_present) cudaFree(e->cr_present);
+  if (e->many_buf) cudaFree(e->many_buf);
   if (e->h2d) { cudaStreamSynchronize(e->h2d); cudaStreamDestroy(e->h2d); }
   if (e->d2h) { cudaStreamSynchronize(e->d2h); cudaStreamDestroy(e->d2h); }
   for (int i = 0; i < jr_engine::NBUF; ++i) {
@@ -824,6 +1017,10 @@ void jr_engine_destroy(jr_engine* e) {
     if (e->tab_free[i]) cudaEventDestroy(e->tab_free[i]);
     if (e->batch_ready[i]) cudaEventDestroy(e->batch_ready[i]);
     if (e->batch_free[i]) cudaEventDestroy(e->batch_free[i]);
+    if (e->fsm_packed[i]) cudaEventDestroy(e->fsm_packed[i]);
+    if (e->fsm_landed[i]) cudaEventDestroy(e->fsm_landed[i]);
+    if (e->fsm_host[i]) cudaFreeHost(e->fsm_host[i]);
+    if (e->fsm_host_hdr[i]) cudaFreeHost(e->fsm_host_hdr[i]);
     if (e->batch[i]) cudaFree(e->batch[i]);
     if (e->tokbuf[i]) cudaFree(e->tokbuf[i]);
   }
@@ -919,41 +1116,76 @@ static jr_status capture_messages(jr_engine* e, int buf, std::vector<jr_msg>& ou
   return JR_OK;
 }
 
+// ---- Instruction-stream drain -----------------------------------------------------------------
+
+static jr_status fsm_records_enqueue(jr_engine* e) {
+  const Dev& d = e->d;
+  if (!(d.flags & JR_F_CAPTURE_FSM)) { set_err("engine created without JR_F_CAPTURE_FSM"); return JR_E_INVAL; }
+  if (e->fsm_npending == jr_engine::NBUF) { set_err("two batches outstanding: call jr_fsm_records_wait first"); return JR_E_INVAL; }
+  const int b = e->fsm_i;
+  e->fsm_i = (b + 1) % jr_engine::NBUF;
+  const size_t plane = (size_t)d.R * d.Gp;
+  if (e->fsm_used[b]) CK(cudaStreamWaitEvent(e->stream, e->fsm_landed[b], 0));  // stage[b] has left the device
+  const uint32_t epoch = ++e->fsm_epoch;
+#ifdef JR_EMU
+  JR_LAUNCH(fsm_scan_kernel, 1, 1, e->stream, d, e->fsm_offs, e->fsm_stage_hdr[b], e->fsm_cap);
+#else
+  JR_LAUNCH(fsm_scan_kernel, 1, SCAN_THREADS, e->stream, d, e->fsm_offs, e->fsm_stage_hdr[b], e->fsm_cap);
+#endif
+  CK(cudaGetLastError());
+  JR_LAUNCH(fsm_pack_kernel, (unsigned)((plane + 255) / 256), 256, e->stream, d, e->fsm_offs, e->fsm_stage_hdr[b],
+            e->fsm_stage[b], (FsmHeader*)nullptr, e->fsm_cap, epoch);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(e->fsm_packed[b], e->stream));
+  CK(cudaStreamWaitEvent(e->d2h, e->fsm_packed[b], 0));
+  JR_LAUNCH(fsm_copy_kernel, 32, 256, e->d2h, e->fsm_stage[b], e->fsm_stage_hdr[b], e->fsm_host[b], e->fsm_host_hdr[b], epoch);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(e->fsm_landed[b], e->d2h));
+  e->fsm_used[b] = true;
+  e->fsm_pending[e->fsm_npending++] = b;
+  return JR_OK;
+}
+
+static jr_status fsm_records_take(jr_engine* e, const jr_fsm_record** recs, jr_fsm_batch* batch) {
+  if (e->fsm_npending == 0) { set_err("no batch outstanding"); return JR_E_INVAL; }
+  const int b = e->fsm_pending[0];
+  e->fsm_pending[0] = e->fsm_pending[1];
+  --e->fsm_npending;
+  CK(cudaEventSynchronize(e->fsm_landed[b]));
+  const FsmHeader& h = *e->fsm_host_hdr[b];
+  if (recs) *recs = reinterpret_cast<const jr_fsm_record*>(e->fsm_host[b]);
+  if (batch) {
+    memset(batch, 0, sizeof *batch);
+    batch->n_records = h.n_records;
+    batch->n_dropped = h.n_dropped;
+    batch->n_instructions = h.n_instructions;
+    for (uint32_t r = 0; r <= JR_MAX_REPLICAS; ++r) batch->node_offset[r] = r <= e->d.R ? h.node_offset[r] : h.node_offset[e->d.R];
+  }
+  if (h.n_dropped) {
+    set_err("%llu Instruction records were dropped (raise fsm_units / fsm_host_records, or drain more often)",
+            (unsigned long long)h.n_dropped);
+    return JR_E_CAPACITY;
+  }
+  return JR_OK;
+}
+
+// Synchronous drain into expanded Instructions (jr_step capture, jr_drain_fsm).
 static jr_status capture_fsm(jr_engine* e, std::vector<jr_fsm_instr>& out) {
   const Dev& d = e->d;
   if (!(d.flags & JR_F_CAPTURE_FSM)) return JR_OK;
-  const size_t plane = (size_t)d.R * d.Gp;
-  uint32_t mx = 0;
-  jr_status st = device_max(e, d.fc, plane, &mx);
+  if (e->fsm_npending) { set_err("jr_fsm_records_async batches are outstanding"); return JR_E_INVAL; }
+  jr_status st = fsm_records_enqueue(e);
   if (st != JR_OK) return st;
-  std::vector<uint32_t> cnt(plane);
-  CK(cudaMemcpyAsync(cnt.data(), d.fc, plane * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
-  std::vector<uint4> units((size_t)mx * plane);
-  if (mx) CK(cudaMemcpyAsync(units.data(), d.fs, units.size() * sizeof(uint4), cudaMemcpyDeviceToHost, e->stream));
-  CK(cudaStreamSynchronize(e->stream));
-  for (uint32_t g = 0; g < d.G; ++g)
-    for (uint32_t r = 0; r < d.R; ++r) {
-      const size_t i = (size_t)r * d.Gp + g;
-      for (uint32_t u = 0; u < cnt[i]; ++u) {
-        const uint4& v = units[(size_t)u * plane + i];
-        jr_fsm_instr f;
-        memset(&f, 0, sizeof f);
-        f.group = g;
-        f.node = r + 1;
-        const uint64_t tok = (uint64_t)v.z | ((uint64_t)v.w << 32);
-        if (v.x & 0x80000000u) {
-          f.kind = JR_FSM_NOTIFY;
-          f.client_kind = (uint8_t)(v.y >> 16);
-          f.client_id = v.y & 0xffffu;
-          f.block = jr_block{v.x & 0x7fffffffu, 0, tok};
-        } else {
-          f.kind = JR_FSM_APPLY;
-          f.block = jr_block{v.x, v.y, tok};
-        }
-        out.push_back(f);
-      }
-    }
-  return JR_OK;
+  const jr_fsm_record* recs = nullptr;
+  jr_fsm_batch batch;
+  const jr_status took = fsm_records_take(e, &recs, &batch);
+  if (took != JR_OK) return took;   // JR_E_CAPACITY: records are missing, so what is left cannot be expanded faithfully
+  size_t n = 0;
+  st = jr_fsm_expand(recs, batch.n_records, d.G, d.R, nullptr, 0, &n);
+  if (st != JR_OK && st != JR_E_CAPACITY) return st;
+  out.resize(n);
+  if (n && (st = jr_fsm_expand(recs, batch.n_records, d.G, d.R, out.data(), n, &n)) != JR_OK) return st;
+  return took;
 }
 
 // ---- jr_step ------------------------------------------------------------------------------
@@ -1054,6 +1286,7 @@ jr_status jr_step(jr_engine* e, jr_step_args* a) {
   if (staged >= 0) {  // proposals buffer may be refilled once the kernels of this step are done
     CK(cudaEventRecord(e->prop_free[staged], e->stream));
     e->prop_used[staged] = true;
+    CK(cudaEventSynchronize(e->prop_ready[staged]));  // a->proposals has been read: the caller may reuse it on return
   }
   const int written = e->cur;
   e->cur ^= 1;
@@ -1072,10 +1305,11 @@ jr_status jr_step(jr_engine* e, jr_step_args* a) {
   }
   if (a->out_fsm) {
     std::vector<jr_fsm_instr> fsm;
-    if ((st = capture_fsm(e, fsm)) != JR_OK) return st;
+    st = capture_fsm(e, fsm);
+    if (st != JR_OK && st != JR_E_CAPACITY) return st;
     a->n_fsm = fsm.size();
     memcpy(a->out_fsm, fsm.data(), std::min(fsm.size(), a->cap_fsm) * sizeof(jr_fsm_instr));
-    ovf |= fsm.size() > a->cap_fsm;
+    ovf |= fsm.size() > a->cap_fsm || st == JR_E_CAPACITY;
   }
   return ovf ? JR_E_CAPACITY : JR_OK;
 }
@@ -1094,7 +1328,7 @@ jr_status jr_run(jr_engine* e, uint64_t now0, uint32_t dt, uint32_t n_steps, uin
   p.cur = e->cur;
   p.proposals = nullptr;
   p.prop_stride = 0;
-  p.phases = PH_RESET_OUT | PH_RESET_FSM | PH_DRAIN | (n_synth ? PH_PROPOSE : 0u) | PH_TICK;
+  p.phases = PH_RESET_OUT | PH_DRAIN | (n_synth ? PH_PROPOSE : 0u) | PH_TICK;   // Instructions accumulate until drained
   jr_status st = launch_step(e, p);
   if (st != JR_OK) return st;
   e->cur ^= (int)(n_steps & 1u);
@@ -1127,7 +1361,7 @@ static jr_status batch_launch(jr_engine* e, int b, uint64_t now0, uint32_t dt, u
   p.cur = e->cur;
   p.proposals = e->batch[b];
   p.prop_stride = e->d.G;
-  p.phases = PH_RESET_OUT | PH_RESET_FSM | PH_DRAIN | PH_PROPOSE | PH_TICK;
+  p.phases = PH_RESET_OUT | PH_DRAIN | PH_PROPOSE | PH_TICK;
   jr_status st = launch_step(e, p);
   if (st != JR_OK) return st;
   CK(cudaEventRecord(e->batch_free[b], e->stream));
@@ -1188,47 +1422,181 @@ jr_status jr_run_tokens(jr_engine* e, uint64_t now0, uint32_t dt, uint32_t n_ste
 jr_status jr_drain_fsm(jr_engine* e, jr_fsm_instr* out, size_t cap, size_t* n) {
   if (!e || !n) return JR_E_INVAL;
   CK(cudaSetDevice(e->cfg.device));
+  if (!(e->d.flags & JR_F_CAPTURE_FSM)) { *n = 0; return JR_OK; }
   std::vector<jr_fsm_instr> fsm;
   jr_status st = capture_fsm(e, fsm);
-  if (st != JR_OK) return st;
+  if (st != JR_OK && st != JR_E_CAPACITY) return st;
   *n = fsm.size();
   if (out) memcpy(out, fsm.data(), std::min(fsm.size(), cap) * sizeof(jr_fsm_instr));
-  return (out && fsm.size() > cap) ? JR_E_CAPACITY : JR_OK;
+  return ((out && fsm.size() > cap) || st == JR_E_CAPACITY) ? JR_E_CAPACITY : JR_OK;
+}
+
+jr_status jr_fsm_records_async(jr_engine* e) {
+  if (!e) return JR_E_INVAL;
+  CK(cudaSetDevice(e->cfg.device));
+  return fsm_records_enqueue(e);
+}
+
+jr_status jr_fsm_records_wait(jr_engine* e, const jr_fsm_record** records, jr_fsm_batch* batch) {
+  if (!e) return JR_E_INVAL;
+  return fsm_records_take(e, records, batch);
+}
+
+// Pure host code: records -> Instructions (include/josefine_raft_abi.h, jr_fsm_record).
+jr_status jr_fsm_expand(const jr_fsm_record* recs, size_t n_records, uint32_t G, uint32_t R, jr_fsm_instr* out, size_t cap,
+                        size_t* n_out) {
+  if (!n_out || (!recs && n_records) || R < 1 || R > JR_MAX_REPLICAS || G < 1) return JR_E_INVAL;
+  // stable counting sort of record indices by (group, node)
+  const size_t nb = (size_t)G * R;
+  std::vector<uint32_t> start(nb + 1, 0u);
+  for (size_t i = 0; i < n_records; ++i) {
+    const uint32_t node = JR_FSMR_NODE(recs[i].hdr);
+    if (recs[i].group >= G || node > R || JR_FSMR_KIND(recs[i].hdr) > JR_FSMR_PATTERN) return JR_E_INVAL;
+    ++start[(size_t)recs[i].group * R + (node - 1) + 1];
+  }
+  for (size_t b = 0; b < nb; ++b) start[b + 1] += start[b];
+  std::vector<uint32_t> order(n_records), fill(start.begin(), start.end() - 1);
+  for (size_t i = 0; i < n_records; ++i)
+    order[fill[(size_t)recs[i].group * R + (JR_FSMR_NODE(recs[i].hdr) - 1)]++] = (uint32_t)i;
+  size_t k = 0;
+  std::vector<uint64_t> is_notify;
+  for (size_t b = 0; b < nb; ++b) {
+    const uint32_t lo = start[b], hi = start[b + 1];
+    if (lo == hi) continue;
+    const uint32_t g = (uint32_t)(b / R), node = (uint32_t)(b % R) + 1;
+    size_t n_apply = 0, n_note = 0;
+    for (uint32_t j = lo; j < hi; ++j) {
+      const jr_fsm_record& rc = recs[order[j]];
+      if (JR_FSMR_KIND(rc.hdr) == JR_FSMR_APPLY) n_apply += JR_FSMR_COUNT(rc.hdr);
+      else if (JR_FSMR_KIND(rc.hdr) == JR_FSMR_NOTIFY) n_note += JR_FSMR_COUNT(rc.hdr);
+    }
+    const size_t total = n_apply + n_note;
+    is_notify.assign((total + 63) / 64, 0ull);
+    size_t marked = 0;
+    for (uint32_t j = lo; j < hi; ++j) {
+      const jr_fsm_record& rc = recs[order[j]];
+      if (JR_FSMR_KIND(rc.hdr) != JR_FSMR_PATTERN) continue;
+      const uint32_t nbits = JR_FSMR_COUNT(rc.hdr);
+      if (nbits > 64) return JR_E_INVAL;
+      for (uint32_t bit = 0; bit < nbits; ++bit)
+        if ((rc.tok0 >> bit) & 1ull) {
+          const size_t pos = (size_t)rc.id0 + bit;
+          if (pos >= total || ((is_notify[pos >> 6] >> (pos & 63)) & 1ull)) return JR_E_INVAL;
+          is_notify[pos >> 6] |= 1ull << (pos & 63);
+          ++marked;
+        }
+    }
+    if (marked != n_note) return JR_E_INVAL;
+    // two cursors, one per kind, both in record order
+    uint32_t ja = lo, jn = lo, ia = 0, in_ = 0;
+    for (size_t pos = 0; pos < total; ++pos) {
+      const bool note = (is_notify[pos >> 6] >> (pos & 63)) & 1ull;
+      uint32_t& j = note ? jn : ja;
+      uint32_t& i = note ? in_ : ia;
+      const uint32_t want = note ? JR_FSMR_NOTIFY : JR_FSMR_APPLY;
+      while (JR_FSMR_KIND(recs[order[j]].hdr) != want || i >= JR_FSMR_COUNT(recs[order[j]].hdr)) { ++j; i = 0; }
+      const jr_fsm_record& rc = recs[order[j]];
+      if (out && k < cap) {
+        jr_fsm_instr f;
+        memset(&f, 0, sizeof f);
+        f.group = g;
+        f.node = node;
+        if (note) {
+          f.kind = JR_FSM_NOTIFY;
+          f.client_kind = (uint8_t)(rc.addr >> 16);
+          f.client_id = rc.addr & 0xffffu;
+          f.block = jr_block{(uint64_t)(rc.id0 + i), 0, rc.tok0 + (uint64_t)i * rc.stride};
+        } else {
+          f.kind = JR_FSM_APPLY;
+          const uint32_t bid = rc.id0 + i;
+          if (JR_FSMR_COUNT(rc.hdr) == 1) f.block = jr_block{bid, (uint32_t)rc.stride, rc.tok0};
+          else f.block = jr_block{bid, bid - 1u, rc.tok0 + (uint64_t)i * rc.stride};
+        }
+        out[k] = f;
+      }
+      ++k;
+      ++i;
+    }
+  }
+  *n_out = k;
+  return (out && k > cap) || (!out && k) ? JR_E_CAPACITY : JR_OK;
 }
 
 // ---- introspection ----------------------------------------------------------------------------
 
-jr_status jr_query(jr_engine* e, uint32_t group, uint32_t node, jr_replica_state* out) {
-  if (!e || !out || group >= e->d.G || node < 1 || node > e->d.R) return JR_E_INVAL;
+static jr_status many_reserve(jr_engine* e, size_t bytes) {
+  if (bytes <= e->many_cap) return JR_OK;
+  if (e->many_buf) cudaFree(e->many_buf);
+  e->many_buf = nullptr;
+  e->many_cap = 0;
+  const size_t want = std::max<size_t>(bytes * 2, 4096);
+  CK(cudaMalloc(&e->many_buf, want));
+  e->many_cap = want;
+  return JR_OK;
+}
+
+jr_status jr_query_many(jr_engine* e, const uint32_t* groups, const uint32_t* nodes, size_t n, jr_replica_state* out) {
+  if (!e || !out || !groups || !nodes) return JR_E_INVAL;
+  if (n == 0) return JR_OK;
+  if (n > 0x7fffffffu) return JR_E_INVAL;
+  for (size_t i = 0; i < n; ++i)
+    if (groups[i] >= e->d.G || nodes[i] < 1 || nodes[i] > e->d.R) return JR_E_INVAL;
   CK(cudaSetDevice(e->cfg.device));
-  JR_LAUNCH(query_kernel, 1, 1, e->stream, e->d, group, node - 1, e->q_state);
+  const size_t idx = ((n * 2 * sizeof(uint32_t)) + 15) / 16 * 16;   // [groups][nodes] then the states
+  jr_status st = many_reserve(e, idx + n * sizeof(jr_replica_state));
+  if (st != JR_OK) return st;
+  uint32_t* dg = (uint32_t*)e->many_buf;
+  uint32_t* dn = dg + n;
+  jr_replica_state* ds = (jr_replica_state*)((char*)e->many_buf + idx);
+  CK(cudaMemcpyAsync(dg, groups, n * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemcpyAsync(dn, nodes, n * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+  JR_LAUNCH(query_kernel, (unsigned)((n + 127) / 128), 128, e->stream, e->d, dg, dn, (uint32_t)n, ds);
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(out, e->q_state, sizeof *out, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(out, ds, n * sizeof(jr_replica_state), cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
+  return JR_OK;
+}
+
+jr_status jr_query(jr_engine* e, uint32_t group, uint32_t node, jr_replica_state* out) {
+  return jr_query_many(e, &group, &node, 1, out);
+}
+
+jr_status jr_chain_read_many(jr_engine* e, const uint32_t* groups, const uint32_t* nodes, const uint64_t* first_id,
+                             const uint32_t* count, size_t n, jr_block* out, uint8_t* present) {
+  if (!e || !groups || !nodes || !first_id || !count) return JR_E_INVAL;
+  if (n == 0) return JR_OK;
+  if (n > 0x7fffffffu) return JR_E_INVAL;
+  std::vector<uint4> reqs(n);
+  size_t total = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if (groups[i] >= e->d.G || nodes[i] < 1 || nodes[i] > e->d.R) return JR_E_INVAL;
+    if (first_id[i] + count[i] > 0xffffffffull) return JR_E_INVAL;
+    reqs[i] = make_uint4(groups[i], nodes[i] - 1, (uint32_t)first_id[i], (uint32_t)total);
+    total += count[i];
+    if (total > 0xffffffffull) return JR_E_INVAL;
+  }
+  if (total == 0) return JR_OK;
+  CK(cudaSetDevice(e->cfg.device));
+  const size_t o_cnt = n * sizeof(uint4), o_blk = (o_cnt + n * sizeof(uint32_t) + 15) / 16 * 16;
+  const size_t o_pre = o_blk + total * sizeof(jr_block);
+  jr_status st = many_reserve(e, o_pre + total);
+  if (st != JR_OK) return st;
+  char* base = (char*)e->many_buf;
+  CK(cudaMemcpyAsync(base, reqs.data(), n * sizeof(uint4), cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemcpyAsync(base + o_cnt, count, n * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+  JR_LAUNCH(chain_read_kernel, (unsigned)n, 128, e->stream, e->d, (const uint4*)base, (const uint32_t*)(base + o_cnt),
+            (jr_block*)(base + o_blk), (uint8_t*)(base + o_pre));
+  CK(cudaGetLastError());
+  if (out) CK(cudaMemcpyAsync(out, base + o_blk, total * sizeof(jr_block), cudaMemcpyDeviceToHost, e->stream));
+  if (present) CK(cudaMemcpyAsync(present, base + o_pre, total, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));   // also covers `reqs`, which lives on this stack
   return JR_OK;
 }
 
 jr_status jr_chain_read(jr_engine* e, uint32_t group, uint32_t node, uint64_t first, uint32_t n, jr_block* out,
                         uint8_t* present) {
-  if (!e || group >= e->d.G || node < 1 || node > e->d.R) return JR_E_INVAL;
-  if (n == 0) return JR_OK;
-  if (first + n > 0xffffffffull) return JR_E_INVAL;
-  CK(cudaSetDevice(e->cfg.device));
-  if (n > e->cr_cap) {
-    if (e->cr_blocks) cudaFree(e->cr_blocks);
-    if (e->cr_present) cudaFree(e->cr_present);
-    e->cr_blocks = nullptr; e->cr_present = nullptr;
-    e->cr_cap = std::max(n, 256u);
-    CK(cudaMalloc(&e->cr_blocks, (size_t)e->cr_cap * sizeof(jr_block)));
-    CK(cudaMalloc(&e->cr_present, e->cr_cap));
-  }
-  JR_LAUNCH(chain_read_kernel, (n + 127) / 128, 128, e->stream, e->d, group, node - 1, (uint32_t)first, n, e->cr_blocks,
-                                                            e->cr_present);
-  CK(cudaGetLastError());
-  if (out) CK(cudaMemcpyAsync(out, e->cr_blocks, (size_t)n * sizeof(jr_block), cudaMemcpyDeviceToHost, e->stream));
-  if (present) CK(cudaMemcpyAsync(present, e->cr_present, n, cudaMemcpyDeviceToHost, e->stream));
-  CK(cudaStreamSynchronize(e->stream));
-  return JR_OK;
+  if (n == 0) return (!e || group >= e->d.G || node < 1 || node > e->d.R) ? JR_E_INVAL : JR_OK;
+  return jr_chain_read_many(e, &group, &node, &first, &n, 1, out, present);
 }
 
 jr_status jr_state_digest(jr_engine* e, uint64_t* out) {
@@ -1284,6 +1652,123 @@ jr_status jr_compact(jr_engine* e) {
   const size_t plane = (size_t)e->d.R * e->d.Gp;
   JR_LAUNCH(compact_kernel, (unsigned)((plane + 127) / 128), 128, e->stream, e->d);
   CK(cudaGetLastError());
+  return JR_OK;
+}
+
+jr_status jr_truncate(jr_engine* e, uint32_t margin) {
+  if (!e) return JR_E_INVAL;
+  CK(cudaSetDevice(e->cfg.device));
+  JR_LAUNCH(truncate_kernel, (e->d.Gp + 127) / 128, 128, e->stream, e->d, margin);
+  CK(cudaGetLastError());
+  return JR_OK;
+}
+
+jr_status jr_node_restart(jr_engine* e, uint32_t group, uint32_t node, uint64_t now_ms, const jr_block* blocks,
+                          size_t n_blocks, uint64_t commit, int commit_key) {
+  if (!e || group >= e->d.G || node < 1 || node > e->d.R || (n_blocks && !blocks)) return JR_E_INVAL;
+  if (n_blocks > e->d.cap || commit >= 0xffffffffull) return JR_E_INVAL;
+  CK(cudaSetDevice(e->cfg.device));
+  jr_replica_state st0;
+  jr_status st = jr_query(e, group, node, &st0);   // (synchronises; also tells the group's floor)
+  if (st != JR_OK) return st;
+  for (size_t k = 0; k < n_blocks; ++k)
+    if (blocks[k].id < st0.chain_floor || blocks[k].id - st0.chain_floor >= e->d.cap || blocks[k].next >= 0xffffffffull) {
+      set_err("blocks[%zu]: id outside [floor, floor + chain_capacity) or next >= 2^32-1 (D4, D7)", k);
+      return JR_E_INVAL;
+    }
+  if ((st = many_reserve(e, std::max<size_t>(n_blocks, 1) * sizeof(jr_block))) != JR_OK) return st;
+  if (n_blocks) CK(cudaMemcpyAsync(e->many_buf, blocks, n_blocks * sizeof(jr_block), cudaMemcpyHostToDevice, e->stream));
+  JR_LAUNCH(node_restart_kernel, 1, 1, e->stream, e->d, group, node - 1, now_ms, (const jr_block*)e->many_buf,
+            (uint32_t)n_blocks, (uint32_t)commit, commit_key ? 1u : 0u);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(e->stream));
+  return JR_OK;
+}
+
+// ---- checkpoint -----------------------------------------------------------------------------------
+namespace {
+struct SaveHeader {
+  uint64_t magic, bytes;
+  jr_config cfg;
+  uint32_t cur, route_valid;
+  uint64_t step_index;
+};
+constexpr uint64_t SAVE_MAGIC = 0x4a52454e47494e32ull;  // "JRENGIN2"
+struct Segment { void* p; size_t n; };
+std::vector<Segment> save_segments(jr_engine* e) {
+  const Dev& d = e->d;
+  const size_t plane = (size_t)d.R * d.Gp;
+  const size_t rows = (size_t)d.capm + 1;
+  std::vector<Segment> v = {
+      {d.p0, plane * sizeof(uint4)}, {d.p1, plane * sizeof(uint4)}, {d.p2, plane * sizeof(uint4)}, {d.p3, plane * sizeof(uint4)},
+      {d.pr, plane * ((d.R + 3) / 4) * sizeof(uint4)}, {d.mk, plane * sizeof(uint32_t)},
+      {d.qt, plane * JR_CLIENT_QUEUE_CAP * sizeof(uint4)}, {d.dg, plane * sizeof(uint4)}, {d.cn, plane * sizeof(uint2)},
+      {d.cnext, plane * rows * sizeof(uint32_t)}, {d.ctok, plane * rows * sizeof(unsigned long long)},
+      {d.ob[0], plane * (size_t)d.U * sizeof(uint4)}, {d.ob[1], plane * (size_t)d.U * sizeof(uint4)},
+      {d.oc[0], plane * sizeof(uint32_t)}, {d.oc[1], plane * sizeof(uint32_t)},
+      {d.fs, plane * ((d.flags & JR_F_CAPTURE_FSM) ? 2 * (size_t)d.F : 1) * sizeof(uint4)}, {d.fc, plane * sizeof(uint2)},
+      {d.tb, (size_t)d.Gp * sizeof(uint32_t)}, {e->route, (size_t)d.G * sizeof(uint32_t)}};
+  return v;
+}
+}  // namespace
+
+jr_status jr_engine_save_size(jr_engine* e, size_t* bytes) {
+  if (!e || !bytes) return JR_E_INVAL;
+  size_t n = sizeof(SaveHeader);
+  for (const Segment& sg : save_segments(e)) n += sg.n;
+  *bytes = n;
+  return JR_OK;
+}
+
+jr_status jr_engine_save(jr_engine* e, void* buf, size_t cap) {
+  if (!e || !buf) return JR_E_INVAL;
+  size_t need = 0;
+  jr_engine_save_size(e, &need);
+  if (cap < need) return JR_E_CAPACITY;
+  CK(cudaSetDevice(e->cfg.device));
+  jr_status st = jr_engine_sync(e);
+  if (st != JR_OK) return st;
+  SaveHeader h;
+  memset(&h, 0, sizeof h);
+  h.magic = SAVE_MAGIC;
+  h.bytes = need;
+  h.cfg = e->cfg;
+  h.cur = (uint32_t)e->cur;
+  h.step_index = e->step_index;
+  memcpy(buf, &h, sizeof h);
+  char* at = (char*)buf + sizeof h;
+  for (const Segment& sg : save_segments(e)) {
+    CK(cudaMemcpyAsync(at, sg.p, sg.n, cudaMemcpyDeviceToHost, e->stream));
+    at += sg.n;
+  }
+  CK(cudaStreamSynchronize(e->stream));
+  return JR_OK;
+}
+
+jr_status jr_engine_restore(jr_engine* e, const void* buf, size_t bytes) {
+  if (!e || !buf || bytes < sizeof(SaveHeader)) return JR_E_INVAL;
+  SaveHeader h;
+  memcpy(&h, buf, sizeof h);
+  size_t need = 0;
+  jr_engine_save_size(e, &need);
+  jr_config a = h.cfg, b = e->cfg;
+  a.device = b.device = 0;   // a checkpoint may move to another GPU
+  if (h.magic != SAVE_MAGIC || h.bytes != need || bytes < need || memcmp(&a, &b, sizeof a) != 0) {
+    set_err("checkpoint does not match this engine's configuration");
+    return JR_E_INVAL;
+  }
+  CK(cudaSetDevice(e->cfg.device));
+  jr_status st = jr_engine_sync(e);
+  if (st != JR_OK) return st;
+  const char* at = (const char*)buf + sizeof h;
+  for (const Segment& sg : save_segments(e)) {
+    CK(cudaMemcpyAsync(sg.p, at, sg.n, cudaMemcpyHostToDevice, e->stream));
+    at += sg.n;
+  }
+  CK(cudaStreamSynchronize(e->stream));
+  e->cur = (int)h.cur;
+  e->step_index = h.step_index;
+  e->fsm_npending = 0;
   return JR_OK;
 }
 

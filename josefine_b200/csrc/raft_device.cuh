@@ -46,13 +46,14 @@ struct Dev {
   uint4* qt;                       // queued client requests [q][replica][group]
   uint4* dg;                       // stream digests {msg, fsm}
   uint2* cn;                       // stream counts {msgs, fsm}
-  uint32_t* cnext;                 // block table: next pointer, [id][replica][group]
+  uint32_t* cnext;                 // block table: next pointer, [id & capm][replica][group] (a window of ids, see tb)
   unsigned long long* ctok;        // block table: payload token
+  uint32_t* tb;                    // [group]: window floor -- ids below it were truncated (jr_truncate, deviation D7)
   uint4* ob[2];                    // mailboxes [unit][replica][group], double buffered
   uint32_t* oc[2];                 // units used per replica
-  uint4* fs;                       // Instruction FIFO [unit][replica][group]
-  uint32_t* fc;
-  uint32_t G, Gp, R, cap, U, F, flags;
+  uint4* fs;                       // Instruction-stream records (jr_fsm_record, 2 x uint4 each) [2*rec + half][replica][group]
+  uint2* fc;                       // {records stored since the last drain, Instructions emitted since the last drain}
+  uint32_t G, Gp, R, cap, capm, U, F, flags;   // cap: ids a window may span; capm: table rows - 1 (power of two >= cap)
   uint32_t emin, emax, hb;
   uint32_t Us, W;                  // shared-memory mailbox units per replica, table-cache entries (power of 2)
   uint32_t use_index;              // receivers use the delivery index (else scan whole mailboxes)
@@ -73,13 +74,17 @@ struct Local {
   uint32_t* cout;
   uint4* tc;        // block-table cache {id, next, token}  [id & (W-1)][replica][lane]
   // Delivery index: bit u of mk[receiver][sender][lane] = unit u of the sender's
-  // mailbox is a header addressed to that receiver (or to Peers).  Bit 31 = the
-  // sender emitted a header at slot >= 31: scan its whole mailbox instead.
-  uint32_t* mk_in;
-  uint32_t* mk_out;
+  // mailbox is a header addressed to that receiver (or to Peers).  MK_SCAN = the
+  // sender emitted a header at slot >= MK_SLOTS: scan its whole mailbox instead.
+  uint16_t* mk_in;
+  uint16_t* mk_out;
+  // Instruction-stream encoder state, FS_WORDS words per thread, word-major ([word][thread]); see fsm_encode
+  uint32_t* fsm;
+  uint32_t nt, tid;  // threads sharing `fsm`, this thread's column
   uint32_t Us, W, lane;
 };
-constexpr uint32_t MK_SCAN = 0x80000000u;
+constexpr uint32_t MK_SCAN = 0x8000u;   // delivery masks are 16 bits: slots 0..14 + this flag
+constexpr uint32_t MK_SLOTS = 15u;
 
 struct StepParams {
   uint64_t now;
@@ -201,6 +206,118 @@ __device__ __forceinline__ unsigned long long* jr_prof_smem() {
 #define JR_PROF_ADD(role, slot, var) do { } while (0)
 #endif
 
+
+// ---------------------------------------------------------------------------------------------
+// Instruction-stream encoder (fsm_tx, fsm.rs:19-29).  A replica's Instructions leave the device
+// run-length encoded as jr_fsm_record (32 B, layout normative in the ABI header):
+//   APPLY run   blocks id0, id0+1, ... whose `next` is id-1 and whose tokens form an arithmetic
+//               progression (count == 1: any block, `next` explicit)
+//   NOTIFY run  block ids id0, id0+1, ..., one client address, tokens in arithmetic progression
+//   PATTERN     which positions of the replica's stream are Notify (bit = 1); positions no PATTERN
+//               record covers are Apply.  Applies and Notifies each keep their own order, so the
+//               three together reproduce the stream exactly.
+// The open runs live in shared memory (FS_WORDS words per thread); a run that cannot be extended
+// is closed into the replica's record FIFO d.fs.  Every launch closes what is open when it ends.
+enum : uint32_t {
+  FS_A_NEXT = 0, FS_A_TOKLO, FS_A_TOKHI, FS_A_STRLO, FS_A_STRHI,          // open APPLY run: next id, last token, stride (count 1: `next` of the block)
+  FS_N_NEXT, FS_N_TOKLO, FS_N_TOKHI, FS_N_STRLO, FS_N_STRHI, FS_N_ADDR,   // open NOTIFY run
+  FS_COUNTS,                                                              // apply count | notify count << 16
+  FS_PBLO, FS_PBHI,                                                       // pattern bits of the current 64-instruction window
+  FS_SEQ,                                                                 // Instructions emitted since the last drain
+  FS_NREC,                                                                // records closed since the last drain (may exceed F: dropped)
+  FS_WORDS
+};
+constexpr uint32_t FSR_APPLY = 0u, FSR_NOTIFY = 1u, FSR_PATTERN = 2u;
+
+struct FsmOut {       // where one replica's records go
+  uint4* slot0;       // d.fs + rg
+  size_t plane;       // R * Gp
+  uint32_t F, g, r;
+};
+
+__device__ __forceinline__ void fsm_put_record(uint32_t* S, uint32_t nt, const FsmOut& o, uint32_t kind, uint32_t count,
+                                               uint32_t id0, uint32_t addr, uint64_t tok0, uint64_t stride) {
+  const uint32_t n = S[FS_NREC * nt];
+  if (n < o.F) {
+    o.slot0[(size_t)(2 * n) * o.plane] = make_uint4(o.g, kind | (o.r << 2) | (count << 8), id0, addr);
+    o.slot0[(size_t)(2 * n + 1) * o.plane] =
+        make_uint4((uint32_t)tok0, (uint32_t)(tok0 >> 32), (uint32_t)stride, (uint32_t)(stride >> 32));
+  }
+  S[FS_NREC * nt] = n + 1;  // past F: counted, not stored (the drain reports JR_E_CAPACITY; consensus is not affected)
+}
+
+__device__ __forceinline__ void fsm_close_run(uint32_t* S, uint32_t nt, const FsmOut& o, bool notify) {
+  const uint32_t counts = S[FS_COUNTS * nt];
+  const uint32_t c = notify ? counts >> 16 : counts & 0xffffu;
+  if (!c) return;
+  const uint32_t b = notify ? FS_N_NEXT : FS_A_NEXT;
+  const uint32_t next_id = S[(b + 0) * nt];
+  const uint64_t last = (uint64_t)S[(b + 1) * nt] | ((uint64_t)S[(b + 2) * nt] << 32);
+  const uint64_t str = (uint64_t)S[(b + 3) * nt] | ((uint64_t)S[(b + 4) * nt] << 32);
+  const uint64_t tok0 = c > 1 ? last - (uint64_t)(c - 1) * str : last;
+  fsm_put_record(S, nt, o, notify ? FSR_NOTIFY : FSR_APPLY, c, next_id - c, notify ? S[FS_N_ADDR * nt] : 0u, tok0, str);
+  S[FS_COUNTS * nt] = notify ? (counts & 0xffffu) : (counts & 0xffff0000u);
+}
+
+__device__ __forceinline__ void fsm_close_pattern(uint32_t* S, uint32_t nt, const FsmOut& o, uint32_t seq0, uint32_t nbits) {
+  const uint32_t lo = S[FS_PBLO * nt], hi = S[FS_PBHI * nt];
+  if (lo | hi) {
+    fsm_put_record(S, nt, o, FSR_PATTERN, nbits, seq0, 0u, (uint64_t)lo | ((uint64_t)hi << 32), 0ull);
+    S[FS_PBLO * nt] = 0;
+    S[FS_PBHI * nt] = 0;
+  }
+}
+
+// One Instruction.  Apply: nxa = block.next; Notify: nxa = client address (kind << 16 | id).
+__device__ __noinline__ void fsm_encode(uint32_t* S, uint32_t nt, FsmOut o, bool notify, uint32_t bid, uint32_t nxa,
+                                        uint64_t tok) {
+  const uint32_t seq = S[FS_SEQ * nt];
+  if (notify) S[((seq & 32u) ? FS_PBHI : FS_PBLO) * nt] |= 1u << (seq & 31u);
+  S[FS_SEQ * nt] = seq + 1u;
+  if (((seq + 1u) & 63u) == 0u) fsm_close_pattern(S, nt, o, seq - 63u, 64u);
+  const uint32_t b = notify ? FS_N_NEXT : FS_A_NEXT;
+  const uint32_t counts = S[FS_COUNTS * nt];
+  const uint32_t c = notify ? counts >> 16 : counts & 0xffffu;
+  if (c) {
+    const uint32_t next_id = S[(b + 0) * nt];
+    const uint64_t last = (uint64_t)S[(b + 1) * nt] | ((uint64_t)S[(b + 2) * nt] << 32);
+    const uint64_t str = (uint64_t)S[(b + 3) * nt] | ((uint64_t)S[(b + 4) * nt] << 32);
+    bool ok = bid == next_id && c < 0xffffu;
+    if (notify) ok = ok && nxa == S[FS_N_ADDR * nt];
+    else ok = ok && nxa == bid - 1u && (c > 1u || (uint32_t)str == bid - 2u);  // count 1: its explicit `next` must be regular too
+    const uint64_t step = tok - last;
+    if (ok && c > 1u) ok = step == str;
+    if (ok) {
+      S[(b + 0) * nt] = bid + 1u;
+      S[(b + 1) * nt] = (uint32_t)tok;
+      S[(b + 2) * nt] = (uint32_t)(tok >> 32);
+      if (c == 1u) {
+        S[(b + 3) * nt] = (uint32_t)step;
+        S[(b + 4) * nt] = (uint32_t)(step >> 32);
+      }
+      S[FS_COUNTS * nt] = counts + (notify ? 0x10000u : 1u);
+      return;
+    }
+    fsm_close_run(S, nt, o, notify);
+  }
+  S[(b + 0) * nt] = bid + 1u;
+  S[(b + 1) * nt] = (uint32_t)tok;
+  S[(b + 2) * nt] = (uint32_t)(tok >> 32);
+  S[(b + 3) * nt] = notify ? 0u : nxa;   // Apply, count 1: the block's `next`
+  S[(b + 4) * nt] = 0u;
+  if (notify) S[FS_N_ADDR * nt] = nxa;
+  S[FS_COUNTS * nt] = S[FS_COUNTS * nt] + (notify ? 0x10000u : 1u);
+}
+
+// Launch end: everything open becomes records; the counters go back to d.fc.
+__device__ __noinline__ void fsm_close_all(uint32_t* S, uint32_t nt, FsmOut o, uint2* fc) {
+  fsm_close_run(S, nt, o, false);
+  fsm_close_run(S, nt, o, true);
+  const uint32_t seq = S[FS_SEQ * nt];
+  if (seq & 63u) fsm_close_pattern(S, nt, o, seq & ~63u, seq & 63u);
+  *fc = make_uint2(S[FS_NREC * nt], seq);
+}
+
 template <int R, bool SORTED = false>
 struct Replica {
   const Dev& d;
@@ -213,11 +330,11 @@ struct Replica {
   uint32_t ocnt0;        // units already in the outbox when this launch started (continuation launches)
   // ---- State (mod.rs:271-287) + role state + Chain scalars (chain.rs:99-104)
   uint64_t term, etime, hbtime;
-  uint32_t voted, leader, etimeout, draws, head, commit, idgen, maxkey;
+  uint32_t voted, leader, etimeout, draws, head, commit, idgen, maxkey, tbase;
   uint32_t role, fault, prmask, nq, dead, ckey, seen, granted;
   uint32_t ph[R];
   // ---- output cursors
-  uint32_t ocnt, fcnt, nmsg, nfsm;
+  uint32_t ocnt, nmsg, nfsm;
   uint64_t mdig, fdig;
   uint32_t mko[R];       // delivery index of this tick's outbox, one mask per receiver (see Local::mk_out)
 
@@ -238,6 +355,7 @@ struct Replica {
     role = m & 255u; fault = (m >> 8) & 255u; prmask = (m >> 16) & 255u;
     nq = (m >> 24) & 7u; dead = (m >> 27) & 1u; ckey = (m >> 28) & 1u;
     maxkey = d.mk[rg];
+    tbase = d.tb[g];
     hbtime = 0; seen = granted = 0;
 #pragma unroll
     for (int i = 0; i < R; ++i) ph[i] = 0;
@@ -257,7 +375,15 @@ struct Replica {
     }
     ocnt = reset_out ? 0u : d.oc[cur][rg];
     ocnt0 = ocnt;
-    fcnt = reset_fsm ? 0u : d.fc[rg];
+    if (d.flags & JR_F_CAPTURE_FSM) {
+      const uint2 fc = reset_fsm ? make_uint2(0u, 0u) : d.fc[rg];
+      uint32_t* S = L.fsm + L.tid;
+      S[FS_COUNTS * L.nt] = 0;
+      S[FS_PBLO * L.nt] = 0;
+      S[FS_PBHI * L.nt] = 0;
+      S[FS_NREC * L.nt] = fc.x;
+      S[FS_SEQ * L.nt] = fc.y;
+    }
     mdig = fdig = 0; nmsg = nfsm = 0;
     if (digest_on()) {
       uint4 v = d.dg[rg];
@@ -293,7 +419,7 @@ struct Replica {
     for (uint32_t u = ocnt0; u < staged; ++u)
       d.ob[cur][((size_t)u * R + r) * d.Gp + g] = L.out[(u * R + r) * 32 + L.lane];
     d.oc[cur][rg] = ocnt;
-    d.fc[rg] = fcnt;
+    if (d.flags & JR_F_CAPTURE_FSM) fsm_close_all(L.fsm + L.tid, L.nt, fsm_out(), d.fc + rg);
     if (digest_on()) {
       d.dg[rg] = make_uint4((uint32_t)mdig, (uint32_t)(mdig >> 32), (uint32_t)fdig, (uint32_t)(fdig >> 32));
       d.cn[rg] = make_uint2(nmsg, nfsm);
@@ -301,7 +427,10 @@ struct Replica {
   }
 
   // ------------------------------------------------------------------ block table (chain.rs)
-  __device__ __forceinline__ size_t tix(uint32_t bid) const { return (size_t)bid * plane + rg; }
+  // The table holds the ids of a window [tbase, tbase + cap): row = id & capm.  Ids below the floor were
+  // truncated (jr_truncate, deviation D7) and read as absent; ids at or past the end cannot be stored.
+  __device__ __forceinline__ size_t tix(uint32_t bid) const { return (size_t)(bid & d.capm) * plane + rg; }
+  __device__ __forceinline__ bool in_window(uint32_t bid) const { return bid - tbase < d.cap; }
   // Block table reads go through a direct-mapped, write-through cache in shared
   // memory (tag = id).  Only this lane writes its own table, so the cache is
   // coherent for the whole launch; it is rebuilt at launch start.
@@ -313,6 +442,7 @@ struct Replica {
       const uint4 e = *tc_slot(bid);
       if (e.x == bid) { next = e.y; tok = (uint64_t)e.z | ((uint64_t)e.w << 32); return; }
     }
+    if (!in_window(bid)) { next = ABSENT; tok = 0; return; }
     next = d.cnext[tix(bid)];   // both loads issue together: one latency
     tok = d.ctok[tix(bid)];
     if (L.W) *tc_slot(bid) = make_uint4(bid, next, (uint32_t)tok, (uint32_t)(tok >> 32));
@@ -328,7 +458,7 @@ struct Replica {
     return t;
   }
   // chain.rs:155-157
-  __device__ __forceinline__ bool has(uint32_t bid) const { return bid < d.cap && tbl_next(bid) != ABSENT; }
+  __device__ __forceinline__ bool has(uint32_t bid) const { return tbl_next(bid) != ABSENT; }
   __device__ __forceinline__ void tbl_put(uint32_t bid, uint32_t next, uint64_t tok) {
     d.cnext[tix(bid)] = next;
     d.ctok[tix(bid)] = tok;
@@ -341,18 +471,20 @@ struct Replica {
   __device__ __forceinline__ void tc_prefetch() const {
     if (!L.W) return;
     for (uint32_t k = 0; k < L.W; ++k) L.tc[(k * R + r) * 32 + L.lane] = make_uint4(0xFFFFFFFFu, ABSENT, 0, 0);
-    for (uint32_t k0 = 0; k0 < L.W && k0 <= maxkey; k0 += 4) {
+    if (maxkey < tbase) return;            // (a silenced replica the window has moved past)
+    const uint32_t span = maxkey - tbase;  // ids tbase..maxkey are the part of the window that may hold blocks
+    for (uint32_t k0 = 0; k0 < L.W && k0 <= span; k0 += 4) {
       uint32_t n[4];
       uint64_t t[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (k0 + j < L.W && k0 + j <= maxkey) {
+        if (k0 + j < L.W && k0 + j <= span) {
           n[j] = d.cnext[tix(maxkey - k0 - j)];
           t[j] = d.ctok[tix(maxkey - k0 - j)];
         }
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (k0 + j < L.W && k0 + j <= maxkey)
+        if (k0 + j < L.W && k0 + j <= span)
           *tc_slot(maxkey - k0 - j) = make_uint4(maxkey - k0 - j, n[j], (uint32_t)t[j], (uint32_t)(t[j] >> 32));
     }
   }
@@ -379,7 +511,7 @@ struct Replica {
     for (uint32_t u = 0; u < cnt;) {
       const uint4 h = u < L.Us ? L.in[(u * R + r) * 32 + L.lane] : __ldcg(d.ob[prv] + ((size_t)u * R + r) * d.Gp + g);
       const uint32_t kind = h.x & 15u, aux = (h.x >> 8) & 255u, to = h.x >> 16;
-      const uint32_t bit = u < 31u ? (1u << u) : MK_SCAN;
+      const uint32_t bit = u < MK_SLOTS ? (1u << u) : MK_SCAN;
       const bool noop = kind == JR_CMD_HEARTBEAT_RESPONSE && (((h.x >> 4) & 1u) || h.w == 0);
       if (!noop || bit == MK_SCAN) {
 #pragma unroll
@@ -389,13 +521,13 @@ struct Replica {
       u += 1u + ((kind == JR_CMD_APPEND_ENTRIES && !((h.x >> 4) & 1u)) ? aux : 0u);
     }
 #pragma unroll
-    for (int t = 0; t < R; ++t) L.mk_in[(t * R + r) * 32 + L.lane] = m[t];
+    for (int t = 0; t < R; ++t) L.mk_in[(t * R + r) * 32 + L.lane] = (uint16_t)m[t];
   }
   // chain.rs:160-175; returns false on fault
   __device__ __forceinline__ bool chain_append(uint64_t tok, uint32_t& out_id) {
     uint32_t bid = idgen++;  // fetch_add precedes the assert
     if (!(bid > head)) { fault = JR_FAULT_APPEND_ID_NOT_GT_HEAD; return false; }
-    if (bid >= d.cap) { fault = JR_FAULT_ENGINE_CHAIN_CAPACITY; return false; }
+    if (!in_window(bid)) { fault = JR_FAULT_ENGINE_CHAIN_CAPACITY; return false; }
     tbl_put(bid, head, tok);
     head = bid;
     out_id = bid;
@@ -404,7 +536,7 @@ struct Replica {
   // chain.rs:178-192
   __device__ __forceinline__ bool chain_extend(uint32_t bid, uint32_t next, uint64_t tok) {
     if (!has(next)) { fault = JR_FAULT_EXTEND_PARENT_MISSING; return false; }
-    if (bid >= d.cap) { fault = JR_FAULT_ENGINE_CHAIN_CAPACITY; return false; }
+    if (!in_window(bid)) { fault = JR_FAULT_ENGINE_CHAIN_CAPACITY; return false; }
     tbl_put(bid, next, tok);
     head = bid;
     return true;
@@ -435,7 +567,7 @@ struct Replica {
   }
 
   __device__ __forceinline__ void mark(uint32_t to, uint32_t slot) {
-    const uint32_t bit = slot < 31u ? (1u << slot) : MK_SCAN;
+    const uint32_t bit = slot < MK_SLOTS ? (1u << slot) : MK_SCAN;
 #pragma unroll
     for (int t = 0; t < R; ++t)
       if (to == TO_PEERS || to == (uint32_t)t + 1u) mko[t] |= bit;
@@ -447,7 +579,7 @@ struct Replica {
   __device__ __forceinline__ void publish_marks() const {
     if (!L.mk_out) return;
 #pragma unroll
-    for (int t = 0; t < R; ++t) L.mk_out[(t * R + r) * 32 + L.lane] = mko[t];
+    for (int t = 0; t < R; ++t) L.mk_out[(t * R + r) * 32 + L.lane] = (uint16_t)mko[t];
   }
 
   // mod.rs:390-400 for every single-unit command.
@@ -464,14 +596,10 @@ struct Replica {
     }
   }
 
+  __device__ __forceinline__ FsmOut fsm_out() const { return FsmOut{d.fs + rg, plane, d.F, g, r}; }
   // fsm_tx.send(Instruction) (fsm.rs:19-29)
   __device__ __forceinline__ void fsm_emit(bool notify, uint32_t bid, uint32_t next_or_addr, uint64_t tok) {
-    if (d.flags & JR_F_CAPTURE_FSM) {
-      if (fcnt >= d.F) { fault = JR_FAULT_ENGINE_FSM_OVERFLOW; return; }
-      d.fs[(size_t)fcnt * plane + rg] =
-          make_uint4(bid | (notify ? 0x80000000u : 0u), next_or_addr, (uint32_t)tok, (uint32_t)(tok >> 32));
-      ++fcnt;
-    }
+    if (d.flags & JR_F_CAPTURE_FSM) fsm_encode(L.fsm + L.tid, L.nt, fsm_out(), notify, bid, next_or_addr, tok);
     if (digest_on()) {
       fdig = digest_fsm_fn(fdig, notify, bid, next_or_addr, tok);
       ++nfsm;
@@ -623,7 +751,7 @@ struct Replica {
     if (hasc && c.block > commit) {
       uint32_t prev = commit;
       chain_commit(c.block);
-      for (uint32_t b = prev; b < c.block; ++b) {  // range(prev..commit), key order
+      for (uint32_t b = max(prev, tbase); b < c.block; ++b) {  // range(prev..commit), key order (nothing below the floor)
         uint32_t nx; uint64_t tk;
         tbl_fetch(b, nx, tk);
         if (nx != ABSENT) { fsm_emit(false, b, nx, tk); if (fault) return; }
@@ -694,7 +822,7 @@ struct Replica {
       uint32_t prev = commit;
       if (!chain_commit(q)) return;
       bool first = true;
-      for (uint32_t b = prev; b <= q; ++b) {  // range(prev..=new).skip(1), key order
+      for (uint32_t b = max(prev, tbase); b <= q; ++b) {  // range(prev..=new).skip(1), key order (nothing below the floor)
         uint32_t nx; uint64_t tk;
         tbl_fetch(b, nx, tk);
         if (nx == ABSENT) continue;
@@ -724,7 +852,7 @@ struct Replica {
         first_peer = r == 0 ? 1u : 0u;
         const uint32_t take = (prmask >> first_peer) & 1u ? JR_MAX_AE_BLOCKS : 1u;
         const uint32_t head0 = get_ph(first_peer);
-        uint32_t bid = head0, pulled = 0, nb = 0;
+        uint32_t bid = max(head0, tbase), pulled = 0, nb = 0;
         while (pulled < 1 + take) {
           uint32_t nx = ABSENT; uint64_t tok = 0;
           while (bid <= maxkey) {
@@ -760,7 +888,7 @@ struct Replica {
         first = memo_first;
         ref = (uint32_t)p != first_peer;  // (the peer scanned up front owns the inline run)
       } else {
-        uint32_t bid = ph[p], pulled = 0;
+        uint32_t bid = max(ph[p], tbase), pulled = 0;
         while (pulled < 1 + take) {
           uint32_t nx = ABSENT; uint64_t tok = 0;
           while (bid <= maxkey) {
@@ -788,7 +916,7 @@ struct Replica {
       if (!put_unit(ocnt, make_uint4(unit_hdr(JR_CMD_APPEND_ENTRIES, ref ? 1u : 0u, nb, p + 1), (uint32_t)term,
                                      (uint32_t)(term >> 32), first)))
         return;
-      mko[p] |= ocnt < 31u ? (1u << ocnt) : MK_SCAN;
+      mko[p] |= ocnt < MK_SLOTS ? (1u << ocnt) : MK_SCAN;
       if (digest_on()) {
         uint64_t h = digest_message_fn(mdig, JR_CMD_APPEND_ENTRIES, p + 1, 0, nb, id(), term, 0, 0, 0, 0);
         ++nmsg;
@@ -919,11 +1047,9 @@ struct Replica {
   __device__ __forceinline__ void plan_tick(Pos& k, const StepParams& p) const {
     k.pend = 0; k.s = 0; k.idx = 0; k.u = 0; k.cnt = 0; k.reps = 0; k.rep_at = 0;
     if (p.phases & PH_DRAIN) {
-      // delivery masks mk_in[me][s] and mailbox counts cin[s] have the same stride over s
-      const uint32_t* src = d.use_index ? L.mk_in + (r * R) * 32 + L.lane : L.cin + L.lane;
 #pragma unroll
       for (int s_ = 0; s_ < R; ++s_)
-        if (src[s_ * 32]) k.pend |= 1u << s_;
+        if (d.use_index ? (uint32_t)L.mk_in[(r * R + s_) * 32 + L.lane] : L.cin[s_ * 32 + L.lane]) k.pend |= 1u << s_;
       k.pend &= ~(1u << r);  // never my own mailbox
     }
     k.tail = 0;

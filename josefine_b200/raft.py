@@ -273,7 +273,61 @@ class RaftApi:
         self._check(self._fn("drain_fsm")(self._h, buf, C.c_size_t(cap), C.byref(n)), "drain_fsm")
         return [buf[i] for i in range(n.value)]
 
+    def discard_fsm(self) -> int:
+        """Drain without returning the Instructions; their number."""
+        n = C.c_size_t(0)
+        self._check(self._fn("drain_fsm")(self._h, None, C.c_size_t(0), C.byref(n)), "drain_fsm")
+        return n.value
+
+    def fsm_records(self) -> Tuple[List[abi.FsmRecord], abi.FsmBatch]:
+        """jr_fsm_records_async + jr_fsm_records_wait: everything accumulated since the last drain, compact form
+        (copied out of the engine's pinned buffer)."""
+        self._check(self._fn("fsm_records_async")(self._h), "fsm_records_async")
+        ptr, batch = C.POINTER(abi.FsmRecord)(), abi.FsmBatch()
+        st = self._fn("fsm_records_wait")(self._h, C.byref(ptr), C.byref(batch))
+        if st not in (abi.OK, abi.E_CAPACITY):
+            self._check(st, "fsm_records_wait")
+        recs = [abi.FsmRecord.from_buffer_copy(ptr[i]) for i in range(batch.n_records)]
+        if st == abi.E_CAPACITY:
+            raise RaftError(st, self._p + "fsm_records_wait", f"{batch.n_dropped} records dropped")
+        return recs, batch
+
+    def fsm_expand(self, records: Sequence[abi.FsmRecord]) -> List[abi.FsmInstr]:
+        """jr_fsm_expand (pure host code of the engine library): records -> Instructions in jr_step order."""
+        return expand_records(self._lib, records, self.n_groups, self.n_replicas)
+
     # -- introspection ------------------------------------------------------------
+    def query_many(self, targets: Sequence[Tuple[int, int]]) -> List[abi.ReplicaState]:
+        """jr_query_many: one kernel + one copy for all (group, node) targets."""
+        n = len(targets)
+        if not hasattr(self._lib, self._p + "query_many"):
+            return [self.query(g, nd) for g, nd in targets]
+        gs = (C.c_uint32 * max(n, 1))(*[t[0] for t in targets])
+        ns = (C.c_uint32 * max(n, 1))(*[t[1] for t in targets])
+        out = (abi.ReplicaState * max(n, 1))()
+        self._check(self._fn("query_many")(self._h, gs, ns, C.c_size_t(n), out), "query_many")
+        return [out[i] for i in range(n)]
+
+    def chain_read_many(self, reqs: Sequence[Tuple[int, int, int, int]]) -> List[List[Optional[Tuple[int, int, int]]]]:
+        """jr_chain_read_many: reqs = (group, node, first_id, count); one kernel + one copy."""
+        if not hasattr(self._lib, self._p + "chain_read_many"):
+            return [self.chain_read(*r) for r in reqs]
+        n = len(reqs)
+        total = sum(r[3] for r in reqs)
+        gs = (C.c_uint32 * max(n, 1))(*[r[0] for r in reqs])
+        ns = (C.c_uint32 * max(n, 1))(*[r[1] for r in reqs])
+        fs = (C.c_uint64 * max(n, 1))(*[r[2] for r in reqs])
+        cs = (C.c_uint32 * max(n, 1))(*[r[3] for r in reqs])
+        out = (abi.Block * max(total, 1))()
+        present = (C.c_uint8 * max(total, 1))()
+        self._check(self._fn("chain_read_many")(self._h, gs, ns, fs, cs, C.c_size_t(n), out, present), "chain_read_many")
+        res, at = [], 0
+        for r in reqs:
+            res.append([(out[at + i].id, out[at + i].next, out[at + i].data) if present[at + i] else None
+                        for i in range(r[3])])
+            at += r[3]
+        return res
+
     def query(self, group: int, node: int) -> abi.ReplicaState:
         st = abi.ReplicaState()
         self._check(self._fn("query")(self._h, C.c_uint32(group), C.c_uint32(node), C.byref(st)), "query")
@@ -308,6 +362,32 @@ class RaftApi:
     # -- maintenance ----------------------------------------------------------------
     def compact(self):
         self._check(self._fn("compact")(self._h), "compact")
+
+    def truncate(self, margin: int = 8):
+        """jr_truncate (deviation D7): drop every block below min(commit of the live replicas) - margin, per group."""
+        self._check(self._fn("truncate")(self._h, C.c_uint32(margin)), "truncate")
+
+    def node_restart(self, group: int, node: int, now_ms: int, blocks: Sequence[Tuple[int, int, int]], commit: int,
+                     commit_key: Optional[bool] = None):
+        """jr_node_restart: RaftHandle::new over a persisted chain (chain.rs:117-137)."""
+        arr = (abi.Block * max(len(blocks), 1))()
+        for i, (bid, nxt, data) in enumerate(blocks):
+            arr[i].id, arr[i].next, arr[i].data = bid, nxt, data
+        ck = (commit > 0) if commit_key is None else commit_key
+        self._check(self._fn("node_restart")(self._h, C.c_uint32(group), C.c_uint32(node), C.c_uint64(now_ms), arr,
+                                             C.c_size_t(len(blocks)), C.c_uint64(commit), C.c_int(int(ck))), "node_restart")
+
+    def save(self) -> bytes:
+        """jr_engine_save: checkpoint of everything the engine holds."""
+        n = C.c_size_t(0)
+        self._check(self._fn("engine_save_size")(self._h, C.byref(n)), "engine_save_size")
+        buf = C.create_string_buffer(n.value)
+        self._check(self._fn("engine_save")(self._h, buf, n), "engine_save")
+        return buf.raw
+
+    def restore(self, blob: bytes):
+        buf = C.create_string_buffer(blob, len(blob))
+        self._check(self._fn("engine_restore")(self._h, buf, C.c_size_t(len(blob))), "engine_restore")
 
     def set_alive(self, group: int, node: int, alive: bool):
         self._check(self._fn("set_alive")(self._h, C.c_uint32(group), C.c_uint32(node), C.c_int(int(alive))),
@@ -375,6 +455,16 @@ def _bind(lib: C.CDLL, p: str):
         "set_alive": [vp, C.c_uint32, C.c_uint32, C.c_int],
         "kill_leaders": [vp, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)],
         "leader_table": [vp, C.POINTER(abi.LeaderEntry)],
+        "fsm_records_async": [vp],
+        "fsm_records_wait": [vp, C.POINTER(C.POINTER(abi.FsmRecord)), C.POINTER(abi.FsmBatch)],
+        "query_many": [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_size_t, C.POINTER(abi.ReplicaState)],
+        "chain_read_many": [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32),
+                            C.c_size_t, C.POINTER(abi.Block), C.POINTER(C.c_uint8)],
+        "truncate": [vp, C.c_uint32],
+        "node_restart": [vp, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(abi.Block), C.c_size_t, C.c_uint64, C.c_int],
+        "engine_save_size": [vp, C.POINTER(C.c_size_t)],
+        "engine_save": [vp, C.c_void_p, C.c_size_t],
+        "engine_restore": [vp, C.c_void_p, C.c_size_t],
     }
     for name, args in sig.items():
         if not hasattr(lib, p + name):   # an older A/B build (JR_ENGINE_LIB): the call site will fail loudly
@@ -382,12 +472,33 @@ def _bind(lib: C.CDLL, p: str):
         fn = getattr(lib, p + name)
         fn.argtypes = args
         fn.restype = C.c_int
+    if hasattr(lib, p + "fsm_expand"):
+        fn = getattr(lib, p + "fsm_expand")
+        fn.argtypes = [C.POINTER(abi.FsmRecord), C.c_size_t, C.c_uint32, C.c_uint32, C.POINTER(abi.FsmInstr), C.c_size_t,
+                       C.POINTER(C.c_size_t)]
+        fn.restype = C.c_int
     et = getattr(lib, p + "election_timeout")
     et.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
     et.restype = C.c_uint32
 
 
 _engine_lib: Optional[C.CDLL] = None
+
+
+def expand_records(lib: C.CDLL, records: Sequence[abi.FsmRecord], n_groups: int, n_replicas: int) -> List[abi.FsmInstr]:
+    """jr_fsm_expand through ctypes (pure host code: needs no GPU)."""
+    n = len(records)
+    arr = (abi.FsmRecord * max(n, 1))(*records)
+    need = C.c_size_t(0)
+    st = lib.jr_fsm_expand(arr, C.c_size_t(n), C.c_uint32(n_groups), C.c_uint32(n_replicas), None, C.c_size_t(0), C.byref(need))
+    if st not in (abi.OK, abi.E_CAPACITY):
+        raise RaftError(st, "jr_fsm_expand")
+    out = (abi.FsmInstr * max(need.value, 1))()
+    if need.value:
+        st = lib.jr_fsm_expand(arr, C.c_size_t(n), C.c_uint32(n_groups), C.c_uint32(n_replicas), out, need, C.byref(need))
+        if st != abi.OK:
+            raise RaftError(st, "jr_fsm_expand")
+    return [out[i] for i in range(need.value)]
 
 
 def _open_engine_library(path: str) -> C.CDLL:

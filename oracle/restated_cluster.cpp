@@ -389,12 +389,12 @@ jr_status jro_step(jro_cluster* c, jr_step_args* a) {
     }
   a->n_msgs = nm;
   a->n_fsm = nf;
+  if (a->out_fsm) clear_fsm(c);  // returned to the caller: taken
   return ovf ? JR_E_CAPACITY : JR_OK;
 }
 
 jr_status jro_run(jro_cluster* c, uint64_t now0, uint32_t dt, uint32_t n_steps, uint32_t n_synth) {
   if (!c || n_synth > 8) return JR_E_INVAL;
-  clear_fsm(c);
   // Groups never interact, so each host thread runs ALL n_steps for its own
   // contiguous slice of groups: no barrier per step, no thread start per step.
   const uint64_t base = c->step_index;
@@ -418,7 +418,6 @@ jr_status jro_run_proposals(jro_cluster* c, uint64_t now0, uint32_t dt, uint32_t
   const uint32_t G = c->cfg.n_groups;
   for (size_t i = 0; i < (size_t)n_steps * G; ++i)
     if (props[i].node > c->cfg.n_replicas) return JR_E_UNKNOWN_NODE;
-  clear_fsm(c);
   const uint64_t base = c->step_index;
   for_groups(c, [&](uint32_t lo, uint32_t hi) {
     for (uint32_t g = lo; g < hi; ++g)
@@ -459,6 +458,7 @@ jr_status jro_drain_fsm(jro_cluster* c, jr_fsm_instr* out, size_t cap, size_t* n
           ++k;
         }
   *n = k;
+  clear_fsm(c);  // the drain takes them (ABI 2)
   return ovf ? JR_E_CAPACITY : JR_OK;
 }
 
@@ -493,6 +493,7 @@ jr_status jro_query(jro_cluster* c, uint32_t group, uint32_t node, jr_replica_st
   o->fault = (uint8_t)n.fault();
   o->alive = n.alive;
   o->n_queued = (uint8_t)n.queued_reqs.size();
+  o->chain_floor = n.chain.floor();
   return JR_OK;
 }
 
@@ -588,6 +589,42 @@ jr_status jro_compact(jro_cluster* c) {
   if (!c) return JR_E_INVAL;
   for (auto& r : c->reps)
     if (r.node->alive && r.node->fault() == 0) r.node->chain.compact();
+  return JR_OK;
+}
+
+// include/josefine_raft_abi.h jr_truncate (deviation D7)
+jr_status jro_truncate(jro_cluster* c, uint32_t margin) {
+  if (!c) return JR_E_INVAL;
+  for (uint32_t g = 0; g < c->cfg.n_groups; ++g) {
+    uint64_t lo = UINT64_MAX;
+    for (uint32_t r = 1; r <= c->cfg.n_replicas; ++r) {
+      const Node& n = *c->at(g, r).node;
+      if (n.alive && n.fault() == 0) lo = std::min<uint64_t>(lo, n.chain.get_commit());
+    }
+    if (lo == UINT64_MAX) continue;
+    const uint64_t floor = lo > margin ? lo - margin : 0;
+    for (uint32_t r = 1; r <= c->cfg.n_replicas; ++r) c->at(g, r).node->chain.truncate(floor);
+  }
+  return JR_OK;
+}
+
+// include/josefine_raft_abi.h jr_node_restart: RaftHandle::new over an existing data directory
+jr_status jro_node_restart(jro_cluster* c, uint32_t group, uint32_t node, uint64_t now_ms, const jr_block* blocks,
+                           size_t n_blocks, uint64_t commit, int commit_key) {
+  if (!c || group >= c->cfg.n_groups || node < 1 || node > c->cfg.n_replicas || (n_blocks && !blocks)) return JR_E_INVAL;
+  Replica& rep = c->at(group, node);
+  const uint64_t floor = rep.node->chain.floor();
+  std::vector<Block> persisted;
+  for (size_t k = 0; k < n_blocks; ++k) {
+    if (blocks[k].id < floor || blocks[k].id - floor >= c->cfg.chain_capacity) return JR_E_INVAL;
+    persisted.push_back(Block{blocks[k].id, blocks[k].next, blocks[k].data});
+  }
+  NodeConfig nc = rep.node->config();
+  const bool strict = (c->cfg.flags & JR_F_SLED_COMMIT_KEY_STRICT) != 0;
+  std::vector<Instruction> undrained = std::move(rep.node->fsm);   // what the old incarnation emitted is still owed to the host
+  rep.node = std::make_unique<Node>(nc, Chain(c->cfg.chain_capacity, strict, persisted, commit, commit_key != 0, floor), now_ms);
+  rep.node->fsm = std::move(undrained);
+  rep.prev_out.clear();
   return JR_OK;
 }
 

@@ -32,8 +32,27 @@ Chain::Chain(uint64_t capacity, bool strict) : strict_(strict), capacity_(capaci
   db_[id] = Block{id, id, 0};
 }
 
+// chain.rs:117-137 reopening a data directory: id_gen = head = commit = the persisted "commit" value (0 if the key
+// is missing); commit == 0 runs init() again, which (re)writes the genesis block and leaves id_gen at 1.
+Chain::Chain(uint64_t capacity, bool strict, const std::vector<Block>& persisted, uint64_t commit, bool commit_key,
+             uint64_t floor)
+    : commit_key_(commit_key), strict_(strict), capacity_(capacity), floor_(floor), id_gen_(commit), commit_(commit),
+      head_(commit) {
+  for (const Block& b : persisted) db_[b.id] = b;
+  if (commit == 0) {
+    uint64_t id = id_gen_++;
+    if (floor_ == 0) db_[id] = Block{id, id, 0};
+  }
+}
+
 void Chain::check_capacity(BlockId id) const {
-  if (id >= capacity_) throw Fault{JR_FAULT_ENGINE_CHAIN_CAPACITY};  // D4
+  if (id < floor_ || id - floor_ >= capacity_) throw Fault{JR_FAULT_ENGINE_CHAIN_CAPACITY};  // D4, D7
+}
+
+void Chain::truncate(BlockId floor) {  // D7
+  if (floor <= floor_) return;
+  db_.erase(db_.begin(), db_.lower_bound(floor));
+  floor_ = floor;
 }
 
 bool Chain::has(BlockId id) const { return db_.count(id) != 0; }  // chain.rs:155-157
@@ -182,6 +201,11 @@ Node::Node(const NodeConfig& cfg)  // follower.rs:68-95
     : chain(cfg.chain_capacity, cfg.strict_commit_key), cfg_(cfg) {
   // init(): set_election_timeout at time 0 of the logical clock
   now_ = 0;
+  set_election_timeout();
+}
+
+Node::Node(const NodeConfig& cfg, Chain persisted, uint64_t now) : chain(std::move(persisted)), cfg_(cfg) {
+  now_ = now;
   set_election_timeout();
 }
 

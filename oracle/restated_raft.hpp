@@ -89,7 +89,12 @@ struct Instruction {
 // block id below 0x63 << 56; `commit_key_` records whether it exists.
 class Chain {
  public:
-  Chain(uint64_t capacity, bool strict_commit_key);          // chain.rs:117-153
+  Chain(uint64_t capacity, bool strict_commit_key);          // chain.rs:117-153, fresh data directory
+  // chain.rs:117-137 over an existing data directory: the persisted blocks and "commit" value
+  Chain(uint64_t capacity, bool strict_commit_key, const std::vector<Block>& persisted, uint64_t commit, bool commit_key,
+        uint64_t floor);
+  void truncate(BlockId floor);                              // deviation D7: keys below `floor` leave the tree
+  BlockId floor() const { return floor_; }
   bool has(BlockId id) const;                                // chain.rs:155-157
   BlockId append(uint64_t data);                             // chain.rs:160-175
   void extend(const Block& b);                               // chain.rs:178-192
@@ -111,6 +116,7 @@ class Chain {
   bool commit_key_ = false;
   bool strict_ = false;
   uint64_t capacity_;
+  BlockId floor_ = 0;
   uint64_t id_gen_ = 0;
   BlockId commit_ = 0;
   BlockId head_ = 0;
@@ -167,6 +173,7 @@ struct NodeConfig {
 class Node {
  public:
   explicit Node(const NodeConfig& cfg);  // follower.rs:68-95
+  Node(const NodeConfig& cfg, Chain persisted, uint64_t now);  // the same over an existing data directory, at time `now`
   // Apply::apply (mod.rs:471-479).  `now` replaces Instant::now() (D1).  Output
   // is appended to rpc / fsm (rpc_tx / fsm_tx, mod.rs:338-340).  A reference
   // panic or Err sets fault() and the node ignores everything afterwards (D3).

@@ -48,12 +48,28 @@ def case_mailbox_overflow_faults_cleanly(make):
     assert api.fault_count() == 3
 
 
-def case_fsm_fifo_overflow_faults_cleanly(make):
-    api = make(1, 1, flags=abi.F_CAPTURE_FSM, fsm_units=4)
-    api.apply(Command.timeout(0, 1))
-    api.run(100, 100, 8, 1)        # 16 Instructions > 4 units in one launch
-    assert api.query(0, 1).fault == abi.FAULT_ENGINE_FSM_OVERFLOW
-    assert len(api.drain_fsm()) == 4
+def case_fsm_fifo_overflow_never_touches_consensus(make):
+    """A full Instruction FIFO is an observability limit: records are dropped and the drain says
+    JR_E_CAPACITY, but the replica does not fault and its state equals that of an engine with a large FIFO."""
+    import pytest
+    from josefine_b200 import RaftError
+    irregular = [[(1, 1000 + 37 * k * k)] for k in range(8)]    # tokens with no common stride: one record per Instruction
+    small = make(1, 1, flags=abi.F_CAPTURE_FSM | abi.F_STREAM_DIGEST, fsm_units=4)
+    big = make(1, 1, flags=abi.F_CAPTURE_FSM | abi.F_STREAM_DIGEST, fsm_units=64)
+    for api in (small, big):
+        api.apply(Command.timeout(0, 1))
+        api.run_proposals(100, 100, irregular)    # 8 Notify + 8 Apply, 16 records > 4 units
+    assert small.query(0, 1).fault == 0 and small.fault_count() == 0
+    assert small.state_digest() == big.state_digest() and small.stream_digest() == big.stream_digest()
+    with pytest.raises(RaftError) as err:
+        small.drain_fsm()
+    assert err.value.status == abi.E_CAPACITY
+    assert len(big.drain_fsm()) == 16
+    assert small.drain_fsm() == [] and big.drain_fsm() == []      # a drain takes what it returns
+    # ... while a regular stream compresses: synthetic tokens advance by a constant stride, so 120 Instructions are
+    # one APPLY run + one NOTIFY run + two 64-bit PATTERN records
+    small.run(1000, 100, 60, 1)
+    assert len(small.drain_fsm(cap=1024)) == 120
 
 
 def case_degenerate_calls(make):

@@ -19,7 +19,7 @@ def _gpu(g, r, **kw):
 
 
 PAIRED = [limit_cases.case_chain_capacity_fault, limit_cases.case_client_queue_overflow]
-SINGLE = [limit_cases.case_mailbox_overflow_faults_cleanly, limit_cases.case_fsm_fifo_overflow_faults_cleanly,
+SINGLE = [limit_cases.case_mailbox_overflow_faults_cleanly, limit_cases.case_fsm_fifo_overflow_never_touches_consensus,
           limit_cases.case_degenerate_calls]
 
 
