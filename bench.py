@@ -7,27 +7,34 @@ previous step, take the step's client proposal (leader) and apply one
 Command::Tick (SURVEY.md section 8d; the reference defines no such unit -- its
 Tick is a 100 ms wall-clock interval, src/raft/server.rs:25).
 
-Workload (config.workload): BASELINE config #3 -- 65,536 groups x 5 replicas per
-GPU, leaders pre-elected on node 1 by a synthetic vote trace, then steady state:
-one client proposal per group per tick, AppendEntries / AppendResponse /
-Heartbeat / HeartbeatResponse traffic between the co-resident replicas.
+Headline workload (config.workload): BASELINE config #3 -- 65,536 groups x 5 replicas
+per GPU, leaders pre-elected on node 1 by a synthetic vote trace, then steady state:
+one client proposal per group per tick, AppendEntries / AppendResponse / Heartbeat /
+HeartbeatResponse traffic between the co-resident replicas.  heartbeat_ms = tick = 100 ms
+and the reference compares with a strict `>` (leader.rs:78-84), so the leader heartbeats
+every SECOND tick; `variants.heartbeat_every_tick` (heartbeat_ms = 99) is the other reading.
 
-A bench "step" = TICKS_PER_STEP consecutive group-ticks of every group (one
-jr_run).  L2 is flushed between timed steps (the per-GPU working set, ~0.1 GB,
-is smaller than the 126 MB L2, so without the flush the state would be served
-from L2 forever); inside a step the ticks run back to back as they do in
-production.  Device time is taken with CUDA events on the engine's stream,
+A bench "step" = TICKS_PER_STEP consecutive group-ticks of every group: one fused launch
+(jr_run / jr_run_tokens), then jr_truncate (deviation D7: the block-table window moves up, so
+an engine runs indefinitely -- no reset anywhere in this file) and the drain of the step's
+Instruction stream (jr_fsm_records_async: scan + pack on the engine stream, copy to pinned
+host memory on the copy stream).  L2 is flushed between timed steps (the working set is
+smaller than the 126 MB L2).  Device time is taken with CUDA events on the engine's stream,
 per step, flush excluded; max over ranks.
 
 Arms:
-  (default)          the CUDA engine.  `value` = device-resident throughput;
-                     `e2e` = the same workload driven tick by tick through the
-                     C-ABI jr_step with HOST buffers: proposals H2D from pinned
-                     memory and the per-group {term, leader, commit} table D2H
-                     every tick.
-  --impl reference   the CPU comparator: the C++ RESTATEMENT of josefine's
-                     src/raft (oracle/; josefine itself is Rust and cannot be
-                     built here) on all host cores, bounded sample.
+  (default)          the CUDA engine.  `value` = device-resident throughput (proposals
+                     generated in the kernel, Instruction stream drained every step);
+                     `e2e` = the same workload through the C ABI with HOST buffers, every
+                     step: tokens H2D from pinned memory, the per-group leader table D2H,
+                     the step's Instruction records D2H and folded on the host.
+                     `e2e_no_output` = the same without the Instruction stream.
+                     `other_configs` = BASELINE configs #2, #4 (per-GPU shard) and #5, each
+                     timed at its size; `parity` = state/stream digests against the C++
+                     restatement on the same inputs, per config, in this run.
+  --impl reference   the CPU comparator: the C++ RESTATEMENT of josefine's src/raft
+                     (oracle/; josefine itself is Rust and cannot be built here) on the
+                     host cores, the SAME config #3 workload at full size.
 """
 from __future__ import annotations
 
@@ -55,12 +62,30 @@ TICKS_PER_STEP = 64
 DT_MS = 100
 SEED = 1
 L2_FLUSH_BYTES = 256 << 20
-CHAIN_CAP_MAX = 6144        # block-table ids per replica (12 B x 327,680 replicas each = 3.9 MB per id, 24 GB total)
+CHAIN_WINDOW = 512          # block ids a replica's table may span above the floor (truncated every step)
+TRUNC_MARGIN = 8
+FSM_UNITS = 16              # record slots per replica between two drains (steady state uses <= 4)
+
+
+def workload_name(G, R):
+    return (f"BASELINE config #3: {G} groups x {R} replicas per GPU, pre-elected leaders, steady-state "
+            f"AppendEntries, 1 proposal/group/tick, {TICKS_PER_STEP} ticks per step")
+
+
+_boot_cache = {}
 
 
 def bootstrap_inject(G, R, node=1, scattered=False):
     """Synthetic vote trace: Timeout on `node` (or on node g % R + 1 with `scattered`), plus
     quorum-1 granted VoteResponses."""
+    key = (G, R, node, scattered)
+    if key not in _boot_cache:
+        _boot_cache.clear()          # (one list at a time: ~200k ctypes structs each)
+        _boot_cache[key] = _bootstrap_inject(G, R, node, scattered)
+    return _boot_cache[key]
+
+
+def _bootstrap_inject(G, R, node, scattered):
     q = 0 if R == 1 else R // 2 + 1
     inj = []
     for g in range(G):
@@ -71,54 +96,65 @@ def bootstrap_inject(G, R, node=1, scattered=False):
     return inj
 
 
-def algorithmic_bytes_per_group_tick(make, R, ticks=64):
-    """Minimum bytes one steady-state group-tick must move with THIS layout
-    (DESIGN.md "Algorithmic bytes"), measured on a small captured run:
-      state   : follower 52 B (P0,P1,P2 + max_key), leader 116 B (+P3, 2 progress planes) -- read AND written
-      mailbox : every 16 B unit written once and read once per addressee (+4 B count, written and read);
-                AppendEntries of one sender that carry the same block run share the block units
-      blocks  : 12 B written per block appended/extended, 12 B read per block shipped or applied, 4 B has() probe
-      fsm     : 16 B per Instruction
+# ---------------------------------------------------------------------------------------------
+# algorithmic bytes
+
+def algorithmic_bytes_per_group_tick(make, R, ticks=64, heartbeat_ms=100):
+    """Bytes one steady-state group-tick must move, from the message mix of a small captured run.
+    Returns (reference_widths, layout):
+      reference_widths  SURVEY.md 8(d): per replica state 40 B read + 40 B written; each message's decision fields
+                        in the reference's own widths, written once and read once per addressee
+                        (AppendEntries 16 + 16/block, AppendResponse 24, Heartbeat 20, HeartbeatResponse 12,
+                        VoteRequest 28, VoteResponse 16, ClientRequest/Response 24); leader progress heads R x 8 B
+                        read + written; block table 16 B per block appended / extended
+      layout            the same count with THIS engine's widths (16 B mailbox units, 52/116 B state planes, 12 B table
+                        rows, 32 B Instruction records) -- wider than the reference's, so it may not raise the claim
     """
     G = 32
     eng = make(G, R, seed=SEED, flags=abi.F_CAPTURE_MESSAGES | abi.F_CAPTURE_FSM, chain_capacity=ticks * 2 + 64,
-               fsm_units=16)
+               fsm_units=64, heartbeat_ms=heartbeat_ms)
     eng.step(0, flags=0, inject=bootstrap_inject(G, R))
     for k in range(16):  # reach the steady regime
         eng.step((k + 1) * DT_MS, n_synth=1)
-    tot = 0
+    ref_w = {abi.CMD_APPEND_ENTRIES: 16, abi.CMD_APPEND_RESPONSE: 24, abi.CMD_HEARTBEAT: 20, abi.CMD_HEARTBEAT_RESPONSE: 12,
+             abi.CMD_VOTE_REQUEST: 28, abi.CMD_VOTE_RESPONSE: 16, abi.CMD_CLIENT_REQUEST: 24, abi.CMD_CLIENT_RESPONSE: 24}
+    tot_ref = tot_lay = 0
     for k in range(16, 16 + ticks):
         res = eng.step((k + 1) * DT_MS, n_synth=1)
-        b = 0
-        b += G * ((R - 1) * 52 + 116) * 2                    # state read + written
-        b += G * R * 4 * 2 + G * R * (R - 1) * 4             # mailbox counts: reset/written, read by each peer
+        ref = G * R * 40 * 2 + G * R * 8 * 2                  # state R+W, progress heads R+W (one leader per group)
+        lay = G * ((R - 1) * 52 + 116) * 2                    # state planes read + written
+        lay += G * R * 4 * 2 + G * R * (R - 1) * 4            # mailbox counts: reset/written, read by each peer
         seen_vreq, seen_runs = set(), set()
         for m in res.messages:
             readers = (R - 1) if m.to_kind == abi.ADDR_PEERS else 1
+            ref += (ref_w.get(m.kind, 8) + 16 * m.n_blocks) * (1 + readers)
+            if m.kind == abi.CMD_APPEND_ENTRIES:
+                ref += 16 * m.n_blocks                        # the follower's table rows
             if m.kind == abi.CMD_VOTE_REQUEST:                # N-1 copies share one unit
                 key = (m.group, m.from_id)
                 if key in seen_vreq:
                     continue
                 seen_vreq.add(key)
-            b += 16 * (1 + readers)                           # header unit: written once, read per addressee
+            lay += 16 * (1 + readers)                         # header unit: written once, read per addressee
             if m.kind == abi.CMD_APPEND_ENTRIES and m.n_blocks:
                 run = (m.group, m.from_id, tuple(m.blocks[i].id for i in range(m.n_blocks)))
                 if run not in seen_runs:                      # identical block runs of one sender are emitted once
                     seen_runs.add(run)
-                    b += m.n_blocks * (12 + 16)               # leader reads the table entries, writes the block units
-                b += m.n_blocks * (16 + 4 + 12)               # each follower reads the units, probes has(next), writes its table
+                    lay += m.n_blocks * (12 + 16)             # leader reads the table entries, writes the block units
+                lay += m.n_blocks * (16 + 4 + 12)             # each follower reads the units, probes has(next), writes its table
         for f in res.fsm:
-            b += 16
-            b += 12                                           # Notify: block written by append; Apply: block read
-        tot += b
-    return tot / (G * ticks)
+            if f.kind == abi.FSM_NOTIFY:
+                ref += 16                                     # the leader's append: one table row
+            lay += 12                                         # Notify: block written by append; Apply: block read
+        tot_ref += ref
+        tot_lay += lay
+    return tot_ref / (G * ticks), tot_lay / (G * ticks)
 
 
 class ClockSampler:
     """nvidia-smi clocks and throttle reasons (profiling recipe's clocks line).  Started before
-    the warm-up so nvidia-smi's start-up latency is absorbed; `window()` then keeps the samples
-    that arrived inside the timed region (or, if the region was shorter than the sampling
-    period, the ones closest to it -- the GPU is under the same load during warm-up)."""
+    the warm-up so nvidia-smi's start-up latency is absorbed; `window()` keeps the samples
+    that arrived inside the timed region."""
 
     def __init__(self, index):
         self.index = index
@@ -167,6 +203,33 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+# ---------------------------------------------------------------------------------------------
+# host placement
+
+def bind_to_gpu_numa_node(index):
+    """Run this process (and first-touch its pinned buffers) on the NUMA node the GPU hangs off."""
+    info = {"gpu": index, "node": None, "cpus": None}
+    try:
+        bus = subprocess.check_output(["nvidia-smi", f"--id={index}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                      text=True, stderr=subprocess.DEVNULL).strip().lower()
+        dom, rest = bus.split(":", 1)
+        path = f"/sys/bus/pci/devices/{dom[-4:]}:{rest}/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info.update(node=node, cpus=len(cpus))
+    except (OSError, ValueError, subprocess.CalledProcessError):
+        pass
+    return info
+
+
 def effective_cores():
     """Host threads this process may really use: affinity mask and cgroup CPU quota, not just cpu_count()."""
     n = os.cpu_count() or 1
@@ -183,249 +246,285 @@ def effective_cores():
     return n
 
 
+# ---------------------------------------------------------------------------------------------
+# CPU comparator: the C++ restatement (oracle/), NOT josefine
+
+def cpu_cluster(G, R, threads, chain_window=CHAIN_WINDOW, heartbeat_ms=100, seed=SEED, flags=0):
+    from oracle.restated import RestatedCluster
+    c = RestatedCluster.create(G, R, n_threads=threads, seed=seed, chain_capacity=chain_window, heartbeat_ms=heartbeat_ms,
+                               flags=flags)
+    c.step(0, flags=0, inject=bootstrap_inject(G, R))
+    c.run(DT_MS, DT_MS, 16, 1)
+    c.truncate(TRUNC_MARGIN)
+    return c
+
+
 def best_cpu_threads(R, cores):
-    """The restatement allocates heavily; more threads than the allocator / cgroup can feed
-    makes it SLOWER.  Probe a few counts on a small sample and keep the fastest, so the CPU
-    arm is measured at its best."""
+    """The restatement allocates heavily; more threads than the allocator / cgroup can feed makes it SLOWER.
+    Probe a few counts on a small sample, once per host (cached under /tmp), and keep the fastest."""
+    cache = f"/tmp/josefine_b200_cpu_threads_{cores}_{R}.json"
+    try:
+        return int(json.load(open(cache))["threads"])
+    except (OSError, ValueError, KeyError):
+        pass
     best, best_rate = 1, 0.0
-    cand = sorted({1, 4, 8, 16, 32, 64, cores} & set(range(1, cores + 1)))
-    for th in cand:
+    for th in sorted({1, 4, 8, 16, 32, 64, cores} & set(range(1, cores + 1))):
         g = max(512, 32 * th)
-        c = cpu_reference_run(g, R, 80, th)
+        c = cpu_cluster(g, R, th)
         t0 = time.perf_counter()
         c.run(DT_MS * 17, DT_MS, 32, 1)
         rate = g * 32 / (time.perf_counter() - t0)
         if rate > best_rate:
             best, best_rate = th, rate
+    try:
+        json.dump({"threads": best}, open(cache, "w"))
+    except OSError:
+        pass
     return best
 
 
-def cpu_reference_run(G, R, ticks, threads):
-    """Times the C++ restatement on `threads` host cores: steady state after bootstrap."""
-    from oracle.restated import RestatedCluster
-    c = RestatedCluster.create(G, R, n_threads=threads, seed=SEED, chain_capacity=ticks * 8 + 4096)
-    c.step(0, flags=0, inject=bootstrap_inject(G, R))
-    c.run(DT_MS, DT_MS, 16, 1)
-    return c
+def cpu_steps(G, R, threads, n_steps):
+    """Seconds per step of the config #3 workload on the restatement: the same calls the GPU arm makes."""
+    c = cpu_cluster(G, R, threads)
+    now = DT_MS * 17
+    out = []
+    for _ in range(n_steps):
+        t0 = time.perf_counter()
+        c.run(now, DT_MS, TICKS_PER_STEP, 1)
+        c.truncate(TRUNC_MARGIN)
+        out.append(time.perf_counter() - t0)
+        now += DT_MS * TICKS_PER_STEP
+    assert c.fault_count() == 0
+    return out
+
+
+def cpu_baseline_block(G, R, steps_best=5, steps_one=1):
+    usable = effective_cores()
+    threads = best_cpu_threads(R, usable)
+    best = cpu_steps(G, R, threads, steps_best + 1)[1:]
+    one = cpu_steps(G, R, 1, steps_one) if threads > 1 else best
+    per_step = G * TICKS_PER_STEP
+    sample = (f"{G} groups x {R} replicas x {TICKS_PER_STEP} ticks per step (the full config #3 step): median of {len(best)} steps at "
+              f"{threads} threads, {len(one)} step at 1 thread; {usable} usable host threads")
+    return {"value": per_step / statistics.median(best), "unit": UNIT, "cores": threads, "kind": "port",
+            "value_1_thread": per_step / statistics.median(one), "sample": sample,
+            "comparator": "C++ restatement of josefine src/raft (oracle/), NOT josefine itself (Rust, unbuildable here)"}
 
 
 def run_reference(args):
-    """--impl reference: the C++ restatement of src/raft on the host cores (bounded sample)."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """--impl reference: the C++ restatement of src/raft on the host cores, config #3 at full size."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    R = REPLICAS
-    cores = best_cpu_threads(R, effective_cores())
-    G = max(4096, 64 * cores)
-    span = 16 * TICKS_PER_STEP            # ticks one cluster lives before it is rebuilt (bounds the std::map chains)
-    st = {"c": None, "left": 0, "now": 0}
-
-    def step():
-        if st["left"] < TICKS_PER_STEP:   # untimed rebuild, like the GPU arm's rebase
-            st["c"] = cpu_reference_run(G, R, span + 64, cores)
-            st["left"], st["now"] = span, DT_MS * 17
-            return 0.0
-        t0 = time.perf_counter()
-        st["c"].run(st["now"], DT_MS, TICKS_PER_STEP, 1)
-        st["now"] += DT_MS * TICKS_PER_STEP
-        st["left"] -= TICKS_PER_STEP
-        return time.perf_counter() - t0
-
-    def timed_step():
-        d = step()
-        return d if d > 0.0 else step()
-
-    for _ in range(args.warmup):
-        timed_step()
-    dt = sum(timed_step() for _ in range(args.steps))
-    value = G * TICKS_PER_STEP * args.steps / dt
-    sample = (f"{G} groups x {R} replicas x {TICKS_PER_STEP} ticks per step, {cores} threads (fastest of a probe over "
-              f"1..{effective_cores()} usable host threads; groups partitioned statically)")
+    G, R = args.groups, args.replicas
+    usable = effective_cores()
+    threads = best_cpu_threads(R, usable)
+    times = cpu_steps(G, R, threads, args.warmup + args.steps)[args.warmup:]
+    one = cpu_steps(G, R, 1, 1) if threads > 1 else times
+    per_step = G * TICKS_PER_STEP
+    value = per_step / statistics.median(times)
+    sample = (f"{G} groups x {R} replicas x {TICKS_PER_STEP} ticks per step, median of {len(times)} steps at {threads} threads "
+              f"(fastest of a cached probe over 1..{usable} usable host threads; groups partitioned statically)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-        "data": "synthetic",
-        "config": {"workload": "BASELINE config #3 steady-state AppendEntries, bounded sample: " + sample,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": statistics.median(times) * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": workload_name(G, R), "groups_per_gpu": G, "replicas": R, "ticks_per_step": TICKS_PER_STEP,
+                   "tick_ms": DT_MS, "seed": SEED,
                    "comparator": "C++ restatement of josefine src/raft (oracle/), NOT josefine itself (Rust, unbuildable here)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "value_1_thread": per_step / statistics.median(one)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--groups", type=int, default=GROUPS_PER_GPU, help="groups per GPU")
-    ap.add_argument("--replicas", type=int, default=REPLICAS)
-    ap.add_argument("--scattered-leaders", action="store_true",
-                    help="diagnostic: leader of group g on node g %% R + 1 instead of node 1 (not the BASELINE workload)")
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-cpu", action="store_true")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-    if args.warmup < 3:
-        args.warmup = 3
+# ---------------------------------------------------------------------------------------------
+# GPU arms
 
-    import torch
-    import torch.distributed as dist
-    from josefine_b200 import RaftEngine
+class Bench:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.args = args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+        self.placement = bind_to_gpu_numa_node(self.local)     # before any pinned allocation (first touch)
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")     # the 1 MB announce must not take SMs from a slot-bound kernel
+            os.environ.setdefault("NCCL_MIN_NCHANNELS", "1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        self.stream = torch.cuda.Stream()      # explicit non-default stream: handle 0 would mean "engine's own"
+        torch.cuda.set_stream(self.stream)
+        self.flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    G, R = args.groups, args.replicas
-    S = TICKS_PER_STEP
-    total_ticks = S * (max(args.warmup, 20) + args.steps) + 64
-    stream = torch.cuda.Stream()          # explicit non-default stream: handle 0 would mean "engine's own"
-    torch.cuda.set_stream(stream)
+    def make(self, g, r, **kw):
+        from josefine_b200 import RaftEngine
+        kw.setdefault("device", self.local)
+        e = RaftEngine.create(g, r, **kw)
+        return e
 
-    def make(g, r, **kw):
-        kw.setdefault("device", local)
-        return RaftEngine.create(g, r, **kw)
-
-    # ---------------- device-resident arm ----------------
-    # The block table grows by one id per tick (12 B x R x G each), so the engine is sized for
-    # at most CHAIN_CAP_MAX ids and REBASED (jr_engine_reset + the bootstrap trace + 16 warm ticks)
-    # between timed steps when it runs low -- never inside a timed event pair.
-    cap = min(total_ticks + 64, CHAIN_CAP_MAX)
-    eng = make(G, R, seed=SEED, group_offset=rank * G, chain_capacity=cap,
-               flags=abi.F_CAPTURE_FSM, fsm_units=2 * S + 8, mailbox_units=64)
-    eng.set_stream(stream.cuda_stream)
-    boot = bootstrap_inject(G, R, scattered=args.scattered_leaders)
-    state = {"ticks_left": 0, "now": 0}
-
-    def rebase(e):
-        e.reset()
-        e.step(0, flags=0, inject=boot)
+    def steady_engine(self, G, R, flags, scattered=False, heartbeat_ms=100, seed=SEED):
+        e = self.make(G, R, seed=seed, group_offset=self.rank * G, chain_capacity=CHAIN_WINDOW, flags=flags,
+                      fsm_units=FSM_UNITS, mailbox_units=64, heartbeat_ms=heartbeat_ms)
+        e.set_stream(self.stream.cuda_stream)
+        e.step(0, flags=0, inject=bootstrap_inject(G, R, scattered=scattered))
         e.run(DT_MS, DT_MS, 16, 1)
-        state["ticks_left"] = cap - 32 - 16
-        state["now"] = DT_MS * 17
+        e.truncate(TRUNC_MARGIN)
+        if flags & abi.F_CAPTURE_FSM:
+            e.discard_fsm()
+        return e
 
-    rebase(eng)
-    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
-    leaders = torch.empty(G * 16, dtype=torch.uint8, device="cuda")
-    gathered = torch.empty(world * G * 16, dtype=torch.uint8, device="cuda") if world > 1 else None
-    side = torch.cuda.Stream() if world > 1 else None
-    announce_done = [None]
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
 
-    def one_step():
-        eng.run(state["now"], DT_MS, S, 1)
-        state["now"] += DT_MS * S
-        state["ticks_left"] -= S
-        if world > 1:
-            # the one cross-shard exchange: leader announce, once per step (every 64 ticks).  The table is packed on
-            # the engine stream; the NCCL all-gather runs on a side stream and overlaps the next step's kernel.
-            if announce_done[0] is not None:
-                stream.wait_event(announce_done[0])            # previous announce must be over before `leaders` is rewritten
-            eng.leader_table_device(leaders.data_ptr())
-            packed = torch.cuda.Event()
-            packed.record(stream)
+    def max_over_ranks(self, v):
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident: proposals generated in the kernel, Instruction stream drained every step
+    def device_resident(self, G, R, steps, warmup, announce=True, sampler=None, **eng_kw):
+        torch, dist = self.torch, self.dist
+        S = TICKS_PER_STEP
+        capture = os.environ.get("JR_BENCH_CAPTURE", "1") != "0"      # diagnostic A/B only; the reported runs capture
+        eng = self.steady_engine(G, R, abi.F_CAPTURE_FSM if capture else 0, **eng_kw)
+        lib, h = eng._lib, eng._h
+        now = [DT_MS * 17]
+        world = self.world
+        leaders = torch.empty(G * 16, dtype=torch.uint8, device="cuda")
+        gathered = torch.empty(world * G * 16, dtype=torch.uint8, device="cuda") if world > 1 else None
+        side = torch.cuda.Stream() if world > 1 else None
+        announce_done = [None]
+        totals = (C.c_uint64 * 3)()
+        applied = (C.c_uint32 * (G * R))()
+        outstanding = [0]
+
+        def take():
+            ptr, batch = C.POINTER(abi.FsmRecord)(), abi.FsmBatch()
+            st = lib.jr_fsm_records_wait(h, C.byref(ptr), C.byref(batch))
+            assert st == 0, (st, batch.n_dropped)
+            st = lib.jr_fsm_fold(C.cast(ptr, C.c_void_p), C.c_size_t(batch.n_records), G, R, applied, totals)
+            assert st == 0
+            outstanding[0] -= 1
+
+        def one_step():
+            eng.run(now[0], DT_MS, S, 1)
+            eng.truncate(TRUNC_MARGIN)
+            now[0] += DT_MS * S
+            if capture:
+                if outstanding[0] == 2:
+                    take()
+                st = lib.jr_fsm_records_async(h)
+                assert st == 0, st
+                outstanding[0] += 1
+            if world > 1 and announce:
+                # the one cross-shard exchange: leader announce, once per step (every 64 ticks).  The table is packed on
+                # the engine stream; the NCCL all-gather runs on a side stream and overlaps the next step's kernel.
+                if announce_done[0] is not None:
+                    self.stream.wait_event(announce_done[0])       # previous announce must be over before `leaders` is rewritten
+                eng.leader_table_device(leaders.data_ptr())
+                packed = torch.cuda.Event()
+                packed.record(self.stream)
+                with torch.cuda.stream(side):
+                    side.wait_event(packed)
+                    dist.all_gather_into_tensor(gathered, leaders)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                announce_done[0] = ev
+
+        for _ in range(max(warmup, 3)):
+            self.flush.fill_(1)
+            one_step()
+        self.barrier()
+        t0 = time.time()
+        evs = []
+        for i in range(steps):
+            self.flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(self.stream)
+            one_step()
+            if world > 1 and announce and i == steps - 1:
+                self.stream.wait_event(announce_done[0])            # the last announce is not hidden by a next step: time it
+            b.record(self.stream)
+            evs.append((a, b))
+        while outstanding[0]:
+            take()
+        self.barrier()
+        clocks = sampler.window(t0, time.time()) if sampler else None
+        per = [a.elapsed_time(b) for a, b in evs]
+        ms = self.max_over_ranks(sum(per))
+        faults = eng.fault_count()
+        table = eng.leader_table()
+        commit_min = min(c for (_, _, c) in table)
+        assert faults == 0, f"{faults} replicas faulted during the timed region"
+        collective_us = None
+        if world > 1 and announce:          # the collective alone, no kernel next to it
+            cev = []
             with torch.cuda.stream(side):
-                side.wait_event(packed)
-                dist.all_gather_into_tensor(gathered, leaders)
-                ev = torch.cuda.Event()
-                ev.record(side)
-            announce_done[0] = ev
-
-    def between_steps():
-        if state["ticks_left"] < S:
-            rebase(eng)
-            if world > 1:      # the rebase is untimed host work of uneven length: re-align the ranks before timing again
-                torch.cuda.synchronize()
-                dist.barrier()
-        flush.fill_(1)
-
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    for _ in range(max(args.warmup, 20)):   # >= 20 untimed steps: also covers nvidia-smi's start-up
-        between_steps()
-        one_step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t_region0 = time.time()
-    evs = []
-    for i in range(args.steps):
-        between_steps()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
-        one_step()
-        if world > 1 and i == args.steps - 1:
-            stream.wait_event(announce_done[0])                # the last announce is not hidden by a next step: time it
-        b.record(stream)
-        evs.append((a, b))
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    clocks = sampler.window(t_region0, time.time()) if rank == 0 else None
-    ms = sum(a.elapsed_time(b) for a, b in evs)
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    faults = eng.fault_count()
-    value = world * G * S * args.steps / (ms * 1e-3)
-    launches = args.steps * (2 if world > 1 else 1)   # one fused step_kernel launch per step (+ leader_table_kernel)
-
-    # ---------------- end-to-end arm (host buffers through the C ABI) ----------------
-    # Every step: jr_run_tokens copies that step's 64-bit payload tokens [S][G] from PINNED host memory
-    # (H2D, on the engine's copy stream), addresses each to the leader the previous step's
-    # jr_leader_table_async announced, and runs the S ticks fused; jr_leader_table_async copies
-    # the per-group {term, leader, commit} result back (D2H).  Two steps are in flight: the host
-    # submits step k+1, then waits for and reads step k's result -- copy-in, kernels and copy-out
-    # of neighbouring steps overlap.
-    e2e = None
-    if not args.no_e2e:
+                for _ in range(12):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(side)
+                    dist.all_gather_into_tensor(gathered, leaders)
+                    b.record(side)
+                    cev.append((a, b))
+            torch.cuda.synchronize()
+            collective_us = statistics.median(a.elapsed_time(b) for a, b in cev[2:]) * 1e3
+        res = {"ms_total": ms, "ms_per_step": ms / steps, "value": world * G * S * steps / (ms * 1e-3),
+               "faulted_replicas": faults, "commit_min": commit_min, "instructions": int(totals[0] + totals[1]),
+               "records": int(totals[2]), "collective_us": collective_us, "clocks": clocks,
+               "ms_per_step_rank_median": statistics.median(per)}
         del eng
         torch.cuda.empty_cache()
-        e2 = make(G, R, seed=SEED, group_offset=rank * G, chain_capacity=cap, mailbox_units=64)
-        e2.set_stream(stream.cuda_stream)
-        rebase(e2)
+        return res
+
+    # ---- end to end through the C ABI with host buffers
+    def end_to_end(self, G, R, steps, warmup, with_output=True):
+        torch = self.torch
+        S = TICKS_PER_STEP
+        eng = self.steady_engine(G, R, abi.F_CAPTURE_FSM if with_output else 0)
+        lib, h = eng._lib, eng._h
         NB = 2
         prop = torch.zeros(NB, S, G, dtype=torch.int64).pin_memory()      # tokens[NB][S][G], one proposal per group-tick
         table = torch.zeros(NB, G, 2, dtype=torch.int64).pin_memory()     # jr_leader_entry[NB][G]
         prop[...] = ((torch.arange(NB * S, dtype=torch.int64).view(NB, S, 1) + 1) << 32) + torch.arange(G, dtype=torch.int64)
-        lib = e2._lib
         pstride, tstride = S * G * 8, G * 16
-        e2.leader_table()                                                 # first announce: where the tokens go
+        eng.leader_table()                                                 # first announce: where the tokens go
+        now = [DT_MS * 17]
+        totals = (C.c_uint64 * 3)()
+        applied = (C.c_uint32 * (G * R))()
+        rec_bytes = [0]
         checks = []
 
-        excluded = [0.0]
-
         def submit(i):
-            if state["ticks_left"] < S:     # block table full: rebase, OUTSIDE the timed region (clock paused)
-                e2.sync()
-                tp = time.perf_counter()
-                rebase(e2)
-                e2.leader_table()
-                excluded[0] += time.perf_counter() - tp
-            tn = state["now"]
-            state["now"] += DT_MS * S
-            state["ticks_left"] -= S
-            st = lib.jr_run_tokens(e2._h, C.c_uint64(tn), C.c_uint32(DT_MS), C.c_uint32(S),
+            st = lib.jr_run_tokens(h, C.c_uint64(now[0]), C.c_uint32(DT_MS), C.c_uint32(S),
                                    C.cast(prop.data_ptr() + (i % NB) * pstride, C.POINTER(C.c_uint64)))   # H2D + route + fused kernel
             assert st == 0, st
-            st = lib.jr_leader_table_async(e2._h, C.cast(table.data_ptr() + (i % NB) * tstride,
-                                                         C.POINTER(abi.LeaderEntry)))   # result D2H
+            now[0] += DT_MS * S
+            assert lib.jr_truncate(h, C.c_uint32(TRUNC_MARGIN)) == 0
+            st = lib.jr_leader_table_async(h, C.cast(table.data_ptr() + (i % NB) * tstride, C.POINTER(abi.LeaderEntry)))   # result D2H
             assert st == 0, st
+            if with_output:
+                assert lib.jr_fsm_records_async(h) == 0                   # Instruction stream D2H
 
         def consume(i):
-            st = lib.jr_leader_table_wait(e2._h)
-            assert st == 0, st
+            assert lib.jr_leader_table_wait(h) == 0
             checks.append(int(table[i % NB, 0, 1].item() >> 32))        # read the step's result: commit of group 0
+            if with_output:
+                ptr, batch = C.POINTER(abi.FsmRecord)(), abi.FsmBatch()
+                st = lib.jr_fsm_records_wait(h, C.byref(ptr), C.byref(batch))
+                assert st == 0, (st, batch.n_dropped)
+                st = lib.jr_fsm_fold(C.cast(ptr, C.c_void_p), C.c_size_t(batch.n_records), G, R, applied, totals)   # the host's fsm::Driver bookkeeping
+                assert st == 0
+                rec_bytes[0] += batch.n_records * 32 + C.sizeof(abi.FsmBatch)
 
         def e2e_steps(n):
             submit(0)
@@ -434,79 +533,285 @@ def main():
                     submit(i + 1)
                 consume(i)
 
-        e2e_steps(max(args.warmup, 2))
-        e2.sync()
-        if world > 1:
-            dist.barrier()
-        excluded[0] = 0.0
+        e2e_steps(max(warmup, 4))
+        eng.sync()
+        self.barrier()
+        for k in range(3):
+            totals[k] = 0
+        rec_bytes[0] = 0
         t0 = time.perf_counter()
-        e2e_steps(args.steps)
-        e2.sync()
-        dt = time.perf_counter() - t0 - excluded[0]
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        e2e = {"value": world * G * S * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": S * G * 8,
-               "d2h_bytes_per_step": G * 16, "ms_per_step": dt * 1e3 / args.steps,
-               "api": "per step: jr_run_tokens(pinned u64 tokens[64][G], routed to the last announced leader) + jr_leader_table_async(pinned jr_leader_entry[G]) "
-                      "+ jr_leader_table_wait; two steps in flight",
-               "commit_last": checks[-1], "faulted_replicas": e2.fault_count(),
+        e2e_steps(steps)
+        eng.sync()
+        dt = self.max_over_ranks(time.perf_counter() - t0)
+        faults = eng.fault_count()
+        assert faults == 0, f"{faults} replicas faulted in the end-to-end arm"
+        if with_output:
+            # every group-tick proposes one block; all R replicas apply it: the stream must carry ~ (R + 1) Instructions per group-tick
+            expect = G * S * steps * (R + 1)
+            got = int(totals[0] + totals[1])
+            assert abs(got - expect) <= expect * 0.02 + 4 * G * R, (got, expect)
+        out = {"value": self.world * G * S * steps / dt, "unit": UNIT, "h2d_bytes_per_step": S * G * 8,
+               "d2h_bytes_per_step": G * 16 + (rec_bytes[0] // steps if with_output else 0), "ms_per_step": dt * 1e3 / steps,
+               "commit_last": checks[-1], "faulted_replicas": faults,
                "timing": "host wall clock around all timed steps incl. the final sync, max over ranks"}
+        if with_output:
+            out.update({"instructions_per_step": int(totals[0] + totals[1]) // steps, "records_per_step": int(totals[2]) // steps,
+                        "d2h_stream_bytes_per_step": rec_bytes[0] // steps,
+                        "api": "per step: jr_run_tokens(pinned u64 tokens[64][G], routed to the last announced leader) + jr_truncate + "
+                               "jr_leader_table_async(pinned jr_leader_entry[G]) + jr_fsm_records_async; then jr_leader_table_wait + "
+                               "jr_fsm_records_wait + jr_fsm_fold over the batch (apply watermark per replica); two steps in flight"})
+        else:
+            out["api"] = ("per step: jr_run_tokens + jr_truncate + jr_leader_table_async + jr_leader_table_wait; engine created without "
+                          "JR_F_CAPTURE_FSM (round 1's end-to-end leg)")
+        del eng
+        torch.cuda.empty_cache()
+        return out
+
+    # ---- BASELINE config #2: 1,024 x 3, cold start -> elections -> 64 proposals -> 256 ticks in all
+    def config2(self, reps):
+        torch = self.torch
+        G, R = 1024, 3
+        eng = self.make(G, R, seed=0, chain_capacity=256, flags=abi.F_CAPTURE_FSM, fsm_units=64)
+        eng.set_stream(self.stream.cuda_stream)
+        per = []
+        for rep in range(reps + 2):
+            eng.reset()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(self.stream)
+            eng.run(DT_MS, DT_MS, 100, 0)              # cold start: seeded timeouts, one election per group
+            eng.run(DT_MS * 101, DT_MS, 64, 1)         # 64 client proposals per group
+            eng.run(DT_MS * 165, DT_MS, 92, 0)
+            b.record(self.stream)
+            torch.cuda.synchronize()
+            if rep >= 2:
+                per.append(a.elapsed_time(b))
+            eng.discard_fsm()
+        leaders = sum(1 for (_, l, _) in eng.leader_table() if l)
+        ms = statistics.median(per)
+        return {"workload": "BASELINE config #2: 1,024 groups x 3 replicas, cold start -> seeded timeouts -> elections -> 64 client "
+                            "proposals/group, 256 ticks (3 fused launches)", "groups": G, "replicas": R, "ticks": 256,
+                "ms_per_trace": ms, "value": G * 256 / (ms * 1e-3), "unit": UNIT, "groups_with_leader": leaders,
+                "faulted_replicas": eng.fault_count(),
+                "note": "32 CTAs on 148 SMs: this size measures launch + per-tick latency, not throughput"}
+
+    # ---- BASELINE config #5: 65,536 x 7, 10% of the groups lose their leader every 100 ticks, compact every 256
+    def config5(self, steps, warmup):
+        torch = self.torch
+        G, R, S = GROUPS_PER_GPU, 7, TICKS_PER_STEP
+        eng = self.steady_engine(G, R, abi.F_CAPTURE_FSM, seed=2)
+        tick = [16]
+        now = lambda: DT_MS * (tick[0] + 1)   # noqa: E731
+        compact_ev, kills = [], []
+
+        def one_step():
+            left = S
+            while left:
+                to_kill = 100 - tick[0] % 100
+                to_compact = 256 - tick[0] % 256
+                n = min(left, to_kill, to_compact)
+                eng.run(now(), DT_MS, n, 1)
+                tick[0] += n
+                left -= n
+                if tick[0] % 100 == 0:
+                    kills.append(eng.kill_leaders(tick[0], 100))
+                if tick[0] % 256 == 0:
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(self.stream)
+                    eng.compact()
+                    b.record(self.stream)
+                    compact_ev.append((a, b))
+            eng.truncate(TRUNC_MARGIN)
+            eng._lib.jr_fsm_records_async(eng._h)
+            ptr, batch = C.POINTER(abi.FsmRecord)(), abi.FsmBatch()
+            assert eng._lib.jr_fsm_records_wait(eng._h, C.byref(ptr), C.byref(batch)) == 0
+
+        for _ in range(warmup):
+            one_step()
+        torch.cuda.synchronize()
+        compact_ev.clear()
+        evs = []
+        for _ in range(steps):
+            self.flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(self.stream)
+            one_step()
+            b.record(self.stream)
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        table = eng.leader_table()
+        live = sum(1 for (_, l, _) in table if l)
+        st = eng.query_many([(g, 1 + (g % R)) for g in range(0, G, 257)])
+        span = statistics.mean(max(int(s.commit) - int(s.chain_floor), 0) for s in st)
+        cms = statistics.median(a.elapsed_time(b) for a, b in compact_ev) if compact_ev else None
+        cbytes = 4 * span * R * G
+        faults = eng.fault_count()
+        res = {"workload": "BASELINE config #5: 65,536 groups x 7 replicas, 1 proposal/group/tick, the leader of 10% of the groups "
+                           "(counter RNG) silenced every 100 ticks, Chain::compact on every replica every 256 ticks, jr_truncate every 64",
+               "groups": G, "replicas": R, "ticks_per_step": S, "steps": steps, "ms_per_step": ms / steps,
+               "value": G * S * steps / (ms * 1e-3), "unit": UNIT, "groups_with_live_leader_at_end": live,
+               "leaders_silenced": int(sum(kills)), "faulted_replicas": faults,
+               "compact_kernel": {"ms": cms, "launches": len(compact_ev), "bytes": cbytes,
+                                  "gbs": (cbytes / (cms * 1e-3) / 1e9) if cms else None,
+                                  "note": "walks ids [floor, commit) of every replica: 4 B x (commit - floor) x R x G; the window is "
+                                          f"~{span:.0f} ids because jr_truncate runs every step"},
+               "note": "SURVEY N1: a follower that ever heard a heartbeat keeps voted_for = the silenced leader and never starts an "
+                       "election, so silenced groups stay leaderless (reference behaviour, reproduced); the live fraction decays"}
+        del eng
+        torch.cuda.empty_cache()
+        return res
+
+    # ---- digest parity against the C++ restatement, same inputs, in this run
+    def parity(self, name, G, R, seed, ticks=TICKS_PER_STEP, kind="steady"):
+        fl = abi.F_STREAM_DIGEST
+        e = self.make(G, R, seed=seed, chain_capacity=CHAIN_WINDOW, flags=fl, fsm_units=FSM_UNITS)
+        e.set_stream(self.stream.cuda_stream)
+        from oracle.restated import RestatedCluster
+        threads = best_cpu_threads(R, effective_cores())
+        o = RestatedCluster.create(G, R, n_threads=threads, seed=seed, chain_capacity=CHAIN_WINDOW, flags=fl)
+        t0 = time.perf_counter()
+        for api in (e, o):
+            if kind == "cold":             # config #2's trace: cold start, elections, 64 proposals, 256 ticks
+                api.run(DT_MS, DT_MS, 100, 0)
+                api.run(DT_MS * 101, DT_MS, 64, 1)
+                api.run(DT_MS * 165, DT_MS, 92, 0)
+                continue
+            api.step(0, flags=0, inject=bootstrap_inject(G, R))
+            api.run(DT_MS, DT_MS, ticks // 2, 1)
+            if kind == "churn":
+                api.kill_leaders(50, 100)
+                api.compact()
+            api.truncate(TRUNC_MARGIN)
+            api.run(DT_MS * (ticks // 2 + 1), DT_MS, ticks - ticks // 2, 1)
+        ok = (e.state_digest() == o.state_digest() and e.stream_digest() == o.stream_digest()
+              and e.fault_count() == o.fault_count() and e.leader_table() == o.leader_table())
+        res = {"config": name, "groups": G, "replicas": R, "ticks": ticks, "bit_exact": bool(ok),
+               "checked": "state digest (all replica state + block tables), Message and Instruction stream digests, fault count, "
+                          "leader table", "against": "C++ restatement of josefine src/raft (oracle/)", "seconds": time.perf_counter() - t0}
+        del e, o
+        self.torch.cuda.empty_cache()
+        return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--groups", type=int, default=GROUPS_PER_GPU, help="groups per GPU")
+    ap.add_argument("--replicas", type=int, default=REPLICAS)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip configs #2/#4/#5 and the variants")
+    ap.add_argument("--no-parity", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    bn = Bench(args)
+    world, rank = bn.world, bn.rank
+    G, R, S = args.groups, args.replicas, TICKS_PER_STEP
+    sampler = ClockSampler(bn.local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+
+    # ---------------- headline: config #3, device resident ----------------
+    main_res = bn.device_resident(G, R, args.steps, max(args.warmup, 20), sampler=sampler)   # >= 20 untimed steps: also nvidia-smi's start-up
+    clocks = main_res.pop("clocks")
+    value, ms = main_res["value"], main_res["ms_total"]
+    launches = args.steps * (5 + (1 if world > 1 else 0))   # step_kernel, truncate, scan, pack, copy (+ leader_table_kernel)
+
+    # ---------------- end to end ----------------
+    e2e = e2e_plain = None
+    if not args.no_e2e:
+        e2e = bn.end_to_end(G, R, args.steps, args.warmup, with_output=True)
+        e2e_plain = bn.end_to_end(G, R, args.steps, args.warmup, with_output=False)
+
+    # ---------------- other BASELINE configs, variants ----------------
+    others, variants = {}, {}
+    short = max(20, args.steps // 4)
+    if not args.no_others:
+        r4 = bn.device_resident(2 * GROUPS_PER_GPU, 5, short, 5)
+        others["config4_shard"] = {
+            "workload": f"BASELINE config #4: 1,048,576 groups x 5 replicas over 8 GPUs = 131,072 per GPU; here {world} GPU(s) x 131,072 "
+                        f"= {world * 2 * GROUPS_PER_GPU} groups, leader announce all-gathered every step" + ("" if world > 1 else " (no peer at N=1)"),
+            "groups_per_gpu": 2 * GROUPS_PER_GPU, "replicas": 5, "steps": short, "ms_per_step": r4["ms_per_step"], "value": r4["value"],
+            "unit": UNIT, "faulted_replicas": r4["faulted_replicas"], "collective_us": r4["collective_us"]}
+        v1 = bn.device_resident(G, R, short, 5, announce=False, scattered=True)
+        variants["scattered_leaders"] = {"value": v1["value"], "ms_per_step": v1["ms_per_step"],
+                                         "what": "leader of group g on node g % R + 1 (what real elections leave behind) instead of node 1"}
+        v2 = bn.device_resident(G, R, short, 5, announce=False, heartbeat_ms=99)
+        variants["heartbeat_every_tick"] = {"value": v2["value"], "ms_per_step": v2["ms_per_step"],
+                                            "what": "heartbeat_ms = 99 < tick: the leader heartbeats every tick (a wall-clock josefine does), not every second one"}
+        if rank == 0:
+            others["config2"] = bn.config2(8)
+            others["config5"] = bn.config5(short, 4)
+        bn.barrier()
 
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            bn.dist.destroy_process_group()
         return
 
+    parity = []
+    if not args.no_parity and world == 1:
+        parity.append(bn.parity("#3 65,536x5 steady", GROUPS_PER_GPU, 5, SEED))
+        if not args.no_others:
+            parity.append(bn.parity("#2 1,024x3 cold start", 1024, 3, 0, ticks=256, kind="cold"))
+            parity.append(bn.parity("#4 shard 131,072x5", 2 * GROUPS_PER_GPU, 5, SEED, ticks=32))
+            parity.append(bn.parity("#5 65,536x7 churn+compact", GROUPS_PER_GPU, 7, 2, ticks=48, kind="churn"))
+        assert all(p["bit_exact"] for p in parity), parity
+
     # ---------------- roofline + cpu baseline (rank 0) ----------------
-    abytes = algorithmic_bytes_per_group_tick(make, R)
+    ref_bytes, lay_bytes = algorithmic_bytes_per_group_tick(bn.make, R)
     peak, peak_src = measured_peak()
-    avg_launch_s = (ms * 1e-3) / args.steps            # one step_kernel launch = S fused ticks of all G groups
-    achieved = abytes * G * S / avg_launch_s / 1e9
+    avg_launch_s = (ms * 1e-3) / args.steps            # one step = S fused ticks of all G groups
     traffic = None
     prof = os.path.join(ROOT, "profiles", "step_kernel_latest.json")
     if os.path.exists(prof):   # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this
         pj = json.load(open(prof))           # command, per launch (one launch = TICKS_PER_STEP ticks)
         if pj.get("ticks_per_launch") == S and pj.get("groups") == G:
             traffic = pj["dram_bytes_per_launch"]
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "step_kernel<5>", "algorithmic_bytes_per_group_tick": abytes,
-                "avg_launch_us": avg_launch_s * 1e6, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": abytes * G * S,
-                "note": f"one launch = {S} fused group-ticks of all {G} groups; replica state stays in registers and the "
-                        "mailboxes in shared memory across those ticks, so DRAM traffic is far below the algorithmic "
-                        "bytes (which count every tick's state + mailbox movement); the engine runs a block's ticks as "
-                        "two ticket-ordered tasks when that fills the last wave of CTAs (DESIGN.md, Split launches); "
-                        "see profiles/"}
+    ach_ref = ref_bytes * G * S / avg_launch_s / 1e9
+    ach_lay = lay_bytes * G * S / avg_launch_s / 1e9
+    roofline = {"bound": "hbm", "achieved": ach_ref, "peak": peak, "unit": "GB/s", "frac": ach_ref / peak,
+                "frac_reference_widths": ach_ref / peak, "frac_layout": ach_lay / peak,
+                "frac_dram": (traffic / avg_launch_s / 1e9 / peak) if traffic else None,
+                "traffic": traffic, "kernel": f"step_kernel<{R}>", "algorithmic_bytes_per_group_tick": ref_bytes,
+                "layout_bytes_per_group_tick": lay_bytes, "avg_launch_us": avg_launch_s * 1e6, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": ref_bytes * G * S,
+                "note": f"`frac` counts the bytes a group-tick moves in the REFERENCE's widths (SURVEY 8d formula applied to this workload's "
+                        f"measured message mix, heartbeat every second tick); frac_layout uses this engine's wider units and is not the claim; "
+                        f"frac_dram is real DRAM traffic from profiles/step_kernel_latest.json.  One launch = {S} fused ticks of {G} groups with "
+                        f"state in registers and mailboxes in shared memory, so most algorithmic bytes never reach DRAM: the kernel is latency "
+                        f"bound, not bandwidth bound (DESIGN.md section 6)."}
     cpu = None
-    if not args.no_cpu:
-        cores = best_cpu_threads(R, effective_cores())
-        cg, ct = max(4096, 64 * cores), 256
-        c = cpu_reference_run(cg, R, ct + 32, cores)
-        t0 = time.perf_counter()
-        c.run(DT_MS * 17, DT_MS, ct, 1)
-        cdt = time.perf_counter() - t0
-        cpu = {"value": cg * ct / cdt, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"C++ restatement of josefine src/raft: {cg} groups x {R} replicas x {ct} ticks, {cores} threads "
-                         f"(fastest of a probe over 1..{effective_cores()} usable host threads)"}
+    if not args.no_cpu and world == 1:
+        cpu = cpu_baseline_block(G, R)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
-        "config": {"workload": f"BASELINE config #3: {G} groups x {R} replicas per GPU, pre-elected leaders, steady-state "
-                               f"AppendEntries, 1 proposal/group/tick",
+        "config": {"workload": workload_name(G, R),
                    "groups_per_gpu": G, "replicas": R, "ticks_per_step": S, "tick_ms": DT_MS, "seed": SEED,
+                   "heartbeat": "heartbeat_ms = tick = 100 and a strict `>` (leader.rs:78-84): every second tick",
+                   "chain_window": CHAIN_WINDOW, "truncate": f"jr_truncate(margin {TRUNC_MARGIN}) every step, inside the timed region (D7); no engine reset",
+                   "output": "Instruction stream drained every step (jr_fsm_records_async), folded on the host one step later",
                    "l2": f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write); ticks inside a step run back to back",
                    "parallelism": f"groups sharded over {world} GPU(s); leader-announce all_gather once per step" if world > 1
-                   else "single GPU", "faulted_replicas": faults,
-                   "untimed_steps_before_timing": max(args.warmup, 20)},
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+                   else "single GPU", "faulted_replicas": main_res["faulted_replicas"], "commit_min": main_res["commit_min"],
+                   "untimed_steps_before_timing": max(args.warmup, 20), "host_placement": bn.placement},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_no_output": e2e_plain, "gpu_launches": launches, "clocks": clocks,
+        "collective_us": main_res["collective_us"], "instructions_per_step": main_res["instructions"] // args.steps,
+        "other_configs": others, "variants": variants, "parity": parity,
     }
     print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        bn.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

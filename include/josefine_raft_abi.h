@@ -413,6 +413,15 @@ jr_status jr_fsm_records_wait(jr_engine* e, const jr_fsm_record** records, jr_fs
  */
 jr_status jr_fsm_expand(const jr_fsm_record* records, size_t n_records, uint32_t n_groups, uint32_t n_replicas,
                         jr_fsm_instr* out, size_t cap, size_t* n_out);
+/*
+ * Pure host function: the bookkeeping of fsm::Driver (fsm.rs:52-88) for a batch, without expanding it.  For every
+ * APPLY record, applied_hi[(node-1) * n_groups + group] becomes the highest block id that replica's driver has
+ * applied (its apply watermark); totals[0] += Apply instructions, totals[1] += Notify instructions,
+ * totals[2] += records.  One linear pass; `applied_hi` (n_replicas * n_groups entries) and `totals` (3 entries)
+ * are caller-owned and accumulate across batches.
+ */
+jr_status jr_fsm_fold(const jr_fsm_record* records, size_t n_records, uint32_t n_groups, uint32_t n_replicas,
+                      uint32_t* applied_hi, uint64_t* totals);
 
 /* ---- introspection --------------------------------------------------------- */
 jr_status jr_query(jr_engine* e, uint32_t group, uint32_t node, jr_replica_state* out);

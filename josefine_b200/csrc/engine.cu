@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(32 * R, step_min_ctas(R)) step_kernel(const De
   L.cout = L.cin + R * 32;
   L.mk_in = reinterpret_cast<uint16_t*>(L.cout + R * 32);
   L.mk_out = L.mk_in + R * R * 32;
-  L.fsm = reinterpret_cast<uint32_t*>(L.mk_out + R * R * 32);   // only there (and only touched) with JR_F_CAPTURE_FSM
+  L.fsm = reinterpret_cast<uint4*>(L.mk_out + R * R * 32);      // only there (and only touched) with JR_F_CAPTURE_FSM
   L.nt = 32 * R; L.tid = threadIdx.x;
   L.Us = d.Us; L.W = d.W; L.lane = lane;
   Replica<R, SORTED> rep(d, L, r, g);
@@ -186,7 +186,7 @@ template <int R>
 __global__ void inject_kernel(const Dev d, const StepParams p, const jr_msg* msgs, const uint4* targets,
                               uint32_t n_targets) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  __shared__ uint32_t fsm_state[FS_WORDS * 64];   // launched with 64 threads per CTA
+  __shared__ uint4 fsm_state[FS_CHUNKS * 64];   // launched with 64 threads per CTA
   Local L;
   L.in = L.out = L.tc = nullptr; L.cin = L.cout = nullptr; L.mk_in = L.mk_out = nullptr; L.Us = 0; L.W = 0; L.lane = 0;
   L.fsm = fsm_state; L.nt = 64; L.tid = threadIdx.x;
@@ -755,7 +755,7 @@ static cudaError_t step_occupancy_r(int* per_sm, int smem) {
 static size_t step_smem_bytes(const Dev& d) {
   return ((size_t)2 * d.Us + d.W) * d.R * 32 * sizeof(uint4) + (size_t)2 * d.R * 32 * sizeof(uint32_t) +
          (size_t)2 * d.R * d.R * 32 * sizeof(uint16_t) +
-         ((d.flags & JR_F_CAPTURE_FSM) ? (size_t)FS_WORDS * d.R * 32 * sizeof(uint32_t) : 0);
+         ((d.flags & JR_F_CAPTURE_FSM) ? (size_t)FS_CHUNKS * d.R * 32 * sizeof(uint4) : 0);
 }
 
 // How many consecutive tasks to cut each block's ticks into: the fewest that minimise the number of
@@ -1429,6 +1429,27 @@ jr_status jr_drain_fsm(jr_engine* e, jr_fsm_instr* out, size_t cap, size_t* n) {
   *n = fsm.size();
   if (out) memcpy(out, fsm.data(), std::min(fsm.size(), cap) * sizeof(jr_fsm_instr));
   return ((out && fsm.size() > cap) || st == JR_E_CAPACITY) ? JR_E_CAPACITY : JR_OK;
+}
+
+jr_status jr_fsm_fold(const jr_fsm_record* recs, size_t n, uint32_t G, uint32_t R, uint32_t* applied_hi, uint64_t* totals) {
+  if ((!recs && n) || !applied_hi || !totals || R < 1 || R > JR_MAX_REPLICAS) return JR_E_INVAL;
+  uint64_t na = 0, nn = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const jr_fsm_record& rc = recs[i];
+    const uint32_t kind = JR_FSMR_KIND(rc.hdr), node = JR_FSMR_NODE(rc.hdr), count = JR_FSMR_COUNT(rc.hdr);
+    if (rc.group >= G || node > R) return JR_E_INVAL;
+    if (kind == JR_FSMR_APPLY) {
+      uint32_t& hi = applied_hi[(size_t)(node - 1) * G + rc.group];
+      hi = std::max(hi, rc.id0 + count - 1);
+      na += count;
+    } else if (kind == JR_FSMR_NOTIFY) {
+      nn += count;
+    }
+  }
+  totals[0] += na;
+  totals[1] += nn;
+  totals[2] += n;
+  return JR_OK;
 }
 
 jr_status jr_fsm_records_async(jr_engine* e) {

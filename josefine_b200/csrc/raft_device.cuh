@@ -78,8 +78,8 @@ struct Local {
   // sender emitted a header at slot >= MK_SLOTS: scan its whole mailbox instead.
   uint16_t* mk_in;
   uint16_t* mk_out;
-  // Instruction-stream encoder state, FS_WORDS words per thread, word-major ([word][thread]); see fsm_encode
-  uint32_t* fsm;
+  // Instruction-stream encoder state, FS_CHUNKS uint4 per thread, chunk-major ([chunk][thread]); see fsm_encode_slow
+  uint4* fsm;
   uint32_t nt, tid;  // threads sharing `fsm`, this thread's column
   uint32_t Us, W, lane;
 };
@@ -212,22 +212,24 @@ __device__ __forceinline__ unsigned long long* jr_prof_smem() {
 // run-length encoded as jr_fsm_record (32 B, layout normative in the ABI header):
 //   APPLY run   blocks id0, id0+1, ... whose `next` is id-1 and whose tokens form an arithmetic
 //               progression (count == 1: any block, `next` explicit)
-//   NOTIFY run  block ids id0, id0+1, ..., one client address, tokens in arithmetic progression
+//   NOTIFY run  block ids id0, id0+1, ... for Address::Client, tokens in arithmetic progression
+//               (count == 1: any client address)
 //   PATTERN     which positions of the replica's stream are Notify (bit = 1); positions no PATTERN
 //               record covers are Apply.  Applies and Notifies each keep their own order, so the
 //               three together reproduce the stream exactly.
-// The open runs live in shared memory (FS_WORDS words per thread); a run that cannot be extended
-// is closed into the replica's record FIFO d.fs.  Every launch closes what is open when it ends.
-enum : uint32_t {
-  FS_A_NEXT = 0, FS_A_TOKLO, FS_A_TOKHI, FS_A_STRLO, FS_A_STRHI,          // open APPLY run: next id, last token, stride (count 1: `next` of the block)
-  FS_N_NEXT, FS_N_TOKLO, FS_N_TOKHI, FS_N_STRLO, FS_N_STRHI, FS_N_ADDR,   // open NOTIFY run
-  FS_COUNTS,                                                              // apply count | notify count << 16
-  FS_PBLO, FS_PBHI,                                                       // pattern bits of the current 64-instruction window
-  FS_SEQ,                                                                 // Instructions emitted since the last drain
-  FS_NREC,                                                                // records closed since the last drain (may exceed F: dropped)
-  FS_WORDS
-};
+// The open runs live in shared memory, four uint4 per thread ([chunk][thread]):
+//   chunk 0  APPLY run : next id, count, last token (lo, hi)
+//   chunk 1             stride (lo, hi; count 1: x = the block's `next`), SEQ, NREC
+//   chunk 2  NOTIFY run: next id, count, last token (lo, hi)
+//   chunk 3             stride (lo, hi; count 1: x = the client address), pattern bits (lo, hi)
+// SEQ = Instructions emitted since the last drain, NREC = records closed since the last drain.
+// Extending an open run (the steady state) is two 128-bit loads and two stores, inline; everything
+// else -- closing a run into the replica's record FIFO d.fs, opening one, a full pattern word --
+// goes through fsm_encode_slow.  Every launch closes what is open when it ends.
+constexpr uint32_t FS_CHUNKS = 4;
 constexpr uint32_t FSR_APPLY = 0u, FSR_NOTIFY = 1u, FSR_PATTERN = 2u;
+constexpr uint32_t FSR_CLIENT = (uint32_t)JR_ADDR_CLIENT << 16;
+constexpr uint32_t FS_MAX_RUN = 0xffffffu;   // the record's count field is 24 bits
 
 struct FsmOut {       // where one replica's records go
   uint4* slot0;       // d.fs + rg
@@ -235,87 +237,83 @@ struct FsmOut {       // where one replica's records go
   uint32_t F, g, r;
 };
 
-__device__ __forceinline__ void fsm_put_record(uint32_t* S, uint32_t nt, const FsmOut& o, uint32_t kind, uint32_t count,
-                                               uint32_t id0, uint32_t addr, uint64_t tok0, uint64_t stride) {
-  const uint32_t n = S[FS_NREC * nt];
-  if (n < o.F) {
-    o.slot0[(size_t)(2 * n) * o.plane] = make_uint4(o.g, kind | (o.r << 2) | (count << 8), id0, addr);
-    o.slot0[(size_t)(2 * n + 1) * o.plane] =
+__device__ __forceinline__ uint32_t fsm_put_record(uint32_t nrec, const FsmOut& o, uint32_t kind, uint32_t count, uint32_t id0,
+                                                   uint32_t addr, uint64_t tok0, uint64_t stride) {
+  if (nrec < o.F) {
+    o.slot0[(size_t)(2 * nrec) * o.plane] = make_uint4(o.g, kind | (o.r << 2) | (count << 8), id0, addr);
+    o.slot0[(size_t)(2 * nrec + 1) * o.plane] =
         make_uint4((uint32_t)tok0, (uint32_t)(tok0 >> 32), (uint32_t)stride, (uint32_t)(stride >> 32));
   }
-  S[FS_NREC * nt] = n + 1;  // past F: counted, not stored (the drain reports JR_E_CAPACITY; consensus is not affected)
+  return nrec + 1;  // past F: counted, not stored (the drain reports JR_E_CAPACITY; consensus is not affected)
 }
 
-__device__ __forceinline__ void fsm_close_run(uint32_t* S, uint32_t nt, const FsmOut& o, bool notify) {
-  const uint32_t counts = S[FS_COUNTS * nt];
-  const uint32_t c = notify ? counts >> 16 : counts & 0xffffu;
-  if (!c) return;
-  const uint32_t b = notify ? FS_N_NEXT : FS_A_NEXT;
-  const uint32_t next_id = S[(b + 0) * nt];
-  const uint64_t last = (uint64_t)S[(b + 1) * nt] | ((uint64_t)S[(b + 2) * nt] << 32);
-  const uint64_t str = (uint64_t)S[(b + 3) * nt] | ((uint64_t)S[(b + 4) * nt] << 32);
+// Close the open run in (c0, c1) into a record.  c0 = {next id, count, tok lo, tok hi}; c1.xy = stride / count-1 payload.
+__device__ __forceinline__ uint32_t fsm_close_run(uint32_t nrec, const FsmOut& o, bool notify, const uint4& c0, uint32_t sx,
+                                                  uint32_t sy) {
+  const uint32_t c = c0.y;
+  if (!c) return nrec;
+  const uint64_t last = (uint64_t)c0.z | ((uint64_t)c0.w << 32);
+  const uint64_t str = (uint64_t)sx | ((uint64_t)sy << 32);
   const uint64_t tok0 = c > 1 ? last - (uint64_t)(c - 1) * str : last;
-  fsm_put_record(S, nt, o, notify ? FSR_NOTIFY : FSR_APPLY, c, next_id - c, notify ? S[FS_N_ADDR * nt] : 0u, tok0, str);
-  S[FS_COUNTS * nt] = notify ? (counts & 0xffffu) : (counts & 0xffff0000u);
+  const uint32_t addr = notify ? (c > 1 ? FSR_CLIENT : sx) : 0u;
+  return fsm_put_record(nrec, o, notify ? FSR_NOTIFY : FSR_APPLY, c, c0.x - c, addr, tok0, (notify && c == 1) ? 0ull : str);
 }
 
-__device__ __forceinline__ void fsm_close_pattern(uint32_t* S, uint32_t nt, const FsmOut& o, uint32_t seq0, uint32_t nbits) {
-  const uint32_t lo = S[FS_PBLO * nt], hi = S[FS_PBHI * nt];
-  if (lo | hi) {
-    fsm_put_record(S, nt, o, FSR_PATTERN, nbits, seq0, 0u, (uint64_t)lo | ((uint64_t)hi << 32), 0ull);
-    S[FS_PBLO * nt] = 0;
-    S[FS_PBHI * nt] = 0;
+// One Instruction, general case.  Apply: nxa = block.next; Notify: nxa = client address (kind << 16 | id).
+__device__ __noinline__ void fsm_encode_slow(uint4* S, uint32_t nt, FsmOut o, bool notify, uint32_t bid, uint32_t nxa, uint64_t tok) {
+  uint4 c1 = S[1 * nt], c3 = S[3 * nt];
+  uint4 run = S[(notify ? 2 : 0) * nt];
+  uint32_t& sx = notify ? c3.x : c1.x;
+  uint32_t& sy = notify ? c3.y : c1.y;
+  const uint32_t seq = c1.z;
+  uint32_t nrec = c1.w;
+  if (notify) {
+    if (seq & 32u) c3.w |= 1u << (seq & 31u);
+    else c3.z |= 1u << (seq & 31u);
   }
-}
-
-// One Instruction.  Apply: nxa = block.next; Notify: nxa = client address (kind << 16 | id).
-__device__ __noinline__ void fsm_encode(uint32_t* S, uint32_t nt, FsmOut o, bool notify, uint32_t bid, uint32_t nxa,
-                                        uint64_t tok) {
-  const uint32_t seq = S[FS_SEQ * nt];
-  if (notify) S[((seq & 32u) ? FS_PBHI : FS_PBLO) * nt] |= 1u << (seq & 31u);
-  S[FS_SEQ * nt] = seq + 1u;
-  if (((seq + 1u) & 63u) == 0u) fsm_close_pattern(S, nt, o, seq - 63u, 64u);
-  const uint32_t b = notify ? FS_N_NEXT : FS_A_NEXT;
-  const uint32_t counts = S[FS_COUNTS * nt];
-  const uint32_t c = notify ? counts >> 16 : counts & 0xffffu;
-  if (c) {
-    const uint32_t next_id = S[(b + 0) * nt];
-    const uint64_t last = (uint64_t)S[(b + 1) * nt] | ((uint64_t)S[(b + 2) * nt] << 32);
-    const uint64_t str = (uint64_t)S[(b + 3) * nt] | ((uint64_t)S[(b + 4) * nt] << 32);
-    bool ok = bid == next_id && c < 0xffffu;
-    if (notify) ok = ok && nxa == S[FS_N_ADDR * nt];
-    else ok = ok && nxa == bid - 1u && (c > 1u || (uint32_t)str == bid - 2u);  // count 1: its explicit `next` must be regular too
+  c1.z = seq + 1u;
+  if (((seq + 1u) & 63u) == 0u && (c3.z | c3.w)) {   // the 64-Instruction pattern window is complete
+    nrec = fsm_put_record(nrec, o, FSR_PATTERN, 64u, seq - 63u, 0u, (uint64_t)c3.z | ((uint64_t)c3.w << 32), 0ull);
+    c3.z = c3.w = 0;
+  }
+  bool extended = false;
+  if (run.y) {
+    const uint64_t last = (uint64_t)run.z | ((uint64_t)run.w << 32);
+    const uint64_t str = (uint64_t)sx | ((uint64_t)sy << 32);
     const uint64_t step = tok - last;
-    if (ok && c > 1u) ok = step == str;
+    bool ok = bid == run.x && run.y < FS_MAX_RUN;
+    if (notify) ok = ok && nxa == FSR_CLIENT && (run.y > 1u || sx == FSR_CLIENT);
+    else ok = ok && nxa == bid - 1u && (run.y > 1u || sx == bid - 2u);   // count 1: its explicit `next` must be regular too
+    if (ok && run.y > 1u) ok = step == str;
     if (ok) {
-      S[(b + 0) * nt] = bid + 1u;
-      S[(b + 1) * nt] = (uint32_t)tok;
-      S[(b + 2) * nt] = (uint32_t)(tok >> 32);
-      if (c == 1u) {
-        S[(b + 3) * nt] = (uint32_t)step;
-        S[(b + 4) * nt] = (uint32_t)(step >> 32);
-      }
-      S[FS_COUNTS * nt] = counts + (notify ? 0x10000u : 1u);
-      return;
+      if (run.y == 1u) { sx = (uint32_t)step; sy = (uint32_t)(step >> 32); }
+      run = make_uint4(bid + 1u, run.y + 1u, (uint32_t)tok, (uint32_t)(tok >> 32));
+      extended = true;
+    } else {
+      nrec = fsm_close_run(nrec, o, notify, run, sx, sy);
     }
-    fsm_close_run(S, nt, o, notify);
   }
-  S[(b + 0) * nt] = bid + 1u;
-  S[(b + 1) * nt] = (uint32_t)tok;
-  S[(b + 2) * nt] = (uint32_t)(tok >> 32);
-  S[(b + 3) * nt] = notify ? 0u : nxa;   // Apply, count 1: the block's `next`
-  S[(b + 4) * nt] = 0u;
-  if (notify) S[FS_N_ADDR * nt] = nxa;
-  S[FS_COUNTS * nt] = S[FS_COUNTS * nt] + (notify ? 0x10000u : 1u);
+  if (!extended) {
+    run = make_uint4(bid + 1u, 1u, (uint32_t)tok, (uint32_t)(tok >> 32));
+    sx = nxa;   // count 1: Apply keeps the block's `next`, Notify the client address
+    sy = 0u;
+  }
+  c1.w = nrec;
+  S[(notify ? 2 : 0) * nt] = run;
+  S[1 * nt] = c1;
+  S[3 * nt] = c3;
 }
 
 // Launch end: everything open becomes records; the counters go back to d.fc.
-__device__ __noinline__ void fsm_close_all(uint32_t* S, uint32_t nt, FsmOut o, uint2* fc) {
-  fsm_close_run(S, nt, o, false);
-  fsm_close_run(S, nt, o, true);
-  const uint32_t seq = S[FS_SEQ * nt];
-  if (seq & 63u) fsm_close_pattern(S, nt, o, seq & ~63u, seq & 63u);
-  *fc = make_uint2(S[FS_NREC * nt], seq);
+__device__ __noinline__ void fsm_close_all(uint4* S, uint32_t nt, FsmOut o, uint2* fc) {
+  const uint4 c0 = S[0], c1 = S[1 * nt], c2 = S[2 * nt], c3 = S[3 * nt];
+  uint32_t nrec = c1.w;
+  nrec = fsm_close_run(nrec, o, false, c0, c1.x, c1.y);
+  nrec = fsm_close_run(nrec, o, true, c2, c3.x, c3.y);
+  const uint32_t seq = c1.z;
+  if ((seq & 63u) && (c3.z | c3.w))
+    nrec = fsm_put_record(nrec, o, FSR_PATTERN, seq & 63u, seq & ~63u, 0u, (uint64_t)c3.z | ((uint64_t)c3.w << 32), 0ull);
+  *fc = make_uint2(nrec, seq);
 }
 
 template <int R, bool SORTED = false>
@@ -377,12 +375,11 @@ struct Replica {
     ocnt0 = ocnt;
     if (d.flags & JR_F_CAPTURE_FSM) {
       const uint2 fc = reset_fsm ? make_uint2(0u, 0u) : d.fc[rg];
-      uint32_t* S = L.fsm + L.tid;
-      S[FS_COUNTS * L.nt] = 0;
-      S[FS_PBLO * L.nt] = 0;
-      S[FS_PBHI * L.nt] = 0;
-      S[FS_NREC * L.nt] = fc.x;
-      S[FS_SEQ * L.nt] = fc.y;
+      uint4* S = L.fsm + L.tid;
+      S[0] = make_uint4(0, 0, 0, 0);
+      S[1 * L.nt] = make_uint4(0, 0, fc.y, fc.x);
+      S[2 * L.nt] = make_uint4(0, 0, 0, 0);
+      S[3 * L.nt] = make_uint4(0, 0, 0, 0);
     }
     mdig = fdig = 0; nmsg = nfsm = 0;
     if (digest_on()) {
@@ -599,7 +596,26 @@ struct Replica {
   __device__ __forceinline__ FsmOut fsm_out() const { return FsmOut{d.fs + rg, plane, d.F, g, r}; }
   // fsm_tx.send(Instruction) (fsm.rs:19-29)
   __device__ __forceinline__ void fsm_emit(bool notify, uint32_t bid, uint32_t next_or_addr, uint64_t tok) {
-    if (d.flags & JR_F_CAPTURE_FSM) fsm_encode(L.fsm + L.tid, L.nt, fsm_out(), notify, bid, next_or_addr, tok);
+    if (d.flags & JR_F_CAPTURE_FSM) {
+      uint4* S = L.fsm + L.tid;
+      // the steady state: this Instruction extends the open run (same test as fsm_encode_slow, count >= 2)
+      const uint4 run = S[(notify ? 2 : 0) * L.nt];
+      const uint4 c1 = S[1 * L.nt];
+      const uint4 sp = notify ? S[3 * L.nt] : c1;
+      const uint64_t step = tok - ((uint64_t)run.z | ((uint64_t)run.w << 32));
+      const bool fast = run.y > 1u && run.y < FS_MAX_RUN && bid == run.x && next_or_addr == (notify ? FSR_CLIENT : bid - 1u) &&
+                        step == ((uint64_t)sp.x | ((uint64_t)sp.y << 32)) && ((c1.z + 1u) & 63u) != 0u;
+      if (fast) {
+        S[(notify ? 2 : 0) * L.nt] = make_uint4(bid + 1u, run.y + 1u, (uint32_t)tok, (uint32_t)(tok >> 32));
+        S[1 * L.nt].z = c1.z + 1u;
+        if (notify) {
+          if (c1.z & 32u) S[3 * L.nt].w = sp.w | (1u << (c1.z & 31u));
+          else S[3 * L.nt].z = sp.z | (1u << (c1.z & 31u));
+        }
+      } else {
+        fsm_encode_slow(S, L.nt, fsm_out(), notify, bid, next_or_addr, tok);
+      }
+    }
     if (digest_on()) {
       fdig = digest_fsm_fn(fdig, notify, bid, next_or_addr, tok);
       ++nfsm;

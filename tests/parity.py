@@ -173,7 +173,7 @@ def scenario_random_inject(p: Pair, seed=0, steps=60, dt=100, per_step=3, max_no
 def scenario_leader_routed_tokens(make_a, make_b, G=12, R=3, seed=6):
     """jr_run_tokens on both implementations: routes before any announce (dropped), fresh routes, routes gone
     stale after a leader is silenced (token lands on a dead node / a follower), re-announce after failover."""
-    cfg = dict(seed=seed, flags=FULL, fsm_units=256)
+    cfg = dict(seed=seed, flags=FULL, fsm_units=256, fsm_host_records=G * R * 64)   # holes in the token grid: short runs
     a, b = make_a(G, R, **cfg), make_b(G, R, **cfg)
     now = [0]
 

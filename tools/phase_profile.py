@@ -15,7 +15,7 @@ import bench  # noqa: E402
 from josefine_b200 import abi, RaftEngine  # noqa: E402
 
 G, R, S = 65536, 5, 64
-e = RaftEngine.create(G, R, seed=1, chain_capacity=1024, flags=abi.F_CAPTURE_FSM, fsm_units=2 * S + 8)
+e = RaftEngine.create(G, R, seed=1, chain_capacity=1024, flags=abi.F_CAPTURE_FSM if os.environ.get('JR_BENCH_CAPTURE', '1') != '0' else 0, fsm_units=16)
 e.step(0, flags=0, inject=bench.bootstrap_inject(G, R))
 e.run(100, 100, 16, 1)
 buf = (C.c_uint64 * 96)()
@@ -24,6 +24,8 @@ e._lib.jr_profile_read(e._h, buf)           # clear
 now = 1700
 for _ in range(5):
     e.run(now, 100, S, 1)
+    e.truncate(8)
+    e.discard_fsm()
     now += 100 * S
 e._lib.jr_profile_read(e._h, buf)
 names = {1: "  drain: Leader::commit", 8: "  drain: mask+unit loads", 9: "  drain: advances", 0: "Tick", 2: "  replicate: first peer (scan)", 3: "  replicate: other peers (refs)", 4: "AppendEntries", 5: "AppendResponse", 6: "Heartbeat",
