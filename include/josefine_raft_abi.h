@@ -167,9 +167,12 @@ typedef struct jr_config {
                                 * nodes are never stepped, and mail addressed to them is only
                                 * returned through out_msgs for the host to forward.           */
   uint32_t fsm_host_records;   /* records one jr_fsm_records_async batch may hold (pinned host memory, two
-                                * buffers of this size); 0 = max(2 * n_groups * n_replicas + 1024,
+                                * buffers of this size); 0 = max(3 * n_groups * n_replicas + 1024,
                                 * min(n_groups * n_replicas * fsm_units, 65536))                            */
-  uint32_t reserved0;
+  uint32_t fsm_raw_units;      /* scratch: raw Instructions one replica may emit per launch before they are encoded into
+                                * records at the launch's end; 0 = 192.  jr_run* cut their work into launches of at most
+                                * fsm_raw_units / 3 ticks; a replica that still emits more loses the excess (the drain
+                                * then returns JR_E_CAPACITY; consensus is unaffected)                              */
 } jr_config;
 
 /* Block (src/raft/chain.rs:86-91); `data` is the payload token (D5). */

@@ -67,7 +67,7 @@ class Config(C.Structure):
         ("heartbeat_ms", C.c_uint32), ("chain_capacity", C.c_uint32),
         ("mailbox_units", C.c_uint32), ("fsm_units", C.c_uint32),
         ("flags", C.c_uint32), ("resident_mask", C.c_uint32),
-        ("fsm_host_records", C.c_uint32), ("reserved0", C.c_uint32),
+        ("fsm_host_records", C.c_uint32), ("fsm_raw_units", C.c_uint32),
     ]
 
 

@@ -115,13 +115,11 @@ __global__ void __launch_bounds__(32 * R, step_min_ctas(R)) step_kernel(const De
   L.cout = L.cin + R * 32;
   L.mk_in = reinterpret_cast<uint16_t*>(L.cout + R * 32);
   L.mk_out = L.mk_in + R * R * 32;
-  L.fsm = reinterpret_cast<uint4*>(L.mk_out + R * R * 32);      // only there (and only touched) with JR_F_CAPTURE_FSM
-  L.nt = 32 * R; L.tid = threadIdx.x;
   L.Us = d.Us; L.W = d.W; L.lane = lane;
   Replica<R, SORTED> rep(d, L, r, g);
   rep.now = p.now;
   rep.cur = p.cur;
-  rep.load(p.phases & PH_RESET_OUT, p.phases & PH_RESET_FSM);
+  rep.load(p.phases & PH_RESET_OUT, p.phases & PH_RESET_FSM, part != 0);
   rep.tc_prefetch();
   rep.stage_inbox(p.phases & PH_DRAIN);
 #ifdef JR_PROFILE
@@ -155,7 +153,7 @@ __global__ void __launch_bounds__(32 * R, step_min_ctas(R)) step_kernel(const De
     q.phases = PH_RESET_OUT | PH_DRAIN | PH_PROPOSE | PH_TICK;
     q.proposals = (p.proposals && p.prop_stride) ? p.proposals + (size_t)(t + 1) * p.prop_stride : nullptr;
   }
-  rep.store();
+  rep.store(part + 1 >= p0.n_parts);
   {  // tell the host whether the next launch should sort: leaders on >= 2 replica indices in this CTA?
     uint32_t* lmask = reinterpret_cast<uint32_t*>(L.tc);  // the table cache is dead now; reuse one word of it
     __syncthreads();
@@ -186,10 +184,8 @@ template <int R>
 __global__ void inject_kernel(const Dev d, const StepParams p, const jr_msg* msgs, const uint4* targets,
                               uint32_t n_targets) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  __shared__ uint4 fsm_state[FS_CHUNKS * 64];   // launched with 64 threads per CTA
   Local L;
   L.in = L.out = L.tc = nullptr; L.cin = L.cout = nullptr; L.mk_in = L.mk_out = nullptr; L.Us = 0; L.W = 0; L.lane = 0;
-  L.fsm = fsm_state; L.nt = 64; L.tid = threadIdx.x;
   if (i >= n_targets) return;
   const uint4 t = targets[i];
   Replica<R> rep(d, L, t.y, t.x);
@@ -754,8 +750,7 @@ static cudaError_t step_occupancy_r(int* per_sm, int smem) {
 
 static size_t step_smem_bytes(const Dev& d) {
   return ((size_t)2 * d.Us + d.W) * d.R * 32 * sizeof(uint4) + (size_t)2 * d.R * 32 * sizeof(uint32_t) +
-         (size_t)2 * d.R * d.R * 32 * sizeof(uint16_t) +
-         ((d.flags & JR_F_CAPTURE_FSM) ? (size_t)FS_CHUNKS * d.R * 32 * sizeof(uint4) : 0);
+         (size_t)2 * d.R * d.R * 32 * sizeof(uint16_t);
 }
 
 // How many consecutive tasks to cut each block's ticks into: the fewest that minimise the number of
@@ -775,7 +770,29 @@ static uint32_t choose_parts(const jr_engine* e, const StepParams& p, uint32_t n
   return best;
 }
 
+static jr_status launch_step_once(jr_engine* e, const StepParams& p_in);
+
+// A capturing engine keeps every launch short enough for the raw Instruction FIFO (Fr entries per replica, encoded when
+// the launch ends): at most Fr / 3 ticks per launch.  Consecutive launches are indistinguishable from one long launch.
 static jr_status launch_step(jr_engine* e, const StepParams& p_in) {
+  const uint32_t limit = (e->d.flags & JR_F_CAPTURE_FSM) ? std::max(1u, e->d.Fr / 3u) : 0xffffffffu;
+  if (p_in.n_ticks <= limit) return launch_step_once(e, p_in);
+  StepParams p = p_in;
+  for (uint32_t done = 0; done < p_in.n_ticks;) {
+    p.n_ticks = std::min(limit, p_in.n_ticks - done);
+    jr_status st = launch_step_once(e, p);
+    if (st != JR_OK) return st;
+    done += p.n_ticks;
+    p.now += (uint64_t)p.n_ticks * p.dt;
+    p.step_index += p.n_ticks;
+    p.cur ^= (int)(p.n_ticks & 1u);
+    if (p.proposals) p.proposals += (size_t)p.n_ticks * p.prop_stride;
+    p.phases = PH_RESET_OUT | PH_DRAIN | (p_in.phases & PH_PROPOSE) | PH_TICK;
+  }
+  return JR_OK;
+}
+
+static jr_status launch_step_once(jr_engine* e, const StepParams& p_in) {
   const uint32_t n_blocks = e->d.Gp / GROUPS_PER_CTA;
   const size_t smem = step_smem_bytes(e->d);
   StepParams p = p_in;
@@ -834,9 +851,12 @@ jr_status jr_engine_create(const jr_config* cfg, jr_engine** out) {
   // RaftConfig::validate, config.rs:70-75 (the rules that have a counterpart here)
   if (cfg->heartbeat_ms < 5) { set_err("heartbeat timeout is too low"); return JR_E_INVAL; }
   if (cfg->election_min_ms < 5) { set_err("election timeout is too low"); return JR_E_INVAL; }
-  if (cfg->chain_capacity < 2 || cfg->chain_capacity > 0x7fffffffu) { set_err("chain_capacity out of range"); return JR_E_INVAL; }
+  if (cfg->chain_capacity < 2 || cfg->chain_capacity > 0x40000000u) { set_err("chain_capacity out of range"); return JR_E_INVAL; }
   if (cfg->mailbox_units < 8 || cfg->fsm_units < 1) { set_err("mailbox_units >= 8, fsm_units >= 1"); return JR_E_INVAL; }
-  if (cfg->fsm_units > (1u << 20)) { set_err("fsm_units <= 2^20"); return JR_E_INVAL; }
+  if (cfg->fsm_units > (1u << 20) || cfg->fsm_raw_units > (1u << 20) || (cfg->fsm_raw_units && cfg->fsm_raw_units < 32)) {
+    set_err("fsm_units <= 2^20, 32 <= fsm_raw_units <= 2^20");
+    return JR_E_INVAL;
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     set_err("no CUDA device; this library has no CPU fallback");
@@ -858,6 +878,7 @@ jr_status jr_engine_create(const jr_config* cfg, jr_engine** out) {
   d.capm -= 1;
   d.U = cfg->mailbox_units;
   d.F = cfg->fsm_units;
+  d.Fr = cfg->fsm_raw_units ? cfg->fsm_raw_units : 192u;
   d.flags = cfg->flags;
   d.emin = cfg->election_min_ms;
   d.emax = cfg->election_max_ms;
@@ -885,11 +906,13 @@ jr_status jr_engine_create(const jr_config* cfg, jr_engine** out) {
   A(d.oc[0], plane); A(d.oc[1], plane);
   A(d.fs, plane * (size_t)((d.flags & JR_F_CAPTURE_FSM) ? 2 * (size_t)d.F : 1));
   A(d.fc, plane);
+  A(d.fq, plane);
+  A(d.fr, plane * (size_t)((d.flags & JR_F_CAPTURE_FSM) ? d.Fr : 1));
   A(d.tb, d.Gp);
   if (d.flags & JR_F_CAPTURE_FSM) {
     const size_t reps = (size_t)cfg->n_groups * cfg->n_replicas;   // default: 2 per replica, but never less than a small engine's whole FIFO space
     const size_t want = cfg->fsm_host_records ? cfg->fsm_host_records
-                                              : std::max(2 * reps + 1024, std::min<size_t>(reps * cfg->fsm_units, 1u << 16));
+                                              : std::max(3 * reps + 1024, std::min<size_t>(reps * cfg->fsm_units, 1u << 16));
     e->fsm_cap = (uint32_t)std::min<size_t>(want, 0x7fffffffu);
     A(e->fsm_offs, plane);
     for (int i = 0; i < jr_engine::NBUF; ++i) { A(e->fsm_stage[i], 2 * (size_t)e->fsm_cap); A(e->fsm_stage_hdr[i], 1); }

@@ -52,8 +52,10 @@ struct Dev {
   uint4* ob[2];                    // mailboxes [unit][replica][group], double buffered
   uint32_t* oc[2];                 // units used per replica
   uint4* fs;                       // Instruction-stream records (jr_fsm_record, 2 x uint4 each) [2*rec + half][replica][group]
+  uint4* fr;                       // raw Instructions of the running launch [unit][replica][group], Fr units (scratch of fsm_flush)
   uint2* fc;                       // {records stored since the last drain, Instructions emitted since the last drain}
-  uint32_t G, Gp, R, cap, capm, U, F, flags;   // cap: ids a window may span; capm: table rows - 1 (power of two >= cap)
+  uint32_t* fq;                    // raw Instructions in d.fr handed from one part of a split launch to the next
+  uint32_t G, Gp, R, cap, capm, U, F, Fr, flags;   // cap: ids a window may span; capm: table rows - 1 (power of two >= cap)
   uint32_t emin, emax, hb;
   uint32_t Us, W;                  // shared-memory mailbox units per replica, table-cache entries (power of 2)
   uint32_t use_index;              // receivers use the delivery index (else scan whole mailboxes)
@@ -78,9 +80,6 @@ struct Local {
   // sender emitted a header at slot >= MK_SLOTS: scan its whole mailbox instead.
   uint16_t* mk_in;
   uint16_t* mk_out;
-  // Instruction-stream encoder state, FS_CHUNKS uint4 per thread, chunk-major ([chunk][thread]); see fsm_encode_slow
-  uint4* fsm;
-  uint32_t nt, tid;  // threads sharing `fsm`, this thread's column
   uint32_t Us, W, lane;
 };
 constexpr uint32_t MK_SCAN = 0x8000u;   // delivery masks are 16 bits: slots 0..14 + this flag
@@ -217,24 +216,24 @@ __device__ __forceinline__ unsigned long long* jr_prof_smem() {
 //   PATTERN     which positions of the replica's stream are Notify (bit = 1); positions no PATTERN
 //               record covers are Apply.  Applies and Notifies each keep their own order, so the
 //               three together reproduce the stream exactly.
-// The open runs live in shared memory, four uint4 per thread ([chunk][thread]):
-//   chunk 0  APPLY run : next id, count, last token (lo, hi)
-//   chunk 1             stride (lo, hi; count 1: x = the block's `next`), SEQ, NREC
-//   chunk 2  NOTIFY run: next id, count, last token (lo, hi)
-//   chunk 3             stride (lo, hi; count 1: x = the client address), pattern bits (lo, hi)
-// SEQ = Instructions emitted since the last drain, NREC = records closed since the last drain.
-// Extending an open run (the steady state) is two 128-bit loads and two stores, inline; everything
-// else -- closing a run into the replica's record FIFO d.fs, opening one, a full pattern word --
-// goes through fsm_encode_slow.  Every launch closes what is open when it ends.
-constexpr uint32_t FS_CHUNKS = 4;
+// The state machine itself only appends the raw Instruction (16 B) to the replica's scratch FIFO
+// d.fr -- one store, no state beyond a counter.  The encoding runs in fsm_flush, once per launch
+// (and when the scratch FIFO fills up), where the open runs can live in registers because nothing
+// of the Replica is live in that function: the hot loop pays no registers and no shared memory.
 constexpr uint32_t FSR_APPLY = 0u, FSR_NOTIFY = 1u, FSR_PATTERN = 2u;
 constexpr uint32_t FSR_CLIENT = (uint32_t)JR_ADDR_CLIENT << 16;
 constexpr uint32_t FS_MAX_RUN = 0xffffffu;   // the record's count field is 24 bits
+constexpr uint32_t FS_NOTIFY_BIT = 0x80000000u;   // raw entry: x = block id | this; y = next / client address; z,w = token
 
 struct FsmOut {       // where one replica's records go
   uint4* slot0;       // d.fs + rg
   size_t plane;       // R * Gp
   uint32_t F, g, r;
+};
+
+struct FsmRun {       // an open run: next id expected, elements so far, last token, stride (count 1: lo word = next / address)
+  uint32_t next_id, count;
+  uint64_t last, stride;
 };
 
 __device__ __forceinline__ uint32_t fsm_put_record(uint32_t nrec, const FsmOut& o, uint32_t kind, uint32_t count, uint32_t id0,
@@ -247,72 +246,58 @@ __device__ __forceinline__ uint32_t fsm_put_record(uint32_t nrec, const FsmOut& 
   return nrec + 1;  // past F: counted, not stored (the drain reports JR_E_CAPACITY; consensus is not affected)
 }
 
-// Close the open run in (c0, c1) into a record.  c0 = {next id, count, tok lo, tok hi}; c1.xy = stride / count-1 payload.
-__device__ __forceinline__ uint32_t fsm_close_run(uint32_t nrec, const FsmOut& o, bool notify, const uint4& c0, uint32_t sx,
-                                                  uint32_t sy) {
-  const uint32_t c = c0.y;
+__device__ __forceinline__ uint32_t fsm_close_run(uint32_t nrec, const FsmOut& o, bool notify, const FsmRun& run) {
+  const uint32_t c = run.count;
   if (!c) return nrec;
-  const uint64_t last = (uint64_t)c0.z | ((uint64_t)c0.w << 32);
-  const uint64_t str = (uint64_t)sx | ((uint64_t)sy << 32);
-  const uint64_t tok0 = c > 1 ? last - (uint64_t)(c - 1) * str : last;
-  const uint32_t addr = notify ? (c > 1 ? FSR_CLIENT : sx) : 0u;
-  return fsm_put_record(nrec, o, notify ? FSR_NOTIFY : FSR_APPLY, c, c0.x - c, addr, tok0, (notify && c == 1) ? 0ull : str);
+  const uint64_t tok0 = c > 1 ? run.last - (uint64_t)(c - 1) * run.stride : run.last;
+  const uint32_t addr = notify ? (c > 1 ? FSR_CLIENT : (uint32_t)run.stride) : 0u;
+  return fsm_put_record(nrec, o, notify ? FSR_NOTIFY : FSR_APPLY, c, run.next_id - c, addr, tok0,
+                        (notify && c == 1) ? 0ull : run.stride);
 }
 
-// One Instruction, general case.  Apply: nxa = block.next; Notify: nxa = client address (kind << 16 | id).
-__device__ __noinline__ void fsm_encode_slow(uint4* S, uint32_t nt, FsmOut o, bool notify, uint32_t bid, uint32_t nxa, uint64_t tok) {
-  uint4 c1 = S[1 * nt], c3 = S[3 * nt];
-  uint4 run = S[(notify ? 2 : 0) * nt];
-  uint32_t& sx = notify ? c3.x : c1.x;
-  uint32_t& sy = notify ? c3.y : c1.y;
-  const uint32_t seq = c1.z;
-  uint32_t nrec = c1.w;
-  if (notify) {
-    if (seq & 32u) c3.w |= 1u << (seq & 31u);
-    else c3.z |= 1u << (seq & 31u);
-  }
-  c1.z = seq + 1u;
-  if (((seq + 1u) & 63u) == 0u && (c3.z | c3.w)) {   // the 64-Instruction pattern window is complete
-    nrec = fsm_put_record(nrec, o, FSR_PATTERN, 64u, seq - 63u, 0u, (uint64_t)c3.z | ((uint64_t)c3.w << 32), 0ull);
-    c3.z = c3.w = 0;
-  }
-  bool extended = false;
-  if (run.y) {
-    const uint64_t last = (uint64_t)run.z | ((uint64_t)run.w << 32);
-    const uint64_t str = (uint64_t)sx | ((uint64_t)sy << 32);
-    const uint64_t step = tok - last;
-    bool ok = bid == run.x && run.y < FS_MAX_RUN;
-    if (notify) ok = ok && nxa == FSR_CLIENT && (run.y > 1u || sx == FSR_CLIENT);
-    else ok = ok && nxa == bid - 1u && (run.y > 1u || sx == bid - 2u);   // count 1: its explicit `next` must be regular too
-    if (ok && run.y > 1u) ok = step == str;
-    if (ok) {
-      if (run.y == 1u) { sx = (uint32_t)step; sy = (uint32_t)(step >> 32); }
-      run = make_uint4(bid + 1u, run.y + 1u, (uint32_t)tok, (uint32_t)(tok >> 32));
-      extended = true;
-    } else {
-      nrec = fsm_close_run(nrec, o, notify, run, sx, sy);
+// Encode the n_raw raw Instructions of this replica (raw0[u * plane], u < min(n_raw, Fr)) behind what d.fc says was
+// emitted before them.  Raw entries beyond Fr were never stored: they count as dropped records.
+__device__ __noinline__ void fsm_flush(const uint4* raw0, uint32_t n_raw, uint32_t Fr, FsmOut o, uint2* fc) {
+  const uint2 c = *fc;
+  uint32_t nrec = c.x, seq = c.y;
+  uint64_t pbits = 0;
+  FsmRun ra{0, 0, 0, 0}, rn{0, 0, 0, 0};
+  const uint32_t n = n_raw < Fr ? n_raw : Fr;
+  for (uint32_t u = 0; u < n; ++u) {
+    const uint4 e = __ldcg(raw0 + (size_t)u * o.plane);
+    const bool notify = (e.x & FS_NOTIFY_BIT) != 0;
+    const uint32_t bid = e.x & ~FS_NOTIFY_BIT, nxa = e.y;
+    const uint64_t tok = (uint64_t)e.z | ((uint64_t)e.w << 32);
+    if (notify) pbits |= 1ull << (seq & 63u);
+    ++seq;
+    if ((seq & 63u) == 0u && pbits) {   // the 64-Instruction pattern window is complete
+      nrec = fsm_put_record(nrec, o, FSR_PATTERN, 64u, seq - 64u, 0u, pbits, 0ull);
+      pbits = 0;
     }
+    FsmRun& run = notify ? rn : ra;
+    bool extended = false;
+    if (run.count) {
+      const uint64_t step = tok - run.last;
+      bool ok = bid == run.next_id && run.count < FS_MAX_RUN;
+      if (notify) ok = ok && nxa == FSR_CLIENT && (run.count > 1u || (uint32_t)run.stride == FSR_CLIENT);
+      else ok = ok && nxa == bid - 1u && (run.count > 1u || (uint32_t)run.stride == bid - 2u);   // count 1: its own `next` must be regular too
+      if (ok && run.count > 1u) ok = step == run.stride;
+      if (ok) {
+        if (run.count == 1u) run.stride = step;
+        run.next_id = bid + 1u;
+        run.count += 1u;
+        run.last = tok;
+        extended = true;
+      } else {
+        nrec = fsm_close_run(nrec, o, notify, run);
+      }
+    }
+    if (!extended) run = FsmRun{bid + 1u, 1u, tok, (uint64_t)nxa};   // count 1: Apply keeps the block's `next`, Notify the client address
   }
-  if (!extended) {
-    run = make_uint4(bid + 1u, 1u, (uint32_t)tok, (uint32_t)(tok >> 32));
-    sx = nxa;   // count 1: Apply keeps the block's `next`, Notify the client address
-    sy = 0u;
-  }
-  c1.w = nrec;
-  S[(notify ? 2 : 0) * nt] = run;
-  S[1 * nt] = c1;
-  S[3 * nt] = c3;
-}
-
-// Launch end: everything open becomes records; the counters go back to d.fc.
-__device__ __noinline__ void fsm_close_all(uint4* S, uint32_t nt, FsmOut o, uint2* fc) {
-  const uint4 c0 = S[0], c1 = S[1 * nt], c2 = S[2 * nt], c3 = S[3 * nt];
-  uint32_t nrec = c1.w;
-  nrec = fsm_close_run(nrec, o, false, c0, c1.x, c1.y);
-  nrec = fsm_close_run(nrec, o, true, c2, c3.x, c3.y);
-  const uint32_t seq = c1.z;
-  if ((seq & 63u) && (c3.z | c3.w))
-    nrec = fsm_put_record(nrec, o, FSR_PATTERN, seq & 63u, seq & ~63u, 0u, (uint64_t)c3.z | ((uint64_t)c3.w << 32), 0ull);
+  nrec = fsm_close_run(nrec, o, false, ra);
+  nrec = fsm_close_run(nrec, o, true, rn);
+  if ((seq & 63u) && pbits) nrec = fsm_put_record(nrec, o, FSR_PATTERN, seq & 63u, seq & ~63u, 0u, pbits, 0ull);
+  if (n_raw > Fr) nrec = (nrec > o.F ? nrec : o.F) + (n_raw - Fr);   // lost Instructions: the drain must say so
   *fc = make_uint2(nrec, seq);
 }
 
@@ -328,12 +313,18 @@ struct Replica {
   uint32_t ocnt0;        // units already in the outbox when this launch started (continuation launches)
   // ---- State (mod.rs:271-287) + role state + Chain scalars (chain.rs:99-104)
   uint64_t term, etime, hbtime;
-  uint32_t voted, leader, etimeout, draws, head, commit, idgen, maxkey, tbase;
-  uint32_t role, fault, prmask, nq, dead, ckey, seen, granted;
-  uint32_t ph[R];
+  uint32_t voted, etimeout, draws, head, commit, idgen, maxkey, tbase;
+  uint32_t role, fault, prmask, nq, dead, ckey;
+  // Role-exclusive state shares registers: a Leader's progress heads ph[0..R), a Candidate's vote masks and a
+  // Follower's leader_id are never live together (every transition below re-initialises what the new role reads).
+  uint32_t ph[R < 3 ? 3 : R];
+#define seen ph[0]
+#define granted ph[1]
+#define leader ph[2]
   // ---- output cursors
-  uint32_t ocnt, nmsg, nfsm;
-  uint64_t mdig, fdig;
+  uint32_t ocnt, fcnt;   // units in the outbox; raw Instructions in d.fr since the last fsm_flush
+  // (the stream digests and counts of JR_F_STREAM_DIGEST stay in d.dg / d.cn: a test feature must not cost the
+  //  product kernel six registers)
   uint32_t mko[R];       // delivery index of this tick's outbox, one mask per receiver (see Local::mk_out)
 
   __device__ __forceinline__ Replica(const Dev& dv, const Local& lv, uint32_t r_, uint32_t g_)
@@ -344,9 +335,9 @@ struct Replica {
   __device__ __forceinline__ bool digest_on() const { return d.flags & JR_F_STREAM_DIGEST; }
 
   // ------------------------------------------------------------------ load/store
-  __device__ __forceinline__ void load(bool reset_out, bool reset_fsm) {
+  __device__ __forceinline__ void load(bool reset_out, bool reset_fsm, bool continues = false) {
     uint4 a = d.p0[rg], b = d.p1[rg], c = d.p2[rg];
-    term = (uint64_t)a.x | ((uint64_t)a.y << 32); voted = a.z; leader = a.w;
+    term = (uint64_t)a.x | ((uint64_t)a.y << 32); voted = a.z;
     etime = (uint64_t)b.x | ((uint64_t)b.y << 32); etimeout = b.z; draws = b.w;
     head = c.x; commit = c.y; idgen = c.z;
     uint32_t m = c.w;
@@ -354,9 +345,10 @@ struct Replica {
     nq = (m >> 24) & 7u; dead = (m >> 27) & 1u; ckey = (m >> 28) & 1u;
     maxkey = d.mk[rg];
     tbase = d.tb[g];
-    hbtime = 0; seen = granted = 0;
+    hbtime = 0;
 #pragma unroll
-    for (int i = 0; i < R; ++i) ph[i] = 0;
+    for (int i = 0; i < (R < 3 ? 3 : R); ++i) ph[i] = 0;
+    leader = a.w;   // Follower.leader_id (0 for the other roles)
     if (role != JR_ROLE_FOLLOWER) {
       uint4 e = d.p3[rg];
       hbtime = (uint64_t)e.x | ((uint64_t)e.y << 32); seen = e.z; granted = e.w;
@@ -373,32 +365,19 @@ struct Replica {
     }
     ocnt = reset_out ? 0u : d.oc[cur][rg];
     ocnt0 = ocnt;
-    if (d.flags & JR_F_CAPTURE_FSM) {
-      const uint2 fc = reset_fsm ? make_uint2(0u, 0u) : d.fc[rg];
-      uint4* S = L.fsm + L.tid;
-      S[0] = make_uint4(0, 0, 0, 0);
-      S[1 * L.nt] = make_uint4(0, 0, fc.y, fc.x);
-      S[2 * L.nt] = make_uint4(0, 0, 0, 0);
-      S[3 * L.nt] = make_uint4(0, 0, 0, 0);
-    }
-    mdig = fdig = 0; nmsg = nfsm = 0;
-    if (digest_on()) {
-      uint4 v = d.dg[rg];
-      mdig = (uint64_t)v.x | ((uint64_t)v.y << 32);
-      fdig = (uint64_t)v.z | ((uint64_t)v.w << 32);
-      uint2 n = d.cn[rg];
-      nmsg = n.x; nfsm = n.y;
-    }
+    fcnt = (continues && (d.flags & JR_F_CAPTURE_FSM)) ? d.fq[rg] : 0u;   // a later part of a split launch appends to the same raw FIFO
+    if (reset_fsm && (d.flags & JR_F_CAPTURE_FSM)) d.fc[rg] = make_uint2(0u, 0u);
   }
 
-  __device__ __forceinline__ void store() {
-    d.p0[rg] = make_uint4((uint32_t)term, (uint32_t)(term >> 32), voted, leader);
+  __device__ __forceinline__ void store(bool last_part = true) {
+    d.p0[rg] = make_uint4((uint32_t)term, (uint32_t)(term >> 32), voted, role == JR_ROLE_FOLLOWER ? leader : 0u);
     d.p1[rg] = make_uint4((uint32_t)etime, (uint32_t)(etime >> 32), etimeout, draws);
     uint32_t m = role | (fault << 8) | (prmask << 16) | (nq << 24) | (dead << 27) | (ckey << 28);
     d.p2[rg] = make_uint4(head, commit, idgen, m);
     d.mk[rg] = maxkey;
     if (role != JR_ROLE_FOLLOWER) {
-      d.p3[rg] = make_uint4((uint32_t)hbtime, (uint32_t)(hbtime >> 32), seen, granted);
+      d.p3[rg] = make_uint4((uint32_t)hbtime, (uint32_t)(hbtime >> 32), role == JR_ROLE_CANDIDATE ? seen : 0u,
+                            role == JR_ROLE_CANDIDATE ? granted : 0u);
       if (role == JR_ROLE_LEADER) {
 #pragma unroll
         for (int q = 0; q < (R + 3) / 4; ++q) {
@@ -416,18 +395,15 @@ struct Replica {
     for (uint32_t u = ocnt0; u < staged; ++u)
       d.ob[cur][((size_t)u * R + r) * d.Gp + g] = L.out[(u * R + r) * 32 + L.lane];
     d.oc[cur][rg] = ocnt;
-    if (d.flags & JR_F_CAPTURE_FSM) fsm_close_all(L.fsm + L.tid, L.nt, fsm_out(), d.fc + rg);
-    if (digest_on()) {
-      d.dg[rg] = make_uint4((uint32_t)mdig, (uint32_t)(mdig >> 32), (uint32_t)fdig, (uint32_t)(fdig >> 32));
-      d.cn[rg] = make_uint2(nmsg, nfsm);
-    }
+    if (last_part) fsm_flush_now();                       // the launch's Instructions become records once, at its end
+    else if (d.flags & JR_F_CAPTURE_FSM) d.fq[rg] = fcnt;
   }
 
   // ------------------------------------------------------------------ block table (chain.rs)
   // The table holds the ids of a window [tbase, tbase + cap): row = id & capm.  Ids below the floor were
   // truncated (jr_truncate, deviation D7) and read as absent; ids at or past the end cannot be stored.
   __device__ __forceinline__ size_t tix(uint32_t bid) const { return (size_t)(bid & d.capm) * plane + rg; }
-  __device__ __forceinline__ bool in_window(uint32_t bid) const { return bid - tbase < d.cap; }
+  __device__ __forceinline__ bool in_window(uint32_t bid) const { return bid - tbase < d.cap && bid < FS_NOTIFY_BIT; }   // (ids < 2^31, D4)
   // Block table reads go through a direct-mapped, write-through cache in shared
   // memory (tag = id).  Only this lane writes its own table, so the cache is
   // coherent for the whole launch; it is rebuilt at launch start.
@@ -588,37 +564,36 @@ struct Replica {
     ++ocnt;
     if (digest_on()) {
       uint32_t n;
-      mdig = digest_send_fn(mdig, id(), kind, to, flag, aux, t, w, &n);
-      nmsg += n;
+      uint4 v = d.dg[rg];
+      const uint64_t h = digest_send_fn((uint64_t)v.x | ((uint64_t)v.y << 32), id(), kind, to, flag, aux, t, w, &n);
+      v.x = (uint32_t)h; v.y = (uint32_t)(h >> 32);
+      d.dg[rg] = v;
+      d.cn[rg].x += n;
     }
   }
 
   __device__ __forceinline__ FsmOut fsm_out() const { return FsmOut{d.fs + rg, plane, d.F, g, r}; }
+  // Encode what sits in the raw FIFO (launch end; tick end when it is nearly full).
+  __device__ __forceinline__ void fsm_flush_now() {
+    if ((d.flags & JR_F_CAPTURE_FSM) && fcnt) {
+      fsm_flush(d.fr + rg, fcnt, d.Fr, fsm_out(), d.fc + rg);
+      fcnt = 0;
+    }
+  }
   // fsm_tx.send(Instruction) (fsm.rs:19-29)
   __device__ __forceinline__ void fsm_emit(bool notify, uint32_t bid, uint32_t next_or_addr, uint64_t tok) {
     if (d.flags & JR_F_CAPTURE_FSM) {
-      uint4* S = L.fsm + L.tid;
-      // the steady state: this Instruction extends the open run (same test as fsm_encode_slow, count >= 2)
-      const uint4 run = S[(notify ? 2 : 0) * L.nt];
-      const uint4 c1 = S[1 * L.nt];
-      const uint4 sp = notify ? S[3 * L.nt] : c1;
-      const uint64_t step = tok - ((uint64_t)run.z | ((uint64_t)run.w << 32));
-      const bool fast = run.y > 1u && run.y < FS_MAX_RUN && bid == run.x && next_or_addr == (notify ? FSR_CLIENT : bid - 1u) &&
-                        step == ((uint64_t)sp.x | ((uint64_t)sp.y << 32)) && ((c1.z + 1u) & 63u) != 0u;
-      if (fast) {
-        S[(notify ? 2 : 0) * L.nt] = make_uint4(bid + 1u, run.y + 1u, (uint32_t)tok, (uint32_t)(tok >> 32));
-        S[1 * L.nt].z = c1.z + 1u;
-        if (notify) {
-          if (c1.z & 32u) S[3 * L.nt].w = sp.w | (1u << (c1.z & 31u));
-          else S[3 * L.nt].z = sp.z | (1u << (c1.z & 31u));
-        }
-      } else {
-        fsm_encode_slow(S, L.nt, fsm_out(), notify, bid, next_or_addr, tok);
-      }
+      if (fcnt < d.Fr)
+        d.fr[(size_t)fcnt * plane + rg] =
+            make_uint4(bid | (notify ? FS_NOTIFY_BIT : 0u), next_or_addr, (uint32_t)tok, (uint32_t)(tok >> 32));
+      ++fcnt;
     }
     if (digest_on()) {
-      fdig = digest_fsm_fn(fdig, notify, bid, next_or_addr, tok);
-      ++nfsm;
+      uint4 v = d.dg[rg];
+      const uint64_t h = digest_fsm_fn((uint64_t)v.z | ((uint64_t)v.w << 32), notify, bid, next_or_addr, tok);
+      v.z = (uint32_t)h; v.w = (uint32_t)(h >> 32);
+      d.dg[rg] = v;
+      d.cn[rg].y += 1u;
     }
   }
 
@@ -934,15 +909,17 @@ struct Replica {
         return;
       mko[p] |= ocnt < MK_SLOTS ? (1u << ocnt) : MK_SCAN;
       if (digest_on()) {
-        uint64_t h = digest_message_fn(mdig, JR_CMD_APPEND_ENTRIES, p + 1, 0, nb, id(), term, 0, 0, 0, 0);
-        ++nmsg;
+        uint4 v = d.dg[rg];
+        uint64_t h = digest_message_fn((uint64_t)v.x | ((uint64_t)v.y << 32), JR_CMD_APPEND_ENTRIES, p + 1, 0, nb, id(), term, 0, 0, 0, 0);
+        d.cn[rg].x += 1u;
         for (uint32_t k = 0; k < nb; ++k) {
           uint4 u = own_unit(first + k);
           h = fold(h, u.x);
           h = fold(h, u.y);
           h = fold(h, (uint64_t)u.z | ((uint64_t)u.w << 32));
         }
-        mdig = h;
+        v.x = (uint32_t)h; v.y = (uint32_t)(h >> 32);
+        d.dg[rg] = v;
       }
       ocnt += ref ? 1u : 1u + nb;
     }
@@ -1232,6 +1209,9 @@ struct Replica {
     }
   }
 };
+#undef seen
+#undef granted
+#undef leader
 
 #endif  // JR_DEVICE_CODE
 }  // namespace jr

@@ -53,6 +53,14 @@ class BatchedDriver:
             self.fsms[key] = self._make(group, node)
         return self.fsms[key]
 
+    def feed_records(self, lib, records, n_groups: int, n_replicas: int) -> List[ClientResponse]:
+        """Consume a batch in the engine's compact form (jr_fsm_record, as jr_fsm_records_wait returns it): the batch is
+        expanded by jr_fsm_expand into the exact Instruction order jr_step would have returned and fed as usual.
+        (A host that only needs the per-replica apply watermark folds the batch with jr_fsm_fold instead -- one linear
+        pass, no expansion; that is what bench.py's end-to-end leg does.)"""
+        from .raft import expand_records
+        return self.feed(expand_records(lib, list(records), n_groups, n_replicas))
+
     def feed(self, instructions: List[abi.FsmInstr]) -> List[ClientResponse]:
         """Consume Instructions in emission order (the engine returns them group-major, node
         ascending, FIFO per node -- per-node order is what the reference guarantees)."""

@@ -273,10 +273,13 @@ class RaftApi:
         self._check(self._fn("drain_fsm")(self._h, buf, C.c_size_t(cap), C.byref(n)), "drain_fsm")
         return [buf[i] for i in range(n.value)]
 
-    def discard_fsm(self) -> int:
-        """Drain without returning the Instructions; their number."""
+    def discard_fsm(self, strict: bool = True) -> int:
+        """Drain without returning the Instructions; their number.  strict=False: records lost to a full FIFO are not an
+        error (start-up phases a caller does not care about)."""
         n = C.c_size_t(0)
-        self._check(self._fn("drain_fsm")(self._h, None, C.c_size_t(0), C.byref(n)), "drain_fsm")
+        st = self._fn("drain_fsm")(self._h, None, C.c_size_t(0), C.byref(n))
+        if not (st == abi.E_CAPACITY and not strict):
+            self._check(st, "drain_fsm")
         return n.value
 
     def fsm_records(self) -> Tuple[List[abi.FsmRecord], abi.FsmBatch]:

@@ -25,7 +25,7 @@ now = 1700
 for _ in range(5):
     e.run(now, 100, S, 1)
     e.truncate(8)
-    e.discard_fsm()
+    e.discard_fsm(strict=False)
     now += 100 * S
 e._lib.jr_profile_read(e._h, buf)
 names = {1: "  drain: Leader::commit", 8: "  drain: mask+unit loads", 9: "  drain: advances", 0: "Tick", 2: "  replicate: first peer (scan)", 3: "  replicate: other peers (refs)", 4: "AppendEntries", 5: "AppendResponse", 6: "Heartbeat",
