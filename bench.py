@@ -444,6 +444,10 @@ class Bench:
         for _ in range(max(warmup, 3)):
             self.flush.fill_(1)
             one_step()
+        while outstanding[0]:
+            take()
+        for k in range(3):
+            totals[k] = 0
         self.barrier()
         t0 = time.time()
         evs = []

@@ -277,7 +277,8 @@ enum {
   JR_STEP_DELIVER = 1u << 0,  /* apply peer mail emitted in the previous step        */
   JR_STEP_TICK = 1u << 1,     /* then apply Command::Tick on every replica           */
   JR_STEP_SYNTH_PROPOSALS = 1u << 2, /* every current Leader receives n_synth ClientRequests */
-  JR_STEP_TRUSTED_PROPOSALS = 1u << 3 /* caller guarantees proposals[g].node <= R: skip the O(G) host check */
+  JR_STEP_TRUSTED_PROPOSALS = 1u << 3, /* caller guarantees proposals[g].node <= R: skip the O(G) host check */
+  JR_STEP_REPORT_FAULTS = 1u << 4     /* fill n_faulted (one more small kernel; the call synchronises) */
 };
 
 /*
@@ -305,6 +306,8 @@ typedef struct jr_step_args {
   jr_fsm_instr* out_fsm;
   size_t cap_fsm;
   size_t n_fsm;                  /* out: instructions, group-major, node asc, FIFO */
+  uint64_t n_faulted;            /* out, with JR_STEP_REPORT_FAULTS: replicas holding a sticky fault (D3) after this step --
+                                  * the reference's `?` / panic leaving event_loop (server.rs:125-159), without a query per node */
 } jr_step_args;
 
 /* Introspection: Raft<T> pub fields (mod.rs:326-341) + role state. */

@@ -5,18 +5,21 @@
 //! add to `src/raft/` to drive `libjosefine_b200.so` through `include/josefine_raft_abi.h`:
 //! `#[repr(C)]` mirrors of the POD structs, the `extern "C"` block, `Command <-> jr_msg`
 //! conversion, and an `event_loop` whose five `raft.apply(..)` sites (src/raft/server.rs:125,
-//! 133,135,143,159) become one `jr_step` per tick.  The Python binding in
+//! 133,135,143,159) each become ONE `jr_step`: the tick site steps with DELIVER|TICK, the inbound-RPC
+//! and client sites step with flags = 0 and the one command injected, so a command is applied the
+//! moment it arrives, exactly as `raft.apply(cmd)` does in the reference.  The Python binding in
 //! `josefine_b200/raft.py` is the one the tests exercise; field order and sizes here follow the
 //! same header and are checked on the C side by `tests/test_abi.py`.
 //!
 //! Mapping (reference item -> here):
 //!   RaftHandle::new                   mod.rs:428-435     -> GpuRaft::new (jr_engine_create, resident_mask = this node)
 //!   Apply::apply(Command::Tick)       server.rs:125      -> GpuRaft::tick (jr_step DELIVER|TICK)
-//!   apply(msg.command) from tcp_rx    server.rs:127-137  -> GpuRaft::on_peer_message (queued, injected at the next tick)
-//!   apply(ClientRequest)              server.rs:156-160  -> GpuRaft::propose
+//!   apply(msg.command) from tcp_rx    server.rs:127-137  -> GpuRaft::on_peer_message (jr_step, flags 0, inject = [msg]: applied at once)
+//!   apply(ClientRequest)              server.rs:156-160  -> GpuRaft::propose        (jr_step, flags 0, inject = [ClientRequest])
 //!   rpc_tx.send(Message)              mod.rs:390-400     -> StepOutput::messages
 //!   fsm_tx.send(Instruction)          leader.rs:94,184   -> StepOutput::instructions
-//!   panic!/Err in the state machine   (see JR_FAULT_*)   -> StepOutput::fault -> event_loop returns Err
+//!   panic!/Err in the state machine   (see JR_FAULT_*)   -> StepOutput::faulted (jr_step_args.n_faulted, JR_STEP_REPORT_FAULTS)
+//!                                                           -> event_loop returns Err; no jr_query per step
 
 #![allow(dead_code)]
 
@@ -30,12 +33,13 @@ use crate::raft::{ClientRequest, ClientRequestId, Command, NodeId};
 
 // ---- POD mirrors of include/josefine_raft_abi.h ------------------------------------------------
 
-pub const JR_ABI_VERSION: u32 = 1;
+pub const JR_ABI_VERSION: u32 = 2;
 pub const JR_MAX_AE_BLOCKS: usize = 5;
 pub const JR_F_CAPTURE_MESSAGES: u32 = 1 << 1;
 pub const JR_F_CAPTURE_FSM: u32 = 1 << 2;
 pub const JR_STEP_DELIVER: u32 = 1 << 0;
 pub const JR_STEP_TICK: u32 = 1 << 1;
+pub const JR_STEP_REPORT_FAULTS: u32 = 1 << 4;
 
 #[repr(C)]
 #[derive(Clone, Copy, Default)]
@@ -54,6 +58,8 @@ pub struct JrConfig {
     pub fsm_units: u32,
     pub flags: u32,
     pub resident_mask: u32,
+    pub fsm_host_records: u32,
+    pub fsm_raw_units: u32,
 }
 
 #[repr(C)]
@@ -121,6 +127,7 @@ pub struct JrStepArgs {
     pub out_fsm: *mut JrFsmInstr,
     pub cap_fsm: usize,
     pub n_fsm: usize,
+    pub n_faulted: u64, // out, with JR_STEP_REPORT_FAULTS
 }
 
 #[repr(C)]
@@ -145,6 +152,7 @@ pub struct JrReplicaState {
     pub fault: u8,
     pub alive: u8,
     pub n_queued: u8,
+    pub chain_floor: u64, // deviation D7
 }
 
 #[link(name = "josefine_b200")]
@@ -286,7 +294,9 @@ fn decode(me: NodeId, m: &JrMsg, tokens: &Tokens) -> Message {
 pub struct StepOutput {
     pub messages: Vec<Message>,
     pub instructions: Vec<Instruction>,
-    pub fault: u8,
+    /// replicas of this engine that hold a sticky fault after the step (the reference would have left
+    /// event_loop through `?` or a panic, server.rs:125-159)
+    pub faulted: u64,
 }
 
 /// One hosted node (this process) of ONE Raft group on the GPU engine.  A multi-raft broker
@@ -295,8 +305,6 @@ pub struct GpuRaft {
     engine: *mut c_void,
     me: NodeId,
     group: u32,
-    pending: Vec<JrMsg>,
-    proposal: Option<JrProposal>,
     tokens: Tokens,
     out_msgs: Vec<JrMsg>,
     out_fsm: Vec<JrFsmInstr>,
@@ -316,46 +324,50 @@ impl GpuRaft {
             engine,
             me,
             group: 0,
-            pending: Vec::new(),
-            proposal: None,
             tokens: Tokens::default(),
             out_msgs: vec![JrMsg::default(); 256],
             out_fsm: vec![JrFsmInstr::default(); 256],
         })
     }
 
-    /// tcp_rx arm (server.rs:127-137)
-    pub fn on_peer_message(&mut self, msg: &Message) {
+    /// tcp_rx arm (server.rs:127-137): `raft.apply(msg.command)` NOW -- an inject-only step (no delivery, no Tick).
+    pub fn on_peer_message(&mut self, now_ms: u64, msg: &Message) -> anyhow::Result<StepOutput> {
         let m = encode(self.group, self.me, msg, &mut self.tokens);
-        self.pending.push(m);
+        self.step(now_ms, 0, &[m])
     }
 
-    /// client arm (server.rs:156-160)
-    pub fn propose(&mut self, id: ClientRequestId, proposal: Proposal) {
+    /// client arm (server.rs:156-160): `raft.apply(Command::ClientRequest(..))` NOW.
+    pub fn propose(&mut self, now_ms: u64, id: ClientRequestId, proposal: Proposal) -> anyhow::Result<StepOutput> {
         let token = self.tokens.intern(proposal.get());
         self.tokens.request.insert(token, (id, Address::Client));
-        self.proposal = Some(JrProposal { token, node: self.me, reserved: 0 });
+        let m = JrMsg { group: self.group, to_kind: A_PEER, to_id: self.me, from_kind: A_LOCAL, kind: K_CLIENT_REQUEST, token,
+                        client_kind: A_CLIENT, ..Default::default() };
+        self.step(now_ms, 0, &[m])
     }
 
-    /// tick arm (server.rs:125): everything queued since the last tick, then Command::Tick.
+    /// tick arm (server.rs:125): Command::Tick.  (With one resident node per engine there is no co-resident mail:
+    /// DELIVER only matters when several nodes of the group live in this engine.)
     pub fn tick(&mut self, now_ms: u64) -> anyhow::Result<StepOutput> {
-        let prop = self.proposal.take();
+        self.step(now_ms, JR_STEP_DELIVER | JR_STEP_TICK, &[])
+    }
+
+    fn step(&mut self, now_ms: u64, flags: u32, inject: &[JrMsg]) -> anyhow::Result<StepOutput> {
         let mut args = JrStepArgs {
             now_ms,
-            flags: JR_STEP_DELIVER | JR_STEP_TICK,
+            flags: flags | JR_STEP_REPORT_FAULTS,
             n_synth: 0,
-            inject: self.pending.as_ptr(),
-            n_inject: self.pending.len(),
-            proposals: prop.as_ref().map_or(std::ptr::null(), |p| p as *const JrProposal),
+            inject: inject.as_ptr(),
+            n_inject: inject.len(),
+            proposals: std::ptr::null(),
             out_msgs: self.out_msgs.as_mut_ptr(),
             cap_msgs: self.out_msgs.len(),
             n_msgs: 0,
             out_fsm: self.out_fsm.as_mut_ptr(),
             cap_fsm: self.out_fsm.len(),
             n_fsm: 0,
+            n_faulted: 0,
         };
         let st = unsafe { jr_step(self.engine, &mut args) };
-        self.pending.clear();
         anyhow::ensure!(st == 0, "jr_step failed: status {}", st);
         let messages = self.out_msgs[..args.n_msgs].iter().map(|m| decode(self.me, m, &self.tokens)).collect();
         let instructions = self.out_fsm[..args.n_fsm]
@@ -375,10 +387,7 @@ impl GpuRaft {
                 }
             })
             .collect();
-        let mut st8 = std::mem::MaybeUninit::<JrReplicaState>::uninit();
-        unsafe { jr_query(self.engine, self.group, self.me, st8.as_mut_ptr()) };
-        let fault = unsafe { st8.assume_init() }.fault;
-        Ok(StepOutput { messages, instructions, fault })
+        Ok(StepOutput { messages, instructions, faulted: args.n_faulted })
     }
 }
 
@@ -388,16 +397,22 @@ impl Drop for GpuRaft {
     }
 }
 
-// event_loop (src/raft/server.rs:103-165) with the engine in place of RaftHandle:
+// event_loop (src/raft/server.rs:103-165) with the engine in place of RaftHandle -- every arm applies its
+// command at once, like the reference; `emit` forwards the outputs and turns a fault into the reference's Err:
 //
+//   let emit = |out: StepOutput| -> Result<()> {
+//       if out.faulted != 0 { return Err(anyhow!("raft fault")); }                   // the reference's `?` / panic
+//       for m in out.messages     { tcp_tx.send(m)?; }                                // server.rs:141-142
+//       for i in out.instructions { fsm_tx.send(i)?; }                                // leader.rs:94,184; follower.rs:205
+//       Ok(())
+//   };
 //   loop { tokio::select! {
-//       _ = shutdown.wait()              => break,
-//       _ = step_interval.tick()         => {
-//           let out = raft.tick(start.elapsed().as_millis() as u64)?;
-//           if out.fault != 0 { return Err(anyhow!("raft fault {}", out.fault)); }   // the reference's `?` / panic
-//           for m in out.messages     { tcp_tx.send(m)?; }
-//           for i in out.instructions { fsm_tx.send(i)?; }
-//       }
-//       Some(msg) = tcp_rx.recv()        => raft.on_peer_message(&msg),
-//       Some((proposal, res)) = client_rx.recv() => { let id = Uuid::new_v4(); requests.insert(id, res); raft.propose(id, proposal); }
+//       _ = shutdown.wait()                       => break,
+//       _ = step_interval.tick()                  => emit(raft.tick(now_ms())?)?,                       // server.rs:125
+//       Some(msg) = tcp_rx.recv()                 => emit(raft.on_peer_message(now_ms(), &msg)?)?,      // server.rs:127-137
+//       Some((proposal, res)) = client_rx.recv()  => { let id = Uuid::new_v4(); requests.insert(id, res);
+//                                                      emit(raft.propose(now_ms(), id, proposal)?)?; }   // server.rs:156-160
 //   } }
+//
+// A broker that hosts MANY groups keeps one engine for all of them and uses the batched calls instead
+// (jr_run_tokens + jr_leader_table_async + jr_fsm_records_async / _wait / jr_fsm_fold): see INTEGRATION.md.

@@ -55,6 +55,7 @@ STEP_DELIVER = 1 << 0
 STEP_TICK = 1 << 1
 STEP_SYNTH_PROPOSALS = 1 << 2
 STEP_TRUSTED_PROPOSALS = 1 << 3
+STEP_REPORT_FAULTS = 1 << 4
 
 FSM_APPLY, FSM_NOTIFY = 0, 1
 
@@ -107,6 +108,7 @@ class StepArgs(C.Structure):
         ("proposals", C.POINTER(Proposal)),
         ("out_msgs", C.POINTER(Msg)), ("cap_msgs", C.c_size_t), ("n_msgs", C.c_size_t),
         ("out_fsm", C.POINTER(FsmInstr)), ("cap_fsm", C.c_size_t), ("n_fsm", C.c_size_t),
+        ("n_faulted", C.c_uint64),
     ]
 
 

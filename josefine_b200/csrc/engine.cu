@@ -535,67 +535,106 @@ struct FsmHeader {          // written by fsm_pack_kernel next to the records
   uint32_t ready;           // epoch of the batch, written last
 };
 
-// One CTA of T <= SCAN_THREADS threads (the CPU emulation runs it with T = 1).  offs[i] = records of replicas
-// before i; hdr totals.  Padded groups (g >= G) contribute nothing.
-__global__ void fsm_scan_kernel(const Dev d, uint32_t* offs, FsmHeader* hdr, uint32_t cap_records) {
-  __shared__ unsigned long long s_rec[SCAN_THREADS], s_drop[SCAN_THREADS], s_ins[SCAN_THREADS];
-  const size_t plane = (size_t)d.R * d.Gp;
-  const uint32_t t = threadIdx.x, T = blockDim.x;
-  const size_t per = (plane + T - 1) / T;
-  const size_t lo = min(plane, per * t), hi = min(plane, per * (t + 1));
-  unsigned long long rec = 0, drop = 0, ins = 0;
-  for (size_t i = lo; i < hi; ++i) {
-    if ((uint32_t)(i % d.Gp) >= d.G) continue;
-    const uint2 c = d.fc[i];
-    rec += min(c.x, d.F);
-    drop += c.x > d.F ? c.x - d.F : 0u;
-    ins += c.y;
-  }
-  s_rec[t] = rec; s_drop[t] = drop; s_ins[t] = ins;
-  __syncthreads();
-  if (t == 0) {
-    unsigned long long run = 0, dr = 0, in = 0;
-    for (uint32_t k = 0; k < T; ++k) {
-      const unsigned long long v = s_rec[k];
-      s_rec[k] = run;
-      run += v;
-      dr += s_drop[k];
-      in += s_ins[k];
-    }
-    hdr->n_records = min(run, (unsigned long long)cap_records);
-    hdr->n_dropped = dr + (run > cap_records ? run - cap_records : 0ull);
-    hdr->n_instructions = in;
-  }
-  __syncthreads();
-  unsigned long long at = s_rec[t];
-  for (size_t i = lo; i < hi; ++i) {
-    offs[i] = (uint32_t)min(at, 0xFFFFFFFFull);
-    if ((uint32_t)(i % d.Gp) < d.G) at += min(d.fc[i].x, d.F);
-    if (i % d.Gp == 0) hdr->node_offset[i / d.Gp] = (uint32_t)min((unsigned long long)offs[i], (unsigned long long)cap_records);
-  }
-  if (t == T - 1) hdr->node_offset[d.R] = (uint32_t)min(at, (unsigned long long)cap_records);
+// Three small kernels (CTAs of T threads; the CPU emulation runs them with T = 1):
+//   fsm_count_kernel  per-CTA sums of the replicas' record counts            -> part[3][n_ctas]
+//   fsm_scan_kernel   one CTA: exclusive scan of those sums, batch totals     -> part[0] becomes CTA offsets, hdr
+//   fsm_pack_kernel   CTA-local scan + CTA offset = each replica's position; copies its records, empties its FIFO
+// Padded groups (g >= G) contribute nothing.
+__device__ __forceinline__ uint32_t fsm_kept(const Dev& d, size_t i, uint2 c) {
+  return (uint32_t)(i % d.Gp) < d.G ? min(c.x, d.F) : 0u;
 }
 
-// Thread i moves its replica's records to out[offs[i] ..] and empties the FIFO.  `out` / `hdr_out` may be mapped host memory.
-__global__ void fsm_pack_kernel(const Dev d, const uint32_t* offs, const FsmHeader* hdr, uint4* out, FsmHeader* hdr_out,
-                                uint32_t cap_records, uint32_t epoch) {
+__global__ void fsm_count_kernel(const Dev d, unsigned long long* part, uint32_t n_ctas) {
+  __shared__ unsigned long long s[3][SCAN_THREADS / 32];
   const size_t plane = (size_t)d.R * d.Gp;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < plane) {
-    if ((uint32_t)(i % d.Gp) < d.G) {
-      const uint32_t n = min(d.fc[i].x, d.F);
-      const uint32_t at = offs[i];
-      for (uint32_t k = 0; k < n && at + k < cap_records; ++k) {
-        out[(size_t)2 * (at + k)] = d.fs[(size_t)(2 * k) * plane + i];
-        out[(size_t)2 * (at + k) + 1] = d.fs[(size_t)(2 * k + 1) * plane + i];
-      }
-    }
-    d.fc[i] = make_uint2(0, 0);
+  unsigned long long rec = 0, drop = 0, ins = 0;
+  if (i < plane && (uint32_t)(i % d.Gp) < d.G) {
+    const uint2 c = d.fc[i];
+    rec = min(c.x, d.F);
+    drop = c.x > d.F ? c.x - d.F : 0u;
+    ins = c.y;
   }
-  if (i == 0 && hdr_out) {
-    FsmHeader h = *hdr;
-    h.ready = epoch;
-    *hdr_out = h;
+#ifdef JR_EMU
+  (void)s;
+#else
+  for (int o = 16; o > 0; o >>= 1) {
+    rec += __shfl_down_sync(0xffffffffu, rec, o);
+    drop += __shfl_down_sync(0xffffffffu, drop, o);
+    ins += __shfl_down_sync(0xffffffffu, ins, o);
+  }
+  if ((threadIdx.x & 31) == 0) { s[0][threadIdx.x >> 5] = rec; s[1][threadIdx.x >> 5] = drop; s[2][threadIdx.x >> 5] = ins; }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  rec = drop = ins = 0;
+  for (uint32_t w = 0; w < (blockDim.x + 31) / 32; ++w) { rec += s[0][w]; drop += s[1][w]; ins += s[2][w]; }
+#endif
+  part[blockIdx.x] = rec;
+  part[n_ctas + blockIdx.x] = drop;
+  part[2 * (size_t)n_ctas + blockIdx.x] = ins;
+}
+
+__global__ void fsm_scan_kernel(unsigned long long* part, uint32_t n_ctas, FsmHeader* hdr, uint32_t cap_records) {
+  __shared__ unsigned long long s_sum[SCAN_THREADS];
+  const uint32_t t = threadIdx.x, T = blockDim.x;
+  const uint32_t per = (n_ctas + T - 1) / T;
+  const uint32_t lo = min(n_ctas, per * t), hi = min(n_ctas, per * (t + 1));
+  unsigned long long sum = 0, drop = 0, ins = 0;
+  for (uint32_t k = lo; k < hi; ++k) { sum += part[k]; drop += part[n_ctas + k]; ins += part[2 * (size_t)n_ctas + k]; }
+  s_sum[t] = sum;
+  __syncthreads();
+  if (t == 0) {
+    unsigned long long run = 0;
+    for (uint32_t k = 0; k < T; ++k) { const unsigned long long v = s_sum[k]; s_sum[k] = run; run += v; }
+    hdr->n_records = min(run, (unsigned long long)cap_records);
+    hdr->n_dropped = run > cap_records ? run - cap_records : 0ull;   // + the per-replica drops, added below
+    hdr->n_instructions = 0;
+  }
+  __syncthreads();
+#ifdef JR_EMU
+  hdr->n_dropped += drop;
+  hdr->n_instructions += ins;
+#else
+  if (drop) atomicAdd(&hdr->n_dropped, drop);
+  if (ins) atomicAdd(&hdr->n_instructions, ins);
+#endif
+  unsigned long long at = s_sum[t];
+  for (uint32_t k = lo; k < hi; ++k) { const unsigned long long v = part[k]; part[k] = at; at += v; }
+}
+
+// Thread i moves its replica's records to out[position ..] and empties the FIFO.  `out` may be mapped host memory.
+__global__ void fsm_pack_kernel(const Dev d, const unsigned long long* part, FsmHeader* hdr, uint4* out, uint32_t cap_records) {
+  __shared__ uint32_t s_warp[SCAN_THREADS / 32];
+  const size_t plane = (size_t)d.R * d.Gp;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n = i < plane ? fsm_kept(d, i, d.fc[i]) : 0u;
+  // exclusive scan of n over the CTA
+  uint32_t pre = 0;
+#ifdef JR_EMU
+  (void)s_warp;
+#else
+  const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  uint32_t inc = n;
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= (uint32_t)o) inc += v;
+  }
+  if (lane == 31) s_warp[w] = inc;
+  __syncthreads();
+  uint32_t base = 0;
+  for (uint32_t k = 0; k < w; ++k) base += s_warp[k];
+  pre = base + inc - n;
+#endif
+  const unsigned long long at64 = part[blockIdx.x] + pre;
+  if (i < plane) {
+    const uint32_t at = (uint32_t)min(at64, (unsigned long long)cap_records);
+    for (uint32_t k = 0; k < n && at + k < cap_records; ++k) {
+      out[(size_t)2 * (at + k)] = d.fs[(size_t)(2 * k) * plane + i];
+      out[(size_t)2 * (at + k) + 1] = d.fs[(size_t)(2 * k + 1) * plane + i];
+    }
+    if (i % d.Gp == 0) hdr->node_offset[i / d.Gp] = at;
+    if (i + 1 == plane) hdr->node_offset[d.R] = (uint32_t)min(at64 + n, (unsigned long long)cap_records);
+    d.fc[i] = make_uint2(0, 0);
   }
 }
 
@@ -627,6 +666,7 @@ __global__ void max_u32_kernel(const uint32_t* v, size_t n, uint32_t* out) {
 // host side
 // ============================================================================
 
+extern "C" { static jr_status stream_sums(jr_engine* e, uint64_t v[5]); }
 static thread_local char g_err[512] = "";
 static void set_err(const char* fmt, ...) {
   va_list ap;
@@ -690,7 +730,7 @@ struct jr_engine {
   size_t many_cap = 0;
   // Instruction-stream drain (JR_F_CAPTURE_FSM): scan -> pack into stage[b] on the engine stream, then
   // fsm_copy_kernel moves stage[b] into the pinned host buffer host[b] on the d2h stream.
-  uint32_t* fsm_offs = nullptr;                               // device, plane entries
+  unsigned long long* fsm_part = nullptr;                     // device, 3 x (CTAs of the count/pack kernels): per-CTA sums -> offsets
   uint32_t fsm_cap = 0;                                       // records per batch
   uint4* fsm_stage[NBUF] = {nullptr, nullptr};                // device, 2 * fsm_cap uint4 each
   FsmHeader* fsm_stage_hdr[NBUF] = {nullptr, nullptr};        // device
@@ -914,7 +954,7 @@ jr_status jr_engine_create(const jr_config* cfg, jr_engine** out) {
     const size_t want = cfg->fsm_host_records ? cfg->fsm_host_records
                                               : std::max(3 * reps + 1024, std::min<size_t>(reps * cfg->fsm_units, 1u << 16));
     e->fsm_cap = (uint32_t)std::min<size_t>(want, 0x7fffffffu);
-    A(e->fsm_offs, plane);
+    A(e->fsm_part, 3 * plane);   // (sized for one-thread CTAs, which is what the CPU emulation launches)
     for (int i = 0; i < jr_engine::NBUF; ++i) { A(e->fsm_stage[i], 2 * (size_t)e->fsm_cap); A(e->fsm_stage_hdr[i], 1); }
   }
   A(e->scratch, 8);
@@ -1151,13 +1191,16 @@ static jr_status fsm_records_enqueue(jr_engine* e) {
   if (e->fsm_used[b]) CK(cudaStreamWaitEvent(e->stream, e->fsm_landed[b], 0));  // stage[b] has left the device
   const uint32_t epoch = ++e->fsm_epoch;
 #ifdef JR_EMU
-  JR_LAUNCH(fsm_scan_kernel, 1, 1, e->stream, d, e->fsm_offs, e->fsm_stage_hdr[b], e->fsm_cap);
+  const uint32_t T = 1, Ts = 1;
 #else
-  JR_LAUNCH(fsm_scan_kernel, 1, SCAN_THREADS, e->stream, d, e->fsm_offs, e->fsm_stage_hdr[b], e->fsm_cap);
+  const uint32_t T = 256, Ts = SCAN_THREADS;
 #endif
+  const uint32_t n_ctas = (uint32_t)((plane + T - 1) / T);
+  JR_LAUNCH(fsm_count_kernel, n_ctas, T, e->stream, d, e->fsm_part, n_ctas);
   CK(cudaGetLastError());
-  JR_LAUNCH(fsm_pack_kernel, (unsigned)((plane + 255) / 256), 256, e->stream, d, e->fsm_offs, e->fsm_stage_hdr[b],
-            e->fsm_stage[b], (FsmHeader*)nullptr, e->fsm_cap, epoch);
+  JR_LAUNCH(fsm_scan_kernel, 1, Ts, e->stream, e->fsm_part, n_ctas, e->fsm_stage_hdr[b], e->fsm_cap);
+  CK(cudaGetLastError());
+  JR_LAUNCH(fsm_pack_kernel, n_ctas, T, e->stream, d, e->fsm_part, e->fsm_stage_hdr[b], e->fsm_stage[b], e->fsm_cap);
   CK(cudaGetLastError());
   CK(cudaEventRecord(e->fsm_packed[b], e->stream));
   CK(cudaStreamWaitEvent(e->d2h, e->fsm_packed[b], 0));
@@ -1333,6 +1376,11 @@ jr_status jr_step(jr_engine* e, jr_step_args* a) {
     a->n_fsm = fsm.size();
     memcpy(a->out_fsm, fsm.data(), std::min(fsm.size(), a->cap_fsm) * sizeof(jr_fsm_instr));
     ovf |= fsm.size() > a->cap_fsm || st == JR_E_CAPACITY;
+  }
+  if (a->flags & JR_STEP_REPORT_FAULTS) {
+    uint64_t v[5];
+    if ((st = stream_sums(e, v)) != JR_OK) return st;
+    a->n_faulted = v[4];
   }
   return ovf ? JR_E_CAPACITY : JR_OK;
 }

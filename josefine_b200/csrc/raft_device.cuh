@@ -263,8 +263,18 @@ __device__ __noinline__ void fsm_flush(const uint4* raw0, uint32_t n_raw, uint32
   uint64_t pbits = 0;
   FsmRun ra{0, 0, 0, 0}, rn{0, 0, 0, 0};
   const uint32_t n = n_raw < Fr ? n_raw : Fr;
+  constexpr uint32_t AHEAD = 8;   // entries are independent loads (L2 / DRAM): fetch a batch, then encode it
+  uint4 buf[AHEAD];
   for (uint32_t u = 0; u < n; ++u) {
-    const uint4 e = __ldcg(raw0 + (size_t)u * o.plane);
+    if ((u % AHEAD) == 0) {
+#pragma unroll
+      for (uint32_t j = 0; j < AHEAD; ++j)
+        if (u + j < n) buf[j] = __ldcg(raw0 + (size_t)(u + j) * o.plane);
+    }
+    uint4 e = buf[0];
+#pragma unroll
+    for (uint32_t j = 1; j < AHEAD; ++j)
+      if ((u % AHEAD) == j) e = buf[j];
     const bool notify = (e.x & FS_NOTIFY_BIT) != 0;
     const uint32_t bid = e.x & ~FS_NOTIFY_BIT, nxa = e.y;
     const uint64_t tok = (uint64_t)e.z | ((uint64_t)e.w << 32);

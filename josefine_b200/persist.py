@@ -92,3 +92,33 @@ def reopen(records: Iterable[Tuple[bytes, bytes]]) -> dict:
                 raise ValueError("record key does not match the block id inside it")
             blocks[bid] = (nxt, data)
     return {"commit": commit, "head": commit, "id_gen": commit, "blocks": blocks}
+
+
+def import_records(records: Iterable[Tuple[bytes, bytes]], tokens: Optional[Dict[bytes, int]] = None):
+    """The arguments of `jr_node_restart` / `RaftApi.node_restart` for a node that reopens a tree holding `records`
+    (chain.rs:117-137): (blocks, commit, commit_key) with blocks = [(id, next, token)].
+
+    Payload bytes stay on the host (deviation D5): `tokens` maps payload bytes to the 64-bit token the host wants the
+    engine to carry for them; a payload without an entry gets the token `chain_records` wrote for token-only payloads
+    (its own 8 little-endian bytes) or, failing that, 0.
+    """
+    st = reopen(records)
+    commit_key = any(k == COMMIT_KEY for k, _ in records) if not isinstance(records, dict) else False
+    blocks = []
+    for bid in sorted(st["blocks"]):
+        nxt, data = st["blocks"][bid]
+        if tokens is not None and data in tokens:
+            tok = tokens[data]
+        elif len(data) == 8:
+            (tok,) = struct.unpack("<Q", data)
+        else:
+            tok = 0
+        blocks.append((bid, nxt, tok))
+    return blocks, st["commit"], commit_key
+
+
+def restart_from_records(api, group: int, node: int, now_ms: int, records, tokens: Optional[Dict[bytes, int]] = None):
+    """`RaftHandle::new` over an existing data directory: load a sled export back into replica (group, node)."""
+    records = list(records)
+    blocks, commit, commit_key = import_records(records, tokens)
+    api.node_restart(group, node, now_ms, blocks, commit, commit_key)

@@ -156,6 +156,7 @@ DEFAULT_CAPTURE_CAP = 1 << 18
 class StepResult:
     messages: List[abi.Msg]
     fsm: List[abi.FsmInstr]
+    n_faulted: Optional[int] = None      # with report_faults: replicas holding a sticky fault after the step
 
 
 class RaftApi:
@@ -191,12 +192,15 @@ class RaftApi:
     # -- stepping ---------------------------------------------------------------
     def step(self, now_ms: int, flags: int = abi.STEP_DELIVER | abi.STEP_TICK,
              inject: Iterable[abi.Msg] = (), proposals: Optional[Sequence[Tuple[int, int]]] = None,
-             n_synth: int = 0, cap_msgs: Optional[int] = None, cap_fsm: Optional[int] = None) -> StepResult:
+             n_synth: int = 0, cap_msgs: Optional[int] = None, cap_fsm: Optional[int] = None,
+             report_faults: bool = False) -> StepResult:
         """One jr_step.  `proposals` is a per-group list of (node, token); node 0 = none."""
         a = abi.StepArgs()
         a.now_ms, a.flags, a.n_synth = now_ms, flags, n_synth
         if n_synth:
             a.flags |= abi.STEP_SYNTH_PROPOSALS
+        if report_faults:
+            a.flags |= abi.STEP_REPORT_FAULTS
         inj = list(inject)
         if inj:
             arr = (abi.Msg * len(inj))(*inj)
@@ -228,7 +232,7 @@ class RaftApi:
         self._check(st, "step")
         msgs = [mbuf[i] for i in range(a.n_msgs)] if cap_m else []
         fsm = [fbuf[i] for i in range(a.n_fsm)] if cap_f else []
-        return StepResult(msgs, fsm)
+        return StepResult(msgs, fsm, a.n_faulted if report_faults else None)
 
     def apply(self, cmd: abi.Msg, now_ms: int = 0) -> StepResult:
         """`raft.apply(cmd)` on one replica: no mail delivery, no implicit Tick."""

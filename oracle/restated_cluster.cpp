@@ -390,6 +390,10 @@ jr_status jro_step(jro_cluster* c, jr_step_args* a) {
   a->n_msgs = nm;
   a->n_fsm = nf;
   if (a->out_fsm) clear_fsm(c);  // returned to the caller: taken
+  if (a->flags & JR_STEP_REPORT_FAULTS) {
+    a->n_faulted = 0;
+    for (auto& r : c->reps) a->n_faulted += r.node->fault() != 0;
+  }
   return ovf ? JR_E_CAPACITY : JR_OK;
 }
 

@@ -124,7 +124,7 @@ def case_truncation_soak(make, make_oracle, G=16, R=5, cap=64, rounds=40, ticks=
     """D7: with jr_truncate after every launch a 64-id window carries a group through 1,000 ticks (ids up to
     ~1,000) with no reset and no fault; everything stays bit-equal to the oracle (which truncates its maps the
     same way), including after leaders are silenced and the window stops moving for those groups."""
-    eng, ora = (m(G, R, seed=3, flags=CAP, chain_capacity=cap, fsm_units=max(32, ticks // 16 + 8)) for m in (make, make_oracle))
+    eng, ora = (m(G, R, seed=3, flags=CAP, chain_capacity=cap, fsm_units=max(32, ticks // 8 + 16)) for m in (make, make_oracle))
     for api in (eng, ora):
         _bootstrap(api, G, R)
     now = 100

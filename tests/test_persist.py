@@ -98,3 +98,34 @@ def test_records_from_the_engine_match_the_oracle():
     check_records(eng, payloads)
     for node in (1, 2, 3):
         assert persist.chain_records(eng, 0, node, payloads) == persist.chain_records(ora, 0, node, payloads)
+
+
+def _restart_roundtrip(make):
+    """Export a follower's chain as sled records, restart the node from them (jr_node_restart = Chain::new over a
+    persisted tree, chain.rs:117-137): head = commit = id_gen = the persisted commit, blocks intact."""
+    api, payloads = committed_cluster(make)
+    st = api.query(0, 2)
+    recs = persist.chain_records(api, 0, 2, payloads)
+    before = api.chain_read(0, 2, 0, int(st.max_key) + 1)
+    tokens = {v: k for k, v in payloads.items()}
+    persist.restart_from_records(api, 0, 2, 9000, recs, tokens)
+    after = api.query(0, 2)
+    assert (after.head, after.commit, after.id_gen) == (st.commit, st.commit, st.commit) and st.commit > 0
+    assert (after.current_term, after.voted_for, after.role, after.fault) == (0, 0, abi.ROLE_FOLLOWER, 0)
+    assert api.chain_read(0, 2, 0, int(st.max_key) + 1) == before
+    return api
+
+
+def test_restart_from_records_on_oracle():
+    _restart_roundtrip(lambda g, r, **kw: RestatedCluster.create(g, r, **kw))
+
+
+def test_restart_from_records_on_device_code():
+    from tests.emu.emu import EmuEngine
+    _restart_roundtrip(lambda g, r, **kw: EmuEngine.create(g, r, **kw))
+
+
+@pytest.mark.gpu
+def test_restart_from_records_on_gpu():
+    from josefine_b200 import RaftEngine
+    _restart_roundtrip(lambda g, r, **kw: RaftEngine.create(g, r, **kw))
