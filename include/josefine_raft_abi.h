@@ -143,7 +143,9 @@ enum {
   JR_F_SLED_COMMIT_KEY_STRICT = 1u << 0, /* deviation D6 off: reproduce the commit-key panic */
   JR_F_CAPTURE_MESSAGES = 1u << 1,       /* jr_step may return every emitted Message (rpc_rx) */
   JR_F_CAPTURE_FSM = 1u << 2,            /* Instructions are stored (jr_step / jr_drain_fsm)  */
-  JR_F_STREAM_DIGEST = 1u << 3           /* keep the running digests jr_stream_digest returns  */
+  JR_F_STREAM_DIGEST = 1u << 3,          /* keep the running digests jr_stream_digest returns  */
+  JR_F_NO_SYMMETRIC_FOLD = 1u << 4       /* jr_run* never take the symmetric-group fast path; results are
+                                          * identical either way -- the flag exists for A/B measurements and tests      */
 };
 
 /* ---- configuration (RaftConfig, src/raft/config.rs:14-41, batched) --------- */
@@ -447,6 +449,9 @@ jr_status jr_state_digest(jr_engine* e, uint64_t* out);
 jr_status jr_stream_digest(jr_engine* e, uint64_t* msg_digest, uint64_t* fsm_digest,
                            uint64_t* n_msgs, uint64_t* n_fsm);
 jr_status jr_fault_count(jr_engine* e, uint64_t* n_faulted);
+/* Diagnostic: how many groups the most recent jr_run* launch applied through the symmetric-group fast path
+ * (0 if it was not offered: see JR_F_NO_SYMMETRIC_FOLD).  Synchronises. */
+jr_status jr_fold_count(jr_engine* e, uint64_t* n_groups);
 
 /* ---- maintenance ----------------------------------------------------------- */
 jr_status jr_compact(jr_engine* e);                                    /* every replica */

@@ -49,6 +49,7 @@ F_SLED_COMMIT_KEY_STRICT = 1 << 0
 F_CAPTURE_MESSAGES = 1 << 1
 F_CAPTURE_FSM = 1 << 2
 F_STREAM_DIGEST = 1 << 3
+F_NO_SYMMETRIC_FOLD = 1 << 4
 
 # step flags
 STEP_DELIVER = 1 << 0
@@ -172,7 +173,7 @@ EXPECTED_SIZES = {
 ENGINE_SYMBOLS = [
     "jr_engine_create", "jr_engine_destroy", "jr_engine_reset", "jr_engine_set_stream", "jr_engine_sync",
     "jr_last_error", "jr_config_default", "jr_step", "jr_run", "jr_run_proposals", "jr_run_tokens", "jr_drain_fsm", "jr_query",
-    "jr_chain_read", "jr_state_digest", "jr_stream_digest", "jr_fault_count", "jr_compact",
+    "jr_chain_read", "jr_state_digest", "jr_stream_digest", "jr_fault_count", "jr_fold_count", "jr_compact",
     "jr_set_alive", "jr_kill_leaders", "jr_leader_table_device", "jr_leader_table", "jr_leader_table_async", "jr_leader_table_wait",
     "jr_election_timeout", "jr_fsm_records_async", "jr_fsm_records_wait", "jr_fsm_expand", "jr_fsm_fold", "jr_query_many",
     "jr_chain_read_many", "jr_truncate", "jr_node_restart", "jr_engine_save_size", "jr_engine_save", "jr_engine_restore",

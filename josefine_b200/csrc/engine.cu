@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "raft_device.cuh"
+#include "sym_fold.cuh"
 
 using namespace jr;
 
@@ -90,7 +91,12 @@ __global__ void __launch_bounds__(32 * R, step_min_ctas(R)) step_kernel(const De
       __syncthreads();
     }
   }
+  if (p0.symblk && p0.symblk[blk]) {   // every group of this block was folded by sym_kernel: only keep the hand-over chain alive
+    if (p0.n_parts > 1 && part + 1 < p0.n_parts && threadIdx.x == 0) st_release_u32(d.done + blk, p0.epoch + part + 1);
+    return;
+  }
   const uint32_t g = blk * GROUPS_PER_CTA + lane;  // padded groups (g >= G) are real, unused replicas
+  const bool folded = p0.symdone && p0.symdone[g];   // this lane's group is done: it idles through the barriers
   // Which replica of group g this thread steps.  Plain variant: replica index = warp index, so a
   // warp runs one role's code when the CTA's leaders share a replica index (and every branch on
   // `r` is provably warp-uniform).  SORTED variant, picked by the host when a previous launch saw
@@ -120,6 +126,7 @@ __global__ void __launch_bounds__(32 * R, step_min_ctas(R)) step_kernel(const De
   rep.now = p.now;
   rep.cur = p.cur;
   rep.load(p.phases & PH_RESET_OUT, p.phases & PH_RESET_FSM, part != 0);
+  if (folded) rep.dead = 1;   // never stepped, never stored
   rep.tc_prefetch();
   rep.stage_inbox(p.phases & PH_DRAIN);
 #ifdef JR_PROFILE
@@ -153,13 +160,13 @@ __global__ void __launch_bounds__(32 * R, step_min_ctas(R)) step_kernel(const De
     q.phases = PH_RESET_OUT | PH_DRAIN | PH_PROPOSE | PH_TICK;
     q.proposals = (p.proposals && p.prop_stride) ? p.proposals + (size_t)(t + 1) * p.prop_stride : nullptr;
   }
-  rep.store(part + 1 >= p0.n_parts);
+  if (!folded) rep.store(part + 1 >= p0.n_parts);
   {  // tell the host whether the next launch should sort: leaders on >= 2 replica indices in this CTA?
     uint32_t* lmask = reinterpret_cast<uint32_t*>(L.tc);  // the table cache is dead now; reuse one word of it
     __syncthreads();
     if (threadIdx.x == 0) *lmask = 0;
     __syncthreads();
-    if (rep.role == JR_ROLE_LEADER && rep.live()) atomicOr(lmask, 1u << r);
+    if (!folded && rep.role == JR_ROLE_LEADER && rep.live()) atomicOr(lmask, 1u << r);
     __syncthreads();
     if (threadIdx.x == 0 && (*lmask & (*lmask - 1u))) atomicOr(d.scatter, 1u);
   }
@@ -741,6 +748,12 @@ struct jr_engine {
   bool fsm_used[NBUF] = {false, false};
   int fsm_i = 0, fsm_pending[NBUF] = {0, 0}, fsm_npending = 0;
   uint32_t fsm_epoch = 0;
+  // symmetric-group fold
+  uint8_t* symdone = nullptr;   // device, Gp entries
+  uint8_t* symblk = nullptr;    // device, Gp / 32 entries
+  int no_fold = 0;              // JR_NO_FOLD=1 (A/B, tests)
+  uint64_t launches_folded = 0;
+  bool last_launch_folded = false;
 };
 
 template <typename T>
@@ -832,10 +845,38 @@ static jr_status launch_step(jr_engine* e, const StepParams& p_in) {
   return JR_OK;
 }
 
+template <int R>
+static void launch_sym_r(jr_engine* e, const StepParams& p) {
+  if constexpr (R >= 2) {
+    JR_LAUNCH(sym_kernel<R>, (e->d.Gp + 127) / 128, 128, e->stream, e->d, p, e->symdone);
+  }
+}
+
+// May this launch be offered to the symmetric-group fold?  (Whether a GROUP takes it is sym_enter's decision.)
+static bool fold_eligible(const jr_engine* e, const StepParams& p) {
+  const Dev& d = e->d;
+  const uint32_t whole = PH_RESET_OUT | PH_DRAIN | PH_TICK;
+  if (e->no_fold || (d.flags & (JR_F_STREAM_DIGEST | JR_F_SLED_COMMIT_KEY_STRICT | JR_F_NO_SYMMETRIC_FOLD))) return false;
+  if (d.R < 2 || d.U < d.R + 7 || d.resident != 0xffu || p.dt == 0) return false;
+  if ((p.phases & ~(uint32_t)PH_PROPOSE) != whole || p.n_ticks < 2) return false;
+  if (p.proposals && p.prop_stride != d.G) return false;
+  return true;
+}
+
 static jr_status launch_step_once(jr_engine* e, const StepParams& p_in) {
   const uint32_t n_blocks = e->d.Gp / GROUPS_PER_CTA;
   const size_t smem = step_smem_bytes(e->d);
   StepParams p = p_in;
+  if (fold_eligible(e, p)) {
+    DISPATCH_R(e->cfg.n_replicas, (launch_sym_r<RR>(e, p)));
+    CK(cudaGetLastError());
+    JR_LAUNCH(sym_blocks_kernel, (n_blocks + 127) / 128, 128, e->stream, e->symdone, e->symblk, n_blocks);
+    CK(cudaGetLastError());
+    p.symdone = e->symdone;
+    p.symblk = e->symblk;
+    e->launches_folded += 1;
+  }
+  e->last_launch_folded = p.symdone != nullptr;
   p.n_parts = choose_parts(e, p, n_blocks);
   p.part_ticks = (p.n_ticks + p.n_parts - 1) / p.n_parts;
   p.n_parts = (p.n_ticks + p.part_ticks - 1) / p.part_ticks;  // no empty trailing part
@@ -949,6 +990,8 @@ jr_status jr_engine_create(const jr_config* cfg, jr_engine** out) {
   A(d.fq, plane);
   A(d.fr, plane * (size_t)((d.flags & JR_F_CAPTURE_FSM) ? d.Fr : 1));
   A(d.tb, d.Gp);
+  A(e->symdone, d.Gp);
+  A(e->symblk, d.Gp / GROUPS_PER_CTA);
   if (d.flags & JR_F_CAPTURE_FSM) {
     const size_t reps = (size_t)cfg->n_groups * cfg->n_replicas;   // default: 2 per replica, but never less than a small engine's whole FIFO space
     const size_t want = cfg->fsm_host_records ? cfg->fsm_host_records
@@ -1000,6 +1043,7 @@ jr_status jr_engine_create(const jr_config* cfg, jr_engine** out) {
     DISPATCH_R(d.R, (aerr = step_smem_attr_r<RR>(smem)));
     if (aerr == cudaSuccess) aerr = cudaHostAlloc((void**)&e->h_scatter, sizeof(uint32_t), 0);
     if (aerr == cudaSuccess) *e->h_scatter = 0;
+    if (const char* ev = getenv("JR_NO_FOLD")) e->no_fold = atoi(ev);
     if (const char* ev = getenv("JR_PARTS")) e->force_parts = (uint32_t)std::min(std::max(atoi(ev), 0), 8);
 #ifndef JR_EMU
     if (aerr == cudaSuccess) {
@@ -1062,9 +1106,9 @@ jr_status jr_engine_reset(jr_engine* e) {
 void jr_engine_destroy(jr_engine* e) {
   if (!e) return;
   if (getenv("JR_DEBUG_VARIANT"))
-    fprintf(stderr, "[jr] engine %p: %llu step launches, %llu role-sorted, %llu split; %u CTA slots\n", (void*)e,
-            (unsigned long long)e->launches_total, (unsigned long long)e->launches_sorted,
-            (unsigned long long)e->launches_split, e->slots);
+    fprintf(stderr, "[jr] engine %p: %llu step launches, %llu role-sorted, %llu split, %llu offered to the fold; %u CTA slots\n",
+            (void*)e, (unsigned long long)e->launches_total, (unsigned long long)e->launches_sorted,
+            (unsigned long long)e->launches_split, (unsigned long long)e->launches_folded, e->slots);
   cudaSetDevice(e->cfg.device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (void* p : e->allocs) cudaFree(p);
@@ -1724,6 +1768,18 @@ jr_status jr_stream_digest(jr_engine* e, uint64_t* md, uint64_t* fd, uint64_t* n
   if (fd) *fd = v[1];
   if (nm) *nm = v[2];
   if (nf) *nf = v[3];
+  return JR_OK;
+}
+
+jr_status jr_fold_count(jr_engine* e, uint64_t* n) {
+  if (!e || !n) return JR_E_INVAL;
+  *n = 0;
+  if (!e->last_launch_folded) return JR_OK;
+  CK(cudaSetDevice(e->cfg.device));
+  std::vector<uint8_t> h(e->d.Gp);
+  CK(cudaMemcpyAsync(h.data(), e->symdone, h.size(), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  for (uint32_t g = 0; g < e->d.G; ++g) *n += h[g];
   return JR_OK;
 }
 

@@ -98,6 +98,10 @@ struct StepParams {
   // Split launch: the n_ticks of every 32-group block are cut into n_parts consecutive runs, one CTA each
   // (grid = n_blocks * n_parts).  Finer tasks fill the last wave of CTAs; see step_kernel.
   uint32_t n_parts = 1, part_ticks = 0, n_blocks = 0, epoch = 0;
+  // Symmetric-group fold (sym_fold.cuh): set when sym_kernel ran in front of this launch.  symdone[g] = 1: group g's
+  // whole launch has been applied already; symblk[b] = 1: that holds for all 32 groups of block b.
+  const uint8_t* symdone = nullptr;
+  const uint8_t* symblk = nullptr;
 };
 
 __host__ __device__ inline uint64_t mix64(uint64_t x) {

@@ -1,0 +1,518 @@
+// sym_fold.cuh -- the symmetric-group fold: a whole fused launch of a group in ONE lane.
+//
+// In a healthy group every follower is in the same state: same term, same head and commit, the same mail from the
+// leader in flight, and the leader holds the same progress entry for each of them.  R-1 replicas then make the same
+// decisions on the same data, tick after tick.  This kernel exploits that symmetry exactly, not approximately:
+// one lane holds the leader's state and ONE follower state that stands for all R-1 followers, keeps the mail
+// between them in registers (it only ever has the shapes listed below), and applies the very handlers of
+// raft_device.cuh -- restated here for scalar operands, each citing the same reference lines -- for all n ticks
+// of the launch.  No mailboxes, no shared memory, no barriers, no divergence between roles; what is left is the data
+// that really has to move: the proposal tokens in, the block-table rows of every replica and the Instruction
+// stream out.
+//
+// Exactness contract:
+//   * sym_kernel first CHECKS that a group is symmetric and that its mail in flight has the canonical shapes
+//     (sym_enter); every other group is left to step_kernel untouched.
+//   * If anything outside the canonical evolution would happen during the launch (a fault, an election timer
+//     that could fire, a HeartbeatResponse{has_committed: false}, ...) the lane ABORTS: it has only written
+//     block-table rows and raw Instruction entries that step_kernel writes identically when it re-runs the group
+//     from the untouched state planes, so an abort costs time, never correctness.
+//   * On success the lane writes the replicas' state planes, progress planes, the mailboxes of the last tick in the
+//     exact unit layout step_kernel produces, and encodes the Instruction streams with the same fsm_flush.
+//   * Stream digests (JR_F_STREAM_DIGEST) need every Message in order, which this path never materialises: engines
+//     created with that flag, or with JR_F_SLED_COMMIT_KEY_STRICT / JR_F_NO_SYMMETRIC_FOLD, never take it.
+//     tests/test_sym_fold.py compares folded runs with step_kernel runs and with the oracle through everything else:
+//     replica state, block tables, leader tables, Instruction streams.
+//
+// Canonical mail (all that can be in flight in a symmetric group):
+//   leader -> each follower, in this order:  [Heartbeat{term, commit}]  [AppendEntries{term, <= 5 blocks}]
+//   each follower -> leader, in this order:  [HeartbeatResponse{commit, has}]  [AppendResponse{term, head}]
+#pragma once
+#include "raft_device.cuh"
+
+namespace jr {
+#ifdef JR_DEVICE_CODE
+
+struct SymMail {
+  uint32_t hb, hb_commit;                 // leader -> followers
+  uint32_t ae, ae_nb, ae_id[JR_MAX_AE_BLOCKS];
+  uint32_t hbr, hbr_commit, hbr_has;      // followers -> leader
+  uint32_t ar, ar_head;
+};
+
+template <int R>
+struct SymGroup {
+  const Dev& d;
+  const uint32_t g;
+  const size_t plane;
+  uint32_t L;                              // leader's replica index
+  uint32_t F0;                             // lowest follower index: its block table stands for every follower's
+  uint64_t term, hbtime, now;
+  uint32_t head, commit, idgen, maxkey, ckey, ph_self, mode_self, ph_f, mode_f;   // leader
+  uint32_t fhead, fcommit, fmaxkey, fckey;                                        // every follower
+  uint32_t n_hb;                           // heartbeats the followers took in this launch
+  uint64_t last_hb;
+  uint32_t tbase;
+  uint32_t lcnt, fcnt;                     // raw Instructions emitted: leader / each follower
+  bool abort;
+
+  __device__ __forceinline__ SymGroup(const Dev& dv, uint32_t g_) : d(dv), g(g_), plane((size_t)R * dv.Gp) {}
+  __device__ __forceinline__ size_t rg(uint32_t r) const { return (size_t)r * d.Gp + g; }
+  __device__ __forceinline__ size_t row(uint32_t r, uint32_t bid) const { return (size_t)(bid & d.capm) * plane + rg(r); }
+  __device__ __forceinline__ bool in_window(uint32_t bid) const { return bid - tbase < d.cap && bid < FS_NOTIFY_BIT; }
+  __device__ __forceinline__ void fetch(uint32_t r, uint32_t bid, uint32_t& next, uint64_t& tok) const {
+    if (!in_window(bid)) { next = ABSENT; tok = 0; return; }
+    next = __ldcg(d.cnext + row(r, bid));   // rows written earlier in this launch by this lane: read them at L2
+    tok = __ldcg(d.ctok + row(r, bid));
+  }
+  __device__ __forceinline__ bool has(uint32_t r, uint32_t bid) const {
+    uint32_t n; uint64_t t;
+    fetch(r, bid, n, t);
+    return n != ABSENT;
+  }
+
+  // fsm_tx.send (fsm.rs:19-29): raw entries, encoded by fsm_flush when the launch ends
+  __device__ __forceinline__ void emit_leader(bool notify, uint32_t bid, uint32_t nxa, uint64_t tok) {
+    if (!(d.flags & JR_F_CAPTURE_FSM)) return;
+    if (lcnt < d.Fr)
+      d.fr[(size_t)lcnt * plane + rg(L)] = make_uint4(bid | (notify ? FS_NOTIFY_BIT : 0u), nxa, (uint32_t)tok, (uint32_t)(tok >> 32));
+    ++lcnt;
+  }
+  __device__ __forceinline__ void emit_followers(uint32_t bid, uint32_t next, uint64_t tok) {
+    if (!(d.flags & JR_F_CAPTURE_FSM)) return;
+    if (fcnt < d.Fr) {
+      const uint4 e = make_uint4(bid, next, (uint32_t)tok, (uint32_t)(tok >> 32));
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if ((uint32_t)r != L) d.fr[(size_t)fcnt * plane + rg(r)] = e;
+    }
+    ++fcnt;
+  }
+
+  // ---- leader (leader.rs) ------------------------------------------------------------------------------------
+  // progress.rs:48-60 over {ph_self, n_new x v_new, (R-1-n_new) x v_old}: heads sorted descending, element [R/2]
+  __device__ __forceinline__ uint32_t committed_index(uint32_t v_new, uint32_t n_new, uint32_t v_old) const {
+    uint32_t v[R];
+    v[0] = ph_self;
+#pragma unroll
+    for (int i = 1; i < R; ++i) v[i] = (uint32_t)i <= n_new ? v_new : v_old;
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+#pragma unroll
+      for (int j = 0; j + 1 < R - i; ++j) {
+        const uint32_t a = v[j], b = v[j + 1];
+        v[j] = max(a, b);
+        v[j + 1] = min(a, b);
+      }
+    return v[R / 2];
+  }
+  // leader.rs:87-99 with the current heads
+  __device__ __forceinline__ void leader_commit(uint32_t v_new, uint32_t n_new, uint32_t v_old) {
+    const uint32_t q = committed_index(v_new, n_new, v_old);
+    if (q <= commit) return;
+    if (!has(L, q)) { abort = true; return; }           // chain.rs:197-202 would panic
+    const uint32_t prev = commit;
+    ckey = 1;
+    commit = q;
+    bool first = true;
+    for (uint32_t b = max(prev, tbase); b <= q; ++b) {   // range(prev..=new).skip(1), key order
+      uint32_t nx; uint64_t tk;
+      fetch(L, b, nx, tk);
+      if (nx == ABSENT) continue;
+      if (first) { first = false; continue; }
+      emit_leader(false, b, nx, tk);
+    }
+  }
+  // leader.rs:177-197
+  __device__ __forceinline__ void client_request(uint64_t tok) {
+    const uint32_t bid = idgen++;
+    if (!(bid > head) || !in_window(bid)) { abort = true; return; }   // chain.rs:163 / engine window: a fault -> step_kernel's business
+    d.cnext[row(L, bid)] = head;
+    d.ctok[row(L, bid)] = tok;
+    if (bid > maxkey) maxkey = bid;
+    head = bid;
+    emit_leader(true, bid, FSR_CLIENT, tok);
+    mode_self = ph_self < head ? 1u : 0u;               // progress.rs:76-94 on the leader's own entry
+    if (ph_self < head) ph_self = head;
+    leader_commit(ph_f, R - 1, ph_f);
+  }
+
+  __device__ __forceinline__ void leader_tick(const SymMail& in, SymMail& out, uint64_t dense_tok, uint32_t n_synth,
+                                              uint64_t step_index) {
+    // peer mail, ascending sender, FIFO per sender: every follower sent the same [HeartbeatResponse][AppendResponse]
+    if (in.hbr && !in.hbr_has && in.hbr_commit > 0) { abort = true; return; }   // leader.rs:222-231 would replicate mid-drain
+    if (in.ar) {
+      const uint32_t old = ph_f, v = in.ar_head;
+      const bool inc = old < v;                          // progress.rs:133-140, the same for every follower
+      const uint32_t nw = inc ? v : old;
+      for (uint32_t j = 1; j <= (uint32_t)(R - 1) && !abort; ++j) leader_commit(nw, j, old);   // leader.rs:211-219 after each response
+      ph_f = nw;
+      mode_f = inc ? 1u : 0u;
+      if (abort) return;
+    }
+    // client arm, server.rs:156-160: the dense proposal, then the synthetic ones
+    if (dense_tok) client_request(dense_tok);
+    for (uint32_t i = 0; i < n_synth && !abort; ++i) client_request(synth_token(step_index, i, d.goff + g));
+    if (abort) return;
+    // Command::Tick, leader.rs:234-245
+    const uint64_t el = now >= hbtime ? now - hbtime : 0;
+    if (el > (uint64_t)d.hb) {
+      out.hb = 1;
+      out.hb_commit = commit;
+      hbtime = now;
+    }
+    // replicate, leader.rs:124-174: Probe -> range(head..).nth(1); Replicate -> range(head..).skip(1).take(5)
+    const uint32_t take = mode_f ? JR_MAX_AE_BLOCKS : 1u;
+    uint32_t bid = max(ph_f, tbase), pulled = 0, nb = 0;
+    while (pulled < 1 + take) {
+      uint32_t nx = ABSENT; uint64_t tk = 0;
+      while (bid <= maxkey) {
+        fetch(L, bid, nx, tk);
+        if (nx != ABSENT) break;
+        ++bid;
+      }
+      if (bid > maxkey) break;
+      if (pulled >= 1) out.ae_id[nb++] = bid;
+      ++pulled;
+      ++bid;
+    }
+    out.ae = 1;
+    out.ae_nb = nb;
+  }
+
+  // ---- follower (follower.rs), once for all R-1 of them ----------------------------------------------------------
+  __device__ __forceinline__ void follower_tick(const SymMail& in, SymMail& out) {
+    if (in.hb) {                                           // follower.rs:178-217
+      ++n_hb;                                              // set_election_timeout: one RNG draw, timer restarted
+      last_hb = now;
+      const uint32_t c = in.hb_commit;
+      const bool hasc = has(F0, c);
+      if (hasc && c > fcommit) {
+        const uint32_t prev = fcommit;
+        fckey = 1;
+        fcommit = c;
+        for (uint32_t b = max(prev, tbase); b < c; ++b) {  // range(prev..commit), key order
+          uint32_t nx; uint64_t tk;
+          fetch(F0, b, nx, tk);
+          if (nx != ABSENT) emit_followers(b, nx, tk);
+        }
+      }
+      out.hbr = 1;
+      out.hbr_commit = fcommit;
+      out.hbr_has = hasc ? 1u : 0u;
+    }
+    if (in.ae) {                                           // follower.rs:130-176 with voted_for == Some(leader)
+      for (uint32_t k = 0; k < in.ae_nb; ++k) {
+        const uint32_t bid = in.ae_id[k];
+        uint32_t nx; uint64_t tk;
+        fetch(L, bid, nx, tk);                             // the block as the leader sent it
+        if (nx == ABSENT || !has(F0, nx) || !in_window(bid)) { abort = true; return; }   // chain.rs:180-185 Err / window: step_kernel's business
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if ((uint32_t)r != L) {
+            d.cnext[row(r, bid)] = nx;
+            d.ctok[row(r, bid)] = tk;
+          }
+        if (bid > fmaxkey) fmaxkey = bid;
+        fhead = bid;                                       // chain.rs:188-190: unconditionally
+      }
+      if (in.ae_nb) {
+        out.ar = 1;
+        out.ar_head = fhead;
+      }
+    }
+    // Command::Tick: the election timer cannot have expired (sym_enter checked the bound)
+  }
+};
+
+// ---- entry: is the group symmetric, is its mail canonical? ---------------------------------------------------------
+template <int R>
+__device__ bool sym_enter(SymGroup<R>& s, SymMail& m, const StepParams& p, int prv) {
+  const Dev& d = s.d;
+  if (s.g >= d.G) return false;
+  // roles: one live leader, R-1 live followers of that leader
+  uint32_t L = R, nlead = 0;
+  uint4 p2[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    p2[r] = d.p2[s.rg(r)];
+    const uint32_t meta = p2[r].w;
+    if (((meta >> 8) & 255u) || ((meta >> 27) & 1u)) return false;          // faulted or silenced
+    if ((meta & 255u) == JR_ROLE_LEADER) { L = r; ++nlead; }
+    else if ((meta & 255u) != JR_ROLE_FOLLOWER) return false;
+    if ((meta >> 24) & 7u) return false;                                      // queued client requests
+  }
+  if (nlead != 1) return false;
+  s.L = L;
+  s.F0 = L == 0 ? 1u : 0u;
+  const uint4 l0 = d.p0[s.rg(L)];
+  s.term = (uint64_t)l0.x | ((uint64_t)l0.y << 32);
+  s.tbase = d.tb[s.g];
+  s.head = p2[L].x; s.commit = p2[L].y; s.idgen = p2[L].z;
+  s.ckey = (p2[L].w >> 28) & 1u;
+  s.maxkey = d.mk[s.rg(L)];
+  if (!(s.idgen > s.head)) return false;                                      // the next append would assert (chain.rs:163)
+  const uint4 l3 = d.p3[s.rg(L)];
+  s.hbtime = (uint64_t)l3.x | ((uint64_t)l3.y << 32);
+  // followers: identical
+  const uint32_t f0 = s.F0;
+  s.fhead = p2[f0].x; s.fcommit = p2[f0].y; s.fckey = (p2[f0].w >> 28) & 1u;
+  s.fmaxkey = d.mk[s.rg(f0)];
+  const uint64_t hbgap = ((uint64_t)d.hb / p.dt + 1) * p.dt;                 // ticks between two heartbeats, in ms
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if ((uint32_t)r == L) continue;
+    const uint4 a = d.p0[s.rg(r)];
+    if (((uint64_t)a.x | ((uint64_t)a.y << 32)) != s.term || a.z != L + 1 || a.w != L + 1) return false;
+    if (p2[r].x != s.fhead || p2[r].y != s.fcommit || ((p2[r].w >> 28) & 1u) != s.fckey) return false;
+    if (d.mk[s.rg(r)] != s.fmaxkey) return false;
+  }
+  if ((uint64_t)d.emin <= hbgap || s.hbtime > p.now) return false;   // between two heartbeats no timer (>= emin) can fire
+  // the leader's view of the followers: one progress entry value for all of them
+  uint32_t ph[R];
+#pragma unroll
+  for (int q = 0; q < (R + 3) / 4; ++q) {
+    const uint4 v = d.pr[(size_t)q * s.plane + s.rg(L)];
+    if (q * 4 + 0 < R) ph[q * 4 + 0] = v.x;
+    if (q * 4 + 1 < R) ph[q * 4 + 1] = v.y;
+    if (q * 4 + 2 < R) ph[q * 4 + 2] = v.z;
+    if (q * 4 + 3 < R) ph[q * 4 + 3] = v.w;
+  }
+  const uint32_t prmask = (p2[L].w >> 16) & 255u;
+  s.ph_self = ph[L]; s.mode_self = (prmask >> L) & 1u;
+  s.ph_f = ph[f0]; s.mode_f = (prmask >> f0) & 1u;
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+    if ((uint32_t)r != L && (ph[r] != s.ph_f || ((prmask >> r) & 1u) != s.mode_f)) return false;
+  // everything the launch will touch lies in the last SYM_WINDOW ids, which every follower holds identically
+  constexpr uint32_t SYM_WINDOW = 16;
+  const uint32_t top = min(s.maxkey, s.fmaxkey);
+  const uint32_t lo = max(top > SYM_WINDOW - 1u ? top - (SYM_WINDOW - 1u) : 0u, s.tbase);   // (below the floor nobody holds anything)
+  if (top < s.tbase || s.ph_f < lo || s.fcommit < lo || s.commit < lo || s.fhead < lo || s.fmaxkey > s.maxkey) return false;
+  const uint64_t grow = (uint64_t)p.n_ticks * (1u + p.n_synth) + 2u;
+  if ((uint64_t)s.maxkey + grow >= (uint64_t)s.tbase + d.cap || (uint64_t)s.maxkey + grow >= FS_NOTIFY_BIT) return false;
+  for (uint32_t b = lo; b <= s.fmaxkey; ++b) {
+    const uint32_t n0 = d.cnext[s.row(f0, b)];
+    const unsigned long long t0 = d.ctok[s.row(f0, b)];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if ((uint32_t)r != L && (uint32_t)r != f0 && (d.cnext[s.row(r, b)] != n0 || (n0 != ABSENT && d.ctok[s.row(r, b)] != t0))) return false;
+  }
+  // mail in flight (the previous tick's outboxes), delivered only with PH_DRAIN
+  m = SymMail{};
+  if (p.phases & PH_DRAIN) {
+  {  // leader: [Heartbeat to Peers] then one AppendEntries per peer, ascending, all carrying the same run
+    const uint32_t cnt = d.oc[prv][s.rg(L)];
+    uint32_t u = 0;
+    auto unit = [&](uint32_t k) { return d.ob[prv][((size_t)k * R + L) * d.Gp + s.g]; };
+    if (cnt > (uint32_t)(1 + JR_MAX_AE_BLOCKS + R)) return false;
+    if (u < cnt) {
+      const uint4 h = unit(u);
+      if ((h.x & 15u) == JR_CMD_HEARTBEAT) {
+        if ((h.x >> 16) != TO_PEERS || ((uint64_t)h.y | ((uint64_t)h.z << 32)) != s.term) return false;
+        m.hb = 1; m.hb_commit = h.w;
+        ++u;
+      }
+    }
+    if (u < cnt) {
+      uint32_t first = 0;
+      for (int r = 0; r < R; ++r) {
+        if ((uint32_t)r == L) continue;
+        if (u >= cnt) return false;
+        const uint4 h = unit(u);
+        if ((h.x & 15u) != JR_CMD_APPEND_ENTRIES || (h.x >> 16) != (uint32_t)r + 1u ||
+            ((uint64_t)h.y | ((uint64_t)h.z << 32)) != s.term) return false;
+        const uint32_t nb = (h.x >> 8) & 255u, ref = (h.x >> 4) & 1u;
+        if (!m.ae) {                                        // the first peer carries the run inline
+          if (ref || nb > JR_MAX_AE_BLOCKS || h.w != u + 1 || u + 1 + nb > cnt) return false;
+          m.ae = 1; m.ae_nb = nb; first = u + 1;
+          for (uint32_t k = 0; k < nb; ++k) {
+            const uint4 bu = unit(first + k);
+            uint32_t nx; uint64_t tk;
+            s.fetch(L, bu.x, nx, tk);                       // the sim re-reads the block from the leader's table: must be what was sent
+            if (nx != bu.y || tk != ((uint64_t)bu.z | ((uint64_t)bu.w << 32))) return false;
+            m.ae_id[k] = bu.x;
+          }
+          u += 1 + nb;
+        } else {                                            // the others point at it
+          if (!ref || nb != m.ae_nb || h.w != first) return false;
+          ++u;
+        }
+      }
+    }
+    if (u != cnt) return false;
+  }
+  {  // followers: [HeartbeatResponse][AppendResponse] to the leader, the same from each
+    const uint32_t cnt = d.oc[prv][s.rg(f0)];
+    if (cnt > 2) return false;
+    uint4 want[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+    for (uint32_t u = 0; u < cnt; ++u) want[u] = d.ob[prv][((size_t)u * R + f0) * d.Gp + s.g];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if ((uint32_t)r == L || (uint32_t)r == f0) continue;
+      if (d.oc[prv][s.rg(r)] != cnt) return false;
+      for (uint32_t u = 0; u < cnt; ++u) {
+        const uint4 v = d.ob[prv][((size_t)u * R + r) * d.Gp + s.g];
+        if (v.x != want[u].x || v.y != want[u].y || v.z != want[u].z || v.w != want[u].w) return false;
+      }
+    }
+    uint32_t u = 0;
+    if (u < cnt && (want[u].x & 15u) == JR_CMD_HEARTBEAT_RESPONSE) {
+      if ((want[u].x >> 16) != L + 1) return false;
+      m.hbr = 1; m.hbr_has = (want[u].x >> 4) & 1u; m.hbr_commit = want[u].w;
+      ++u;
+    }
+    if (u < cnt && (want[u].x & 15u) == JR_CMD_APPEND_RESPONSE) {
+      if ((want[u].x >> 16) != L + 1 || ((uint64_t)want[u].y | ((uint64_t)want[u].z << 32)) != s.term) return false;
+      m.ar = 1; m.ar_head = want[u].w;
+      ++u;
+    }
+    if (u != cnt) return false;
+  }
+  }
+  // Election timers (mod.rs:352-357): no follower may time out before the first heartbeat of this launch reaches it.
+  // The leader heartbeats at the first tick with now - heartbeat_time > heartbeat_ms (leader.rs:78-84,237-240); the
+  // follower takes it one tick later, before its own Tick.  (Afterwards the static bound above holds.)
+  uint64_t t_arr = 0;
+  if (!m.hb) {
+    const uint64_t due = s.hbtime + (uint64_t)d.hb + 1;                     // smallest `now` that heartbeats
+    t_arr = (due > p.now ? (due - p.now + p.dt - 1) / p.dt : 0) + 1;
+  }
+  const uint64_t checked = t_arr < p.n_ticks ? t_arr : p.n_ticks;           // ticks whose Tick runs on the old timer
+  if (checked) {
+    const uint64_t t_last = p.now + (checked - 1) * p.dt;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if ((uint32_t)r == L) continue;
+      const uint4 b = d.p1[s.rg(r)];
+      const uint64_t etime = (uint64_t)b.x | ((uint64_t)b.y << 32);
+      if (t_last >= etime && t_last - etime > (uint64_t)b.z) return false;
+    }
+  }
+  return true;
+}
+
+// ---- exit: write everything step_kernel would have left behind -------------------------------------------------------
+template <int R>
+__device__ void sym_leave(SymGroup<R>& s, const SymMail& last, int cur_last) {
+  const Dev& d = s.d;
+  const uint32_t L = s.L;
+  {  // leader: P2, P3, progress planes, max key (P0 / P1 are untouched by a steady leader)
+    const size_t i = s.rg(L);
+    uint32_t prmask = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) prmask |= (((uint32_t)r == L ? s.mode_self : s.mode_f) & 1u) << r;
+    const uint32_t keep = d.p2[i].w & ~((255u << 16) | (1u << 28));
+    d.p2[i] = make_uint4(s.head, s.commit, s.idgen, keep | (prmask << 16) | (s.ckey << 28));
+    d.p3[i] = make_uint4((uint32_t)s.hbtime, (uint32_t)(s.hbtime >> 32), 0u, 0u);
+#pragma unroll
+    for (int q = 0; q < (R + 3) / 4; ++q) {
+      uint32_t v[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (q * 4 + k < R) v[k] = (uint32_t)(q * 4 + k) == L ? s.ph_self : s.ph_f;
+      d.pr[(size_t)q * s.plane + i] = make_uint4(v[0], v[1], v[2], v[3]);
+    }
+    d.mk[i] = s.maxkey;
+    // outbox of the last tick: [Heartbeat][AppendEntries x (R-1): first inline, the rest pointing at its run]
+    uint32_t u = 0;
+    auto put = [&](uint32_t k, uint4 v) { d.ob[cur_last][((size_t)k * R + L) * d.Gp + s.g] = v; };
+    if (last.hb) put(u++, make_uint4(unit_hdr(JR_CMD_HEARTBEAT, 0, 0, TO_PEERS), (uint32_t)s.term, (uint32_t)(s.term >> 32), last.hb_commit));
+    if (last.ae) {
+      uint32_t first = 0;
+      bool have = false;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if ((uint32_t)r == L) continue;
+        if (!have) {
+          first = u + 1;
+          put(u, make_uint4(unit_hdr(JR_CMD_APPEND_ENTRIES, 0, last.ae_nb, r + 1), (uint32_t)s.term, (uint32_t)(s.term >> 32), first));
+          for (uint32_t k = 0; k < last.ae_nb; ++k) {
+            uint32_t nx; uint64_t tk;
+            s.fetch(L, last.ae_id[k], nx, tk);
+            put(first + k, make_uint4(last.ae_id[k], nx, (uint32_t)tk, (uint32_t)(tk >> 32)));
+          }
+          u += 1 + last.ae_nb;
+          have = true;
+        } else {
+          put(u++, make_uint4(unit_hdr(JR_CMD_APPEND_ENTRIES, 1, last.ae_nb, r + 1), (uint32_t)s.term, (uint32_t)(s.term >> 32), first));
+        }
+      }
+    }
+    d.oc[cur_last][i] = u;
+    if ((d.flags & JR_F_CAPTURE_FSM) && s.lcnt) fsm_flush(d.fr + i, s.lcnt, d.Fr, FsmOut{d.fs + i, s.plane, d.F, s.g, L}, d.fc + i);
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {   // followers: P1 (timer, RNG), P2, max key, outbox
+    if ((uint32_t)r == L) continue;
+    const size_t i = s.rg(r);
+    if (s.n_hb) {                  // follower.rs:103-113 per heartbeat: only the last draw is visible
+      const uint4 b = d.p1[i];
+      const uint32_t draws = b.w + s.n_hb;
+      d.p1[i] = make_uint4((uint32_t)s.last_hb, (uint32_t)(s.last_hb >> 32),
+                           election_timeout_draw(d.seed, d.goff + s.g, r + 1, draws - 1, d.emin, d.emax), draws);
+    }
+    const uint4 c = d.p2[i];
+    d.p2[i] = make_uint4(s.fhead, s.fcommit, c.z, (c.w & ~(1u << 28)) | (s.fckey << 28));
+    d.mk[i] = s.fmaxkey;
+    uint32_t u = 0;
+    if (last.hbr)
+      d.ob[cur_last][((size_t)u++ * R + r) * d.Gp + s.g] =
+          make_uint4(unit_hdr(JR_CMD_HEARTBEAT_RESPONSE, last.hbr_has, 0, L + 1), 0u, 0u, last.hbr_commit);
+    if (last.ar)
+      d.ob[cur_last][((size_t)u++ * R + r) * d.Gp + s.g] =
+          make_uint4(unit_hdr(JR_CMD_APPEND_RESPONSE, 1, 0, L + 1), (uint32_t)s.term, (uint32_t)(s.term >> 32), last.ar_head);
+    d.oc[cur_last][i] = u;
+    if ((d.flags & JR_F_CAPTURE_FSM) && s.fcnt) fsm_flush(d.fr + i, s.fcnt, d.Fr, FsmOut{d.fs + i, s.plane, d.F, s.g, (uint32_t)r}, d.fc + i);
+  }
+}
+
+// One lane per group.  symdone[g] = 1: the whole launch of group g has been applied here; 0: step_kernel runs it.
+template <int R>
+__global__ void __launch_bounds__(128) sym_kernel(const Dev d, const StepParams p, uint8_t* symdone) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= d.Gp) return;
+  SymGroup<R> s(d, g);
+  SymMail a, b;
+  s.abort = false;
+  s.lcnt = s.fcnt = 0;
+  s.n_hb = 0;
+  s.last_hb = 0;
+  bool ok = sym_enter<R>(s, a, p, 1 - p.cur);
+  if (ok) {
+    const jr_proposal* props = p.proposals;
+    s.now = p.now;
+    for (uint32_t t = 0; t < p.n_ticks && !s.abort; ++t) {
+      b = SymMail{};
+      uint64_t tok = 0;
+      if ((p.phases & PH_PROPOSE) && props) {
+        const uint4 pr = __ldg(reinterpret_cast<const uint4*>(props) + g);
+        if (pr.z == s.L + 1) tok = (uint64_t)pr.x | ((uint64_t)pr.y << 32);
+        else if (pr.z != 0) s.abort = true;               // a proposal for a follower: proxied ClientRequest, not canonical
+        props += p.prop_stride;
+      }
+      if (s.abort) break;
+      s.leader_tick(a, b, tok, (p.phases & PH_PROPOSE) ? p.n_synth : 0u, p.step_index + t);
+      if (s.abort) break;
+      s.follower_tick(a, b);
+      a = b;
+      s.now += p.dt;
+    }
+    ok = !s.abort;
+    if (ok) sym_leave<R>(s, a, p.cur ^ (int)((p.n_ticks - 1) & 1u));
+  }
+  symdone[g] = ok ? 1 : 0;
+}
+
+// symblk[b] = every group of 32-group block b was folded (step_kernel CTAs of such blocks return at once)
+__global__ void sym_blocks_kernel(const uint8_t* symdone, uint8_t* symblk, uint32_t n_blocks) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_blocks) return;
+  const uint4* v = reinterpret_cast<const uint4*>(symdone + (size_t)b * GROUPS_PER_CTA);
+  const uint4 x = v[0], y = v[1];
+  const uint32_t all = 0x01010101u;
+  symblk[b] = (x.x == all && x.y == all && x.z == all && x.w == all && y.x == all && y.y == all && y.z == all && y.w == all) ? 1 : 0;
+}
+
+#endif  // JR_DEVICE_CODE
+}  // namespace jr

@@ -361,6 +361,12 @@ class RaftApi:
                     "stream_digest")
         return a.value, b.value, c.value, d.value
 
+    def fold_count(self) -> int:
+        """Groups the last jr_run* launch applied through the symmetric-group fast path (engine only)."""
+        v = C.c_uint64(0)
+        self._check(self._fn("fold_count")(self._h, C.byref(v)), "fold_count")
+        return v.value
+
     def fault_count(self) -> int:
         v = C.c_uint64(0)
         self._check(self._fn("fault_count")(self._h, C.byref(v)), "fault_count")
@@ -458,6 +464,7 @@ def _bind(lib: C.CDLL, p: str):
         "state_digest": [vp, C.POINTER(C.c_uint64)],
         "stream_digest": [vp] + [C.POINTER(C.c_uint64)] * 4,
         "fault_count": [vp, C.POINTER(C.c_uint64)],
+        "fold_count": [vp, C.POINTER(C.c_uint64)],
         "compact": [vp],
         "set_alive": [vp, C.c_uint32, C.c_uint32, C.c_int],
         "kill_leaders": [vp, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)],

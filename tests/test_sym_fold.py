@@ -1,0 +1,165 @@
+"""The symmetric-group fold (josefine_b200/csrc/sym_fold.cuh): jr_run* applies a whole launch of a symmetric group in
+one lane.  It must be indistinguishable from step_kernel: replica state, block tables, leader tables and Instruction
+streams equal those of an engine that never folds (JR_F_NO_SYMMETRIC_FOLD) AND those of the oracle.  (Engines with
+JR_F_STREAM_DIGEST never fold, so the digest-based parity suites keep testing step_kernel; here everything except
+the Message stream is compared.)"""
+import pytest
+
+from josefine_b200 import abi, Command, fsm_tuple
+from tests import parity
+from tests.stream_cases import _bootstrap, strided_tokens
+
+CAP = abi.F_CAPTURE_FSM
+
+
+def _oracle(g, r, **kw):
+    from oracle.restated import RestatedCluster
+    return RestatedCluster.create(g, r, **kw)
+
+
+def _emu(g, r, **kw):
+    from tests.emu.emu import EmuEngine
+    return EmuEngine.create(g, r, **kw)
+
+
+def _gpu(g, r, **kw):
+    from josefine_b200 import RaftEngine
+    return RaftEngine.create(g, r, **kw)
+
+
+def trio(make, G, R, **cfg):
+    cfg.setdefault("flags", CAP)
+    fold = make(G, R, **cfg)
+    plain = make(G, R, **dict(cfg, flags=cfg["flags"] | abi.F_NO_SYMMETRIC_FOLD))
+    ora = _oracle(G, R, **cfg)
+    return fold, plain, ora
+
+
+def same(apis, chain_ids=48, fsm_cap=1 << 16):
+    a = apis[0]
+    streams = [[fsm_tuple(f) for f in api.drain_fsm(cap=fsm_cap)] for api in apis]
+    for other, st in zip(apis[1:], streams[1:]):
+        assert streams[0] == st, "Instruction streams differ"
+        parity.compare_states(a, other, chain_ids=chain_ids)
+        assert a.state_digest() == other.state_digest()
+        assert a.leader_table() == other.leader_table()
+        assert a.fault_count() == other.fault_count()
+
+
+def case_steady(make, R, G=40, hb=100, dt=100, launches=5, ticks=33, n_synth=1):
+    apis = trio(make, G, R, seed=R, heartbeat_ms=hb, chain_capacity=512, fsm_units=256)
+    for api in apis:
+        _bootstrap(api, G, R)
+    now = dt
+    folded = []
+    for k in range(launches):
+        for api in apis:
+            api.run(now, dt, ticks, n_synth)
+        now += dt * ticks
+        folded.append(apis[0].fold_count())
+        assert apis[1].fold_count() == 0
+        same(apis)
+    return folded
+
+
+def case_tokens_kill_truncate(make, G=48, R=5):
+    """jr_run_tokens (routed proposals, some ticks without one), leaders silenced in between (those groups leave the fold),
+    jr_truncate moving the window under it."""
+    apis = trio(make, G, R, seed=9, chain_capacity=128, fsm_units=64)
+    for api in apis:
+        _bootstrap(api, G, R)
+        api.run(100, 100, 12, 1)
+        api.leader_table()
+    now, tick = 1300, 0
+    folded = []
+    for rnd in range(6):
+        toks = strided_tokens(20, G, tick)
+        for k in range(20):
+            if (k + rnd) % 7 == 3:
+                toks[k] = [0] * G                       # a tick without proposals
+        for api in apis:
+            api.run_tokens(now, 100, toks)
+            api.truncate(6)
+        now += 2000
+        tick += 20
+        folded.append(apis[0].fold_count())
+        same(apis, chain_ids=0)
+        if rnd == 2:
+            assert len({api.kill_leaders(4, 300) for api in apis}) == 1
+        if rnd == 3:
+            for api in apis:
+                api.leader_table()                      # re-announce: dead groups now drop their tokens
+    reqs = [(g, n, max(int(apis[0].query(g, n).chain_floor), 0), 40) for g in range(0, G, 7) for n in (1, 2)]
+    assert apis[0].chain_read_many(reqs) == apis[1].chain_read_many(reqs) == apis[2].chain_read_many(reqs)
+    return folded
+
+
+def case_misrouted_and_asymmetric(make, G=16, R=3):
+    """Groups that must NOT fold: a proposal aimed at a follower (proxied ClientRequest), a follower silenced (asymmetric),
+    elections in progress.  Everything still equals the oracle, the eligible rest folds."""
+    apis = trio(make, G, R, seed=4, chain_capacity=256, fsm_units=128)
+    for api in apis:
+        _bootstrap(api, G, R)
+        api.run(100, 100, 10, 1)
+        api.set_alive(3, 2, False)                      # group 3 loses a follower
+    props = [[((2 if g == 5 else 1), 7000 + 100 * k + g) for g in range(G)] for k in range(12)]   # group 5: proposals to follower 2
+    for api in apis:
+        api.run_proposals(1100, 100, props)
+    n = apis[0].fold_count()
+    same(apis)
+    for api in apis:
+        api.run(2300, 100, 15, 1)         # group 5 still has proxied mail in flight when this launch starts
+    same(apis)
+    for api in apis:
+        api.run(3800, 100, 15, 1)
+    same(apis)
+    return n, apis[0].fold_count()
+
+
+@pytest.mark.parametrize("R", [2, 3, 5, 7])
+def test_steady_fold_on_device_code(R):
+    folded = case_steady(_emu, R)
+    assert folded[0] == 0 and all(f == 40 for f in folded[1:]), folded   # first launch starts from the election's mail: not canonical
+
+
+@pytest.mark.parametrize("hb,dt", [(99, 100), (100, 50), (250, 100), (100, 100)])
+def test_heartbeat_cadences_on_device_code(hb, dt):
+    folded = case_steady(_emu, 5, G=8, hb=hb, dt=dt, launches=4, ticks=21)
+    assert folded[-1] == 8, folded
+
+
+def test_no_proposals_and_two_per_tick_on_device_code():
+    assert case_steady(_emu, 5, G=8, n_synth=0)[-1] == 8
+    assert case_steady(_emu, 3, G=8, n_synth=2)[-1] == 8
+
+
+def test_tokens_kill_truncate_on_device_code():
+    folded = case_tokens_kill_truncate(_emu)
+    assert folded[1] == 48 and 0 < folded[-1] < 48, folded
+
+
+def test_misrouted_and_asymmetric_on_device_code():
+    n1, n2 = case_misrouted_and_asymmetric(_emu)
+    assert n1 == 16 - 2 and n2 == 16 - 1, (n1, n2)      # groups 3 and 5 stay out; group 5 comes back once proposals go to the leader
+
+
+def test_split_launches_with_fold_on_device_code(monkeypatch):
+    monkeypatch.setenv("JR_PARTS", "3")
+    assert case_steady(_emu, 3, G=70, launches=3, ticks=25)[-1] == 70
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("R", [3, 5, 7])
+def test_steady_fold_on_gpu(R):
+    folded = case_steady(_gpu, R, G=3000, launches=4, ticks=40)
+    assert all(f == 3000 for f in folded[1:]), folded
+
+
+@pytest.mark.gpu
+def test_tokens_kill_truncate_on_gpu():
+    case_tokens_kill_truncate(_gpu, G=2048)
+
+
+@pytest.mark.gpu
+def test_misrouted_and_asymmetric_on_gpu():
+    case_misrouted_and_asymmetric(_gpu)
