@@ -491,7 +491,7 @@ class Bench:
         return res
 
     # ---- end to end through the C ABI with host buffers
-    def end_to_end(self, G, R, steps, warmup, with_output=True):
+    def end_to_end(self, G, R, steps, warmup, with_output=True, dense_input=False):
         torch = self.torch
         S = TICKS_PER_STEP
         eng = self.steady_engine(G, R, abi.F_CAPTURE_FSM if with_output else 0)
@@ -500,7 +500,14 @@ class Bench:
         prop = torch.zeros(NB, S, G, dtype=torch.int64).pin_memory()      # tokens[NB][S][G], one proposal per group-tick
         table = torch.zeros(NB, G, 2, dtype=torch.int64).pin_memory()     # jr_leader_entry[NB][G]
         prop[...] = ((torch.arange(NB * S, dtype=torch.int64).view(NB, S, 1) + 1) << 32) + torch.arange(G, dtype=torch.int64)
-        pstride, tstride = S * G * 8, G * 16
+        # the same proposals in run-length form: jr_token_run[NB][G] = {base, stride}; tick k proposes base + k * stride
+        runs = torch.zeros(NB, G, 2, dtype=torch.int64).pin_memory()
+        runs[:, :, 1] = 1 << 32
+        for b in range(NB):
+            runs[b, :, 0] = ((b * S + 1) << 32) + torch.arange(G, dtype=torch.int64)
+        if not dense_input:
+            del prop
+        pstride, tstride, rstride = S * G * 8, G * 16, G * 16
         eng.leader_table()                                                 # first announce: where the tokens go
         now = [DT_MS * 17]
         totals = (C.c_uint64 * 3)()
@@ -509,8 +516,12 @@ class Bench:
         checks = []
 
         def submit(i):
-            st = lib.jr_run_tokens(h, C.c_uint64(now[0]), C.c_uint32(DT_MS), C.c_uint32(S),
-                                   C.cast(prop.data_ptr() + (i % NB) * pstride, C.POINTER(C.c_uint64)))   # H2D + route + fused kernel
+            if dense_input:
+                st = lib.jr_run_tokens(h, C.c_uint64(now[0]), C.c_uint32(DT_MS), C.c_uint32(S),
+                                       C.cast(prop.data_ptr() + (i % NB) * pstride, C.POINTER(C.c_uint64)))   # H2D + route + fused kernel
+            else:
+                st = lib.jr_run_token_runs(h, C.c_uint64(now[0]), C.c_uint32(DT_MS), C.c_uint32(S),
+                                           C.cast(runs.data_ptr() + (i % NB) * rstride, C.POINTER(abi.TokenRun)))   # 16 B per group H2D
             assert st == 0, st
             now[0] += DT_MS * S
             assert lib.jr_truncate(h, C.c_uint32(TRUNC_MARGIN)) == 0
@@ -554,14 +565,17 @@ class Bench:
             expect = G * S * steps * (R + 1)
             got = int(totals[0] + totals[1])
             assert abs(got - expect) <= expect * 0.02 + 4 * G * R, (got, expect)
-        out = {"value": self.world * G * S * steps / dt, "unit": UNIT, "h2d_bytes_per_step": S * G * 8,
+        out = {"value": self.world * G * S * steps / dt, "unit": UNIT, "h2d_bytes_per_step": S * G * 8 if dense_input else G * 16,
+               "input": "dense: one u64 token per group-tick (jr_run_tokens)" if dense_input else
+                        "run-length: one {base, stride} per group and step (jr_run_token_runs); the same tokens",
                "d2h_bytes_per_step": G * 16 + (rec_bytes[0] // steps if with_output else 0), "ms_per_step": dt * 1e3 / steps,
                "commit_last": checks[-1], "faulted_replicas": faults,
                "timing": "host wall clock around all timed steps incl. the final sync, max over ranks"}
         if with_output:
             out.update({"instructions_per_step": int(totals[0] + totals[1]) // steps, "records_per_step": int(totals[2]) // steps,
                         "d2h_stream_bytes_per_step": rec_bytes[0] // steps,
-                        "api": "per step: jr_run_tokens(pinned u64 tokens[64][G], routed to the last announced leader) + jr_truncate + "
+                        "api": "per step: " + ("jr_run_tokens(pinned u64 tokens[64][G]" if dense_input else "jr_run_token_runs(pinned jr_token_run[G]") +
+                               ", routed to the last announced leader) + jr_truncate + "
                                "jr_leader_table_async(pinned jr_leader_entry[G]) + jr_fsm_records_async; then jr_leader_table_wait + "
                                "jr_fsm_records_wait + jr_fsm_fold over the batch (apply watermark per replica); two steps in flight"})
         else:
@@ -729,10 +743,11 @@ def main():
     launches = args.steps * (5 + (1 if world > 1 else 0))   # step_kernel, truncate, scan, pack, copy (+ leader_table_kernel)
 
     # ---------------- end to end ----------------
-    e2e = e2e_plain = None
+    e2e = e2e_plain = e2e_dense = None
     if not args.no_e2e:
         e2e = bn.end_to_end(G, R, args.steps, args.warmup, with_output=True)
-        e2e_plain = bn.end_to_end(G, R, args.steps, args.warmup, with_output=False)
+        e2e_dense = bn.end_to_end(G, R, args.steps, args.warmup, with_output=True, dense_input=True)
+        e2e_plain = bn.end_to_end(G, R, args.steps, args.warmup, with_output=False, dense_input=True)
 
     # ---------------- other BASELINE configs, variants ----------------
     others, variants = {}, {}
@@ -809,7 +824,7 @@ def main():
                    "parallelism": f"groups sharded over {world} GPU(s); leader-announce all_gather once per step" if world > 1
                    else "single GPU", "faulted_replicas": main_res["faulted_replicas"], "commit_min": main_res["commit_min"],
                    "untimed_steps_before_timing": max(args.warmup, 20), "host_placement": bn.placement},
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_no_output": e2e_plain, "gpu_launches": launches, "clocks": clocks,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_dense_input": e2e_dense, "e2e_no_output": e2e_plain, "gpu_launches": launches, "clocks": clocks,
         "collective_us": main_res["collective_us"], "instructions_per_step": main_res["instructions"] // args.steps,
         "other_configs": others, "variants": variants, "parity": parity,
     }

@@ -15,6 +15,7 @@
  *   jr_run             <- N consecutive event_loop turns with no host traffic (Tick + peer mail)
  *   jr_run_proposals   <- N consecutive event_loop turns incl. the client arm (server.rs:156-160)
  *   jr_run_tokens      <- the same, with proposals addressed to the last announced leader
+ *   jr_run_token_runs  <- the same, one arithmetic token run per group instead of one token per group-tick
  *   jr_query           <- pub fields id/state/role/chain  src/raft/mod.rs:326-341,437-447;
  *                         Chain::get_head/get_commit      src/raft/chain.rs:230-236
  *   jr_chain_read      <- Chain::range / Chain::has       src/raft/chain.rs:155-157,208-228
@@ -235,14 +236,16 @@ typedef struct jr_fsm_instr {
  *   JR_FSMR_APPLY    `count` Apply instructions of blocks id0, id0+1, ...; element i carries
  *                    Block{id0+i, next_i, tok0 + i*stride} with next_i = id0+i-1.  count == 1 is the
  *                    general case: any block, next = (uint32_t)stride, data = tok0.
+ *                    addr != 0: a node mask (bit id-1) -- the run belongs to the stream of EVERY node in the
+ *                    mask (symmetric followers apply the same blocks), in front of that node's own records.
  *   JR_FSMR_NOTIFY   `count` Notify instructions for block ids id0, id0+1, ..., all with client address
  *                    (addr >> 16, addr & 0xffff); element i carries request token tok0 + i*stride.
- *   JR_FSMR_PATTERN  interleaving: bit b (0 <= b < count <= 64) of tok0 set = the (id0+b)-th Instruction this
- *                    replica emitted since the last drain is a Notify.  Positions no PATTERN record marks are
- *                    Apply.  Applies and Notifies each appear in record order, so the records of one replica
+ *   JR_FSMR_PATTERN  interleaving: bit b (0 <= b < count <= 160; bits 0-63 in tok0, 64-127 in stride, 128-159 in addr)
+ *                    set = the (id0+b)-th Instruction this replica emitted since the last drain is a Notify.
+ *                    Positions no PATTERN record marks are Apply.  Applies and Notifies each appear in record order, so the records of one replica
  *                    reproduce its stream exactly (jr_fsm_expand does).
- * A steady-state follower needs one APPLY record per drain, a leader one APPLY + one NOTIFY + one PATTERN per
- * 64 Instructions, whatever the number of fused ticks -- when tokens advance by a constant stride.
+ * A steady-state follower needs one APPLY record per launch, a leader one APPLY + one NOTIFY + one PATTERN per
+ * 160 Instructions, whatever the number of fused ticks -- when tokens advance by a constant stride.
  */
 enum { JR_FSMR_APPLY = 0, JR_FSMR_NOTIFY = 1, JR_FSMR_PATTERN = 2 };
 typedef struct jr_fsm_record {
@@ -398,6 +401,19 @@ jr_status jr_run_proposals(jr_engine* e, uint64_t now0_ms, uint32_t dt_ms, uint3
  */
 jr_status jr_run_tokens(jr_engine* e, uint64_t now0_ms, uint32_t dt_ms, uint32_t n_steps,
                         const uint64_t* tokens);
+/*
+ * jr_run_tokens with the input in run-length form: `runs` is HOST memory holding ONE jr_token_run per group; tick k
+ * proposes token runs[g].base + k * runs[g].stride for group g (base == 0: the group proposes nothing in this call).
+ * Bit for bit equal to jr_run_tokens with tokens[k*G + g] = base + k*stride; 16 bytes per group and call instead of
+ * 8 bytes per group-tick on the host-to-device link.  A host that numbers a partition's requests consecutively
+ * (sequence numbers, log offsets) describes a whole quantum this way -- the mirror image of jr_fsm_record on the way out.
+ */
+typedef struct jr_token_run {
+  uint64_t base;
+  uint64_t stride;
+} jr_token_run;
+jr_status jr_run_token_runs(jr_engine* e, uint64_t now0_ms, uint32_t dt_ms, uint32_t n_steps,
+                            const jr_token_run* runs);
 /* Take the Instructions accumulated by jr_run* since the last drain, expanded: group-major, node ascending,
  * FIFO per node (the order jr_step returns).  *n = Instructions there were; JR_E_CAPACITY if `out` is too
  * small or records were dropped (fsm_units / fsm_host_records too small).  Synchronous; the FIFOs are empty

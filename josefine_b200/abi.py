@@ -102,6 +102,10 @@ class Proposal(C.Structure):
     _fields_ = [("token", C.c_uint64), ("node", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class TokenRun(C.Structure):
+    _fields_ = [("base", C.c_uint64), ("stride", C.c_uint64)]
+
+
 class StepArgs(C.Structure):
     _fields_ = [
         ("now_ms", C.c_uint64), ("flags", C.c_uint32), ("n_synth", C.c_uint32),
@@ -165,14 +169,14 @@ class LeaderEntry(C.Structure):
 # sizes the header implies (checked in tests/test_abi.py against offsetof-free arithmetic)
 EXPECTED_SIZES = {
     "Config": 72, "Block": 24, "Msg": 64 + 24 * MAX_AE_BLOCKS, "FsmInstr": 16 + 24,
-    "Proposal": 16, "LeaderEntry": 16, "FsmRecord": 32, "FsmBatch": 24 + 4 * (MAX_REPLICAS + 1) + 4,
+    "Proposal": 16, "TokenRun": 16, "LeaderEntry": 16, "FsmRecord": 32, "FsmBatch": 24 + 4 * (MAX_REPLICAS + 1) + 4,
     "ReplicaState": 160,
 }
 
 # every symbol include/josefine_raft_abi.h declares
 ENGINE_SYMBOLS = [
     "jr_engine_create", "jr_engine_destroy", "jr_engine_reset", "jr_engine_set_stream", "jr_engine_sync",
-    "jr_last_error", "jr_config_default", "jr_step", "jr_run", "jr_run_proposals", "jr_run_tokens", "jr_drain_fsm", "jr_query",
+    "jr_last_error", "jr_config_default", "jr_step", "jr_run", "jr_run_proposals", "jr_run_tokens", "jr_run_token_runs", "jr_drain_fsm", "jr_query",
     "jr_chain_read", "jr_state_digest", "jr_stream_digest", "jr_fault_count", "jr_fold_count", "jr_compact",
     "jr_set_alive", "jr_kill_leaders", "jr_leader_table_device", "jr_leader_table", "jr_leader_table_async", "jr_leader_table_wait",
     "jr_election_timeout", "jr_fsm_records_async", "jr_fsm_records_wait", "jr_fsm_expand", "jr_fsm_fold", "jr_query_many",

@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(32 * R, step_min_ctas(R)) step_kernel(const De
     p.step_index += t0;
     p.cur ^= (int)(t0 & 1u);
     if (p.proposals) p.proposals += (size_t)t0 * p0.prop_stride;
+    p.tok_tick += t0;
     if (part) {
       p.phases = PH_RESET_OUT | PH_DRAIN | PH_PROPOSE | PH_TICK;
       if (threadIdx.x == 0)
@@ -159,6 +160,7 @@ __global__ void __launch_bounds__(32 * R, step_min_ctas(R)) step_kernel(const De
     q.step_index += 1;
     q.phases = PH_RESET_OUT | PH_DRAIN | PH_PROPOSE | PH_TICK;
     q.proposals = (p.proposals && p.prop_stride) ? p.proposals + (size_t)(t + 1) * p.prop_stride : nullptr;
+    q.tok_tick += 1;
   }
   if (!folded) rep.store(part + 1 >= p0.n_parts);
   {  // tell the host whether the next launch should sort: leaders on >= 2 replica indices in this CTA?
@@ -840,6 +842,7 @@ static jr_status launch_step(jr_engine* e, const StepParams& p_in) {
     p.step_index += p.n_ticks;
     p.cur ^= (int)(p.n_ticks & 1u);
     if (p.proposals) p.proposals += (size_t)p.n_ticks * p.prop_stride;
+    p.tok_tick += p.n_ticks;
     p.phases = PH_RESET_OUT | PH_DRAIN | (p_in.phases & PH_PROPOSE) | PH_TICK;
   }
   return JR_OK;
@@ -860,7 +863,7 @@ static bool fold_eligible(const jr_engine* e, const StepParams& p) {
   if (d.R < 2 || d.U < d.R + 7 || d.resident != 0xffu || p.dt == 0) return false;
   if ((p.phases & ~(uint32_t)PH_PROPOSE) != whole || p.n_ticks < 2) return false;
   if (p.proposals && p.prop_stride != d.G) return false;
-  return true;
+  return true;   // (tok_runs: always per-tick)
 }
 
 static jr_status launch_step_once(jr_engine* e, const StepParams& p_in) {
@@ -1534,6 +1537,40 @@ jr_status jr_run_tokens(jr_engine* e, uint64_t now0, uint32_t dt, uint32_t n_ste
   return batch_launch(e, b, now0, dt, n_steps);
 }
 
+jr_status jr_run_token_runs(jr_engine* e, uint64_t now0, uint32_t dt, uint32_t n_steps, const jr_token_run* runs) {
+  if (!e || !runs) return JR_E_INVAL;
+  if (n_steps == 0) return JR_OK;
+  CK(cudaSetDevice(e->cfg.device));
+  const uint32_t G = e->d.G;
+  const int b = e->batch_i;
+  e->batch_i = (b + 1) % jr_engine::NBUF;
+  jr_status st = batch_reserve(e, b, G);   // batch[b] doubles as the staging buffer: G x 16 bytes
+  if (st != JR_OK) return st;
+  CK(cudaMemcpyAsync(e->batch[b], runs, (size_t)G * sizeof(jr_token_run), cudaMemcpyHostToDevice, e->h2d));
+  CK(cudaEventRecord(e->batch_ready[b], e->h2d));
+  CK(cudaStreamWaitEvent(e->stream, e->batch_ready[b], 0));
+  StepParams p;
+  p.now = now0;
+  p.step_index = e->step_index;
+  p.n_synth = 0;
+  p.n_ticks = n_steps;
+  p.dt = dt;
+  p.cur = e->cur;
+  p.proposals = nullptr;
+  p.prop_stride = 0;
+  p.tok_runs = reinterpret_cast<const uint4*>(e->batch[b]);
+  p.tok_route = e->route;    // on the engine stream: ordered after the leader_table_kernel that last wrote it
+  p.tok_tick = 0;
+  p.phases = PH_RESET_OUT | PH_DRAIN | PH_PROPOSE | PH_TICK;
+  st = launch_step(e, p);
+  if (st != JR_OK) return st;
+  CK(cudaEventRecord(e->batch_free[b], e->stream));
+  e->batch_used[b] = true;
+  e->cur ^= (int)(n_steps & 1u);
+  e->step_index += n_steps;
+  return JR_OK;
+}
+
 jr_status jr_drain_fsm(jr_engine* e, jr_fsm_instr* out, size_t cap, size_t* n) {
   if (!e || !n) return JR_E_INVAL;
   CK(cudaSetDevice(e->cfg.device));
@@ -1554,9 +1591,19 @@ jr_status jr_fsm_fold(const jr_fsm_record* recs, size_t n, uint32_t G, uint32_t 
     const uint32_t kind = JR_FSMR_KIND(rc.hdr), node = JR_FSMR_NODE(rc.hdr), count = JR_FSMR_COUNT(rc.hdr);
     if (rc.group >= G || node > R) return JR_E_INVAL;
     if (kind == JR_FSMR_APPLY) {
-      uint32_t& hi = applied_hi[(size_t)(node - 1) * G + rc.group];
-      hi = std::max(hi, rc.id0 + count - 1);
-      na += count;
+      if (rc.addr) {   // shared by the nodes of the mask
+        if (rc.addr >> R) return JR_E_INVAL;
+        for (uint32_t n = 0; n < R; ++n)
+          if ((rc.addr >> n) & 1u) {
+            uint32_t& hi = applied_hi[(size_t)n * G + rc.group];
+            hi = std::max(hi, rc.id0 + count - 1);
+            na += count;
+          }
+      } else {
+        uint32_t& hi = applied_hi[(size_t)(node - 1) * G + rc.group];
+        hi = std::max(hi, rc.id0 + count - 1);
+        na += count;
+      }
     } else if (kind == JR_FSMR_NOTIFY) {
       nn += count;
     }
@@ -1582,18 +1629,35 @@ jr_status jr_fsm_records_wait(jr_engine* e, const jr_fsm_record** records, jr_fs
 jr_status jr_fsm_expand(const jr_fsm_record* recs, size_t n_records, uint32_t G, uint32_t R, jr_fsm_instr* out, size_t cap,
                         size_t* n_out) {
   if (!n_out || (!recs && n_records) || R < 1 || R > JR_MAX_REPLICAS || G < 1) return JR_E_INVAL;
-  // stable counting sort of record indices by (group, node)
+  // stable counting sort of record indices by (group, node).  An APPLY record with a node mask (addr != 0: symmetric
+  // followers share it) goes into the bucket of every node of the mask, in front of that node's own records: masked
+  // records are only ever produced while the nodes' own streams are still empty.
   const size_t nb = (size_t)G * R;
   std::vector<uint32_t> start(nb + 1, 0u);
+  auto masked = [&](const jr_fsm_record& rc) { return JR_FSMR_KIND(rc.hdr) == JR_FSMR_APPLY && rc.addr != 0; };
   for (size_t i = 0; i < n_records; ++i) {
     const uint32_t node = JR_FSMR_NODE(recs[i].hdr);
     if (recs[i].group >= G || node > R || JR_FSMR_KIND(recs[i].hdr) > JR_FSMR_PATTERN) return JR_E_INVAL;
-    ++start[(size_t)recs[i].group * R + (node - 1) + 1];
+    if (masked(recs[i])) {
+      if (recs[i].addr >> R) return JR_E_INVAL;
+      for (uint32_t n = 0; n < R; ++n)
+        if ((recs[i].addr >> n) & 1u) ++start[(size_t)recs[i].group * R + n + 1];
+    } else {
+      ++start[(size_t)recs[i].group * R + (node - 1) + 1];
+    }
   }
   for (size_t b = 0; b < nb; ++b) start[b + 1] += start[b];
-  std::vector<uint32_t> order(n_records), fill(start.begin(), start.end() - 1);
-  for (size_t i = 0; i < n_records; ++i)
-    order[fill[(size_t)recs[i].group * R + (JR_FSMR_NODE(recs[i].hdr) - 1)]++] = (uint32_t)i;
+  std::vector<uint32_t> order(start[nb]), fill(start.begin(), start.end() - 1);
+  for (int pass = 0; pass < 2; ++pass)
+    for (size_t i = 0; i < n_records; ++i) {
+      if (masked(recs[i]) != (pass == 0)) continue;
+      if (pass == 0) {
+        for (uint32_t n = 0; n < R; ++n)
+          if ((recs[i].addr >> n) & 1u) order[fill[(size_t)recs[i].group * R + n]++] = (uint32_t)i;
+      } else {
+        order[fill[(size_t)recs[i].group * R + (JR_FSMR_NODE(recs[i].hdr) - 1)]++] = (uint32_t)i;
+      }
+    }
   size_t k = 0;
   std::vector<uint64_t> is_notify;
   for (size_t b = 0; b < nb; ++b) {
@@ -1613,9 +1677,9 @@ jr_status jr_fsm_expand(const jr_fsm_record* recs, size_t n_records, uint32_t G,
       const jr_fsm_record& rc = recs[order[j]];
       if (JR_FSMR_KIND(rc.hdr) != JR_FSMR_PATTERN) continue;
       const uint32_t nbits = JR_FSMR_COUNT(rc.hdr);
-      if (nbits > 64) return JR_E_INVAL;
+      if (nbits > 160) return JR_E_INVAL;
       for (uint32_t bit = 0; bit < nbits; ++bit)
-        if ((rc.tok0 >> bit) & 1ull) {
+        if ((bit < 64 ? rc.tok0 >> bit : bit < 128 ? rc.stride >> (bit - 64) : (uint64_t)rc.addr >> (bit - 128)) & 1ull) {
           const size_t pos = (size_t)rc.id0 + bit;
           if (pos >= total || ((is_notify[pos >> 6] >> (pos & 63)) & 1ull)) return JR_E_INVAL;
           is_notify[pos >> 6] |= 1ull << (pos & 63);

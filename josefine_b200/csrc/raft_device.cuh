@@ -102,6 +102,11 @@ struct StepParams {
   // whole launch has been applied already; symblk[b] = 1: that holds for all 32 groups of block b.
   const uint8_t* symdone = nullptr;
   const uint8_t* symblk = nullptr;
+  // jr_run_token_runs: the dense proposal of tick k is computed instead of loaded: runs[g] = {base lo, hi, stride lo, hi},
+  // token = base + (tok_tick + k) * stride (base 0: none), node = route[g].  Excludes `proposals`.
+  const uint4* tok_runs = nullptr;
+  const uint32_t* tok_route = nullptr;
+  uint32_t tok_tick = 0;
 };
 
 __host__ __device__ inline uint64_t mix64(uint64_t x) {
@@ -227,12 +232,14 @@ __device__ __forceinline__ unsigned long long* jr_prof_smem() {
 constexpr uint32_t FSR_APPLY = 0u, FSR_NOTIFY = 1u, FSR_PATTERN = 2u;
 constexpr uint32_t FSR_CLIENT = (uint32_t)JR_ADDR_CLIENT << 16;
 constexpr uint32_t FS_MAX_RUN = 0xffffffu;   // the record's count field is 24 bits
+constexpr uint32_t FS_PATTERN_BITS = 160u;   // Instructions one PATTERN record covers
 constexpr uint32_t FS_NOTIFY_BIT = 0x80000000u;   // raw entry: x = block id | this; y = next / client address; z,w = token
 
 struct FsmOut {       // where one replica's records go
   uint4* slot0;       // d.fs + rg
   size_t plane;       // R * Gp
   uint32_t F, g, r;
+  uint32_t mask = 0;  // APPLY records stand for every node whose bit (id - 1) is set (symmetric followers, sym_fold.cuh)
 };
 
 struct FsmRun {       // an open run: next id expected, elements so far, last token, stride (count 1: lo word = next / address)
@@ -254,7 +261,7 @@ __device__ __forceinline__ uint32_t fsm_close_run(uint32_t nrec, const FsmOut& o
   const uint32_t c = run.count;
   if (!c) return nrec;
   const uint64_t tok0 = c > 1 ? run.last - (uint64_t)(c - 1) * run.stride : run.last;
-  const uint32_t addr = notify ? (c > 1 ? FSR_CLIENT : (uint32_t)run.stride) : 0u;
+  const uint32_t addr = notify ? (c > 1 ? FSR_CLIENT : (uint32_t)run.stride) : o.mask;
   return fsm_put_record(nrec, o, notify ? FSR_NOTIFY : FSR_APPLY, c, run.next_id - c, addr, tok0,
                         (notify && c == 1) ? 0ull : run.stride);
 }
@@ -264,7 +271,10 @@ __device__ __forceinline__ uint32_t fsm_close_run(uint32_t nrec, const FsmOut& o
 __device__ __noinline__ void fsm_flush(const uint4* raw0, uint32_t n_raw, uint32_t Fr, FsmOut o, uint2* fc) {
   const uint2 c = *fc;
   uint32_t nrec = c.x, seq = c.y;
-  uint64_t pbits = 0;
+  // pattern window: FS_PATTERN_BITS Instructions per PATTERN record (bits 0-63 in tok0, 64-127 in stride, 128-159 in addr);
+  // a window starts where the previous flush stopped (wseq) and is closed when full or when this flush ends
+  uint64_t pb0 = 0, pb1 = 0;
+  uint32_t pb2 = 0, wseq = seq;
   FsmRun ra{0, 0, 0, 0}, rn{0, 0, 0, 0};
   const uint32_t n = n_raw < Fr ? n_raw : Fr;
   constexpr uint32_t AHEAD = 8;   // entries are independent loads (L2 / DRAM): fetch a batch, then encode it
@@ -282,11 +292,17 @@ __device__ __noinline__ void fsm_flush(const uint4* raw0, uint32_t n_raw, uint32
     const bool notify = (e.x & FS_NOTIFY_BIT) != 0;
     const uint32_t bid = e.x & ~FS_NOTIFY_BIT, nxa = e.y;
     const uint64_t tok = (uint64_t)e.z | ((uint64_t)e.w << 32);
-    if (notify) pbits |= 1ull << (seq & 63u);
+    if (notify) {
+      const uint32_t b = seq - wseq;
+      if (b < 64u) pb0 |= 1ull << b;
+      else if (b < 128u) pb1 |= 1ull << (b - 64u);
+      else pb2 |= 1u << (b - 128u);
+    }
     ++seq;
-    if ((seq & 63u) == 0u && pbits) {   // the 64-Instruction pattern window is complete
-      nrec = fsm_put_record(nrec, o, FSR_PATTERN, 64u, seq - 64u, 0u, pbits, 0ull);
-      pbits = 0;
+    if (seq - wseq == FS_PATTERN_BITS) {   // the pattern window is complete
+      if (pb0 | pb1 | pb2) nrec = fsm_put_record(nrec, o, FSR_PATTERN, FS_PATTERN_BITS, wseq, pb2, pb0, pb1);
+      pb0 = pb1 = 0; pb2 = 0;
+      wseq = seq;
     }
     FsmRun& run = notify ? rn : ra;
     bool extended = false;
@@ -310,7 +326,7 @@ __device__ __noinline__ void fsm_flush(const uint4* raw0, uint32_t n_raw, uint32
   }
   nrec = fsm_close_run(nrec, o, false, ra);
   nrec = fsm_close_run(nrec, o, true, rn);
-  if ((seq & 63u) && pbits) nrec = fsm_put_record(nrec, o, FSR_PATTERN, seq & 63u, seq & ~63u, 0u, pbits, 0ull);
+  if (pb0 | pb1 | pb2) nrec = fsm_put_record(nrec, o, FSR_PATTERN, seq - wseq, wseq, pb2, pb0, pb1);
   if (n_raw > Fr) nrec = (nrec > o.F ? nrec : o.F) + (n_raw - Fr);   // lost Instructions: the drain must say so
   *fc = make_uint2(nrec, seq);
 }
@@ -1070,8 +1086,16 @@ struct Replica {
     if (k.tail == 0) {  // event_loop client arm, server.rs:156-160
       k.tail = 1;
       k.tail_i = 0;
-      if ((p.phases & PH_PROPOSE) && p.proposals && g < d.G) {
-        const uint4 pr = __ldg(reinterpret_cast<const uint4*>(p.proposals) + g);
+      if ((p.phases & PH_PROPOSE) && (p.proposals || p.tok_runs) && g < d.G) {
+        uint4 pr;
+        if (p.tok_runs) {   // run-length input: the token is base + tick * stride
+          const uint4 rn = __ldg(p.tok_runs + g);
+          const uint64_t base = (uint64_t)rn.x | ((uint64_t)rn.y << 32);
+          const uint64_t tok = base + (uint64_t)p.tok_tick * ((uint64_t)rn.z | ((uint64_t)rn.w << 32));
+          pr = make_uint4((uint32_t)tok, (uint32_t)(tok >> 32), base ? __ldg(p.tok_route + g) : 0u, 0u);
+        } else {
+          pr = __ldg(reinterpret_cast<const uint4*>(p.proposals) + g);
+        }
         if (pr.z == me) {
           c.kind = JR_CMD_CLIENT_REQUEST; c.block = (uint32_t)JR_ADDR_CLIENT << 16;
           c.term = (uint64_t)pr.x | ((uint64_t)pr.y << 32);

@@ -55,6 +55,7 @@ struct SymGroup {
   uint32_t tbase;
   uint32_t lcnt, fcnt;                     // raw Instructions emitted: leader / each follower
   bool abort;
+  bool share;                              // the followers' Instruction FIFOs are all empty: their records can be shared
 
   __device__ __forceinline__ SymGroup(const Dev& dv, uint32_t g_) : d(dv), g(g_), plane((size_t)R * dv.Gp) {}
   __device__ __forceinline__ size_t rg(uint32_t r) const { return (size_t)r * d.Gp + g; }
@@ -82,9 +83,13 @@ struct SymGroup {
     if (!(d.flags & JR_F_CAPTURE_FSM)) return;
     if (fcnt < d.Fr) {
       const uint4 e = make_uint4(bid, next, (uint32_t)tok, (uint32_t)(tok >> 32));
+      if (share) {
+        d.fr[(size_t)fcnt * plane + rg(F0)] = e;           // one copy: sym_leave encodes it once, for all followers
+      } else {
 #pragma unroll
-      for (int r = 0; r < R; ++r)
-        if ((uint32_t)r != L) d.fr[(size_t)fcnt * plane + rg(r)] = e;
+        for (int r = 0; r < R; ++r)
+          if ((uint32_t)r != L) d.fr[(size_t)fcnt * plane + rg(r)] = e;
+      }
     }
     ++fcnt;
   }
@@ -442,6 +447,14 @@ __device__ void sym_leave(SymGroup<R>& s, const SymMail& last, int cur_last) {
     d.oc[cur_last][i] = u;
     if ((d.flags & JR_F_CAPTURE_FSM) && s.lcnt) fsm_flush(d.fr + i, s.lcnt, d.Fr, FsmOut{d.fs + i, s.plane, d.F, s.g, L}, d.fc + i);
   }
+  // The followers emitted the same Instructions.  If none of them has anything pending since the last drain, ONE set of
+  // records (in the lowest follower's FIFO, APPLY records carrying the mask of all followers) stands for all of them;
+  // the others only advance their Instruction counters.  Otherwise every follower gets its own copy.
+  const bool shared_records = s.share;
+  uint32_t fmask = 0;
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+    if ((uint32_t)r != L) fmask |= 1u << r;
 #pragma unroll
   for (int r = 0; r < R; ++r) {   // followers: P1 (timer, RNG), P2, max key, outbox
     if ((uint32_t)r == L) continue;
@@ -463,7 +476,11 @@ __device__ void sym_leave(SymGroup<R>& s, const SymMail& last, int cur_last) {
       d.ob[cur_last][((size_t)u++ * R + r) * d.Gp + s.g] =
           make_uint4(unit_hdr(JR_CMD_APPEND_RESPONSE, 1, 0, L + 1), (uint32_t)s.term, (uint32_t)(s.term >> 32), last.ar_head);
     d.oc[cur_last][i] = u;
-    if ((d.flags & JR_F_CAPTURE_FSM) && s.fcnt) fsm_flush(d.fr + i, s.fcnt, d.Fr, FsmOut{d.fs + i, s.plane, d.F, s.g, (uint32_t)r}, d.fc + i);
+    if ((d.flags & JR_F_CAPTURE_FSM) && s.fcnt) {
+      if (!shared_records) fsm_flush(d.fr + i, s.fcnt, d.Fr, FsmOut{d.fs + i, s.plane, d.F, s.g, (uint32_t)r}, d.fc + i);
+      else if ((uint32_t)r == s.F0) fsm_flush(d.fr + i, s.fcnt, d.Fr, FsmOut{d.fs + i, s.plane, d.F, s.g, (uint32_t)r, fmask}, d.fc + i);
+      else d.fc[i] = make_uint2(0u, s.fcnt < d.Fr ? s.fcnt : d.Fr);   // counted here, carried by F0's masked records
+    }
   }
 }
 
@@ -478,18 +495,34 @@ __global__ void __launch_bounds__(128) sym_kernel(const Dev d, const StepParams 
   s.lcnt = s.fcnt = 0;
   s.n_hb = 0;
   s.last_hb = 0;
+  s.share = false;
   bool ok = sym_enter<R>(s, a, p, 1 - p.cur);
   if (ok) {
+    s.share = (d.flags & JR_F_CAPTURE_FSM) != 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if ((uint32_t)r == s.L) continue;
+      const uint2 c = d.fc[s.rg(r)];
+      if (c.x | c.y) s.share = false;
+    }
     const jr_proposal* props = p.proposals;
     s.now = p.now;
     for (uint32_t t = 0; t < p.n_ticks && !s.abort; ++t) {
       b = SymMail{};
       uint64_t tok = 0;
-      if ((p.phases & PH_PROPOSE) && props) {
-        const uint4 pr = __ldg(reinterpret_cast<const uint4*>(props) + g);
+      if ((p.phases & PH_PROPOSE) && (props || p.tok_runs)) {
+        uint4 pr;
+        if (p.tok_runs) {
+          const uint4 rn = __ldg(p.tok_runs + g);
+          const uint64_t base = (uint64_t)rn.x | ((uint64_t)rn.y << 32);
+          const uint64_t tk = base + (uint64_t)(p.tok_tick + t) * ((uint64_t)rn.z | ((uint64_t)rn.w << 32));
+          pr = make_uint4((uint32_t)tk, (uint32_t)(tk >> 32), base ? __ldg(p.tok_route + g) : 0u, 0u);
+        } else {
+          pr = __ldg(reinterpret_cast<const uint4*>(props) + g);
+          props += p.prop_stride;
+        }
         if (pr.z == s.L + 1) tok = (uint64_t)pr.x | ((uint64_t)pr.y << 32);
         else if (pr.z != 0) s.abort = true;               // a proposal for a follower: proxied ClientRequest, not canonical
-        props += p.prop_stride;
       }
       if (s.abort) break;
       s.leader_tick(a, b, tok, (p.phases & PH_PROPOSE) ? p.n_synth : 0u, p.step_index + t);

@@ -277,6 +277,17 @@ class RaftApi:
         self._check(self._fn("drain_fsm")(self._h, buf, C.c_size_t(cap), C.byref(n)), "drain_fsm")
         return [buf[i] for i in range(n.value)]
 
+    def run_token_runs(self, now0_ms: int, dt_ms: int, n_steps: int, runs: Sequence[Tuple[int, int]]):
+        """jr_run_token_runs: group g proposes base + k * stride at tick k (base 0 = nothing), routed like run_tokens."""
+        if len(runs) != self.n_groups:
+            raise ValueError("one (base, stride) run per group")
+        arr = (abi.TokenRun * self.n_groups)()
+        for g, (base, stride) in enumerate(runs):
+            arr[g].base, arr[g].stride = base, stride
+        self._check(self._fn("run_token_runs")(self._h, C.c_uint64(now0_ms), C.c_uint32(dt_ms), C.c_uint32(n_steps), arr), "run_token_runs")
+        if self._p == "jr_":
+            self._check(self._lib.jr_engine_sync(self._h), "engine_sync")   # `arr` is pageable and about to be freed
+
     def discard_fsm(self, strict: bool = True) -> int:
         """Drain without returning the Instructions; their number.  strict=False: records lost to a full FIFO are not an
         error (start-up phases a caller does not care about)."""
@@ -457,6 +468,7 @@ def _bind(lib: C.CDLL, p: str):
         "run": [vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32],
         "run_proposals": [vp, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(abi.Proposal), C.c_uint32],
         "run_tokens": [vp, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)],
+        "run_token_runs": [vp, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(abi.TokenRun)],
         "drain_fsm": [vp, C.POINTER(abi.FsmInstr), C.c_size_t, C.POINTER(C.c_size_t)],
         "query": [vp, C.c_uint32, C.c_uint32, C.POINTER(abi.ReplicaState)],
         "chain_read": [vp, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.POINTER(abi.Block),

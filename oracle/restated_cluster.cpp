@@ -449,6 +449,16 @@ jr_status jro_run_tokens(jro_cluster* c, uint64_t now0, uint32_t dt, uint32_t n_
   return jro_run_proposals(c, now0, dt, n_steps, props.data(), 0);
 }
 
+// include/josefine_raft_abi.h jr_run_token_runs: tokens[k*G + g] = base[g] + k * stride[g]
+jr_status jro_run_token_runs(jro_cluster* c, uint64_t now0, uint32_t dt, uint32_t n_steps, const jr_token_run* runs) {
+  if (!c || !runs) return JR_E_INVAL;
+  const uint32_t G = c->cfg.n_groups;
+  std::vector<uint64_t> tokens((size_t)n_steps * G);
+  for (uint32_t k = 0; k < n_steps; ++k)
+    for (uint32_t g = 0; g < G; ++g) tokens[(size_t)k * G + g] = runs[g].base ? runs[g].base + (uint64_t)k * runs[g].stride : 0;
+  return jro_run_tokens(c, now0, dt, n_steps, tokens.data());
+}
+
 jr_status jro_drain_fsm(jro_cluster* c, jr_fsm_instr* out, size_t cap, size_t* n) {
   if (!c || !n) return JR_E_INVAL;
   size_t k = 0;

@@ -67,7 +67,7 @@ def case_fsm_fifo_overflow_never_touches_consensus(make):
     assert len(big.drain_fsm()) == 16
     assert small.drain_fsm() == [] and big.drain_fsm() == []      # a drain takes what it returns
     # ... while a regular stream compresses: synthetic tokens advance by a constant stride, so 120 Instructions are
-    # one APPLY run + one NOTIFY run + two 64-bit PATTERN records
+    # one APPLY run + one NOTIFY run + one PATTERN record
     small.run(1000, 100, 60, 1)
     assert len(small.drain_fsm(cap=1024)) == 120
 

@@ -163,3 +163,32 @@ def test_tokens_kill_truncate_on_gpu():
 @pytest.mark.gpu
 def test_misrouted_and_asymmetric_on_gpu():
     case_misrouted_and_asymmetric(_gpu)
+
+
+def case_token_runs_equal_tokens(make, G=24, R=5):
+    """jr_run_token_runs(base, stride) == jr_run_tokens(base + k * stride), folded or not, and on the oracle."""
+    fold, plain, ora = trio(make, G, R, seed=6, chain_capacity=256, fsm_units=64)
+    ref = make(G, R, seed=6, chain_capacity=256, fsm_units=64, flags=CAP)
+    for api in (fold, plain, ora, ref):
+        _bootstrap(api, G, R)
+        api.run(100, 100, 12, 1)
+        api.leader_table()
+    now = 1300
+    for rnd in range(3):
+        runs = [(0, 0) if (g + rnd) % 6 == 0 else (((rnd + 1) << 40) + g + 1, 1 << 20) for g in range(G)]
+        n = 17 + rnd
+        for api in (fold, plain, ora):
+            api.run_token_runs(now, 100, n, runs)
+        ref.run_tokens(now, 100, [[(b + k * s) if b else 0 for (b, s) in runs] for k in range(n)])
+        now += 100 * n
+        same([fold, plain, ora, ref])
+    return fold.fold_count()
+
+
+def test_token_runs_on_device_code():
+    assert case_token_runs_equal_tokens(_emu) == 24
+
+
+@pytest.mark.gpu
+def test_token_runs_on_gpu():
+    assert case_token_runs_equal_tokens(_gpu, G=1500) == 1500
