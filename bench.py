@@ -26,9 +26,12 @@ Arms:
   (default)          the CUDA engine.  `value` = device-resident throughput (proposals
                      generated in the kernel, Instruction stream drained every step);
                      `e2e` = the same workload through the C ABI with HOST buffers, every
-                     step: tokens H2D from pinned memory, the per-group leader table D2H,
-                     the step's Instruction records D2H and folded on the host.
-                     `e2e_no_output` = the same without the Instruction stream.
+                     step: the step's proposals H2D from pinned memory in run-length form
+                     (jr_run_token_runs: {base, stride} per group), the per-group leader
+                     table D2H, the step's Instruction records D2H and folded on the host.
+                     `e2e_dense_input` = the same with one 8-byte token per group-tick
+                     (jr_run_tokens, round 1's input); `e2e_no_output` = round 1's leg:
+                     dense input, engine created without the Instruction stream.
                      `other_configs` = BASELINE configs #2, #4 (per-GPU shard) and #5, each
                      timed at its size; `parity` = state/stream digests against the C++
                      restatement on the same inputs, per config, in this run.
@@ -65,6 +68,7 @@ L2_FLUSH_BYTES = 256 << 20
 CHAIN_WINDOW = 512          # block ids a replica's table may span above the floor (truncated every step)
 TRUNC_MARGIN = 8
 FSM_UNITS = 16              # record slots per replica between two drains (steady state uses <= 4)
+FOLD_THREADS = 4            # host threads folding a batch of Instruction records (jr_fsm_fold_mt)
 
 
 def workload_name(G, R):
@@ -412,7 +416,7 @@ class Bench:
             ptr, batch = C.POINTER(abi.FsmRecord)(), abi.FsmBatch()
             st = lib.jr_fsm_records_wait(h, C.byref(ptr), C.byref(batch))
             assert st == 0, (st, batch.n_dropped)
-            st = lib.jr_fsm_fold(C.cast(ptr, C.c_void_p), C.c_size_t(batch.n_records), G, R, applied, totals)
+            st = lib.jr_fsm_fold_mt(C.cast(ptr, C.c_void_p), C.c_size_t(batch.n_records), G, R, applied, totals, FOLD_THREADS)
             assert st == 0
             outstanding[0] -= 1
 
@@ -421,11 +425,11 @@ class Bench:
             eng.truncate(TRUNC_MARGIN)
             now[0] += DT_MS * S
             if capture:
-                if outstanding[0] == 2:
-                    take()
                 st = lib.jr_fsm_records_async(h)
                 assert st == 0, st
                 outstanding[0] += 1
+                if outstanding[0] == 2:      # consume the PREVIOUS step's stream while this step runs
+                    take()
             if world > 1 and announce:
                 # the one cross-shard exchange: leader announce, once per step (every 64 ticks).  The table is packed on
                 # the engine stream; the NCCL all-gather runs on a side stream and overlaps the next step's kernel.
@@ -537,7 +541,7 @@ class Bench:
                 ptr, batch = C.POINTER(abi.FsmRecord)(), abi.FsmBatch()
                 st = lib.jr_fsm_records_wait(h, C.byref(ptr), C.byref(batch))
                 assert st == 0, (st, batch.n_dropped)
-                st = lib.jr_fsm_fold(C.cast(ptr, C.c_void_p), C.c_size_t(batch.n_records), G, R, applied, totals)   # the host's fsm::Driver bookkeeping
+                st = lib.jr_fsm_fold_mt(C.cast(ptr, C.c_void_p), C.c_size_t(batch.n_records), G, R, applied, totals, FOLD_THREADS)   # the host's fsm::Driver bookkeeping
                 assert st == 0
                 rec_bytes[0] += batch.n_records * 32 + C.sizeof(abi.FsmBatch)
 

@@ -446,6 +446,10 @@ jr_status jr_fsm_expand(const jr_fsm_record* records, size_t n_records, uint32_t
  */
 jr_status jr_fsm_fold(const jr_fsm_record* records, size_t n_records, uint32_t n_groups, uint32_t n_replicas,
                       uint32_t* applied_hi, uint64_t* totals);
+/* The same on n_threads host threads (contiguous slices of the batch; a batch is sorted by (node, group), so two
+ * slices touch the same watermark only at their seam, which is resolved with a max).  n_threads <= 1: jr_fsm_fold. */
+jr_status jr_fsm_fold_mt(const jr_fsm_record* records, size_t n_records, uint32_t n_groups, uint32_t n_replicas,
+                         uint32_t* applied_hi, uint64_t* totals, uint32_t n_threads);
 
 /* ---- introspection --------------------------------------------------------- */
 jr_status jr_query(jr_engine* e, uint32_t group, uint32_t node, jr_replica_state* out);

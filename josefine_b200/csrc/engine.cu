@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "raft_device.cuh"
@@ -1611,6 +1612,50 @@ jr_status jr_fsm_fold(const jr_fsm_record* recs, size_t n, uint32_t G, uint32_t 
   totals[0] += na;
   totals[1] += nn;
   totals[2] += n;
+  return JR_OK;
+}
+
+// Masked records update several watermarks, so slices are not disjoint in general: every thread folds into a PRIVATE
+// max only where it has to -- here simply by making the shared update an atomic max (relaxed; values only grow).
+jr_status jr_fsm_fold_mt(const jr_fsm_record* recs, size_t n, uint32_t G, uint32_t R, uint32_t* applied_hi, uint64_t* totals,
+                         uint32_t n_threads) {
+  if (n_threads <= 1 || n < 4096) return jr_fsm_fold(recs, n, G, R, applied_hi, totals);
+  if ((!recs && n) || !applied_hi || !totals || R < 1 || R > JR_MAX_REPLICAS) return JR_E_INVAL;
+  n_threads = std::min<uint32_t>(n_threads, 64);
+  std::vector<std::thread> th;
+  std::vector<uint64_t> part((size_t)n_threads * 3, 0);
+  std::vector<int> bad(n_threads, 0);
+  for (uint32_t t = 0; t < n_threads; ++t)
+    th.emplace_back([&, t] {
+      const size_t lo = n * t / n_threads, hi = n * (t + 1) / n_threads;
+      uint64_t na = 0, nn = 0;
+      auto bump = [&](size_t idx, uint32_t v) {
+        uint32_t cur = __atomic_load_n(applied_hi + idx, __ATOMIC_RELAXED);
+        while (cur < v && !__atomic_compare_exchange_n(applied_hi + idx, &cur, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+      };
+      for (size_t i = lo; i < hi; ++i) {
+        const jr_fsm_record& rc = recs[i];
+        const uint32_t kind = JR_FSMR_KIND(rc.hdr), node = JR_FSMR_NODE(rc.hdr), count = JR_FSMR_COUNT(rc.hdr);
+        if (rc.group >= G || node > R || (kind == JR_FSMR_APPLY && (rc.addr >> R))) { bad[t] = 1; return; }
+        if (kind == JR_FSMR_APPLY) {
+          if (rc.addr) {
+            for (uint32_t k = 0; k < R; ++k)
+              if ((rc.addr >> k) & 1u) { bump((size_t)k * G + rc.group, rc.id0 + count - 1); na += count; }
+          } else {
+            bump((size_t)(node - 1) * G + rc.group, rc.id0 + count - 1);
+            na += count;
+          }
+        } else if (kind == JR_FSMR_NOTIFY) {
+          nn += count;
+        }
+      }
+      part[(size_t)t * 3 + 0] = na; part[(size_t)t * 3 + 1] = nn; part[(size_t)t * 3 + 2] = hi - lo;
+    });
+  for (auto& x : th) x.join();
+  for (uint32_t t = 0; t < n_threads; ++t) {
+    if (bad[t]) return JR_E_INVAL;
+    totals[0] += part[(size_t)t * 3]; totals[1] += part[(size_t)t * 3 + 1]; totals[2] += part[(size_t)t * 3 + 2];
+  }
   return JR_OK;
 }
 

@@ -40,6 +40,14 @@ struct SymMail {
   uint32_t ar, ar_head;
 };
 
+// The last SYM_ROWS block-table rows of one replica, direct mapped by id: everything a steady group reads was written a
+// few ticks ago, so after the fill at entry no table READ leaves the SM (the rows themselves are still written through).
+constexpr uint32_t SYM_ROWS = 8;
+struct SymRows {
+  uint32_t tag[SYM_ROWS], next[SYM_ROWS];
+  uint64_t tok[SYM_ROWS];
+};
+
 template <int R>
 struct SymGroup {
   const Dev& d;
@@ -53,6 +61,7 @@ struct SymGroup {
   uint32_t n_hb;                           // heartbeats the followers took in this launch
   uint64_t last_hb;
   uint32_t tbase;
+  SymRows lrows, frows;                    // row caches: the leader's table, the followers' (identical) tables
   uint32_t lcnt, fcnt;                     // raw Instructions emitted: leader / each follower
   bool abort;
   bool share;                              // the followers' Instruction FIFOs are all empty: their records can be shared
@@ -61,12 +70,37 @@ struct SymGroup {
   __device__ __forceinline__ size_t rg(uint32_t r) const { return (size_t)r * d.Gp + g; }
   __device__ __forceinline__ size_t row(uint32_t r, uint32_t bid) const { return (size_t)(bid & d.capm) * plane + rg(r); }
   __device__ __forceinline__ bool in_window(uint32_t bid) const { return bid - tbase < d.cap && bid < FS_NOTIFY_BIT; }
-  __device__ __forceinline__ void fetch(uint32_t r, uint32_t bid, uint32_t& next, uint64_t& tok) const {
+  // r is the leader (its own table) or F0 (the followers' table)
+  __device__ __forceinline__ void fetch(uint32_t r, uint32_t bid, uint32_t& next, uint64_t& tok) {
     if (!in_window(bid)) { next = ABSENT; tok = 0; return; }
+    SymRows& c = r == L ? lrows : frows;
+    const uint32_t k = bid % SYM_ROWS;
+    if (c.tag[k] == bid) { next = c.next[k]; tok = c.tok[k]; return; }
     next = __ldcg(d.cnext + row(r, bid));   // rows written earlier in this launch by this lane: read them at L2
     tok = __ldcg(d.ctok + row(r, bid));
+    c.tag[k] = bid; c.next[k] = next; c.tok[k] = tok;
   }
-  __device__ __forceinline__ bool has(uint32_t r, uint32_t bid) const {
+  __device__ __forceinline__ void cache_put(SymRows& c, uint32_t bid, uint32_t next, uint64_t tok) {
+    const uint32_t k = bid % SYM_ROWS;
+    c.tag[k] = bid; c.next[k] = next; c.tok[k] = tok;
+  }
+  __device__ __forceinline__ void cache_fill(uint32_t r, uint32_t top) {   // independent loads, issued together
+    SymRows& c = r == L ? lrows : frows;
+#pragma unroll
+    for (uint32_t k = 0; k < SYM_ROWS; ++k) { c.tag[k] = ABSENT; c.next[k] = ABSENT; c.tok[k] = 0; }
+    uint32_t nx[SYM_ROWS];
+    uint64_t tk[SYM_ROWS];
+#pragma unroll
+    for (uint32_t j = 0; j < SYM_ROWS; ++j)
+      if (j <= top && in_window(top - j)) {
+        nx[j] = d.cnext[row(r, top - j)];
+        tk[j] = d.ctok[row(r, top - j)];
+      }
+#pragma unroll
+    for (uint32_t j = 0; j < SYM_ROWS; ++j)
+      if (j <= top && in_window(top - j)) cache_put(c, top - j, nx[j], tk[j]);
+  }
+  __device__ __forceinline__ bool has(uint32_t r, uint32_t bid) {
     uint32_t n; uint64_t t;
     fetch(r, bid, n, t);
     return n != ABSENT;
@@ -134,6 +168,7 @@ struct SymGroup {
     if (!(bid > head) || !in_window(bid)) { abort = true; return; }   // chain.rs:163 / engine window: a fault -> step_kernel's business
     d.cnext[row(L, bid)] = head;
     d.ctok[row(L, bid)] = tok;
+    cache_put(lrows, bid, head, tok);
     if (bid > maxkey) maxkey = bid;
     head = bid;
     emit_leader(true, bid, FSR_CLIENT, tok);
@@ -218,6 +253,7 @@ struct SymGroup {
             d.cnext[row(r, bid)] = nx;
             d.ctok[row(r, bid)] = tk;
           }
+        cache_put(frows, bid, nx, tk);
         if (bid > fmaxkey) fmaxkey = bid;
         fhead = bid;                                       // chain.rs:188-190: unconditionally
       }
@@ -496,8 +532,12 @@ __global__ void __launch_bounds__(128) sym_kernel(const Dev d, const StepParams 
   s.n_hb = 0;
   s.last_hb = 0;
   s.share = false;
+#pragma unroll
+  for (uint32_t k = 0; k < SYM_ROWS; ++k) { s.lrows.tag[k] = ABSENT; s.frows.tag[k] = ABSENT; }
   bool ok = sym_enter<R>(s, a, p, 1 - p.cur);
   if (ok) {
+    s.cache_fill(s.L, s.maxkey);
+    s.cache_fill(s.F0, s.fmaxkey);
     s.share = (d.flags & JR_F_CAPTURE_FSM) != 0;
 #pragma unroll
     for (int r = 0; r < R; ++r) {

@@ -507,6 +507,10 @@ def _bind(lib: C.CDLL, p: str):
         fn = getattr(lib, p + "fsm_fold")
         fn.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         fn.restype = C.c_int
+    if hasattr(lib, p + "fsm_fold_mt"):
+        fn = getattr(lib, p + "fsm_fold_mt")
+        fn.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
+        fn.restype = C.c_int
     et = getattr(lib, p + "election_timeout")
     et.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
     et.restype = C.c_uint32

@@ -35,8 +35,9 @@ def trio(make, G, R, **cfg):
     return fold, plain, ora
 
 
-def same(apis, chain_ids=48, fsm_cap=1 << 16):
+def same(apis, chain_ids=48, fsm_cap=None):
     a = apis[0]
+    fsm_cap = fsm_cap or max(1 << 16, a.n_groups * a.n_replicas * 160)
     streams = [[fsm_tuple(f) for f in api.drain_fsm(cap=fsm_cap)] for api in apis]
     for other, st in zip(apis[1:], streams[1:]):
         assert streams[0] == st, "Instruction streams differ"
