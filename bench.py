@@ -68,7 +68,7 @@ L2_FLUSH_BYTES = 256 << 20
 CHAIN_WINDOW = 512          # block ids a replica's table may span above the floor (truncated every step)
 TRUNC_MARGIN = 8
 FSM_UNITS = 16              # record slots per replica between two drains (steady state uses <= 4)
-FOLD_THREADS = 4            # host threads folding a batch of Instruction records (jr_fsm_fold_mt)
+FOLD_THREADS = int(os.environ.get("JR_FOLD_THREADS", "1"))   # host threads folding a batch of Instruction records (jr_fsm_fold_mt); more than one only pays on hosts with idle cores
 
 
 def workload_name(G, R):
@@ -534,22 +534,37 @@ class Bench:
             if with_output:
                 assert lib.jr_fsm_records_async(h) == 0                   # Instruction stream D2H
 
+        trace = {"submit": 0.0, "table_wait": 0.0, "records_wait": 0.0, "fold": 0.0} if os.environ.get("JR_BENCH_TRACE") else None
+
         def consume(i):
+            t0 = time.perf_counter()
             assert lib.jr_leader_table_wait(h) == 0
             checks.append(int(table[i % NB, 0, 1].item() >> 32))        # read the step's result: commit of group 0
+            t1 = time.perf_counter()
             if with_output:
                 ptr, batch = C.POINTER(abi.FsmRecord)(), abi.FsmBatch()
                 st = lib.jr_fsm_records_wait(h, C.byref(ptr), C.byref(batch))
                 assert st == 0, (st, batch.n_dropped)
+                t2 = time.perf_counter()
                 st = lib.jr_fsm_fold_mt(C.cast(ptr, C.c_void_p), C.c_size_t(batch.n_records), G, R, applied, totals, FOLD_THREADS)   # the host's fsm::Driver bookkeeping
                 assert st == 0
                 rec_bytes[0] += batch.n_records * 32 + C.sizeof(abi.FsmBatch)
+                if trace is not None:
+                    trace["table_wait"] += t1 - t0
+                    trace["records_wait"] += t2 - t1
+                    trace["fold"] += time.perf_counter() - t2
 
         def e2e_steps(n):
+            ts = time.perf_counter()
             submit(0)
+            if trace is not None:
+                trace["submit"] += time.perf_counter() - ts
             for i in range(n):
                 if i + 1 < n:
+                    ts = time.perf_counter()
                     submit(i + 1)
+                    if trace is not None:
+                        trace["submit"] += time.perf_counter() - ts
                 consume(i)
 
         e2e_steps(max(warmup, 4))
@@ -575,6 +590,8 @@ class Bench:
                "d2h_bytes_per_step": G * 16 + (rec_bytes[0] // steps if with_output else 0), "ms_per_step": dt * 1e3 / steps,
                "commit_last": checks[-1], "faulted_replicas": faults,
                "timing": "host wall clock around all timed steps incl. the final sync, max over ranks"}
+        if trace is not None:
+            out["host_ms_per_step"] = {k: v * 1e3 / (steps + max(warmup, 4)) for k, v in trace.items()}
         if with_output:
             out.update({"instructions_per_step": int(totals[0] + totals[1]) // steps, "records_per_step": int(totals[2]) // steps,
                         "d2h_stream_bytes_per_step": rec_bytes[0] // steps,

@@ -40,12 +40,47 @@ struct SymMail {
   uint32_t ar, ar_head;
 };
 
-// The last SYM_ROWS block-table rows of one replica, direct mapped by id: everything a steady group reads was written a
-// few ticks ago, so after the fill at entry no table READ leaves the SM (the rows themselves are still written through).
-constexpr uint32_t SYM_ROWS = 8;
+// The top SYM_ROWS block-table rows of one replica -- ids top, top-1, ... -- as a SHIFT REGISTER: every access uses
+// compile-time indices (unrolled selects), so the rows live in registers, not in local memory.  Everything a steady
+// group reads was written a few ticks ago, so after the fill at entry no table READ leaves the SM (rows are still
+// written through to HBM).  UNKNOWN = not loaded yet; ABSENT = known to be absent.
+constexpr uint32_t SYM_ROWS = 6;
+constexpr uint32_t SYM_UNKNOWN = 0xFFFFFFFEu;
 struct SymRows {
-  uint32_t tag[SYM_ROWS], next[SYM_ROWS];
+  uint32_t top;                 // id of entry 0
+  uint32_t next[SYM_ROWS];
   uint64_t tok[SYM_ROWS];
+  __device__ __forceinline__ void clear(uint32_t t) {
+    top = t;
+#pragma unroll
+    for (uint32_t k = 0; k < SYM_ROWS; ++k) { next[k] = SYM_UNKNOWN; tok[k] = 0; }
+  }
+  __device__ __forceinline__ bool get(uint32_t bid, uint32_t& nx, uint64_t& tk) const {
+    const uint32_t j = top - bid;   // wraps to a huge value for bid > top
+    bool hit = false;
+#pragma unroll
+    for (uint32_t k = 0; k < SYM_ROWS; ++k)
+      if (j == k && next[k] != SYM_UNKNOWN) { nx = next[k]; tk = tok[k]; hit = true; }
+    return hit;
+  }
+  __device__ __forceinline__ void set(uint32_t bid, uint32_t nx, uint64_t tk) {   // bid <= top: overwrite in place (or too old: ignore)
+    const uint32_t j = top - bid;
+#pragma unroll
+    for (uint32_t k = 0; k < SYM_ROWS; ++k)
+      if (j == k) { next[k] = nx; tok[k] = tk; }
+  }
+  __device__ __forceinline__ void push(uint32_t bid, uint32_t nx, uint64_t tk) {  // any bid: ids between the old top and bid are absent
+    if (bid <= top) { set(bid, nx, tk); return; }
+    uint32_t gap = bid - top;
+    if (gap > SYM_ROWS) gap = SYM_ROWS;
+    for (uint32_t step = 0; step < gap; ++step) {
+#pragma unroll
+      for (uint32_t k = SYM_ROWS - 1; k > 0; --k) { next[k] = next[k - 1]; tok[k] = tok[k - 1]; }
+      next[0] = ABSENT; tok[0] = 0;
+    }
+    top = bid;
+    next[0] = nx; tok[0] = tk;
+  }
 };
 
 template <int R>
@@ -73,32 +108,25 @@ struct SymGroup {
   // r is the leader (its own table) or F0 (the followers' table)
   __device__ __forceinline__ void fetch(uint32_t r, uint32_t bid, uint32_t& next, uint64_t& tok) {
     if (!in_window(bid)) { next = ABSENT; tok = 0; return; }
-    SymRows& c = r == L ? lrows : frows;
-    const uint32_t k = bid % SYM_ROWS;
-    if (c.tag[k] == bid) { next = c.next[k]; tok = c.tok[k]; return; }
+    if (r == L ? lrows.get(bid, next, tok) : frows.get(bid, next, tok)) return;
     next = __ldcg(d.cnext + row(r, bid));   // rows written earlier in this launch by this lane: read them at L2
     tok = __ldcg(d.ctok + row(r, bid));
-    c.tag[k] = bid; c.next[k] = next; c.tok[k] = tok;
+    if (r == L) lrows.set(bid, next, tok);
+    else frows.set(bid, next, tok);
   }
-  __device__ __forceinline__ void cache_put(SymRows& c, uint32_t bid, uint32_t next, uint64_t tok) {
-    const uint32_t k = bid % SYM_ROWS;
-    c.tag[k] = bid; c.next[k] = next; c.tok[k] = tok;
-  }
-  __device__ __forceinline__ void cache_fill(uint32_t r, uint32_t top) {   // independent loads, issued together
-    SymRows& c = r == L ? lrows : frows;
+  // (the cache object is named at the call site: selecting one of the two by a runtime condition would force both
+  //  into local memory)
+  __device__ __forceinline__ void cache_fill(SymRows& c, uint32_t r, uint32_t top) {   // independent loads, issued together
+    c.clear(top);
 #pragma unroll
-    for (uint32_t k = 0; k < SYM_ROWS; ++k) { c.tag[k] = ABSENT; c.next[k] = ABSENT; c.tok[k] = 0; }
-    uint32_t nx[SYM_ROWS];
-    uint64_t tk[SYM_ROWS];
-#pragma unroll
-    for (uint32_t j = 0; j < SYM_ROWS; ++j)
+    for (uint32_t j = 0; j < SYM_ROWS; ++j) {
       if (j <= top && in_window(top - j)) {
-        nx[j] = d.cnext[row(r, top - j)];
-        tk[j] = d.ctok[row(r, top - j)];
+        c.next[j] = d.cnext[row(r, top - j)];
+        c.tok[j] = d.ctok[row(r, top - j)];
+      } else {
+        c.next[j] = ABSENT;           // below id 0 / outside the window: nothing there
       }
-#pragma unroll
-    for (uint32_t j = 0; j < SYM_ROWS; ++j)
-      if (j <= top && in_window(top - j)) cache_put(c, top - j, nx[j], tk[j]);
+    }
   }
   __device__ __forceinline__ bool has(uint32_t r, uint32_t bid) {
     uint32_t n; uint64_t t;
@@ -147,6 +175,9 @@ struct SymGroup {
   }
   // leader.rs:87-99 with the current heads
   __device__ __forceinline__ void leader_commit(uint32_t v_new, uint32_t n_new, uint32_t v_old) {
+    // committed_index() exceeds `commit` iff at least R/2+1 heads do: count first, sort only when it matters
+    const uint32_t above = (ph_self > commit ? 1u : 0u) + (v_new > commit ? n_new : 0u) + (v_old > commit ? (uint32_t)(R - 1) - n_new : 0u);
+    if (above < (uint32_t)(R / 2 + 1)) return;
     const uint32_t q = committed_index(v_new, n_new, v_old);
     if (q <= commit) return;
     if (!has(L, q)) { abort = true; return; }           // chain.rs:197-202 would panic
@@ -168,7 +199,7 @@ struct SymGroup {
     if (!(bid > head) || !in_window(bid)) { abort = true; return; }   // chain.rs:163 / engine window: a fault -> step_kernel's business
     d.cnext[row(L, bid)] = head;
     d.ctok[row(L, bid)] = tok;
-    cache_put(lrows, bid, head, tok);
+    lrows.push(bid, head, tok);
     if (bid > maxkey) maxkey = bid;
     head = bid;
     emit_leader(true, bid, FSR_CLIENT, tok);
@@ -253,7 +284,7 @@ struct SymGroup {
             d.cnext[row(r, bid)] = nx;
             d.ctok[row(r, bid)] = tk;
           }
-        cache_put(frows, bid, nx, tk);
+        frows.push(bid, nx, tk);
         if (bid > fmaxkey) fmaxkey = bid;
         fhead = bid;                                       // chain.rs:188-190: unconditionally
       }
@@ -268,7 +299,7 @@ struct SymGroup {
 
 // ---- entry: is the group symmetric, is its mail canonical? ---------------------------------------------------------
 template <int R>
-__device__ bool sym_enter(SymGroup<R>& s, SymMail& m, const StepParams& p, int prv) {
+__device__ __forceinline__ bool sym_enter(SymGroup<R>& s, SymMail& m, const StepParams& p, int prv) {
   const Dev& d = s.d;
   if (s.g >= d.G) return false;
   // roles: one live leader, R-1 live followers of that leader
@@ -289,15 +320,22 @@ __device__ bool sym_enter(SymGroup<R>& s, SymMail& m, const StepParams& p, int p
   const uint4 l0 = d.p0[s.rg(L)];
   s.term = (uint64_t)l0.x | ((uint64_t)l0.y << 32);
   s.tbase = d.tb[s.g];
-  s.head = p2[L].x; s.commit = p2[L].y; s.idgen = p2[L].z;
-  s.ckey = (p2[L].w >> 28) & 1u;
+  uint4 pl = p2[0], pf = p2[0];             // the leader's and the first follower's P2 (static selects: no local array)
+  const uint32_t f0i = L == 0 ? 1u : 0u;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if ((uint32_t)r == L) pl = p2[r];
+    if ((uint32_t)r == f0i) pf = p2[r];
+  }
+  s.head = pl.x; s.commit = pl.y; s.idgen = pl.z;
+  s.ckey = (pl.w >> 28) & 1u;
   s.maxkey = d.mk[s.rg(L)];
   if (!(s.idgen > s.head)) return false;                                      // the next append would assert (chain.rs:163)
   const uint4 l3 = d.p3[s.rg(L)];
   s.hbtime = (uint64_t)l3.x | ((uint64_t)l3.y << 32);
   // followers: identical
   const uint32_t f0 = s.F0;
-  s.fhead = p2[f0].x; s.fcommit = p2[f0].y; s.fckey = (p2[f0].w >> 28) & 1u;
+  s.fhead = pf.x; s.fcommit = pf.y; s.fckey = (pf.w >> 28) & 1u;
   s.fmaxkey = d.mk[s.rg(f0)];
   const uint64_t hbgap = ((uint64_t)d.hb / p.dt + 1) * p.dt;                 // ticks between two heartbeats, in ms
 #pragma unroll
@@ -319,9 +357,15 @@ __device__ bool sym_enter(SymGroup<R>& s, SymMail& m, const StepParams& p, int p
     if (q * 4 + 2 < R) ph[q * 4 + 2] = v.z;
     if (q * 4 + 3 < R) ph[q * 4 + 3] = v.w;
   }
-  const uint32_t prmask = (p2[L].w >> 16) & 255u;
-  s.ph_self = ph[L]; s.mode_self = (prmask >> L) & 1u;
-  s.ph_f = ph[f0]; s.mode_f = (prmask >> f0) & 1u;
+  const uint32_t prmask = (pl.w >> 16) & 255u;
+  s.ph_self = 0; s.ph_f = 0;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if ((uint32_t)r == L) s.ph_self = ph[r];
+    if ((uint32_t)r == f0) s.ph_f = ph[r];
+  }
+  s.mode_self = (prmask >> L) & 1u;
+  s.mode_f = (prmask >> f0) & 1u;
 #pragma unroll
   for (int r = 0; r < R; ++r)
     if ((uint32_t)r != L && (ph[r] != s.ph_f || ((prmask >> r) & 1u) != s.mode_f)) return false;
@@ -435,7 +479,7 @@ __device__ bool sym_enter(SymGroup<R>& s, SymMail& m, const StepParams& p, int p
 
 // ---- exit: write everything step_kernel would have left behind -------------------------------------------------------
 template <int R>
-__device__ void sym_leave(SymGroup<R>& s, const SymMail& last, int cur_last) {
+__device__ __forceinline__ void sym_leave(SymGroup<R>& s, const SymMail& last, int cur_last) {
   const Dev& d = s.d;
   const uint32_t L = s.L;
   {  // leader: P2, P3, progress planes, max key (P0 / P1 are untouched by a steady leader)
@@ -522,7 +566,7 @@ __device__ void sym_leave(SymGroup<R>& s, const SymMail& last, int cur_last) {
 
 // One lane per group.  symdone[g] = 1: the whole launch of group g has been applied here; 0: step_kernel runs it.
 template <int R>
-__global__ void __launch_bounds__(128) sym_kernel(const Dev d, const StepParams p, uint8_t* symdone) {
+__global__ void __launch_bounds__(128, 4) sym_kernel(const Dev d, const StepParams p, uint8_t* symdone) {
   const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= d.Gp) return;
   SymGroup<R> s(d, g);
@@ -532,12 +576,12 @@ __global__ void __launch_bounds__(128) sym_kernel(const Dev d, const StepParams 
   s.n_hb = 0;
   s.last_hb = 0;
   s.share = false;
-#pragma unroll
-  for (uint32_t k = 0; k < SYM_ROWS; ++k) { s.lrows.tag[k] = ABSENT; s.frows.tag[k] = ABSENT; }
+  s.lrows.clear(0);
+  s.frows.clear(0);
   bool ok = sym_enter<R>(s, a, p, 1 - p.cur);
   if (ok) {
-    s.cache_fill(s.L, s.maxkey);
-    s.cache_fill(s.F0, s.fmaxkey);
+    s.cache_fill(s.lrows, s.L, s.maxkey);
+    s.cache_fill(s.frows, s.F0, s.fmaxkey);
     s.share = (d.flags & JR_F_CAPTURE_FSM) != 0;
 #pragma unroll
     for (int r = 0; r < R; ++r) {

@@ -125,7 +125,7 @@ def test_full_size_stream_equals_oracle_65536x5_256_ticks():
         a = np.frombuffer(out_e, dtype=np.uint8, count=n_e.value * C.sizeof(abi.FsmInstr))
         b = np.frombuffer(out_o, dtype=np.uint8, count=n_o.value * C.sizeof(abi.FsmInstr))
         assert np.array_equal(a, b), f"launch {launch}: expanded stream differs from the oracle's"
-        assert batch.n_records < 10 * G                               # compact: O(1) records per replica per launch
+        assert batch.n_records < (12 if launch == 0 else 8) * G      # compact: O(1) records per replica per launch (the first also holds the start-up)
         total += n_e.value
         # client path on a subset: records -> BatchedDriver vs oracle Instructions -> BatchedDriver
         sub_recs = [abi.FsmRecord.from_buffer_copy(recs[i]) for i in range(batch.n_records) if recs[i].group < sub]

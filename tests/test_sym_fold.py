@@ -66,7 +66,7 @@ def case_steady(make, R, G=40, hb=100, dt=100, launches=5, ticks=33, n_synth=1):
 def case_tokens_kill_truncate(make, G=48, R=5):
     """jr_run_tokens (routed proposals, some ticks without one), leaders silenced in between (those groups leave the fold),
     jr_truncate moving the window under it."""
-    apis = trio(make, G, R, seed=9, chain_capacity=128, fsm_units=64)
+    apis = trio(make, G, R, seed=9, chain_capacity=128, fsm_units=64, fsm_host_records=G * R * 32)   # holes in the token grid: short runs
     for api in apis:
         _bootstrap(api, G, R)
         api.run(100, 100, 12, 1)
