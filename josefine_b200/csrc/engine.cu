@@ -10,6 +10,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <mutex>
 #include <new>
 #include <thread>
 #include <vector>
@@ -1615,47 +1617,105 @@ jr_status jr_fsm_fold(const jr_fsm_record* recs, size_t n, uint32_t G, uint32_t 
   return JR_OK;
 }
 
-// Masked records update several watermarks, so slices are not disjoint in general: every thread folds into a PRIVATE
-// max only where it has to -- here simply by making the shared update an atomic max (relaxed; values only grow).
+// jr_fsm_fold_mt: a small persistent pool (created on first use and deliberately never destroyed: its workers sleep on
+// a condition variable for the life of the process) folds contiguous slices of the batch.  Masked records update several
+// watermarks and slices meet at seams, so the shared update is an atomic max (relaxed; values only grow).
+namespace {
+struct FoldJob {
+  const jr_fsm_record* recs = nullptr;
+  size_t n = 0;
+  uint32_t G = 0, R = 0, parts = 0;
+  uint32_t* applied = nullptr;
+  uint64_t na[64], nn[64];
+  int bad[64];
+};
+void fold_slice(FoldJob& j, uint32_t t) {
+  const size_t lo = j.n * t / j.parts, hi = j.n * (t + 1) / j.parts;
+  uint64_t na = 0, nn = 0;
+  auto bump = [&](size_t idx, uint32_t v) {
+    uint32_t cur = __atomic_load_n(j.applied + idx, __ATOMIC_RELAXED);
+    while (cur < v && !__atomic_compare_exchange_n(j.applied + idx, &cur, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+  };
+  for (size_t i = lo; i < hi; ++i) {
+    const jr_fsm_record& rc = j.recs[i];
+    const uint32_t kind = JR_FSMR_KIND(rc.hdr), node = JR_FSMR_NODE(rc.hdr), count = JR_FSMR_COUNT(rc.hdr);
+    if (rc.group >= j.G || node > j.R || (kind == JR_FSMR_APPLY && (rc.addr >> j.R))) { j.bad[t] = 1; return; }
+    if (kind == JR_FSMR_APPLY) {
+      if (rc.addr) {
+        for (uint32_t k = 0; k < j.R; ++k)
+          if ((rc.addr >> k) & 1u) { bump((size_t)k * j.G + rc.group, rc.id0 + count - 1); na += count; }
+      } else {
+        bump((size_t)(node - 1) * j.G + rc.group, rc.id0 + count - 1);
+        na += count;
+      }
+    } else if (kind == JR_FSMR_NOTIFY) {
+      nn += count;
+    }
+  }
+  j.na[t] = na;
+  j.nn[t] = nn;
+}
+class FoldPool {
+ public:
+  static FoldPool& get() { static FoldPool* p = new FoldPool(); return *p; }   // leaked on purpose (see above)
+  void run(FoldJob& j) {
+    std::unique_lock<std::mutex> l(m_);
+    while (n_workers_ + 1 < j.parts) {   // worker k serves slice k + 1; the caller folds slice 0
+      const uint32_t k = n_workers_++;
+      std::thread([this, k] { loop(k); }).detach();
+    }
+    job_ = &j;
+    left_ = j.parts - 1;
+    ++gen_;
+    l.unlock();
+    cv_.notify_all();
+    fold_slice(j, 0);
+    l.lock();
+    done_.wait(l, [this] { return left_ == 0; });
+    job_ = nullptr;
+  }
+ private:
+  void loop(uint32_t k) {
+    uint64_t seen = 0;
+    for (;;) {
+      FoldJob* j;
+      {
+        std::unique_lock<std::mutex> l(m_);
+        cv_.wait(l, [&] { return gen_ != seen && job_ && k + 1 < job_->parts; });
+        seen = gen_;
+        j = job_;
+      }
+      fold_slice(*j, k + 1);
+      std::lock_guard<std::mutex> l(m_);
+      if (--left_ == 0) done_.notify_all();
+    }
+  }
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  uint32_t n_workers_ = 0;
+  FoldJob* job_ = nullptr;
+  uint32_t left_ = 0;
+  uint64_t gen_ = 0;
+};
+}  // namespace
+
 jr_status jr_fsm_fold_mt(const jr_fsm_record* recs, size_t n, uint32_t G, uint32_t R, uint32_t* applied_hi, uint64_t* totals,
                          uint32_t n_threads) {
   if (n_threads <= 1 || n < 4096) return jr_fsm_fold(recs, n, G, R, applied_hi, totals);
   if ((!recs && n) || !applied_hi || !totals || R < 1 || R > JR_MAX_REPLICAS) return JR_E_INVAL;
-  n_threads = std::min<uint32_t>(n_threads, 64);
-  std::vector<std::thread> th;
-  std::vector<uint64_t> part((size_t)n_threads * 3, 0);
-  std::vector<int> bad(n_threads, 0);
-  for (uint32_t t = 0; t < n_threads; ++t)
-    th.emplace_back([&, t] {
-      const size_t lo = n * t / n_threads, hi = n * (t + 1) / n_threads;
-      uint64_t na = 0, nn = 0;
-      auto bump = [&](size_t idx, uint32_t v) {
-        uint32_t cur = __atomic_load_n(applied_hi + idx, __ATOMIC_RELAXED);
-        while (cur < v && !__atomic_compare_exchange_n(applied_hi + idx, &cur, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
-      };
-      for (size_t i = lo; i < hi; ++i) {
-        const jr_fsm_record& rc = recs[i];
-        const uint32_t kind = JR_FSMR_KIND(rc.hdr), node = JR_FSMR_NODE(rc.hdr), count = JR_FSMR_COUNT(rc.hdr);
-        if (rc.group >= G || node > R || (kind == JR_FSMR_APPLY && (rc.addr >> R))) { bad[t] = 1; return; }
-        if (kind == JR_FSMR_APPLY) {
-          if (rc.addr) {
-            for (uint32_t k = 0; k < R; ++k)
-              if ((rc.addr >> k) & 1u) { bump((size_t)k * G + rc.group, rc.id0 + count - 1); na += count; }
-          } else {
-            bump((size_t)(node - 1) * G + rc.group, rc.id0 + count - 1);
-            na += count;
-          }
-        } else if (kind == JR_FSMR_NOTIFY) {
-          nn += count;
-        }
-      }
-      part[(size_t)t * 3 + 0] = na; part[(size_t)t * 3 + 1] = nn; part[(size_t)t * 3 + 2] = hi - lo;
-    });
-  for (auto& x : th) x.join();
-  for (uint32_t t = 0; t < n_threads; ++t) {
-    if (bad[t]) return JR_E_INVAL;
-    totals[0] += part[(size_t)t * 3]; totals[1] += part[(size_t)t * 3 + 1]; totals[2] += part[(size_t)t * 3 + 2];
+  static std::mutex* one_at_a_time = new std::mutex();
+  std::lock_guard<std::mutex> guard(*one_at_a_time);
+  FoldJob j;
+  j.recs = recs; j.n = n; j.G = G; j.R = R; j.applied = applied_hi;
+  j.parts = std::min<uint32_t>(n_threads, 64);
+  for (uint32_t t = 0; t < j.parts; ++t) { j.na[t] = j.nn[t] = 0; j.bad[t] = 0; }
+  FoldPool::get().run(j);
+  for (uint32_t t = 0; t < j.parts; ++t) {
+    if (j.bad[t]) return JR_E_INVAL;
+    totals[0] += j.na[t];
+    totals[1] += j.nn[t];
   }
+  totals[2] += n;
   return JR_OK;
 }
 
