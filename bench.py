@@ -350,6 +350,7 @@ class Bench:
     def __init__(self, args):
         import torch
         import torch.distributed as dist
+        torch.set_num_threads(1)      # no OpenMP team spinning next to the threads that feed and drain the engine
         self.torch, self.dist = torch, dist
         self.args = args
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -488,7 +489,7 @@ class Bench:
                     cev.append((a, b))
             torch.cuda.synchronize()
             collective_us = statistics.median(a.elapsed_time(b) for a, b in cev[2:]) * 1e3
-        res = {"ms_total": ms, "ms_per_step": ms / steps, "value": world * G * S * steps / (ms * 1e-3),
+        res = {"ms_total": ms, "ms_per_step": ms / steps, "value": world * G * S * steps / (ms * 1e-3), "folded_groups_last_step": eng.fold_count(),
                "faulted_replicas": faults, "commit_min": commit_min, "instructions": int(totals[0] + totals[1]),
                "records": int(totals[2]), "collective_us": collective_us, "clocks": clocks,
                "ms_per_step_rank_median": statistics.median(per)}
@@ -511,6 +512,7 @@ class Bench:
         runs[:, :, 1] = 1 << 32
         for b in range(NB):
             runs[b, :, 0] = ((b * S + 1) << 32) + torch.arange(G, dtype=torch.int64)
+        runs_np = runs.numpy()        # same pinned memory; numpy's in-place add stays on this thread
         if not dense_input:
             del prop
         pstride, tstride, rstride = S * G * 8, G * 16, G * 16
@@ -522,14 +524,16 @@ class Bench:
         checks = []
 
         def submit(i):
+            k = seq[0]
+            seq[0] += 1
             if dense_input:
                 st = lib.jr_run_tokens(h, C.c_uint64(now[0]), C.c_uint32(DT_MS), C.c_uint32(S),
                                        C.cast(prop.data_ptr() + (i % NB) * pstride, C.POINTER(C.c_uint64)))   # H2D + route + fused kernel
             else:
-                if i >= NB:   # (buffer i % NB was copied up when step i - NB started, and that step has been consumed)
-                    runs[i % NB, :, 0] += (NB * S) << 32          # the host's next quantum of request numbers: tokens never repeat
+                if k >= NB:   # (buffer k % NB was copied up when step k - NB started, and that step has been consumed)
+                    runs_np[k % NB, :, 0] += (NB * S) << 32       # the host's next quantum of request numbers: tokens never repeat
                 st = lib.jr_run_token_runs(h, C.c_uint64(now[0]), C.c_uint32(DT_MS), C.c_uint32(S),
-                                           C.cast(runs.data_ptr() + (i % NB) * rstride, C.POINTER(abi.TokenRun)))   # 16 B per group H2D
+                                           C.cast(runs.data_ptr() + (k % NB) * rstride, C.POINTER(abi.TokenRun)))   # 16 B per group H2D
             assert st == 0, st
             now[0] += DT_MS * S
             assert lib.jr_truncate(h, C.c_uint32(TRUNC_MARGIN)) == 0
@@ -557,6 +561,8 @@ class Bench:
                     trace["table_wait"] += t1 - t0
                     trace["records_wait"] += t2 - t1
                     trace["fold"] += time.perf_counter() - t2
+
+        seq = [0]      # steps submitted so far (token bases advance with it, across warm-up and timed loops)
 
         def e2e_steps(n):
             ts = time.perf_counter()
@@ -589,6 +595,7 @@ class Bench:
             got = int(totals[0] + totals[1])
             assert abs(got - expect) <= expect * 0.02 + 4 * G * R, (got, expect)
         out = {"value": self.world * G * S * steps / dt, "unit": UNIT, "h2d_bytes_per_step": S * G * 8 if dense_input else G * 16,
+               "folded_groups_last_step": eng.fold_count(),
                "input": "dense: one u64 token per group-tick (jr_run_tokens)" if dense_input else
                         "run-length: one {base, stride} per group and step (jr_run_token_runs); the same tokens",
                "d2h_bytes_per_step": G * 16 + (rec_bytes[0] // steps if with_output else 0), "ms_per_step": dt * 1e3 / steps,

@@ -278,51 +278,52 @@ __device__ __noinline__ void fsm_flush(const uint4* raw0, uint32_t n_raw, uint32
   FsmRun ra{0, 0, 0, 0}, rn{0, 0, 0, 0};
   const uint32_t n = n_raw < Fr ? n_raw : Fr;
   constexpr uint32_t AHEAD = 8;   // entries are independent loads (L2 / DRAM): fetch a batch, then encode it
-  uint4 buf[AHEAD];
-  for (uint32_t u = 0; u < n; ++u) {
-    if ((u % AHEAD) == 0) {
+  for (uint32_t u0 = 0; u0 < n; u0 += AHEAD) {
+    uint4 buf[AHEAD];
 #pragma unroll
-      for (uint32_t j = 0; j < AHEAD; ++j)
-        if (u + j < n) buf[j] = __ldcg(raw0 + (size_t)(u + j) * o.plane);
-    }
-    uint4 e = buf[0];
+    for (uint32_t j = 0; j < AHEAD; ++j)
+      if (u0 + j < n) buf[j] = __ldcg(raw0 + (size_t)(u0 + j) * o.plane);
 #pragma unroll
-    for (uint32_t j = 1; j < AHEAD; ++j)
-      if ((u % AHEAD) == j) e = buf[j];
-    const bool notify = (e.x & FS_NOTIFY_BIT) != 0;
-    const uint32_t bid = e.x & ~FS_NOTIFY_BIT, nxa = e.y;
-    const uint64_t tok = (uint64_t)e.z | ((uint64_t)e.w << 32);
-    if (notify) {
-      const uint32_t b = seq - wseq;
-      if (b < 64u) pb0 |= 1ull << b;
-      else if (b < 128u) pb1 |= 1ull << (b - 64u);
-      else pb2 |= 1u << (b - 128u);
-    }
-    ++seq;
-    if (seq - wseq == FS_PATTERN_BITS) {   // the pattern window is complete
-      if (pb0 | pb1 | pb2) nrec = fsm_put_record(nrec, o, FSR_PATTERN, FS_PATTERN_BITS, wseq, pb2, pb0, pb1);
-      pb0 = pb1 = 0; pb2 = 0;
-      wseq = seq;
-    }
-    FsmRun& run = notify ? rn : ra;
-    bool extended = false;
-    if (run.count) {
-      const uint64_t step = tok - run.last;
-      bool ok = bid == run.next_id && run.count < FS_MAX_RUN;
-      if (notify) ok = ok && nxa == FSR_CLIENT && (run.count > 1u || (uint32_t)run.stride == FSR_CLIENT);
-      else ok = ok && nxa == bid - 1u && (run.count > 1u || (uint32_t)run.stride == bid - 2u);   // count 1: its own `next` must be regular too
-      if (ok && run.count > 1u) ok = step == run.stride;
-      if (ok) {
-        if (run.count == 1u) run.stride = step;
-        run.next_id = bid + 1u;
-        run.count += 1u;
-        run.last = tok;
-        extended = true;
-      } else {
-        nrec = fsm_close_run(nrec, o, notify, run);
+    for (uint32_t j = 0; j < AHEAD; ++j) {
+      if (u0 + j >= n) break;
+      const uint4 e = buf[j];
+      const bool notify = (e.x & FS_NOTIFY_BIT) != 0;
+      const uint32_t bid = e.x & ~FS_NOTIFY_BIT, nxa = e.y;
+      const uint64_t tok = (uint64_t)e.z | ((uint64_t)e.w << 32);
+      if (notify) {
+        const uint32_t b = seq - wseq;
+        if (b < 64u) pb0 |= 1ull << b;
+        else if (b < 128u) pb1 |= 1ull << (b - 64u);
+        else pb2 |= 1u << (b - 128u);
       }
+      ++seq;
+      if (seq - wseq == FS_PATTERN_BITS) {   // the pattern window is complete
+        if (pb0 | pb1 | pb2) nrec = fsm_put_record(nrec, o, FSR_PATTERN, FS_PATTERN_BITS, wseq, pb2, pb0, pb1);
+        pb0 = pb1 = 0; pb2 = 0;
+        wseq = seq;
+      }
+      FsmRun run = notify ? rn : ra;   // (a copy, written back below: a reference picked at run time would force both runs into local memory)
+      bool extended = false;
+      if (run.count) {
+        const uint64_t step = tok - run.last;
+        bool ok = bid == run.next_id && run.count < FS_MAX_RUN;
+        if (notify) ok = ok && nxa == FSR_CLIENT && (run.count > 1u || (uint32_t)run.stride == FSR_CLIENT);
+        else ok = ok && nxa == bid - 1u && (run.count > 1u || (uint32_t)run.stride == bid - 2u);   // count 1: its own `next` must be regular too
+        if (ok && run.count > 1u) ok = step == run.stride;
+        if (ok) {
+          if (run.count == 1u) run.stride = step;
+          run.next_id = bid + 1u;
+          run.count += 1u;
+          run.last = tok;
+          extended = true;
+        } else {
+          nrec = fsm_close_run(nrec, o, notify, run);
+        }
+      }
+      if (!extended) run = FsmRun{bid + 1u, 1u, tok, (uint64_t)nxa};   // count 1: Apply keeps the block's `next`, Notify the client address
+      if (notify) rn = run;
+      else ra = run;
     }
-    if (!extended) run = FsmRun{bid + 1u, 1u, tok, (uint64_t)nxa};   // count 1: Apply keeps the block's `next`, Notify the client address
   }
   nrec = fsm_close_run(nrec, o, false, ra);
   nrec = fsm_close_run(nrec, o, true, rn);

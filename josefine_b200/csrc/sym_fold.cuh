@@ -40,48 +40,13 @@ struct SymMail {
   uint32_t ar, ar_head;
 };
 
-// The top SYM_ROWS block-table rows of one replica -- ids top, top-1, ... -- as a SHIFT REGISTER: every access uses
-// compile-time indices (unrolled selects), so the rows live in registers, not in local memory.  Everything a steady
-// group reads was written a few ticks ago, so after the fill at entry no table READ leaves the SM (rows are still
-// written through to HBM).  UNKNOWN = not loaded yet; ABSENT = known to be absent.
-constexpr uint32_t SYM_ROWS = 6;
-constexpr uint32_t SYM_UNKNOWN = 0xFFFFFFFEu;
-struct SymRows {
-  uint32_t top;                 // id of entry 0
-  uint32_t next[SYM_ROWS];
-  uint64_t tok[SYM_ROWS];
-  __device__ __forceinline__ void clear(uint32_t t) {
-    top = t;
-#pragma unroll
-    for (uint32_t k = 0; k < SYM_ROWS; ++k) { next[k] = SYM_UNKNOWN; tok[k] = 0; }
-  }
-  __device__ __forceinline__ bool get(uint32_t bid, uint32_t& nx, uint64_t& tk) const {
-    const uint32_t j = top - bid;   // wraps to a huge value for bid > top
-    bool hit = false;
-#pragma unroll
-    for (uint32_t k = 0; k < SYM_ROWS; ++k)
-      if (j == k && next[k] != SYM_UNKNOWN) { nx = next[k]; tk = tok[k]; hit = true; }
-    return hit;
-  }
-  __device__ __forceinline__ void set(uint32_t bid, uint32_t nx, uint64_t tk) {   // bid <= top: overwrite in place (or too old: ignore)
-    const uint32_t j = top - bid;
-#pragma unroll
-    for (uint32_t k = 0; k < SYM_ROWS; ++k)
-      if (j == k) { next[k] = nx; tok[k] = tk; }
-  }
-  __device__ __forceinline__ void push(uint32_t bid, uint32_t nx, uint64_t tk) {  // any bid: ids between the old top and bid are absent
-    if (bid <= top) { set(bid, nx, tk); return; }
-    uint32_t gap = bid - top;
-    if (gap > SYM_ROWS) gap = SYM_ROWS;
-    for (uint32_t step = 0; step < gap; ++step) {
-#pragma unroll
-      for (uint32_t k = SYM_ROWS - 1; k > 0; --k) { next[k] = next[k - 1]; tok[k] = tok[k - 1]; }
-      next[0] = ABSENT; tok[0] = 0;
-    }
-    top = bid;
-    next[0] = nx; tok[0] = tk;
-  }
-};
+// Block-table rows the fold has touched recently, per lane, in SHARED memory: two direct-mapped caches (the leader's
+// table, the followers' identical tables) of SYM_ROWS entries {id, next, token}, laid out [cache][slot][lane] so that a
+// lane's access is one conflict-free 128-bit LDS/STS.  Everything a steady group reads was written a few ticks ago, so
+// after the fill at entry no table READ leaves the SM (rows are still written through to HBM).  (A register shift
+// register cost ~400 instructions per tick in compare/select chains; local-memory arrays were slower still.)
+constexpr uint32_t SYM_ROWS = 8;
+constexpr uint32_t SYM_LANES = 128;   // threads per CTA of sym_kernel
 
 template <int R>
 struct SymGroup {
@@ -96,7 +61,7 @@ struct SymGroup {
   uint32_t n_hb;                           // heartbeats the followers took in this launch
   uint64_t last_hb;
   uint32_t tbase;
-  SymRows lrows, frows;                    // row caches: the leader's table, the followers' (identical) tables
+  uint4* rows;                             // this lane's column of the CTA's row caches (see above)
   uint32_t lcnt, fcnt;                     // raw Instructions emitted: leader / each follower
   bool abort;
   bool share;                              // the followers' Instruction FIFOs are all empty: their records can be shared
@@ -104,29 +69,36 @@ struct SymGroup {
   __device__ __forceinline__ SymGroup(const Dev& dv, uint32_t g_) : d(dv), g(g_), plane((size_t)R * dv.Gp) {}
   __device__ __forceinline__ size_t rg(uint32_t r) const { return (size_t)r * d.Gp + g; }
   __device__ __forceinline__ size_t row(uint32_t r, uint32_t bid) const { return (size_t)(bid & d.capm) * plane + rg(r); }
-  __device__ __forceinline__ bool in_window(uint32_t bid) const { return bid - tbase < d.cap && bid < FS_NOTIFY_BIT; }
+  __device__ __forceinline__ bool in_window(uint32_t bid) const { return bid - tbase < d.cap; }   // (sym_enter made sure ids stay below 2^31)
+  __device__ __forceinline__ uint4& slot(uint32_t r, uint32_t bid) const { return rows[((r == L ? 0u : SYM_ROWS) + (bid % SYM_ROWS)) * SYM_LANES]; }
+  __device__ __forceinline__ void cache_put(uint32_t r, uint32_t bid, uint32_t nx, uint64_t tk) const {
+    slot(r, bid) = make_uint4(bid, nx, (uint32_t)tk, (uint32_t)(tk >> 32));
+  }
   // r is the leader (its own table) or F0 (the followers' table)
   __device__ __forceinline__ void fetch(uint32_t r, uint32_t bid, uint32_t& next, uint64_t& tok) {
     if (!in_window(bid)) { next = ABSENT; tok = 0; return; }
-    if (r == L ? lrows.get(bid, next, tok) : frows.get(bid, next, tok)) return;
+    const uint4 e = slot(r, bid);
+    if (e.x == bid) { next = e.y; tok = (uint64_t)e.z | ((uint64_t)e.w << 32); return; }
     next = __ldcg(d.cnext + row(r, bid));   // rows written earlier in this launch by this lane: read them at L2
     tok = __ldcg(d.ctok + row(r, bid));
-    if (r == L) lrows.set(bid, next, tok);
-    else frows.set(bid, next, tok);
+    cache_put(r, bid, next, tok);
   }
-  // (the cache object is named at the call site: selecting one of the two by a runtime condition would force both
-  //  into local memory)
-  __device__ __forceinline__ void cache_fill(SymRows& c, uint32_t r, uint32_t top) {   // independent loads, issued together
-    c.clear(top);
+  __device__ __forceinline__ void cache_clear() const {
 #pragma unroll
-    for (uint32_t j = 0; j < SYM_ROWS; ++j) {
+    for (uint32_t k = 0; k < 2 * SYM_ROWS; ++k) rows[k * SYM_LANES] = make_uint4(ABSENT, ABSENT, 0u, 0u);   // tag ABSENT matches no id
+  }
+  __device__ __forceinline__ void cache_fill(uint32_t r, uint32_t top) const {   // independent loads, issued together
+    uint32_t nx[SYM_ROWS];
+    uint64_t tk[SYM_ROWS];
+#pragma unroll
+    for (uint32_t j = 0; j < SYM_ROWS; ++j)
       if (j <= top && in_window(top - j)) {
-        c.next[j] = d.cnext[row(r, top - j)];
-        c.tok[j] = d.ctok[row(r, top - j)];
-      } else {
-        c.next[j] = ABSENT;           // below id 0 / outside the window: nothing there
+        nx[j] = d.cnext[row(r, top - j)];
+        tk[j] = d.ctok[row(r, top - j)];
       }
-    }
+#pragma unroll
+    for (uint32_t j = 0; j < SYM_ROWS; ++j)
+      if (j <= top && in_window(top - j)) cache_put(r, top - j, nx[j], tk[j]);
   }
   __device__ __forceinline__ bool has(uint32_t r, uint32_t bid) {
     uint32_t n; uint64_t t;
@@ -199,7 +171,7 @@ struct SymGroup {
     if (!(bid > head) || !in_window(bid)) { abort = true; return; }   // chain.rs:163 / engine window: a fault -> step_kernel's business
     d.cnext[row(L, bid)] = head;
     d.ctok[row(L, bid)] = tok;
-    lrows.push(bid, head, tok);
+    cache_put(L, bid, head, tok);
     if (bid > maxkey) maxkey = bid;
     head = bid;
     emit_leader(true, bid, FSR_CLIENT, tok);
@@ -284,7 +256,7 @@ struct SymGroup {
             d.cnext[row(r, bid)] = nx;
             d.ctok[row(r, bid)] = tk;
           }
-        frows.push(bid, nx, tk);
+        cache_put(F0, bid, nx, tk);
         if (bid > fmaxkey) fmaxkey = bid;
         fhead = bid;                                       // chain.rs:188-190: unconditionally
       }
@@ -566,7 +538,7 @@ __device__ __forceinline__ void sym_leave(SymGroup<R>& s, const SymMail& last, i
 
 // One lane per group.  symdone[g] = 1: the whole launch of group g has been applied here; 0: step_kernel runs it.
 template <int R>
-__global__ void __launch_bounds__(128, 4) sym_kernel(const Dev d, const StepParams p, uint8_t* symdone) {
+__global__ void __launch_bounds__(SYM_LANES, 4) sym_kernel(const Dev d, const StepParams p, uint8_t* symdone) {
   const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= d.Gp) return;
   SymGroup<R> s(d, g);
@@ -576,12 +548,13 @@ __global__ void __launch_bounds__(128, 4) sym_kernel(const Dev d, const StepPara
   s.n_hb = 0;
   s.last_hb = 0;
   s.share = false;
-  s.lrows.clear(0);
-  s.frows.clear(0);
+  __shared__ uint4 row_cache[2 * SYM_ROWS * SYM_LANES];
+  s.rows = row_cache + threadIdx.x;
+  s.cache_clear();
   bool ok = sym_enter<R>(s, a, p, 1 - p.cur);
   if (ok) {
-    s.cache_fill(s.lrows, s.L, s.maxkey);
-    s.cache_fill(s.frows, s.F0, s.fmaxkey);
+    s.cache_fill(s.L, s.maxkey);
+    s.cache_fill(s.F0, s.fmaxkey);
     s.share = (d.flags & JR_F_CAPTURE_FSM) != 0;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
