@@ -820,23 +820,28 @@ def main():
     ref_bytes, lay_bytes = algorithmic_bytes_per_group_tick(bn.make, R)
     peak, peak_src = measured_peak()
     avg_launch_s = (ms * 1e-3) / args.steps            # one step = S fused ticks of all G groups
-    traffic = None
-    prof = os.path.join(ROOT, "profiles", "step_kernel_latest.json")
-    if os.path.exists(prof):   # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this
-        pj = json.load(open(prof))           # command, per launch (one launch = TICKS_PER_STEP ticks)
-        if pj.get("ticks_per_launch") == S and pj.get("groups") == G:
-            traffic = pj["dram_bytes_per_launch"]
+    traffic, kernel_s = None, None
+    kernel_name = f"step_kernel<{R}>"
+    for name in ("dominant_kernel_latest.json", "step_kernel_latest.json"):
+        prof = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(prof):   # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this
+            pj = json.load(open(prof))       # command, per launch (one launch = TICKS_PER_STEP ticks)
+            if pj.get("ticks_per_launch") == S and pj.get("groups") == G:
+                traffic = pj["dram_bytes_per_launch"]
+                kernel_name = pj["kernel"].split("(")[0].replace("void ", "")
+                kernel_s = pj["duration_s"]
+                break
     ach_ref = ref_bytes * G * S / avg_launch_s / 1e9
     ach_lay = lay_bytes * G * S / avg_launch_s / 1e9
     roofline = {"bound": "hbm", "achieved": ach_ref, "peak": peak, "unit": "GB/s", "frac": ach_ref / peak,
                 "frac_reference_widths": ach_ref / peak, "frac_layout": ach_lay / peak,
-                "frac_dram": (traffic / avg_launch_s / 1e9 / peak) if traffic else None,
-                "traffic": traffic, "kernel": f"step_kernel<{R}>", "algorithmic_bytes_per_group_tick": ref_bytes,
+                "frac_dram": (traffic / kernel_s / 1e9 / peak) if traffic else None,
+                "traffic": traffic, "kernel": kernel_name, "algorithmic_bytes_per_group_tick": ref_bytes,
                 "layout_bytes_per_group_tick": lay_bytes, "avg_launch_us": avg_launch_s * 1e6, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ref_bytes * G * S,
                 "note": f"`frac` counts the bytes a group-tick moves in the REFERENCE's widths (SURVEY 8d formula applied to this workload's "
                         f"measured message mix, heartbeat every second tick); frac_layout uses this engine's wider units and is not the claim; "
-                        f"frac_dram is real DRAM traffic from profiles/step_kernel_latest.json.  One launch = {S} fused ticks of {G} groups with "
+                        f"frac_dram is the real DRAM traffic of the dominant kernel (profiles/dominant_kernel_latest.json) over its own duration.  One launch = {S} fused ticks of {G} groups with "
                         f"state in registers and mailboxes in shared memory, so most algorithmic bytes never reach DRAM: the kernel is latency "
                         f"bound, not bandwidth bound (DESIGN.md section 6)."}
     cpu = None

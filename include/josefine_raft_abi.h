@@ -446,8 +446,9 @@ jr_status jr_fsm_expand(const jr_fsm_record* records, size_t n_records, uint32_t
  */
 jr_status jr_fsm_fold(const jr_fsm_record* records, size_t n_records, uint32_t n_groups, uint32_t n_replicas,
                       uint32_t* applied_hi, uint64_t* totals);
-/* The same on n_threads host threads (contiguous slices of the batch; a batch is sorted by (node, group), so two
- * slices touch the same watermark only at their seam, which is resolved with a max).  n_threads <= 1: jr_fsm_fold. */
+/* The same on n_threads host threads, for a batch as jr_fsm_records_wait returns it (sorted by (node, group)): thread t
+ * folds the groups [G*t/T, G*(t+1)/T) of every node section, so no two threads touch the same watermark.  An unsorted
+ * batch, or n_threads <= 1, is folded on the calling thread. */
 jr_status jr_fsm_fold_mt(const jr_fsm_record* records, size_t n_records, uint32_t n_groups, uint32_t n_replicas,
                          uint32_t* applied_hi, uint64_t* totals, uint32_t n_threads);
 

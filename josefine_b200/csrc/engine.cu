@@ -1618,38 +1618,55 @@ jr_status jr_fsm_fold(const jr_fsm_record* recs, size_t n, uint32_t G, uint32_t 
 }
 
 // jr_fsm_fold_mt: a small persistent pool (created on first use and deliberately never destroyed: its workers sleep on
-// a condition variable for the life of the process) folds contiguous slices of the batch.  Masked records update several
-// watermarks and slices meet at seams, so the shared update is an atomic max (relaxed; values only grow).
+// a condition variable for the life of the process).  A batch is sorted by (node, group); thread t folds the records of
+// groups [G*t/T, G*(t+1)/T) of EVERY node section (found by binary search), so no two threads ever touch the same
+// watermark -- masked records included, because all nodes of a group belong to the same thread -- and no atomics are
+// needed.  A batch that is not sorted that way is folded on the calling thread.
 namespace {
 struct FoldJob {
   const jr_fsm_record* recs = nullptr;
   size_t n = 0;
   uint32_t G = 0, R = 0, parts = 0;
   uint32_t* applied = nullptr;
+  size_t sec[JR_MAX_REPLICAS + 1];   // record index where node k+1's section starts
   uint64_t na[64], nn[64];
   int bad[64];
 };
+inline uint64_t rec_key(const jr_fsm_record& rc) { return ((uint64_t)JR_FSMR_NODE(rc.hdr) << 32) | rc.group; }
+size_t lower_bound_key(const jr_fsm_record* recs, size_t lo, size_t hi, uint64_t key) {
+  while (lo < hi) {
+    const size_t mid = lo + (hi - lo) / 2;
+    if (rec_key(recs[mid]) < key) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
 void fold_slice(FoldJob& j, uint32_t t) {
-  const size_t lo = j.n * t / j.parts, hi = j.n * (t + 1) / j.parts;
+  const uint32_t g_lo = (uint32_t)((uint64_t)j.G * t / j.parts), g_hi = (uint32_t)((uint64_t)j.G * (t + 1) / j.parts);
   uint64_t na = 0, nn = 0;
-  auto bump = [&](size_t idx, uint32_t v) {
-    uint32_t cur = __atomic_load_n(j.applied + idx, __ATOMIC_RELAXED);
-    while (cur < v && !__atomic_compare_exchange_n(j.applied + idx, &cur, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
-  };
-  for (size_t i = lo; i < hi; ++i) {
-    const jr_fsm_record& rc = j.recs[i];
-    const uint32_t kind = JR_FSMR_KIND(rc.hdr), node = JR_FSMR_NODE(rc.hdr), count = JR_FSMR_COUNT(rc.hdr);
-    if (rc.group >= j.G || node > j.R || (kind == JR_FSMR_APPLY && (rc.addr >> j.R))) { j.bad[t] = 1; return; }
-    if (kind == JR_FSMR_APPLY) {
-      if (rc.addr) {
-        for (uint32_t k = 0; k < j.R; ++k)
-          if ((rc.addr >> k) & 1u) { bump((size_t)k * j.G + rc.group, rc.id0 + count - 1); na += count; }
-      } else {
-        bump((size_t)(node - 1) * j.G + rc.group, rc.id0 + count - 1);
-        na += count;
+  for (uint32_t node = 1; node <= j.R; ++node) {
+    const size_t lo = lower_bound_key(j.recs, j.sec[node - 1], j.sec[node], ((uint64_t)node << 32) | g_lo);
+    const size_t hi = lower_bound_key(j.recs, lo, j.sec[node], ((uint64_t)node << 32) | g_hi);
+    for (size_t i = lo; i < hi; ++i) {
+      const jr_fsm_record& rc = j.recs[i];
+      const uint32_t kind = JR_FSMR_KIND(rc.hdr), count = JR_FSMR_COUNT(rc.hdr);
+      if (kind == JR_FSMR_APPLY) {
+        if (rc.addr) {
+          if (rc.addr >> j.R) { j.bad[t] = 1; return; }
+          for (uint32_t k = 0; k < j.R; ++k)
+            if ((rc.addr >> k) & 1u) {
+              uint32_t& hi_w = j.applied[(size_t)k * j.G + rc.group];
+              hi_w = std::max(hi_w, rc.id0 + count - 1);
+              na += count;
+            }
+        } else {
+          uint32_t& hi_w = j.applied[(size_t)(node - 1) * j.G + rc.group];
+          hi_w = std::max(hi_w, rc.id0 + count - 1);
+          na += count;
+        }
+      } else if (kind == JR_FSMR_NOTIFY) {
+        nn += count;
       }
-    } else if (kind == JR_FSMR_NOTIFY) {
-      nn += count;
     }
   }
   j.na[t] = na;
@@ -1703,11 +1720,20 @@ jr_status jr_fsm_fold_mt(const jr_fsm_record* recs, size_t n, uint32_t G, uint32
                          uint32_t n_threads) {
   if (n_threads <= 1 || n < 4096) return jr_fsm_fold(recs, n, G, R, applied_hi, totals);
   if ((!recs && n) || !applied_hi || !totals || R < 1 || R > JR_MAX_REPLICAS) return JR_E_INVAL;
-  static std::mutex* one_at_a_time = new std::mutex();
-  std::lock_guard<std::mutex> guard(*one_at_a_time);
   FoldJob j;
   j.recs = recs; j.n = n; j.G = G; j.R = R; j.applied = applied_hi;
   j.parts = std::min<uint32_t>(n_threads, 64);
+  // node sections; then a cheap sortedness probe (a full check would cost as much as the fold)
+  j.sec[0] = 0;
+  for (uint32_t node = 1; node <= R; ++node) j.sec[node] = lower_bound_key(recs, j.sec[node - 1], n, (uint64_t)(node + 1) << 32);
+  bool sorted = j.sec[R] == n && recs[n - 1].group < G;
+  for (size_t probe = 1; sorted && probe < 64; ++probe) {
+    const size_t i = n * probe / 64;
+    sorted = i == 0 || rec_key(recs[i - 1]) <= rec_key(recs[i]);
+  }
+  if (!sorted) return jr_fsm_fold(recs, n, G, R, applied_hi, totals);
+  static std::mutex* one_at_a_time = new std::mutex();
+  std::lock_guard<std::mutex> guard(*one_at_a_time);
   for (uint32_t t = 0; t < j.parts; ++t) { j.na[t] = j.nn[t] = 0; j.bad[t] = 0; }
   FoldPool::get().run(j);
   for (uint32_t t = 0; t < j.parts; ++t) {

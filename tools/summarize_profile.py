@@ -3,7 +3,7 @@
 profiles/: a JSON with the numbers bench.py and DESIGN.md quote, and a text report with
 the per-function instruction attribution (tools/ncu_lines.py).
 
-usage: summarize_profile.py <report.ncu-rep> <round-tag> [groups] [ticks_per_launch]
+usage: summarize_profile.py <report.ncu-rep> <round-tag> [groups] [ticks_per_launch] [kernel-substring (default step_kernel)]
 """
 import contextlib
 import csv
@@ -37,11 +37,12 @@ def main():
     rep, tag = sys.argv[1], sys.argv[2]
     groups = int(sys.argv[3]) if len(sys.argv) > 3 else 65536
     ticks = int(sys.argv[4]) if len(sys.argv) > 4 else 64
+    ksub = sys.argv[5] if len(sys.argv) > 5 else "step_kernel"
     txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hdr, units, body = rows[0], rows[1], rows[2:]
     kcol = hdr.index("Kernel Name")
-    row = [r for r in body if "step_kernel" in r[kcol]][0]
+    row = [r for r in body if ksub in r[kcol]][0]
     m = {}
     for w in WANT:
         if w in hdr:
@@ -50,8 +51,8 @@ def main():
             m[w] = v * SCALE.get(units[i], 1.0) if units[i] in SCALE else v
     out = {
         "round": tag, "kernel": row[kcol], "groups": groups, "replicas": 5, "ticks_per_launch": ticks,
-        "command": "ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 6 -c 1 "
-                   "python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu",
+        "command": f"ncu --set full --clock-control none --import-source on -k regex:{ksub} -s <warm-up launches> -c 1 "
+                   "python bench.py --no-e2e --no-cpu --no-others --no-parity --steps 4 --warmup 3",
         "note": "under ncu the kernel runs with cold caches and serialised replays; use shares, not absolutes",
         "duration_s": m.get("gpu__time_duration.sum"),
         "dram_bytes_read": m.get("dram__bytes_read.sum"), "dram_bytes_write": m.get("dram__bytes_write.sum"),
@@ -59,17 +60,19 @@ def main():
         "metrics": m,
     }
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
-    with open(os.path.join(ROOT, "profiles", f"{tag}_step_kernel.json"), "w") as f:
+    with open(os.path.join(ROOT, "profiles", f"{tag}_{ksub}.json"), "w") as f:
         json.dump(out, f, indent=1)
-    with open(os.path.join(ROOT, "profiles", "step_kernel_latest.json"), "w") as f:
+    latest = "step_kernel_latest.json" if ksub == "step_kernel" else "dominant_kernel_latest.json"
+    with open(os.path.join(ROOT, "profiles", latest), "w") as f:     # bench.py's roofline.traffic reads dominant_kernel_latest.json first
         json.dump(out, f, indent=1)
     buf = io.StringIO()
     with contextlib.redirect_stdout(buf):
-        print(f"# {tag}: per-function warp-instructions of step_kernel<5>, per CTA-tick "
-              f"(2048 CTAs x {ticks} ticks; 5 warps per CTA)")
-        ncu_lines.by_function(rep, os.path.join(ROOT, "josefine_b200/csrc/libjosefine_b200.so"), "step_kernelILi5E",
-                              os.path.join(ROOT, "josefine_b200/csrc/raft_device.cuh"), 0, (groups // 32) * ticks)
-    with open(os.path.join(ROOT, "profiles", f"{tag}_step_kernel_functions.txt"), "w") as f:
+        print(f"# {tag}: per-function warp-instructions of {ksub}<5>, per 32 groups and tick "
+              f"({groups // 32} x {ticks} ticks)")
+        ncu_lines.by_function(rep, os.path.join(ROOT, "josefine_b200/csrc/libjosefine_b200.so"), ksub + "ILi5E",
+                              os.path.join(ROOT, "josefine_b200/csrc/sym_fold.cuh" if ksub == "sym_kernel" else "josefine_b200/csrc/raft_device.cuh"),
+                              0, (groups // 32) * ticks)
+    with open(os.path.join(ROOT, "profiles", f"{tag}_{ksub}_functions.txt"), "w") as f:
         f.write(buf.getvalue())
     print(json.dumps({k: out[k] for k in ("duration_s", "dram_bytes_read", "dram_bytes_write")}))
 
