@@ -68,7 +68,7 @@ L2_FLUSH_BYTES = 256 << 20
 CHAIN_WINDOW = 512          # block ids a replica's table may span above the floor (truncated every step)
 TRUNC_MARGIN = 8
 FSM_UNITS = 16              # record slots per replica between two drains (steady state uses <= 4)
-FOLD_THREADS = int(os.environ.get("JR_FOLD_THREADS", "1"))   # host threads folding a batch of Instruction records (jr_fsm_fold_mt); more than one only pays on hosts with idle cores
+FOLD_THREADS = int(os.environ.get("JR_FOLD_THREADS", "4"))   # host threads folding a batch of Instruction records (jr_fsm_fold_mt, groups partitioned over threads)
 
 
 def workload_name(G, R):
@@ -609,7 +609,8 @@ class Bench:
                         "api": "per step: " + ("jr_run_tokens(pinned u64 tokens[64][G]" if dense_input else "jr_run_token_runs(pinned jr_token_run[G]") +
                                ", routed to the last announced leader) + jr_truncate + "
                                "jr_leader_table_async(pinned jr_leader_entry[G]) + jr_fsm_records_async; then jr_leader_table_wait + "
-                               "jr_fsm_records_wait + jr_fsm_fold over the batch (apply watermark per replica); two steps in flight"})
+                               f"jr_fsm_records_wait + jr_fsm_fold_mt over the batch on {FOLD_THREADS} host threads (apply watermark per replica); two steps in flight",
+                        "host_fold_threads": FOLD_THREADS})
         else:
             out["api"] = ("per step: jr_run_tokens + jr_truncate + jr_leader_table_async + jr_leader_table_wait; engine created without "
                           "JR_F_CAPTURE_FSM (round 1's end-to-end leg)")
