@@ -79,6 +79,7 @@ extern "C" {
 
 /* ---- limits ------------------------------------------------------------ */
 #define JR_MAX_REPLICAS 8u        /* R <= 8 (reference configs use 3, 5, 7)         */
+#define JR_STAGING_DEPTH 3u       /* steps a host may keep in flight on the async paths */
 #define JR_MAX_AE_BLOCKS 5u       /* MAX_INFLIGHT, src/raft/progress.rs:117          */
 #define JR_MAX_NODE_ID 65534u     /* deviation D4                                    */
 #define JR_CLIENT_QUEUE_CAP 4u    /* queued_reqs bound per replica (reference: Vec)  */
@@ -422,11 +423,11 @@ jr_status jr_drain_fsm(jr_engine* e, jr_fsm_instr* out, size_t cap, size_t* n);
 /*
  * The batched output path.  jr_fsm_records_async ENQUEUES, after everything submitted so far: pack all records
  * accumulated since the last drain into one dense array sorted by (node, group) and write it to the engine's
- * next pinned host buffer (two buffers; the kernel writes host memory directly, no staging copy).  The FIFOs are
- * empty afterwards.  jr_fsm_records_wait blocks until the OLDEST outstanding batch has landed and returns it:
- * `*records` points into the engine's buffer and stays valid until the second jr_fsm_records_async call after
- * this one.  JR_E_CAPACITY (batch still returned) if records were dropped.  At most two batches may be
- * outstanding.  Requires JR_F_CAPTURE_FSM.
+ * next pinned host buffer (JR_STAGING_DEPTH = 3 buffers, filled by the copy engine: the SMs stay with the next
+ * step).  The FIFOs are empty afterwards.  jr_fsm_records_wait blocks until the OLDEST outstanding batch has landed
+ * and returns it: `*records` points into the engine's buffer and stays valid until the JR_STAGING_DEPTH-1'th
+ * jr_fsm_records_async call after this one.  JR_E_CAPACITY (batch still returned) if records were dropped.  At
+ * most JR_STAGING_DEPTH batches may be outstanding.  Requires JR_F_CAPTURE_FSM.
  */
 jr_status jr_fsm_records_async(jr_engine* e);
 jr_status jr_fsm_records_wait(jr_engine* e, const jr_fsm_record** records, jr_fsm_batch* batch);
@@ -509,8 +510,8 @@ jr_status jr_leader_table(jr_engine* e, jr_leader_entry* host_out);
  * pinned memory and is valid after the next jr_engine_sync().  Lets a caller pipeline
  * jr_step (proposals H2D) / kernels / results D2H tick after tick. */
 jr_status jr_leader_table_async(jr_engine* e, jr_leader_entry* host_out);
-/* Block until the OLDEST outstanding jr_leader_table_async copy has landed (FIFO; at most two are
- * in flight).  Lets the host consume tick/step k's result while k+1 is already running. */
+/* Block until the OLDEST outstanding jr_leader_table_async copy has landed (FIFO; at most JR_STAGING_DEPTH
+ * are in flight).  Lets the host consume tick/step k's result while k+1 is already running. */
 jr_status jr_leader_table_wait(jr_engine* e);
 
 /* ---- deviation D2, normative ------------------------------------------------

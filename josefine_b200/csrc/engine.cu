@@ -15,6 +15,10 @@
 #include <new>
 #include <thread>
 #include <vector>
+#ifdef __linux__
+#include <pthread.h>
+#include <sched.h>
+#endif
 
 #include "raft_device.cuh"
 #include "sym_fold.cuh"
@@ -717,7 +721,7 @@ struct jr_engine {
   // Copy/compute overlap for the host-buffer path: proposals are staged H2D on `h2d`,
   // leader tables leave D2H on `d2h`, both double buffered and fenced with events, so the
   // copy-in of tick k+1, the kernels of tick k and the copy-out of tick k-1 run concurrently.
-  static constexpr int NBUF = 2;
+  static constexpr int NBUF = JR_STAGING_DEPTH;   // staging depth: a host may keep three steps in flight (copy-out, host fold and the next submit overlap)
   jr_proposal* prop[NBUF] = {nullptr, nullptr};         // device, G entries each
   jr_leader_entry* leaders[NBUF] = {nullptr, nullptr};  // device, G entries each
   cudaStream_t h2d = nullptr, d2h = nullptr;
@@ -750,6 +754,9 @@ struct jr_engine {
   FsmHeader* fsm_host_hdr[NBUF] = {nullptr, nullptr};         // pinned + mapped host
   cudaEvent_t fsm_packed[NBUF] = {nullptr, nullptr};          // pack into stage[b] finished (engine stream)
   cudaEvent_t fsm_landed[NBUF] = {nullptr, nullptr};          // copy into host[b] finished (d2h stream)
+  size_t fsm_copied[NBUF] = {0, 0};                           // records of stage[b] the enqueued copy covers
+  size_t fsm_last_records = 0;                                // size of the last batch taken (the next copy's guess)
+  int fsm_copy_by_sm = 0;                                     // JR_FSM_COPY=sm (A/B): fsm_copy_kernel instead of the copy engine
   bool fsm_used[NBUF] = {false, false};
   int fsm_i = 0, fsm_pending[NBUF] = {0, 0}, fsm_npending = 0;
   uint32_t fsm_epoch = 0;
@@ -854,7 +861,7 @@ static jr_status launch_step(jr_engine* e, const StepParams& p_in) {
 template <int R>
 static void launch_sym_r(jr_engine* e, const StepParams& p) {
   if constexpr (R >= 2) {
-    JR_LAUNCH(sym_kernel<R>, (e->d.Gp + 127) / 128, 128, e->stream, e->d, p, e->symdone);
+    JR_LAUNCH(sym_kernel<R>, (e->d.Gp + SYM_LANES - 1) / SYM_LANES, SYM_LANES, e->stream, e->d, p, e->symdone);
   }
 }
 
@@ -1050,6 +1057,7 @@ jr_status jr_engine_create(const jr_config* cfg, jr_engine** out) {
     if (aerr == cudaSuccess) aerr = cudaHostAlloc((void**)&e->h_scatter, sizeof(uint32_t), 0);
     if (aerr == cudaSuccess) *e->h_scatter = 0;
     if (const char* ev = getenv("JR_NO_FOLD")) e->no_fold = atoi(ev);
+    if (const char* ev = getenv("JR_FSM_COPY")) e->fsm_copy_by_sm = strcmp(ev, "sm") == 0;
     if (const char* ev = getenv("JR_PARTS")) e->force_parts = (uint32_t)std::min(std::max(atoi(ev), 0), 8);
 #ifndef JR_EMU
     if (aerr == cudaSuccess) {
@@ -1234,7 +1242,7 @@ static jr_status capture_messages(jr_engine* e, int buf, std::vector<jr_msg>& ou
 static jr_status fsm_records_enqueue(jr_engine* e) {
   const Dev& d = e->d;
   if (!(d.flags & JR_F_CAPTURE_FSM)) { set_err("engine created without JR_F_CAPTURE_FSM"); return JR_E_INVAL; }
-  if (e->fsm_npending == jr_engine::NBUF) { set_err("two batches outstanding: call jr_fsm_records_wait first"); return JR_E_INVAL; }
+  if (e->fsm_npending == jr_engine::NBUF) { set_err("%d batches outstanding: call jr_fsm_records_wait first", jr_engine::NBUF); return JR_E_INVAL; }
   const int b = e->fsm_i;
   e->fsm_i = (b + 1) % jr_engine::NBUF;
   const size_t plane = (size_t)d.R * d.Gp;
@@ -1254,8 +1262,20 @@ static jr_status fsm_records_enqueue(jr_engine* e) {
   CK(cudaGetLastError());
   CK(cudaEventRecord(e->fsm_packed[b], e->stream));
   CK(cudaStreamWaitEvent(e->d2h, e->fsm_packed[b], 0));
-  JR_LAUNCH(fsm_copy_kernel, 32, 256, e->d2h, e->fsm_stage[b], e->fsm_stage_hdr[b], e->fsm_host[b], e->fsm_host_hdr[b], epoch);
-  CK(cudaGetLastError());
+  if (e->fsm_copy_by_sm) {
+    JR_LAUNCH(fsm_copy_kernel, 32, 256, e->d2h, e->fsm_stage[b], e->fsm_stage_hdr[b], e->fsm_host[b], e->fsm_host_hdr[b], epoch);
+    CK(cudaGetLastError());
+    e->fsm_copied[b] = e->fsm_cap;
+  } else {
+    // Copy engine, speculatively: the batch size is only known on the device, so copy as many records as the previous
+    // batch held plus a margin; fsm_records_take fetches the rest in the (rare) case the batch turned out larger.
+    // (fsm_copy_kernel's stores to host memory share LSUs with the next step's kernel: one wave of CTAs, so the
+    // slowest SM sets its duration.  A DMA copy takes nothing from the SMs.)
+    const size_t guess = std::min<size_t>(e->fsm_cap, std::max<size_t>(e->fsm_last_records + e->fsm_last_records / 8 + 1024, 16384));
+    if (guess) CK(cudaMemcpyAsync(e->fsm_host[b], e->fsm_stage[b], guess * sizeof(jr_fsm_record), cudaMemcpyDeviceToHost, e->d2h));
+    CK(cudaMemcpyAsync(e->fsm_host_hdr[b], e->fsm_stage_hdr[b], sizeof(FsmHeader), cudaMemcpyDeviceToHost, e->d2h));
+    e->fsm_copied[b] = guess;
+  }
   CK(cudaEventRecord(e->fsm_landed[b], e->d2h));
   e->fsm_used[b] = true;
   e->fsm_pending[e->fsm_npending++] = b;
@@ -1265,10 +1285,19 @@ static jr_status fsm_records_enqueue(jr_engine* e) {
 static jr_status fsm_records_take(jr_engine* e, const jr_fsm_record** recs, jr_fsm_batch* batch) {
   if (e->fsm_npending == 0) { set_err("no batch outstanding"); return JR_E_INVAL; }
   const int b = e->fsm_pending[0];
-  e->fsm_pending[0] = e->fsm_pending[1];
+  for (int k = 0; k + 1 < jr_engine::NBUF; ++k) e->fsm_pending[k] = e->fsm_pending[k + 1];
   --e->fsm_npending;
   CK(cudaEventSynchronize(e->fsm_landed[b]));
   const FsmHeader& h = *e->fsm_host_hdr[b];
+  if (h.n_records > e->fsm_copied[b]) {   // the speculative copy was short: fetch the tail now (stage[b] is still intact)
+    const size_t have = e->fsm_copied[b];
+    CK(cudaMemcpyAsync(reinterpret_cast<jr_fsm_record*>(e->fsm_host[b]) + have, reinterpret_cast<const jr_fsm_record*>(e->fsm_stage[b]) + have,
+                       ((size_t)h.n_records - have) * sizeof(jr_fsm_record), cudaMemcpyDeviceToHost, e->d2h));
+    CK(cudaEventRecord(e->fsm_landed[b], e->d2h));
+    CK(cudaEventSynchronize(e->fsm_landed[b]));
+    e->fsm_copied[b] = h.n_records;
+  }
+  e->fsm_last_records = h.n_records;
   if (recs) *recs = reinterpret_cast<const jr_fsm_record*>(e->fsm_host[b]);
   if (batch) {
     memset(batch, 0, sizeof *batch);
@@ -1679,7 +1708,26 @@ class FoldPool {
     std::unique_lock<std::mutex> l(m_);
     while (n_workers_ + 1 < j.parts) {   // worker k serves slice k + 1; the caller folds slice 0
       const uint32_t k = n_workers_++;
-      std::thread([this, k] { loop(k); }).detach();
+      std::thread th([this, k] { loop(k); });
+#ifdef __linux__
+      // JR_FOLD_PIN=1: worker k stays on one CPU of the caller's affinity mask (counted from its top), so the short
+      // bursts of a fold do not wander over every core of the mask (each wake-up on a new core costs a CFS quota slice).
+      if (const char* ev = getenv("JR_FOLD_PIN"); ev && atoi(ev)) {
+        cpu_set_t mask;
+        if (sched_getaffinity(0, sizeof mask, &mask) == 0) {
+          int want = (int)k, chosen = -1;
+          for (int c = CPU_SETSIZE - 1; c >= 0 && chosen < 0; --c)
+            if (CPU_ISSET(c, &mask) && want-- == 0) chosen = c;
+          if (chosen >= 0) {
+            cpu_set_t one;
+            CPU_ZERO(&one);
+            CPU_SET(chosen, &one);
+            pthread_setaffinity_np(th.native_handle(), sizeof one, &one);
+          }
+        }
+      }
+#endif
+      th.detach();
     }
     job_ = &j;
     left_ = j.parts - 1;
@@ -2157,8 +2205,8 @@ jr_status jr_leader_table_async(jr_engine* e, jr_leader_entry* host_out) {
   CK(cudaEventRecord(e->tab_free[b], e->d2h));
   e->tab_used[b] = true;
   if (e->tab_npending == jr_engine::NBUF) {  // the oldest one is about to be overwritten anyway
-    e->tab_pending[0] = e->tab_pending[1];
-    e->tab_npending = 1;
+    for (int k = 0; k + 1 < jr_engine::NBUF; ++k) e->tab_pending[k] = e->tab_pending[k + 1];
+    --e->tab_npending;
   }
   e->tab_pending[e->tab_npending++] = b;
   return JR_OK;
@@ -2168,7 +2216,7 @@ jr_status jr_leader_table_wait(jr_engine* e) {
   if (!e) return JR_E_INVAL;
   if (e->tab_npending == 0) return JR_OK;
   const int b = e->tab_pending[0];
-  e->tab_pending[0] = e->tab_pending[1];
+  for (int k = 0; k + 1 < jr_engine::NBUF; ++k) e->tab_pending[k] = e->tab_pending[k + 1];
   --e->tab_npending;
   CK(cudaEventSynchronize(e->tab_free[b]));
   return JR_OK;

@@ -266,16 +266,70 @@ __device__ __forceinline__ uint32_t fsm_close_run(uint32_t nrec, const FsmOut& o
                         (notify && c == 1) ? 0ull : run.stride);
 }
 
+// Streaming encoder of one replica's Instruction stream: fsm_flush feeds it the raw FIFO of a launch; the symmetric-group
+// fold (sym_fold.cuh) feeds it every Instruction as it is produced, with this state parked in shared memory in between.
+struct FsmEnc {
+  uint32_t nrec, seq;        // records / Instructions since the last drain
+  // pattern window: FS_PATTERN_BITS Instructions per PATTERN record (bits 0-63 in tok0, 64-127 in stride, 128-159 in addr);
+  // a window starts where the previous launch stopped (wseq) and is closed when full or when the launch ends
+  uint32_t wseq, pb2;
+  uint64_t pb0, pb1;
+  FsmRun ra, rn;             // the open APPLY / NOTIFY run
+};
+
+__device__ __forceinline__ void fsm_enc_begin(FsmEnc& s, uint2 c) {
+  s.nrec = c.x; s.seq = s.wseq = c.y;
+  s.pb0 = s.pb1 = 0; s.pb2 = 0;
+  s.ra = FsmRun{0, 0, 0, 0};
+  s.rn = FsmRun{0, 0, 0, 0};
+}
+
+template <bool NOTIFY>
+__device__ __forceinline__ void fsm_enc_push(FsmEnc& s, const FsmOut& o, uint32_t bid, uint32_t nxa, uint64_t tok) {
+  if (NOTIFY) {
+    const uint32_t b = s.seq - s.wseq;
+    if (b < 64u) s.pb0 |= 1ull << b;
+    else if (b < 128u) s.pb1 |= 1ull << (b - 64u);
+    else s.pb2 |= 1u << (b - 128u);
+  }
+  ++s.seq;
+  if (s.seq - s.wseq == FS_PATTERN_BITS) {   // the pattern window is complete
+    if (s.pb0 | s.pb1 | s.pb2) s.nrec = fsm_put_record(s.nrec, o, FSR_PATTERN, FS_PATTERN_BITS, s.wseq, s.pb2, s.pb0, s.pb1);
+    s.pb0 = s.pb1 = 0; s.pb2 = 0;
+    s.wseq = s.seq;
+  }
+  FsmRun& run = NOTIFY ? s.rn : s.ra;   // (picked at compile time: both runs stay in registers)
+  if (run.count) {
+    const uint64_t step = tok - run.last;
+    bool ok = bid == run.next_id && run.count < FS_MAX_RUN;
+    if (NOTIFY) ok = ok && nxa == FSR_CLIENT && (run.count > 1u || (uint32_t)run.stride == FSR_CLIENT);
+    else ok = ok && nxa == bid - 1u && (run.count > 1u || (uint32_t)run.stride == bid - 2u);   // count 1: its own `next` must be regular too
+    if (ok && run.count > 1u) ok = step == run.stride;
+    if (ok) {
+      if (run.count == 1u) run.stride = step;
+      run.next_id = bid + 1u;
+      run.count += 1u;
+      run.last = tok;
+      return;
+    }
+    s.nrec = fsm_close_run(s.nrec, o, NOTIFY, run);
+  }
+  run = FsmRun{bid + 1u, 1u, tok, (uint64_t)nxa};   // count 1: Apply keeps the block's `next`, Notify the client address
+}
+
+// Close the open runs and the pattern window; returns the replica's new {records, Instructions} counters.
+__device__ __forceinline__ uint2 fsm_enc_end(FsmEnc& s, const FsmOut& o) {
+  s.nrec = fsm_close_run(s.nrec, o, false, s.ra);
+  s.nrec = fsm_close_run(s.nrec, o, true, s.rn);
+  if (s.pb0 | s.pb1 | s.pb2) s.nrec = fsm_put_record(s.nrec, o, FSR_PATTERN, s.seq - s.wseq, s.wseq, s.pb2, s.pb0, s.pb1);
+  return make_uint2(s.nrec, s.seq);
+}
+
 // Encode the n_raw raw Instructions of this replica (raw0[u * plane], u < min(n_raw, Fr)) behind what d.fc says was
 // emitted before them.  Raw entries beyond Fr were never stored: they count as dropped records.
 __device__ __noinline__ void fsm_flush(const uint4* raw0, uint32_t n_raw, uint32_t Fr, FsmOut o, uint2* fc) {
-  const uint2 c = *fc;
-  uint32_t nrec = c.x, seq = c.y;
-  // pattern window: FS_PATTERN_BITS Instructions per PATTERN record (bits 0-63 in tok0, 64-127 in stride, 128-159 in addr);
-  // a window starts where the previous flush stopped (wseq) and is closed when full or when this flush ends
-  uint64_t pb0 = 0, pb1 = 0;
-  uint32_t pb2 = 0, wseq = seq;
-  FsmRun ra{0, 0, 0, 0}, rn{0, 0, 0, 0};
+  FsmEnc s;
+  fsm_enc_begin(s, *fc);
   const uint32_t n = n_raw < Fr ? n_raw : Fr;
   constexpr uint32_t AHEAD = 8;   // entries are independent loads (L2 / DRAM): fetch a batch, then encode it
   for (uint32_t u0 = 0; u0 < n; u0 += AHEAD) {
@@ -287,49 +341,15 @@ __device__ __noinline__ void fsm_flush(const uint4* raw0, uint32_t n_raw, uint32
     for (uint32_t j = 0; j < AHEAD; ++j) {
       if (u0 + j >= n) break;
       const uint4 e = buf[j];
-      const bool notify = (e.x & FS_NOTIFY_BIT) != 0;
-      const uint32_t bid = e.x & ~FS_NOTIFY_BIT, nxa = e.y;
+      const uint32_t bid = e.x & ~FS_NOTIFY_BIT;
       const uint64_t tok = (uint64_t)e.z | ((uint64_t)e.w << 32);
-      if (notify) {
-        const uint32_t b = seq - wseq;
-        if (b < 64u) pb0 |= 1ull << b;
-        else if (b < 128u) pb1 |= 1ull << (b - 64u);
-        else pb2 |= 1u << (b - 128u);
-      }
-      ++seq;
-      if (seq - wseq == FS_PATTERN_BITS) {   // the pattern window is complete
-        if (pb0 | pb1 | pb2) nrec = fsm_put_record(nrec, o, FSR_PATTERN, FS_PATTERN_BITS, wseq, pb2, pb0, pb1);
-        pb0 = pb1 = 0; pb2 = 0;
-        wseq = seq;
-      }
-      FsmRun run = notify ? rn : ra;   // (a copy, written back below: a reference picked at run time would force both runs into local memory)
-      bool extended = false;
-      if (run.count) {
-        const uint64_t step = tok - run.last;
-        bool ok = bid == run.next_id && run.count < FS_MAX_RUN;
-        if (notify) ok = ok && nxa == FSR_CLIENT && (run.count > 1u || (uint32_t)run.stride == FSR_CLIENT);
-        else ok = ok && nxa == bid - 1u && (run.count > 1u || (uint32_t)run.stride == bid - 2u);   // count 1: its own `next` must be regular too
-        if (ok && run.count > 1u) ok = step == run.stride;
-        if (ok) {
-          if (run.count == 1u) run.stride = step;
-          run.next_id = bid + 1u;
-          run.count += 1u;
-          run.last = tok;
-          extended = true;
-        } else {
-          nrec = fsm_close_run(nrec, o, notify, run);
-        }
-      }
-      if (!extended) run = FsmRun{bid + 1u, 1u, tok, (uint64_t)nxa};   // count 1: Apply keeps the block's `next`, Notify the client address
-      if (notify) rn = run;
-      else ra = run;
+      if (e.x & FS_NOTIFY_BIT) fsm_enc_push<true>(s, o, bid, e.y, tok);
+      else fsm_enc_push<false>(s, o, bid, e.y, tok);
     }
   }
-  nrec = fsm_close_run(nrec, o, false, ra);
-  nrec = fsm_close_run(nrec, o, true, rn);
-  if (pb0 | pb1 | pb2) nrec = fsm_put_record(nrec, o, FSR_PATTERN, seq - wseq, wseq, pb2, pb0, pb1);
-  if (n_raw > Fr) nrec = (nrec > o.F ? nrec : o.F) + (n_raw - Fr);   // lost Instructions: the drain must say so
-  *fc = make_uint2(nrec, seq);
+  uint2 c = fsm_enc_end(s, o);
+  if (n_raw > Fr) c.x = (c.x > o.F ? c.x : o.F) + (n_raw - Fr);   // lost Instructions: the drain must say so
+  *fc = c;
 }
 
 template <int R, bool SORTED = false>

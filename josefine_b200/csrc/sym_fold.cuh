@@ -46,7 +46,19 @@ struct SymMail {
 // after the fill at entry no table READ leaves the SM (rows are still written through to HBM).  (A register shift
 // register cost ~400 instructions per tick in compare/select chains; local-memory arrays were slower still.)
 constexpr uint32_t SYM_ROWS = 8;
-constexpr uint32_t SYM_LANES = 128;   // threads per CTA of sym_kernel
+#ifndef JR_SYM_LANES
+#define JR_SYM_LANES 128   // (A/B builds override it)
+#endif
+constexpr uint32_t SYM_LANES = JR_SYM_LANES;   // threads per CTA of sym_kernel: one warp per SM sub-partition
+// The Instruction streams are encoded AS THEY ARE PRODUCED, by the same streaming encoder fsm_flush uses (fsm_enc_push):
+// its state is parked in shared memory between two Instructions, [slot][lane] like the row caches.  (The raw FIFO +
+// fsm_flush round trip of step_kernel cost this kernel a quarter of its instructions and half of its DRAM traffic.)
+//   leader    e0 = {nrec, seq0, wseq, pb2}  e1 = {pb0, pb1}  e2 = {ra.next_id, ra.count, ra.last}
+//             e3 = {ra.stride, rn.stride}   e4 = {rn.next_id, rn.count, rn.last}
+//   followers f0 = {nrec, seq0, wseq, -}    f1 = {ra.next_id, ra.count, ra.last}   f2 = {ra.stride, -}   (no Notify: pb = 0)
+// seq = seq0 + the lane's Instruction counter (lcnt / fcnt), which lives in a register anyway.
+constexpr uint32_t SYM_ENC_L = 5, SYM_ENC_F = 3;
+constexpr uint32_t SYM_SMEM_UNITS = 2 * SYM_ROWS + SYM_ENC_L + SYM_ENC_F;   // uint4 per lane
 
 template <int R>
 struct SymGroup {
@@ -62,6 +74,7 @@ struct SymGroup {
   uint64_t last_hb;
   uint32_t tbase;
   uint4* rows;                             // this lane's column of the CTA's row caches (see above)
+  uint4* enc;                              // this lane's column of the encoder states (see above)
   uint32_t lcnt, fcnt;                     // raw Instructions emitted: leader / each follower
   bool abort;
   bool share;                              // the followers' Instruction FIFOs are all empty: their records can be shared
@@ -106,26 +119,82 @@ struct SymGroup {
     return n != ABSENT;
   }
 
-  // fsm_tx.send (fsm.rs:19-29): raw entries, encoded by fsm_flush when the launch ends
-  __device__ __forceinline__ void emit_leader(bool notify, uint32_t bid, uint32_t nxa, uint64_t tok) {
+  // fsm_tx.send (fsm.rs:19-29)
+  __device__ __forceinline__ uint4& eq(uint32_t k) const { return enc[k * SYM_LANES]; }
+  __device__ __forceinline__ FsmOut leader_out() const { return FsmOut{d.fs + rg(L), plane, d.F, g, L}; }
+  __device__ __forceinline__ FsmOut followers_out() const {   // one set of records for all followers: node mask in the APPLY records
+    return FsmOut{d.fs + rg(F0), plane, d.F, g, F0, ((1u << R) - 1u) & ~(1u << L)};
+  }
+  __device__ __forceinline__ void enc_init(uint2 leader_fc) const {
+    eq(0) = make_uint4(leader_fc.x, leader_fc.y, leader_fc.y, 0u);
+#pragma unroll
+    for (uint32_t k = 1; k < SYM_ENC_L + SYM_ENC_F; ++k) eq(k) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  template <bool NOTIFY>
+  __device__ __forceinline__ void emit_leader(uint32_t bid, uint32_t nxa, uint64_t tok) {
     if (!(d.flags & JR_F_CAPTURE_FSM)) return;
-    if (lcnt < d.Fr)
-      d.fr[(size_t)lcnt * plane + rg(L)] = make_uint4(bid | (notify ? FS_NOTIFY_BIT : 0u), nxa, (uint32_t)tok, (uint32_t)(tok >> 32));
+    if (lcnt >= d.Fr) { abort = true; return; }          // step_kernel's raw FIFO would overflow (it drops and counts): its business
+    FsmEnc e;
+    const uint4 q0 = eq(0);
+    e.nrec = q0.x; e.seq = q0.y + lcnt; e.wseq = q0.z; e.pb2 = q0.w;
     ++lcnt;
+    const bool window = NOTIFY || e.seq + 1u - e.wseq == FS_PATTERN_BITS;   // pattern words: read by a Notify and when the window closes
+    uint4 q1 = make_uint4(0u, 0u, 0u, 0u);
+    if (window) q1 = eq(1);
+    e.pb0 = (uint64_t)q1.x | ((uint64_t)q1.y << 32);
+    e.pb1 = (uint64_t)q1.z | ((uint64_t)q1.w << 32);
+    const uint4 qr = eq(NOTIFY ? 4 : 2), qs = eq(3);
+    FsmRun& run = NOTIFY ? e.rn : e.ra;
+    run.next_id = qr.x; run.count = qr.y;
+    run.last = (uint64_t)qr.z | ((uint64_t)qr.w << 32);
+    run.stride = NOTIFY ? ((uint64_t)qs.z | ((uint64_t)qs.w << 32)) : ((uint64_t)qs.x | ((uint64_t)qs.y << 32));
+    fsm_enc_push<NOTIFY>(e, leader_out(), bid, nxa, tok);
+    if (e.nrec != q0.x || e.wseq != q0.z || e.pb2 != q0.w) eq(0) = make_uint4(e.nrec, q0.y, e.wseq, e.pb2);
+    if (window) eq(1) = make_uint4((uint32_t)e.pb0, (uint32_t)(e.pb0 >> 32), (uint32_t)e.pb1, (uint32_t)(e.pb1 >> 32));
+    eq(NOTIFY ? 4 : 2) = make_uint4(run.next_id, run.count, (uint32_t)run.last, (uint32_t)(run.last >> 32));
+    uint2* st = reinterpret_cast<uint2*>(&eq(3)) + (NOTIFY ? 1 : 0);
+    *st = make_uint2((uint32_t)run.stride, (uint32_t)(run.stride >> 32));
+  }
+  __device__ __forceinline__ uint2 leader_end() {          // close the leader's runs: its new {records, Instructions}
+    FsmEnc e;
+    const uint4 q0 = eq(0), q1 = eq(1), q2 = eq(2), q3 = eq(3), q4 = eq(4);
+    e.nrec = q0.x; e.seq = q0.y + lcnt; e.wseq = q0.z; e.pb2 = q0.w;
+    e.pb0 = (uint64_t)q1.x | ((uint64_t)q1.y << 32);
+    e.pb1 = (uint64_t)q1.z | ((uint64_t)q1.w << 32);
+    e.ra = FsmRun{q2.x, q2.y, (uint64_t)q2.z | ((uint64_t)q2.w << 32), (uint64_t)q3.x | ((uint64_t)q3.y << 32)};
+    e.rn = FsmRun{q4.x, q4.y, (uint64_t)q4.z | ((uint64_t)q4.w << 32), (uint64_t)q3.z | ((uint64_t)q3.w << 32)};
+    return fsm_enc_end(e, leader_out());
   }
   __device__ __forceinline__ void emit_followers(uint32_t bid, uint32_t next, uint64_t tok) {
     if (!(d.flags & JR_F_CAPTURE_FSM)) return;
-    if (fcnt < d.Fr) {
+    if (fcnt >= d.Fr) { abort = true; return; }
+    if (share) {                                           // encoded once, for all followers
+      FsmEnc e;
+      const uint4 q0 = eq(SYM_ENC_L), q1 = eq(SYM_ENC_L + 1);
+      const uint2 q2 = *reinterpret_cast<const uint2*>(&eq(SYM_ENC_L + 2));
+      e.nrec = q0.x; e.seq = q0.y + fcnt; e.wseq = q0.z; e.pb2 = 0;
+      e.pb0 = e.pb1 = 0;
+      e.ra = FsmRun{q1.x, q1.y, (uint64_t)q1.z | ((uint64_t)q1.w << 32), (uint64_t)q2.x | ((uint64_t)q2.y << 32)};
+      fsm_enc_push<false>(e, followers_out(), bid, next, tok);
+      if (e.nrec != q0.x || e.wseq != q0.z) eq(SYM_ENC_L) = make_uint4(e.nrec, q0.y, e.wseq, 0u);
+      eq(SYM_ENC_L + 1) = make_uint4(e.ra.next_id, e.ra.count, (uint32_t)e.ra.last, (uint32_t)(e.ra.last >> 32));
+      *reinterpret_cast<uint2*>(&eq(SYM_ENC_L + 2)) = make_uint2((uint32_t)e.ra.stride, (uint32_t)(e.ra.stride >> 32));
+    } else {                                               // followers with records pending: raw entries, fsm_flush at the end
       const uint4 e = make_uint4(bid, next, (uint32_t)tok, (uint32_t)(tok >> 32));
-      if (share) {
-        d.fr[(size_t)fcnt * plane + rg(F0)] = e;           // one copy: sym_leave encodes it once, for all followers
-      } else {
 #pragma unroll
-        for (int r = 0; r < R; ++r)
-          if ((uint32_t)r != L) d.fr[(size_t)fcnt * plane + rg(r)] = e;
-      }
+      for (int r = 0; r < R; ++r)
+        if ((uint32_t)r != L) d.fr[(size_t)fcnt * plane + rg(r)] = e;
     }
     ++fcnt;
+  }
+  __device__ __forceinline__ uint2 followers_end() {
+    FsmEnc e;
+    const uint4 q0 = eq(SYM_ENC_L), q1 = eq(SYM_ENC_L + 1), q2 = eq(SYM_ENC_L + 2);
+    e.nrec = q0.x; e.seq = q0.y + fcnt; e.wseq = q0.z; e.pb2 = 0;
+    e.pb0 = e.pb1 = 0;
+    e.ra = FsmRun{q1.x, q1.y, (uint64_t)q1.z | ((uint64_t)q1.w << 32), (uint64_t)q2.x | ((uint64_t)q2.y << 32)};
+    e.rn = FsmRun{0, 0, 0, 0};
+    return fsm_enc_end(e, followers_out());
   }
 
   // ---- leader (leader.rs) ------------------------------------------------------------------------------------
@@ -162,7 +231,7 @@ struct SymGroup {
       fetch(L, b, nx, tk);
       if (nx == ABSENT) continue;
       if (first) { first = false; continue; }
-      emit_leader(false, b, nx, tk);
+      emit_leader<false>(b, nx, tk);
     }
   }
   // leader.rs:177-197
@@ -174,7 +243,7 @@ struct SymGroup {
     cache_put(L, bid, head, tok);
     if (bid > maxkey) maxkey = bid;
     head = bid;
-    emit_leader(true, bid, FSR_CLIENT, tok);
+    emit_leader<true>(bid, FSR_CLIENT, tok);
     mode_self = ph_self < head ? 1u : 0u;               // progress.rs:76-94 on the leader's own entry
     if (ph_self < head) ph_self = head;
     leader_commit(ph_f, R - 1, ph_f);
@@ -497,16 +566,12 @@ __device__ __forceinline__ void sym_leave(SymGroup<R>& s, const SymMail& last, i
       }
     }
     d.oc[cur_last][i] = u;
-    if ((d.flags & JR_F_CAPTURE_FSM) && s.lcnt) fsm_flush(d.fr + i, s.lcnt, d.Fr, FsmOut{d.fs + i, s.plane, d.F, s.g, L}, d.fc + i);
+    if ((d.flags & JR_F_CAPTURE_FSM) && s.lcnt) d.fc[i] = s.leader_end();
   }
   // The followers emitted the same Instructions.  If none of them has anything pending since the last drain, ONE set of
   // records (in the lowest follower's FIFO, APPLY records carrying the mask of all followers) stands for all of them;
   // the others only advance their Instruction counters.  Otherwise every follower gets its own copy.
   const bool shared_records = s.share;
-  uint32_t fmask = 0;
-#pragma unroll
-  for (int r = 0; r < R; ++r)
-    if ((uint32_t)r != L) fmask |= 1u << r;
 #pragma unroll
   for (int r = 0; r < R; ++r) {   // followers: P1 (timer, RNG), P2, max key, outbox
     if ((uint32_t)r == L) continue;
@@ -530,15 +595,15 @@ __device__ __forceinline__ void sym_leave(SymGroup<R>& s, const SymMail& last, i
     d.oc[cur_last][i] = u;
     if ((d.flags & JR_F_CAPTURE_FSM) && s.fcnt) {
       if (!shared_records) fsm_flush(d.fr + i, s.fcnt, d.Fr, FsmOut{d.fs + i, s.plane, d.F, s.g, (uint32_t)r}, d.fc + i);
-      else if ((uint32_t)r == s.F0) fsm_flush(d.fr + i, s.fcnt, d.Fr, FsmOut{d.fs + i, s.plane, d.F, s.g, (uint32_t)r, fmask}, d.fc + i);
-      else d.fc[i] = make_uint2(0u, s.fcnt < d.Fr ? s.fcnt : d.Fr);   // counted here, carried by F0's masked records
+      else if ((uint32_t)r == s.F0) d.fc[i] = s.followers_end();
+      else d.fc[i] = make_uint2(0u, s.fcnt);               // counted here, carried by F0's masked records
     }
   }
 }
 
 // One lane per group.  symdone[g] = 1: the whole launch of group g has been applied here; 0: step_kernel runs it.
 template <int R>
-__global__ void __launch_bounds__(SYM_LANES, 4) sym_kernel(const Dev d, const StepParams p, uint8_t* symdone) {
+__global__ void __launch_bounds__(SYM_LANES, 512 / SYM_LANES) sym_kernel(const Dev d, const StepParams p, uint8_t* symdone) {
   const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= d.Gp) return;
   SymGroup<R> s(d, g);
@@ -548,8 +613,9 @@ __global__ void __launch_bounds__(SYM_LANES, 4) sym_kernel(const Dev d, const St
   s.n_hb = 0;
   s.last_hb = 0;
   s.share = false;
-  __shared__ uint4 row_cache[2 * SYM_ROWS * SYM_LANES];
-  s.rows = row_cache + threadIdx.x;
+  __shared__ uint4 lane_smem[SYM_SMEM_UNITS * SYM_LANES];
+  s.rows = lane_smem + threadIdx.x;
+  s.enc = lane_smem + 2 * SYM_ROWS * SYM_LANES + threadIdx.x;
   s.cache_clear();
   bool ok = sym_enter<R>(s, a, p, 1 - p.cur);
   if (ok) {
@@ -562,6 +628,7 @@ __global__ void __launch_bounds__(SYM_LANES, 4) sym_kernel(const Dev d, const St
       const uint2 c = d.fc[s.rg(r)];
       if (c.x | c.y) s.share = false;
     }
+    s.enc_init((d.flags & JR_F_CAPTURE_FSM) ? d.fc[s.rg(s.L)] : make_uint2(0u, 0u));
     const jr_proposal* props = p.proposals;
     s.now = p.now;
     for (uint32_t t = 0; t < p.n_ticks && !s.abort; ++t) {

@@ -64,18 +64,18 @@ def measure(bn, label, G, R, steps, capture=True, flush=True, **kw):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("steps", nargs="?", type=int, default=60)
+    ap.add_argument("--only", type=int, default=99, help="run only the first N variants")
     a = ap.parse_args()
     bn = bench.Bench(argparse.Namespace())
     G, R = bench.GROUPS_PER_GPU, bench.REPLICAS
-    measure(bn, "headline", G, R, a.steps)
-    measure(bn, "headline, warm L2 (no flush)", G, R, a.steps, flush=False)
-    measure(bn, "headline, no capture", G, R, a.steps, capture=False)
-    measure(bn, "scattered leaders", G, R, a.steps, scattered=True)
-    measure(bn, "heartbeat every tick", G, R, a.steps, heartbeat_ms=99)
-    measure(bn, "131,072 groups", 2 * G, R, a.steps)
-    os.environ["JR_NO_FOLD"] = "1"
-    measure(bn, "headline, fold off (step_kernel)", G, R, a.steps)
-    measure(bn, "no capture, fold off", G, R, a.steps, capture=False)
+    variants = [("headline", G, {}), ("headline, no capture", G, {"capture": False}), ("scattered leaders", G, {"scattered": True}),
+                ("headline, warm L2 (no flush)", G, {"flush": False}), ("heartbeat every tick", G, {"heartbeat_ms": 99}),
+                ("131,072 groups", 2 * G, {}), ("headline, fold off (step_kernel)", G, {"_nofold": True}),
+                ("no capture, fold off", G, {"capture": False, "_nofold": True})]
+    for label, g, kw in variants[:a.only]:
+        if kw.pop("_nofold", False):
+            os.environ["JR_NO_FOLD"] = "1"
+        measure(bn, label, g, R, a.steps, **kw)
 
 
 if __name__ == "__main__":
