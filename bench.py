@@ -374,7 +374,7 @@ class Bench:
         e = RaftEngine.create(g, r, **kw)
         return e
 
-    def steady_engine(self, G, R, flags, scattered=False, heartbeat_ms=100, seed=SEED):
+    def steady_engine(self, G, R, flags, scattered=False, heartbeat_ms=100, seed=SEED, auto_truncate=True):
         e = self.make(G, R, seed=seed, group_offset=self.rank * G, chain_capacity=CHAIN_WINDOW, flags=flags,
                       fsm_units=FSM_UNITS, mailbox_units=64, heartbeat_ms=heartbeat_ms)
         e.set_stream(self.stream.cuda_stream)
@@ -383,6 +383,8 @@ class Bench:
         e.truncate(TRUNC_MARGIN)
         if flags & abi.F_CAPTURE_FSM:
             e.discard_fsm(strict=False)      # the bootstrap's irregular start-up stream is not part of the workload
+        if auto_truncate:
+            e.set_auto_truncate(TRUNC_MARGIN)    # every fused run ends with jr_truncate(margin): same result as calling it, one pass less
         return e
 
     def barrier(self):
@@ -424,8 +426,7 @@ class Bench:
             outstanding[0] -= 1
 
         def one_step():
-            eng.run(now[0], DT_MS, S, 1)
-            eng.truncate(TRUNC_MARGIN)
+            eng.run(now[0], DT_MS, S, 1)          # (ends with jr_truncate: jr_set_auto_truncate)
             now[0] += DT_MS * S
             if capture:
                 st = lib.jr_fsm_records_async(h)
@@ -536,7 +537,6 @@ class Bench:
                                            C.cast(runs.data_ptr() + (k % NB) * rstride, C.POINTER(abi.TokenRun)))   # 16 B per group H2D
             assert st == 0, st
             now[0] += DT_MS * S
-            assert lib.jr_truncate(h, C.c_uint32(TRUNC_MARGIN)) == 0
             st = lib.jr_leader_table_async(h, C.cast(table.data_ptr() + (i % NB) * tstride, C.POINTER(abi.LeaderEntry)))   # result D2H
             assert st == 0, st
             if with_output:
@@ -608,12 +608,12 @@ class Bench:
             out.update({"instructions_per_step": int(totals[0] + totals[1]) // steps, "records_per_step": int(totals[2]) // steps,
                         "d2h_stream_bytes_per_step": rec_bytes[0] // steps,
                         "api": "per step: " + ("jr_run_tokens(pinned u64 tokens[64][G]" if dense_input else "jr_run_token_runs(pinned jr_token_run[G]") +
-                               ", routed to the last announced leader) + jr_truncate + "
+                               ", routed to the last announced leader; ends with jr_truncate: jr_set_auto_truncate) + "
                                "jr_leader_table_async(pinned jr_leader_entry[G]) + jr_fsm_records_async; then jr_leader_table_wait + "
                                f"jr_fsm_records_wait + jr_fsm_fold_mt over the batch on {FOLD_THREADS} host threads (apply watermark per replica); {NB} steps in flight",
                         "host_fold_threads": FOLD_THREADS})
         else:
-            out["api"] = ("per step: jr_run_tokens + jr_truncate + jr_leader_table_async + jr_leader_table_wait; engine created without "
+            out["api"] = ("per step: jr_run_tokens (ends with jr_truncate) + jr_leader_table_async + jr_leader_table_wait; engine created without "
                           "JR_F_CAPTURE_FSM (round 1's end-to-end leg)")
         del eng
         torch.cuda.empty_cache()
@@ -650,7 +650,7 @@ class Bench:
     def config5(self, steps, warmup):
         torch = self.torch
         G, R, S = GROUPS_PER_GPU, 7, TICKS_PER_STEP
-        eng = self.steady_engine(G, R, abi.F_CAPTURE_FSM, seed=2)
+        eng = self.steady_engine(G, R, abi.F_CAPTURE_FSM, seed=2, auto_truncate=False)    # several runs per step here: one explicit jr_truncate at its end
         tick = [16]
         now = lambda: DT_MS * (tick[0] + 1)   # noqa: E731
         compact_ev, kills = [], []
@@ -774,7 +774,7 @@ def main():
     main_res = bn.device_resident(G, R, args.steps, max(args.warmup, 20), sampler=sampler)   # >= 20 untimed steps: also nvidia-smi's start-up
     clocks = main_res.pop("clocks")
     value, ms = main_res["value"], main_res["ms_total"]
-    launches = args.steps * (5 + (1 if world > 1 else 0))   # step_kernel, truncate, scan, pack, copy (+ leader_table_kernel)
+    launches = args.steps * (6 + (1 if world > 1 else 0))   # sym2_kernel, step_kernel, truncate_kernel, fsm count / scan / pack (+ leader_table_kernel); the copy-out is a DMA
 
     # ---------------- end to end ----------------
     e2e = e2e_plain = e2e_dense = None
@@ -857,7 +857,7 @@ def main():
         "config": {"workload": workload_name(G, R),
                    "groups_per_gpu": G, "replicas": R, "ticks_per_step": S, "tick_ms": DT_MS, "seed": SEED,
                    "heartbeat": "heartbeat_ms = tick = 100 and a strict `>` (leader.rs:78-84): every second tick",
-                   "chain_window": CHAIN_WINDOW, "truncate": f"jr_truncate(margin {TRUNC_MARGIN}) every step, inside the timed region (D7); no engine reset",
+                   "chain_window": CHAIN_WINDOW, "truncate": f"jr_truncate(margin {TRUNC_MARGIN}) at the end of every fused run (jr_set_auto_truncate), inside the timed region (D7); no engine reset",
                    "output": "Instruction stream drained every step (jr_fsm_records_async), folded on the host one step later",
                    "l2": f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write); ticks inside a step run back to back",
                    "parallelism": f"groups sharded over {world} GPU(s); leader-announce all_gather once per step" if world > 1

@@ -482,6 +482,10 @@ jr_status jr_set_alive(jr_engine* e, uint32_t group, uint32_t node, int alive);
  * below it is dropped from all replicas of the group.  Groups without a live replica keep their floor.
  * Asynchronous on the engine stream. */
 jr_status jr_truncate(jr_engine* e, uint32_t margin);
+/* D7, fused: while enabled, every jr_run / jr_run_proposals / jr_run_tokens / jr_run_token_runs call ends with
+ * jr_truncate(margin) -- same result as calling it right after, but groups the symmetric-group fast path applied are
+ * truncated by the lane that stepped them (no extra pass over their planes).  Off by default. */
+jr_status jr_set_auto_truncate(jr_engine* e, int enabled, uint32_t margin);
 /*
  * Node restart: replica (group, node) becomes what RaftHandle::new builds over an existing data directory
  * (mod.rs:428-435 -> follower.rs:68-95 -> Chain::new, chain.rs:117-137): a Follower with State::default

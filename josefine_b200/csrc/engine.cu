@@ -15,10 +15,6 @@
 #include <new>
 #include <thread>
 #include <vector>
-#ifdef __linux__
-#include <pthread.h>
-#include <sched.h>
-#endif
 
 #include "raft_device.cuh"
 #include "sym_fold.cuh"
@@ -79,7 +75,7 @@ __global__ void __launch_bounds__(32 * R, step_min_ctas(R)) step_kernel(const De
   uint32_t blk = blockIdx.x, part = 0;
   if (p0.n_parts > 1) {
     uint32_t* s_ticket = reinterpret_cast<uint32_t*>(smem);  // free until stage_inbox: fenced by the two barriers
-    if (threadIdx.x == 0) *s_ticket = atomicAdd(d.scatter + 1, 1u);
+    if (threadIdx.x == 0) *s_ticket = atomicAdd(d.scatter + 1, 1u) - p0.ticket_base;
     __syncthreads();
     const uint32_t ticket = *s_ticket;
     __syncthreads();
@@ -177,7 +173,7 @@ __global__ void __launch_bounds__(32 * R, step_min_ctas(R)) step_kernel(const De
     __syncthreads();
     if (!folded && rep.role == JR_ROLE_LEADER && rep.live()) atomicOr(lmask, 1u << r);
     __syncthreads();
-    if (threadIdx.x == 0 && (*lmask & (*lmask - 1u))) atomicOr(d.scatter, 1u);
+    if (threadIdx.x == 0 && (*lmask & (*lmask - 1u))) *(volatile uint32_t*)d.hscat = p0.epoch;   // advisory, read by the host a launch or two later
   }
   if (p0.n_parts > 1 && part + 1 < p0.n_parts) {  // hand the block over to its next part
     __threadfence();
@@ -490,9 +486,10 @@ __global__ void chain_read_kernel(const Dev d, const uint4* reqs, const uint32_t
 // jr_truncate (deviation D7).  One thread per group: new floor = min(commit over live replicas) - margin, never
 // below the old one; every block below it leaves the table of EVERY replica of the group (rows are reused by
 // the ids one window further up, so they must read as absent).
-__global__ void truncate_kernel(const Dev d, uint32_t margin) {
+__global__ void truncate_kernel(const Dev d, uint32_t margin, const uint8_t* skip) {
   const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= d.Gp) return;
+  if (skip && skip[g]) return;   // truncated by the lane that folded the group (sym2_kernel)
   const size_t plane = (size_t)d.R * d.Gp;
   const uint32_t old = d.tb[g];
   uint32_t lo = 0xFFFFFFFFu;
@@ -597,6 +594,7 @@ __global__ void fsm_scan_kernel(unsigned long long* part, uint32_t n_ctas, FsmHe
   const uint32_t lo = min(n_ctas, per * t), hi = min(n_ctas, per * (t + 1));
   unsigned long long sum = 0, drop = 0, ins = 0;
   for (uint32_t k = lo; k < hi; ++k) { sum += part[k]; drop += part[n_ctas + k]; ins += part[2 * (size_t)n_ctas + k]; }
+#ifdef JR_EMU
   s_sum[t] = sum;
   __syncthreads();
   if (t == 0) {
@@ -607,6 +605,36 @@ __global__ void fsm_scan_kernel(unsigned long long* part, uint32_t n_ctas, FsmHe
     hdr->n_instructions = 0;
   }
   __syncthreads();
+#else
+  {  // exclusive scan of the T per-thread sums: warp shuffles, then the warp totals (T <= 1024: one warp's worth)
+    __shared__ unsigned long long s_warp[32];
+    const uint32_t lane = t & 31u, w = t >> 5;
+    unsigned long long inc = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= (uint32_t)o) inc += v;
+    }
+    if (lane == 31) s_warp[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+      const unsigned long long mine = lane < (T + 31) / 32 ? s_warp[lane] : 0ull;
+      unsigned long long wi = mine;
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long v = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= (uint32_t)o) wi += v;
+      }
+      s_warp[lane] = wi - mine;                           // exclusive prefix of the warp totals
+      if (lane == 31) {
+        hdr->n_records = min(wi, (unsigned long long)cap_records);
+        hdr->n_dropped = wi > cap_records ? wi - cap_records : 0ull;   // + the per-replica drops, added below
+        hdr->n_instructions = 0;
+      }
+    }
+    __syncthreads();
+    s_sum[t] = s_warp[w] + inc - sum;
+  }
+  __syncthreads();
+#endif
 #ifdef JR_EMU
   hdr->n_dropped += drop;
   hdr->n_instructions += ins;
@@ -705,7 +733,8 @@ struct jr_engine {
   Dev d;
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
-  volatile uint32_t* h_scatter = nullptr;  // pinned: last scatter flag copied back (may lag one launch)
+  volatile uint32_t* h_scatter = nullptr;  // pinned + mapped: epoch of the last launch that saw scattered leaders (written by the kernel)
+  uint32_t ticket_sum = 0;                 // tickets taken so far (the counter is never reset: each launch gets its base)
   int force_sorted = 0;      // JR_STEP_VARIANT=sorted|plain pins the kernel variant (tests, A/B)
   uint64_t launches_sorted = 0, launches_total = 0, launches_split = 0;
   uint32_t slots = 0;        // CTAs of the step kernel the device holds at once (occupancy x SMs)
@@ -763,7 +792,10 @@ struct jr_engine {
   // symmetric-group fold
   uint8_t* symdone = nullptr;   // device, Gp entries
   uint8_t* symblk = nullptr;    // device, Gp / 32 entries
+  bool auto_trunc = false;      // jr_set_auto_truncate
+  uint32_t auto_trunc_margin = 0;
   int no_fold = 0;              // JR_NO_FOLD=1 (A/B, tests)
+  int sym_one_lane = 0;         // JR_SYM_ONE_LANE=1 (A/B, tests): sym_kernel (one lane per group) instead of sym2_kernel
   uint64_t launches_folded = 0;
   bool last_launch_folded = false;
 };
@@ -845,6 +877,7 @@ static jr_status launch_step(jr_engine* e, const StepParams& p_in) {
   StepParams p = p_in;
   for (uint32_t done = 0; done < p_in.n_ticks;) {
     p.n_ticks = std::min(limit, p_in.n_ticks - done);
+    p.trunc = (p_in.trunc && done + p.n_ticks == p_in.n_ticks) ? 1u : 0u;   // the call ends with ONE truncation
     jr_status st = launch_step_once(e, p);
     if (st != JR_OK) return st;
     done += p.n_ticks;
@@ -861,7 +894,11 @@ static jr_status launch_step(jr_engine* e, const StepParams& p_in) {
 template <int R>
 static void launch_sym_r(jr_engine* e, const StepParams& p) {
   if constexpr (R >= 2) {
-    JR_LAUNCH(sym_kernel<R>, (e->d.Gp + SYM_LANES - 1) / SYM_LANES, SYM_LANES, e->stream, e->d, p, e->symdone);
+    if (e->sym_one_lane)
+      JR_LAUNCH(sym_kernel<R>, (e->d.Gp + SYM_LANES - 1) / SYM_LANES, SYM_LANES, e->stream, e->d, p, e->symdone);
+    else
+      JR_LAUNCH_SMEM(sym2_kernel<R>, (e->d.Gp + SYM2_GROUPS - 1) / SYM2_GROUPS, 2 * SYM2_GROUPS,
+                     (size_t)SYM2_UNITS * SYM2_GROUPS * sizeof(uint4), e->stream, e->d, p, e->symdone, e->symblk);
   }
 }
 
@@ -883,8 +920,10 @@ static jr_status launch_step_once(jr_engine* e, const StepParams& p_in) {
   if (fold_eligible(e, p)) {
     DISPATCH_R(e->cfg.n_replicas, (launch_sym_r<RR>(e, p)));
     CK(cudaGetLastError());
-    JR_LAUNCH(sym_blocks_kernel, (n_blocks + 127) / 128, 128, e->stream, e->symdone, e->symblk, n_blocks);
-    CK(cudaGetLastError());
+    if (e->sym_one_lane) {   // (sym2_kernel writes symblk itself)
+      JR_LAUNCH(sym_blocks_kernel, (n_blocks + 127) / 128, 128, e->stream, e->symdone, e->symblk, n_blocks);
+      CK(cudaGetLastError());
+    }
     p.symdone = e->symdone;
     p.symblk = e->symblk;
     e->launches_folded += 1;
@@ -897,11 +936,17 @@ static jr_status launch_step_once(jr_engine* e, const StepParams& p_in) {
   p.epoch = (uint32_t)(e->launches_total + 1) * 8u;
   const uint32_t grid = n_blocks * p.n_parts;
   // Variant choice from the (possibly one launch stale) scatter flag: it only affects speed.
-  const bool sorted = e->force_sorted > 0 || (e->force_sorted == 0 && e->h_scatter && *e->h_scatter != 0);
-  CK(cudaMemsetAsync(e->d.scatter, 0, 2 * sizeof(uint32_t), e->stream));  // scatter flag + ticket counter
+  // (the kernel stores its epoch into that mapped host word: no memset, no copy-back in the launch path)
+  const bool sorted = e->force_sorted > 0 || (e->force_sorted == 0 && e->h_scatter && *e->h_scatter != 0 && p.epoch - *e->h_scatter <= 2u * 8u);
+  p.ticket_base = e->ticket_sum;
+  if (p.n_parts > 1) e->ticket_sum += grid;
   DISPATCH_R(e->cfg.n_replicas, (launch_step_r<RR>(e, p, sorted, grid, smem)));
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync((void*)e->h_scatter, e->d.scatter, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+  if (p.trunc) {   // sym2_kernel truncated the groups it folded
+    JR_LAUNCH(truncate_kernel, (e->d.Gp + 127) / 128, 128, e->stream, e->d, p.trunc_margin,
+              (const uint8_t*)((p.symdone && !e->sym_one_lane) ? p.symdone : nullptr));
+    CK(cudaGetLastError());
+  }
   e->launches_sorted += sorted ? 1 : 0;
   e->launches_split += p.n_parts > 1 ? 1 : 0;
   e->launches_total += 1;
@@ -1054,9 +1099,11 @@ jr_status jr_engine_create(const jr_config* cfg, jr_engine** out) {
     const int smem = (int)step_smem_bytes(d);
     cudaError_t aerr = cudaSuccess;
     DISPATCH_R(d.R, (aerr = step_smem_attr_r<RR>(smem)));
-    if (aerr == cudaSuccess) aerr = cudaHostAlloc((void**)&e->h_scatter, sizeof(uint32_t), 0);
+    if (aerr == cudaSuccess) aerr = cudaHostAlloc((void**)&e->h_scatter, sizeof(uint32_t), cudaHostAllocMapped);
     if (aerr == cudaSuccess) *e->h_scatter = 0;
+    if (aerr == cudaSuccess) aerr = cudaHostGetDevicePointer((void**)&e->d.hscat, (void*)e->h_scatter, 0);
     if (const char* ev = getenv("JR_NO_FOLD")) e->no_fold = atoi(ev);
+    if (const char* ev = getenv("JR_SYM_ONE_LANE")) e->sym_one_lane = atoi(ev);
     if (const char* ev = getenv("JR_FSM_COPY")) e->fsm_copy_by_sm = strcmp(ev, "sm") == 0;
     if (const char* ev = getenv("JR_PARTS")) e->force_parts = (uint32_t)std::min(std::max(atoi(ev), 0), 8);
 #ifndef JR_EMU
@@ -1479,6 +1526,8 @@ jr_status jr_run(jr_engine* e, uint64_t now0, uint32_t dt, uint32_t n_steps, uin
   p.proposals = nullptr;
   p.prop_stride = 0;
   p.phases = PH_RESET_OUT | PH_DRAIN | (n_synth ? PH_PROPOSE : 0u) | PH_TICK;   // Instructions accumulate until drained
+  p.trunc = e->auto_trunc ? 1u : 0u;
+  p.trunc_margin = e->auto_trunc_margin;
   jr_status st = launch_step(e, p);
   if (st != JR_OK) return st;
   e->cur ^= (int)(n_steps & 1u);
@@ -1512,6 +1561,8 @@ static jr_status batch_launch(jr_engine* e, int b, uint64_t now0, uint32_t dt, u
   p.proposals = e->batch[b];
   p.prop_stride = e->d.G;
   p.phases = PH_RESET_OUT | PH_DRAIN | PH_PROPOSE | PH_TICK;
+  p.trunc = e->auto_trunc ? 1u : 0u;
+  p.trunc_margin = e->auto_trunc_margin;
   jr_status st = launch_step(e, p);
   if (st != JR_OK) return st;
   CK(cudaEventRecord(e->batch_free[b], e->stream));
@@ -1594,6 +1645,8 @@ jr_status jr_run_token_runs(jr_engine* e, uint64_t now0, uint32_t dt, uint32_t n
   p.tok_route = e->route;    // on the engine stream: ordered after the leader_table_kernel that last wrote it
   p.tok_tick = 0;
   p.phases = PH_RESET_OUT | PH_DRAIN | PH_PROPOSE | PH_TICK;
+  p.trunc = e->auto_trunc ? 1u : 0u;
+  p.trunc_margin = e->auto_trunc_margin;
   st = launch_step(e, p);
   if (st != JR_OK) return st;
   CK(cudaEventRecord(e->batch_free[b], e->stream));
@@ -1709,24 +1762,6 @@ class FoldPool {
     while (n_workers_ + 1 < j.parts) {   // worker k serves slice k + 1; the caller folds slice 0
       const uint32_t k = n_workers_++;
       std::thread th([this, k] { loop(k); });
-#ifdef __linux__
-      // JR_FOLD_PIN=1: worker k stays on one CPU of the caller's affinity mask (counted from its top), so the short
-      // bursts of a fold do not wander over every core of the mask (each wake-up on a new core costs a CFS quota slice).
-      if (const char* ev = getenv("JR_FOLD_PIN"); ev && atoi(ev)) {
-        cpu_set_t mask;
-        if (sched_getaffinity(0, sizeof mask, &mask) == 0) {
-          int want = (int)k, chosen = -1;
-          for (int c = CPU_SETSIZE - 1; c >= 0 && chosen < 0; --c)
-            if (CPU_ISSET(c, &mask) && want-- == 0) chosen = c;
-          if (chosen >= 0) {
-            cpu_set_t one;
-            CPU_ZERO(&one);
-            CPU_SET(chosen, &one);
-            pthread_setaffinity_np(th.native_handle(), sizeof one, &one);
-          }
-        }
-      }
-#endif
       th.detach();
     }
     job_ = &j;
@@ -2049,8 +2084,15 @@ jr_status jr_compact(jr_engine* e) {
 jr_status jr_truncate(jr_engine* e, uint32_t margin) {
   if (!e) return JR_E_INVAL;
   CK(cudaSetDevice(e->cfg.device));
-  JR_LAUNCH(truncate_kernel, (e->d.Gp + 127) / 128, 128, e->stream, e->d, margin);
+  JR_LAUNCH(truncate_kernel, (e->d.Gp + 127) / 128, 128, e->stream, e->d, margin, (const uint8_t*)nullptr);
   CK(cudaGetLastError());
+  return JR_OK;
+}
+
+jr_status jr_set_auto_truncate(jr_engine* e, int enabled, uint32_t margin) {
+  if (!e) return JR_E_INVAL;
+  e->auto_trunc = enabled != 0;
+  e->auto_trunc_margin = margin;
   return JR_OK;
 }
 

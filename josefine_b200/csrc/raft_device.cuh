@@ -60,6 +60,7 @@ struct Dev {
   uint32_t Us, W;                  // shared-memory mailbox units per replica, table-cache entries (power of 2)
   uint32_t use_index;              // receivers use the delivery index (else scan whole mailboxes)
   uint32_t resident;               // bit r: replica index r is hosted here (others are inert, see jr_config)
+  uint32_t* hscat;                 // mapped HOST word: the epoch of the last launch in which some CTA saw leaders on >= 2 replica indices
   uint32_t* scatter;               // [0] set by a launch when some CTA has leaders on >= 2 replica indices;
                                    // [1] task ticket counter of the running step launch (both zeroed per launch)
   uint32_t* done;                  // [CTA-sized group block]: epoch + parts finished (split launches, see step_kernel)
@@ -98,6 +99,8 @@ struct StepParams {
   // Split launch: the n_ticks of every 32-group block are cut into n_parts consecutive runs, one CTA each
   // (grid = n_blocks * n_parts).  Finer tasks fill the last wave of CTAs; see step_kernel.
   uint32_t n_parts = 1, part_ticks = 0, n_blocks = 0, epoch = 0;
+  uint32_t trunc = 0, trunc_margin = 0;   // jr_set_auto_truncate: this launch ends with jr_truncate(trunc_margin)
+  uint32_t ticket_base = 0;      // value of the ticket counter when this launch starts (every CTA of a split launch takes exactly one)
   // Symmetric-group fold (sym_fold.cuh): set when sym_kernel ran in front of this launch.  symdone[g] = 1: group g's
   // whole launch has been applied already; symblk[b] = 1: that holds for all 32 groups of block b.
   const uint8_t* symdone = nullptr;

@@ -36,6 +36,7 @@ namespace jr {
 struct SymMail {
   uint32_t hb, hb_commit;                 // leader -> followers
   uint32_t ae, ae_nb, ae_id[JR_MAX_AE_BLOCKS];
+  uint32_t mk;                            // the leader's largest block id when it sent this (sym2_kernel: which cache slots it may be rewriting)
   uint32_t hbr, hbr_commit, hbr_has;      // followers -> leader
   uint32_t ar, ar_head;
 };
@@ -59,9 +60,19 @@ constexpr uint32_t SYM_LANES = JR_SYM_LANES;   // threads per CTA of sym_kernel:
 // seq = seq0 + the lane's Instruction counter (lcnt / fcnt), which lives in a register anyway.
 constexpr uint32_t SYM_ENC_L = 5, SYM_ENC_F = 3;
 constexpr uint32_t SYM_SMEM_UNITS = 2 * SYM_ROWS + SYM_ENC_L + SYM_ENC_F;   // uint4 per lane
+// sym2_kernel: TWO lanes per group, in two warps of the same CTA -- one runs the leader's handlers, the other the
+// followers' -- because within a tick the two sides only depend on the mail of the PREVIOUS tick.  The kernel is latency
+// bound with 3.5 warps per SM sub-partition; this doubles the warps and halves each warp's serial chain.  The mail goes
+// through shared memory, double buffered, one __syncthreads() per tick:
+//   leader -> followers   A = {hb | ae << 1 | nb << 4 | abort << 8, hb_commit, leader's max key, id0}   B = {id1 .. id4}
+//   followers -> leader   C = {hbr | has << 1 | ar << 2 | abort << 8, hbr_commit, ar_head, -}
+constexpr uint32_t SYM2_GROUPS = 64;                                        // groups per CTA: 128 threads
+constexpr uint32_t SYM2_UNITS = SYM_SMEM_UNITS + 2 * 2 + 2 * 1;            // uint4 per group
+constexpr uint32_t SYM2_ABORT = 1u << 8;
 
-template <int R>
+template <int R, bool SPLIT = false>
 struct SymGroup {
+  static constexpr uint32_t STRIDE = SPLIT ? SYM2_GROUPS : SYM_LANES;   // columns of the CTA's per-group shared memory
   const Dev& d;
   const uint32_t g;
   const size_t plane;
@@ -73,9 +84,11 @@ struct SymGroup {
   uint32_t n_hb;                           // heartbeats the followers took in this launch
   uint64_t last_hb;
   uint32_t tbase;
+  uint32_t flo;                            // lowest id whose row sym_enter found identical in every follower
   uint4* rows;                             // this lane's column of the CTA's row caches (see above)
   uint4* enc;                              // this lane's column of the encoder states (see above)
   uint32_t lcnt, fcnt;                     // raw Instructions emitted: leader / each follower
+  uint32_t n_app;                          // most blocks the leader can append in one tick (dense + synthetic proposals)
   bool abort;
   bool share;                              // the followers' Instruction FIFOs are all empty: their records can be shared
 
@@ -83,7 +96,7 @@ struct SymGroup {
   __device__ __forceinline__ size_t rg(uint32_t r) const { return (size_t)r * d.Gp + g; }
   __device__ __forceinline__ size_t row(uint32_t r, uint32_t bid) const { return (size_t)(bid & d.capm) * plane + rg(r); }
   __device__ __forceinline__ bool in_window(uint32_t bid) const { return bid - tbase < d.cap; }   // (sym_enter made sure ids stay below 2^31)
-  __device__ __forceinline__ uint4& slot(uint32_t r, uint32_t bid) const { return rows[((r == L ? 0u : SYM_ROWS) + (bid % SYM_ROWS)) * SYM_LANES]; }
+  __device__ __forceinline__ uint4& slot(uint32_t r, uint32_t bid) const { return rows[((r == L ? 0u : SYM_ROWS) + (bid % SYM_ROWS)) * STRIDE]; }
   __device__ __forceinline__ void cache_put(uint32_t r, uint32_t bid, uint32_t nx, uint64_t tk) const {
     slot(r, bid) = make_uint4(bid, nx, (uint32_t)tk, (uint32_t)(tk >> 32));
   }
@@ -94,11 +107,26 @@ struct SymGroup {
     if (e.x == bid) { next = e.y; tok = (uint64_t)e.z | ((uint64_t)e.w << 32); return; }
     next = __ldcg(d.cnext + row(r, bid));   // rows written earlier in this launch by this lane: read them at L2
     tok = __ldcg(d.ctok + row(r, bid));
-    cache_put(r, bid, next, tok);
+    if (!SPLIT) cache_put(r, bid, next, tok);   // (split kernel: a cache is only written at entry and by appends, see fetch_sent)
   }
-  __device__ __forceinline__ void cache_clear() const {
+  // sym2_kernel, follower lane: a block the leader sent one tick ago, read from the LEADER's row cache, which the leader
+  // lane is appending to right now.  Its appends of this tick are the ids (mk_sent, mk_sent + n_app]; a slot one of them
+  // maps to is not read (the row is in global memory, written before the last barrier).  No other write happens to that
+  // cache after entry, so every slot this reads is quiescent.
+  __device__ __forceinline__ void fetch_sent(uint32_t bid, uint32_t mk_sent, uint32_t n_app, uint32_t& next, uint64_t& tok) {
+    if (!SPLIT) { fetch(L, bid, next, tok); return; }
+    if (!in_window(bid)) { next = ABSENT; tok = 0; return; }
+    if (bid + SYM_ROWS > mk_sent + n_app) {
+      const uint4 e = slot(L, bid);
+      if (e.x == bid) { next = e.y; tok = (uint64_t)e.z | ((uint64_t)e.w << 32); return; }
+    }
+    next = __ldcg(d.cnext + row(L, bid));
+    tok = __ldcg(d.ctok + row(L, bid));
+  }
+  __device__ __forceinline__ void cache_clear(uint32_t first = 0, uint32_t n = 2 * SYM_ROWS) const {
 #pragma unroll
-    for (uint32_t k = 0; k < 2 * SYM_ROWS; ++k) rows[k * SYM_LANES] = make_uint4(ABSENT, ABSENT, 0u, 0u);   // tag ABSENT matches no id
+    for (uint32_t k = 0; k < 2 * SYM_ROWS; ++k)
+      if (k >= first && k < first + n) rows[k * STRIDE] = make_uint4(ABSENT, ABSENT, 0u, 0u);   // tag ABSENT matches no id
   }
   __device__ __forceinline__ void cache_fill(uint32_t r, uint32_t top) const {   // independent loads, issued together
     uint32_t nx[SYM_ROWS];
@@ -118,17 +146,32 @@ struct SymGroup {
     fetch(r, bid, n, t);
     return n != ABSENT;
   }
+  // The followers' table, read through the lowest follower's: only rows sym_enter compared across followers (>= flo),
+  // rows this launch wrote to all of them, or ids below the floor (absent everywhere) may be answered that way.
+  __device__ __forceinline__ void fetch_f(uint32_t bid, uint32_t& next, uint64_t& tok) {
+    if (in_window(bid) && bid < flo) { abort = true; next = ABSENT; tok = 0; return; }
+    fetch(F0, bid, next, tok);
+  }
+  __device__ __forceinline__ bool has_f(uint32_t bid) {
+    uint32_t n; uint64_t t;
+    fetch_f(bid, n, t);
+    return n != ABSENT;
+  }
 
   // fsm_tx.send (fsm.rs:19-29)
-  __device__ __forceinline__ uint4& eq(uint32_t k) const { return enc[k * SYM_LANES]; }
+  __device__ __forceinline__ uint4& eq(uint32_t k) const { return enc[k * STRIDE]; }
   __device__ __forceinline__ FsmOut leader_out() const { return FsmOut{d.fs + rg(L), plane, d.F, g, L}; }
   __device__ __forceinline__ FsmOut followers_out() const {   // one set of records for all followers: node mask in the APPLY records
     return FsmOut{d.fs + rg(F0), plane, d.F, g, F0, ((1u << R) - 1u) & ~(1u << L)};
   }
-  __device__ __forceinline__ void enc_init(uint2 leader_fc) const {
+  __device__ __forceinline__ void enc_init_leader(uint2 leader_fc) const {
     eq(0) = make_uint4(leader_fc.x, leader_fc.y, leader_fc.y, 0u);
 #pragma unroll
-    for (uint32_t k = 1; k < SYM_ENC_L + SYM_ENC_F; ++k) eq(k) = make_uint4(0u, 0u, 0u, 0u);
+    for (uint32_t k = 1; k < SYM_ENC_L; ++k) eq(k) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __device__ __forceinline__ void enc_init_followers() const {
+#pragma unroll
+    for (uint32_t k = SYM_ENC_L; k < SYM_ENC_L + SYM_ENC_F; ++k) eq(k) = make_uint4(0u, 0u, 0u, 0u);
   }
   template <bool NOTIFY>
   __device__ __forceinline__ void emit_leader(uint32_t bid, uint32_t nxa, uint64_t tok) {
@@ -290,6 +333,7 @@ struct SymGroup {
     }
     out.ae = 1;
     out.ae_nb = nb;
+    out.mk = maxkey;
   }
 
   // ---- follower (follower.rs), once for all R-1 of them ----------------------------------------------------------
@@ -298,14 +342,14 @@ struct SymGroup {
       ++n_hb;                                              // set_election_timeout: one RNG draw, timer restarted
       last_hb = now;
       const uint32_t c = in.hb_commit;
-      const bool hasc = has(F0, c);
+      const bool hasc = has_f(c);
       if (hasc && c > fcommit) {
         const uint32_t prev = fcommit;
         fckey = 1;
         fcommit = c;
         for (uint32_t b = max(prev, tbase); b < c; ++b) {  // range(prev..commit), key order
           uint32_t nx; uint64_t tk;
-          fetch(F0, b, nx, tk);
+          fetch_f(b, nx, tk);
           if (nx != ABSENT) emit_followers(b, nx, tk);
         }
       }
@@ -317,8 +361,8 @@ struct SymGroup {
       for (uint32_t k = 0; k < in.ae_nb; ++k) {
         const uint32_t bid = in.ae_id[k];
         uint32_t nx; uint64_t tk;
-        fetch(L, bid, nx, tk);                             // the block as the leader sent it
-        if (nx == ABSENT || !has(F0, nx) || !in_window(bid)) { abort = true; return; }   // chain.rs:180-185 Err / window: step_kernel's business
+        fetch_sent(bid, in.mk, n_app, nx, tk);             // the block as the leader sent it
+        if (nx == ABSENT || !has_f(nx) || !in_window(bid)) { abort = true; return; }   // chain.rs:180-185 Err / window: step_kernel's business
 #pragma unroll
         for (int r = 0; r < R; ++r)
           if ((uint32_t)r != L) {
@@ -339,8 +383,8 @@ struct SymGroup {
 };
 
 // ---- entry: is the group symmetric, is its mail canonical? ---------------------------------------------------------
-template <int R>
-__device__ __forceinline__ bool sym_enter(SymGroup<R>& s, SymMail& m, const StepParams& p, int prv) {
+template <int R, bool SPLIT>
+__device__ __forceinline__ bool sym_enter(SymGroup<R, SPLIT>& s, SymMail& m, const StepParams& p, int prv) {
   const Dev& d = s.d;
   if (s.g >= d.G) return false;
   // roles: one live leader, R-1 live followers of that leader
@@ -410,19 +454,43 @@ __device__ __forceinline__ bool sym_enter(SymGroup<R>& s, SymMail& m, const Step
 #pragma unroll
   for (int r = 0; r < R; ++r)
     if ((uint32_t)r != L && (ph[r] != s.ph_f || ((prmask >> r) & 1u) != s.mode_f)) return false;
-  // everything the launch will touch lies in the last SYM_WINDOW ids, which every follower holds identically
+  // Everything the launch reads of a follower's table lies in [flo, fmaxkey] (or is written by the launch itself):
+  // the commit a heartbeat names (>= commit), the apply range (from fcommit), the parents of the blocks behind ph_f.
+  // Those rows must be identical in every follower, because the lowest follower's table stands for all of them; a read
+  // below flo that is not below the floor aborts the lane (fetch_f).  At most SYM_WINDOW ids, else step_kernel's business.
   constexpr uint32_t SYM_WINDOW = 16;
   const uint32_t top = min(s.maxkey, s.fmaxkey);
-  const uint32_t lo = max(top > SYM_WINDOW - 1u ? top - (SYM_WINDOW - 1u) : 0u, s.tbase);   // (below the floor nobody holds anything)
-  if (top < s.tbase || s.ph_f < lo || s.fcommit < lo || s.commit < lo || s.fhead < lo || s.fmaxkey > s.maxkey) return false;
+  const uint32_t lo_min = max(top > SYM_WINDOW - 1u ? top - (SYM_WINDOW - 1u) : 0u, s.tbase);   // (below the floor nobody holds anything)
+  if (top < s.tbase || s.ph_f < lo_min || s.fcommit < lo_min || s.commit < lo_min || s.fhead < lo_min || s.fmaxkey > s.maxkey) return false;
+  const uint32_t lo = min(min(s.ph_f, s.fcommit), min(s.commit, s.fhead));
+  s.flo = lo;
   const uint64_t grow = (uint64_t)p.n_ticks * (1u + p.n_synth) + 2u;
   if ((uint64_t)s.maxkey + grow >= (uint64_t)s.tbase + d.cap || (uint64_t)s.maxkey + grow >= FS_NOTIFY_BIT) return false;
-  for (uint32_t b = lo; b <= s.fmaxkey; ++b) {
-    const uint32_t n0 = d.cnext[s.row(f0, b)];
-    const unsigned long long t0 = d.ctok[s.row(f0, b)];
+  {  // batches of independent loads, no exit in between: the latency of ~100 dependent loads was 14% of the kernel
+    constexpr uint32_t B = 4;
+    bool same = true;
+    for (uint32_t b0 = lo; b0 <= s.fmaxkey && same; b0 += B) {
+      uint32_t n0[B];
+      unsigned long long t0[B];
 #pragma unroll
-    for (int r = 0; r < R; ++r)
-      if ((uint32_t)r != L && (uint32_t)r != f0 && (d.cnext[s.row(r, b)] != n0 || (n0 != ABSENT && d.ctok[s.row(r, b)] != t0))) return false;
+      for (uint32_t j = 0; j < B; ++j) {
+        const uint32_t b = min(b0 + j, s.fmaxkey);          // (the tail re-checks the last id: no divergent guards)
+        n0[j] = d.cnext[s.row(f0, b)];
+        t0[j] = d.ctok[s.row(f0, b)];
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if ((uint32_t)r == L || (uint32_t)r == f0) continue;
+#pragma unroll
+        for (uint32_t j = 0; j < B; ++j) {
+          const uint32_t b = min(b0 + j, s.fmaxkey);
+          const uint32_t n = d.cnext[s.row(r, b)];
+          const unsigned long long t = d.ctok[s.row(r, b)];
+          same = same && n == n0[j] && (n0[j] == ABSENT || t == t0[j]);
+        }
+      }
+    }
+    if (!same) return false;
   }
   // mail in flight (the previous tick's outboxes), delivered only with PH_DRAIN
   m = SymMail{};
@@ -519,8 +587,8 @@ __device__ __forceinline__ bool sym_enter(SymGroup<R>& s, SymMail& m, const Step
 }
 
 // ---- exit: write everything step_kernel would have left behind -------------------------------------------------------
-template <int R>
-__device__ __forceinline__ void sym_leave(SymGroup<R>& s, const SymMail& last, int cur_last) {
+template <int R, bool SPLIT>
+__device__ __forceinline__ void sym_leave_leader(SymGroup<R, SPLIT>& s, const SymMail& last, int cur_last) {
   const Dev& d = s.d;
   const uint32_t L = s.L;
   {  // leader: P2, P3, progress planes, max key (P0 / P1 are untouched by a steady leader)
@@ -568,6 +636,12 @@ __device__ __forceinline__ void sym_leave(SymGroup<R>& s, const SymMail& last, i
     d.oc[cur_last][i] = u;
     if ((d.flags & JR_F_CAPTURE_FSM) && s.lcnt) d.fc[i] = s.leader_end();
   }
+}
+
+template <int R, bool SPLIT>
+__device__ __forceinline__ void sym_leave_followers(SymGroup<R, SPLIT>& s, const SymMail& last, int cur_last) {
+  const Dev& d = s.d;
+  const uint32_t L = s.L;
   // The followers emitted the same Instructions.  If none of them has anything pending since the last drain, ONE set of
   // records (in the lowest follower's FIFO, APPLY records carrying the mask of all followers) stands for all of them;
   // the others only advance their Instruction counters.  Otherwise every follower gets its own copy.
@@ -613,11 +687,12 @@ __global__ void __launch_bounds__(SYM_LANES, 512 / SYM_LANES) sym_kernel(const D
   s.n_hb = 0;
   s.last_hb = 0;
   s.share = false;
+  s.n_app = 1u + p.n_synth;
   __shared__ uint4 lane_smem[SYM_SMEM_UNITS * SYM_LANES];
   s.rows = lane_smem + threadIdx.x;
   s.enc = lane_smem + 2 * SYM_ROWS * SYM_LANES + threadIdx.x;
   s.cache_clear();
-  bool ok = sym_enter<R>(s, a, p, 1 - p.cur);
+  bool ok = sym_enter(s, a, p, 1 - p.cur);
   if (ok) {
     s.cache_fill(s.L, s.maxkey);
     s.cache_fill(s.F0, s.fmaxkey);
@@ -628,7 +703,8 @@ __global__ void __launch_bounds__(SYM_LANES, 512 / SYM_LANES) sym_kernel(const D
       const uint2 c = d.fc[s.rg(r)];
       if (c.x | c.y) s.share = false;
     }
-    s.enc_init((d.flags & JR_F_CAPTURE_FSM) ? d.fc[s.rg(s.L)] : make_uint2(0u, 0u));
+    s.enc_init_leader((d.flags & JR_F_CAPTURE_FSM) ? d.fc[s.rg(s.L)] : make_uint2(0u, 0u));
+    s.enc_init_followers();
     const jr_proposal* props = p.proposals;
     s.now = p.now;
     for (uint32_t t = 0; t < p.n_ticks && !s.abort; ++t) {
@@ -656,9 +732,163 @@ __global__ void __launch_bounds__(SYM_LANES, 512 / SYM_LANES) sym_kernel(const D
       s.now += p.dt;
     }
     ok = !s.abort;
-    if (ok) sym_leave<R>(s, a, p.cur ^ (int)((p.n_ticks - 1) & 1u));
+    if (ok) {
+      const int cur_last = p.cur ^ (int)((p.n_ticks - 1) & 1u);
+      sym_leave_leader(s, a, cur_last);
+      sym_leave_followers(s, a, cur_last);
+    }
   }
   symdone[g] = ok ? 1 : 0;
+}
+
+// Two lanes per group (see SYM2_GROUPS above).  Both lanes run sym_enter on the same, still untouched planes and reach
+// the same verdict; afterwards each keeps to its side: the leader lane owns the leader's table cache, encoder state,
+// planes and outbox, the follower lane those of the followers.  Either side may abort: it says so in its mail, the
+// other side sees it one barrier later, and after the last barrier both check the other's final mail, so a group is
+// either left (by both) or not at all.
+#ifndef JR_SYM2_MINCTAS
+#define JR_SYM2_MINCTAS 7
+#endif
+#ifndef JR_SYM2_ROLES
+#define JR_SYM2_ROLES 3   // (register-need experiments: 1 = leader code only, 2 = follower code only)
+#endif
+template <int R>
+__global__ void __launch_bounds__(2 * SYM2_GROUPS, JR_SYM2_MINCTAS) sym2_kernel(const Dev d, const StepParams p, uint8_t* symdone, uint8_t* symblk) {
+  JR_DYN_SMEM(uint4, smem);
+  constexpr uint32_t S = SYM2_GROUPS;
+  const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const bool lead = ((w ^ blockIdx.x) & 1u) == 0;          // roles alternate from CTA to CTA: no SM sub-partition gets leaders only
+  const uint32_t gi = (w >> 1) * 32u + lane;               // group within the CTA
+  const uint32_t g = blockIdx.x * S + gi;                  // (g >= Gp: sym_enter says no; the lane only keeps the barriers company)
+  SymGroup<R, true> s(d, g);
+  s.abort = false;
+  s.lcnt = s.fcnt = 0;
+  s.n_hb = 0;
+  s.last_hb = 0;
+  s.share = false;
+  s.n_app = 1u + p.n_synth;
+  s.rows = smem + gi;
+  s.enc = smem + 2 * SYM_ROWS * S + gi;
+  uint4* mail = smem + SYM_SMEM_UNITS * S + gi;            // [k * S]: k = 2 * buf + {0, 1} leader -> followers, 4 + buf followers -> leader
+  s.cache_clear(lead ? 0u : SYM_ROWS, SYM_ROWS);
+  const uint32_t blk = g / GROUPS_PER_CTA;                  // step_kernel's 32-group block of this warp pair
+  if (lead && lane == 0 && g < d.Gp) symblk[blk] = 1;      // (cleared below by any lane whose group is not folded)
+  __syncthreads();
+  SymMail a;
+  bool dead = !sym_enter(s, a, p, 1 - p.cur);
+  __syncthreads();                                         // the other lane's sym_enter may still be reading this lane's (empty) cache
+  if (!dead) {
+    if (lead) {
+      s.cache_fill(s.L, s.maxkey);
+      s.enc_init_leader((d.flags & JR_F_CAPTURE_FSM) ? d.fc[s.rg(s.L)] : make_uint2(0u, 0u));
+      // the mail in flight, where tick 0 looks for it
+      mail[2 * S] = make_uint4(a.hb | (a.ae << 1) | (a.ae_nb << 4), a.hb_commit, s.maxkey, a.ae_id[0]);
+      mail[3 * S] = make_uint4(a.ae_id[1], a.ae_id[2], a.ae_id[3], a.ae_id[4]);
+    } else {
+      s.cache_fill(s.F0, s.fmaxkey);
+      s.enc_init_followers();
+      s.share = (d.flags & JR_F_CAPTURE_FSM) != 0;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if ((uint32_t)r == s.L) continue;
+        const uint2 c = d.fc[s.rg(r)];
+        if (c.x | c.y) s.share = false;
+      }
+      mail[5 * S] = make_uint4(a.hbr | (a.hbr_has << 1) | (a.ar << 2), a.hbr_commit, a.ar_head, 0u);
+    }
+  }
+  __syncthreads();
+  const jr_proposal* props = p.proposals;
+  s.now = p.now;
+  uint32_t cur = 0;                                        // mail buffer written this tick; 1 - cur is read
+  for (uint32_t t = 0; t < p.n_ticks; ++t) {
+    if (lead && (JR_SYM2_ROLES & 1)) {
+      if (!dead) {
+        const uint4 c = mail[(4 + (1 - cur)) * S];
+        if (c.x & SYM2_ABORT) dead = true;
+        else {
+          SymMail in{}, out{};
+          in.hbr = c.x & 1u; in.hbr_has = (c.x >> 1) & 1u; in.ar = (c.x >> 2) & 1u;
+          in.hbr_commit = c.y; in.ar_head = c.z;
+          uint64_t tok = 0;
+          if ((p.phases & PH_PROPOSE) && (props || p.tok_runs)) {
+            uint4 pr;
+            if (p.tok_runs) {
+              const uint4 rn = __ldg(p.tok_runs + g);
+              const uint64_t base = (uint64_t)rn.x | ((uint64_t)rn.y << 32);
+              const uint64_t tk = base + (uint64_t)(p.tok_tick + t) * ((uint64_t)rn.z | ((uint64_t)rn.w << 32));
+              pr = make_uint4((uint32_t)tk, (uint32_t)(tk >> 32), base ? __ldg(p.tok_route + g) : 0u, 0u);
+            } else {
+              pr = __ldg(reinterpret_cast<const uint4*>(props + (size_t)t * p.prop_stride) + g);
+            }
+            if (pr.z == s.L + 1) tok = (uint64_t)pr.x | ((uint64_t)pr.y << 32);
+            else if (pr.z != 0) s.abort = true;           // a proposal for a follower: proxied ClientRequest, not canonical
+          }
+          if (!s.abort) s.leader_tick(in, out, tok, (p.phases & PH_PROPOSE) ? p.n_synth : 0u, p.step_index + t);
+          if (s.abort) dead = true;
+          else {
+            // (.y: the leader's commit -- what a Heartbeat of this tick carries, leader.rs:78-84; the last one also bounds the truncation)
+            mail[(2 * cur) * S] = make_uint4(out.hb | (out.ae << 1) | (out.ae_nb << 4), s.commit, s.maxkey, out.ae_id[0]);
+            mail[(2 * cur + 1) * S] = make_uint4(out.ae_id[1], out.ae_id[2], out.ae_id[3], out.ae_id[4]);
+          }
+        }
+      }
+      if (dead) mail[(2 * cur) * S] = make_uint4(SYM2_ABORT, 0u, 0u, 0u);
+    } else if (!lead && (JR_SYM2_ROLES & 2)) {
+      if (!dead) {
+        const uint4 ma = mail[(2 * (1 - cur)) * S], mb = mail[(2 * (1 - cur) + 1) * S];
+        if (ma.x & SYM2_ABORT) dead = true;
+        else {
+          SymMail in{}, out{};
+          in.hb = ma.x & 1u; in.ae = (ma.x >> 1) & 1u; in.ae_nb = (ma.x >> 4) & 15u;
+          in.hb_commit = ma.y; in.mk = ma.z;
+          in.ae_id[0] = ma.w; in.ae_id[1] = mb.x; in.ae_id[2] = mb.y; in.ae_id[3] = mb.z; in.ae_id[4] = mb.w;
+          s.follower_tick(in, out);
+          if (s.abort) dead = true;
+          else mail[(4 + cur) * S] = make_uint4(out.hbr | (out.hbr_has << 1) | (out.ar << 2), out.hbr_commit, out.ar_head, 0u);
+        }
+      }
+      if (dead) mail[(4 + cur) * S] = make_uint4(SYM2_ABORT, 0u, 0u, 0u);
+    }
+    s.now += p.dt;
+    __syncthreads();
+    cur ^= 1u;
+  }
+  const uint32_t lastb = cur ^ 1u;                         // the buffers the last tick wrote
+  const uint4 la = mail[(2 * lastb) * S], lb = mail[(2 * lastb + 1) * S], lc = mail[(4 + lastb) * S];
+  const bool ok = !dead && !((la.x | lc.x) & SYM2_ABORT);
+  if (ok) {
+    const int cur_last = p.cur ^ (int)((p.n_ticks - 1) & 1u);
+    SymMail last{};
+    if (lead) {
+      last.hb = la.x & 1u; last.ae = (la.x >> 1) & 1u; last.ae_nb = (la.x >> 4) & 15u;
+      last.hb_commit = la.y;
+      last.ae_id[0] = la.w; last.ae_id[1] = lb.x; last.ae_id[2] = lb.y; last.ae_id[3] = lb.z; last.ae_id[4] = lb.w;
+      sym_leave_leader(s, last, cur_last);
+    } else {
+      last.hbr = lc.x & 1u; last.hbr_has = (lc.x >> 1) & 1u; last.ar = (lc.x >> 2) & 1u;
+      last.hbr_commit = lc.y; last.ar_head = lc.z;
+      sym_leave_followers(s, last, cur_last);
+    }
+  }
+  if (p.trunc) {   // jr_truncate(margin) for this group (truncate_kernel, engine.cu): every replica is live, the
+    //              leader's commit after the last tick travels in its last mail
+    __syncthreads();   // the leader lane's sym_leave may still be reading rows this is about to blank
+    if (ok && !lead) {
+      const uint32_t lo = min(s.fcommit, la.y);
+      const uint32_t floor = lo > p.trunc_margin ? lo - p.trunc_margin : 0u;
+      if (floor > s.tbase) {
+        for (uint32_t b = s.tbase; b < floor && b - s.tbase < d.cap; ++b)
+#pragma unroll
+          for (int r = 0; r < R; ++r) d.cnext[s.row(r, b)] = ABSENT;
+        d.tb[g] = floor;
+      }
+    }
+  }
+  if (lead && g < d.Gp) {
+    symdone[g] = ok ? 1 : 0;
+    if (!ok) symblk[blk] = 0;
+  }
 }
 
 // symblk[b] = every group of 32-group block b was folded (step_kernel CTAs of such blocks return at once)

@@ -391,6 +391,10 @@ class RaftApi:
         """jr_truncate (deviation D7): drop every block below min(commit of the live replicas) - margin, per group."""
         self._check(self._fn("truncate")(self._h, C.c_uint32(margin)), "truncate")
 
+    def set_auto_truncate(self, margin: Optional[int] = 8):
+        """jr_set_auto_truncate: every fused run ends with jr_truncate(margin); None switches it off."""
+        self._check(self._fn("set_auto_truncate")(self._h, C.c_int(0 if margin is None else 1), C.c_uint32(margin or 0)), "set_auto_truncate")
+
     def node_restart(self, group: int, node: int, now_ms: int, blocks: Sequence[Tuple[int, int, int]], commit: int,
                      commit_key: Optional[bool] = None):
         """jr_node_restart: RaftHandle::new over a persisted chain (chain.rs:117-137)."""

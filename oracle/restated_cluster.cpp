@@ -191,6 +191,8 @@ struct jro_cluster {
   uint64_t step_index = 0;
   std::vector<Replica> reps;  // [g * R + (node-1)]
   std::vector<uint32_t> route;  // [g]: leader_id of the last jro_leader_table call (0 = none), for jro_run_tokens
+  bool auto_trunc = false;      // jr_set_auto_truncate: every fused run ends with jro_truncate(auto_trunc_margin)
+  uint32_t auto_trunc_margin = 0;
   Replica& at(uint32_t g, uint32_t node) { return reps[(size_t)g * cfg.n_replicas + (node - 1)]; }
 };
 
@@ -397,6 +399,15 @@ jr_status jro_step(jro_cluster* c, jr_step_args* a) {
   return ovf ? JR_E_CAPACITY : JR_OK;
 }
 
+jr_status jro_truncate(jro_cluster* c, uint32_t margin);
+// include/josefine_raft_abi.h jr_set_auto_truncate
+jr_status jro_set_auto_truncate(jro_cluster* c, int enabled, uint32_t margin) {
+  if (!c) return JR_E_INVAL;
+  c->auto_trunc = enabled != 0;
+  c->auto_trunc_margin = margin;
+  return JR_OK;
+}
+
 jr_status jro_run(jro_cluster* c, uint64_t now0, uint32_t dt, uint32_t n_steps, uint32_t n_synth) {
   if (!c || n_synth > 8) return JR_E_INVAL;
   // Groups never interact, so each host thread runs ALL n_steps for its own
@@ -412,6 +423,7 @@ jr_status jro_run(jro_cluster* c, uint64_t now0, uint32_t dt, uint32_t n_steps, 
       }
   });
   c->step_index += n_steps;
+  if (c->auto_trunc && n_steps) return jro_truncate(c, c->auto_trunc_margin);
   return JR_OK;
 }
 
@@ -433,6 +445,7 @@ jr_status jro_run_proposals(jro_cluster* c, uint64_t now0, uint32_t dt, uint32_t
       }
   });
   c->step_index += n_steps;
+  if (c->auto_trunc && n_steps) return jro_truncate(c, c->auto_trunc_margin);
   return JR_OK;
 }
 

@@ -127,6 +127,7 @@ template <class T> inline cudaError_t cudaMalloc(T** p, size_t n) { *p = (T*)ali
 inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
 enum { cudaHostAllocMapped = 2 };
 inline cudaError_t cudaHostAlloc(void** p, size_t n, int) { *p = malloc(n); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+inline cudaError_t cudaHostGetDevicePointer(void** d, void* h, unsigned) { *d = h; return cudaSuccess; }
 inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }

@@ -95,6 +95,43 @@ def case_tokens_kill_truncate(make, G=48, R=5):
     return folded
 
 
+def case_auto_truncate(make, G=96, R=5):
+    """jr_set_auto_truncate: a fused run that ends with its own truncation (done by the folding lane for folded groups,
+    by truncate_kernel for the rest) equals run + jr_truncate on a non-folding engine and on the oracle -- and the
+    oracle's own auto mode equals its explicit calls.  Some leaders are silenced on the way so both paths are taken."""
+    cfg = dict(seed=11, chain_capacity=128, fsm_units=128, fsm_host_records=G * R * 32)
+    apis = trio(make, G, R, **cfg)
+    ora_auto = _oracle(G, R, flags=CAP, **cfg)
+    apis = list(apis) + [ora_auto]
+    for api in apis:
+        _bootstrap(api, G, R)
+        api.run(100, 100, 12, 1)
+    apis[0].set_auto_truncate(5)
+    ora_auto.set_auto_truncate(5)
+    now = 1300
+    folded = []
+    for rnd in range(6):
+        ticks = 17 + 3 * rnd
+        for i, api in enumerate(apis):
+            api.run(now, 100, ticks, 1)
+            if i in (1, 2):
+                api.truncate(5)
+        now += 100 * ticks
+        folded.append(apis[0].fold_count())
+        same(apis, chain_ids=0)
+        if rnd == 2:
+            assert len({api.kill_leaders(8, 250) for api in apis}) == 1
+    floors = [int(apis[0].query(g, 1).chain_floor) for g in range(0, G, 5)]
+    assert max(floors) > 60                                       # the window really moved
+    apis[0].set_auto_truncate(None)
+    ora_auto.set_auto_truncate(None)
+    for i, api in enumerate(apis):
+        api.run(now, 100, 9, 1)                                   # switched off again: floors stay
+    assert [int(apis[0].query(g, 1).chain_floor) for g in range(0, G, 5)] == floors
+    same(apis, chain_ids=0)
+    return folded
+
+
 def case_misrouted_and_asymmetric(make, G=16, R=3):
     """Groups that must NOT fold: a proposal aimed at a follower (proxied ClientRequest), a follower silenced (asymmetric),
     elections in progress.  Everything still equals the oracle, the eligible rest folds."""
@@ -139,6 +176,11 @@ def test_tokens_kill_truncate_on_device_code():
     assert folded[1] == 48 and 0 < folded[-1] < 48, folded
 
 
+def test_auto_truncate_on_device_code():
+    folded = case_auto_truncate(_emu)
+    assert folded[0] == 96 and 0 < folded[-1] < 96
+
+
 def test_misrouted_and_asymmetric_on_device_code():
     n1, n2 = case_misrouted_and_asymmetric(_emu)
     assert n1 == 16 - 2 and n2 == 16 - 1, (n1, n2)      # groups 3 and 5 stay out; group 5 comes back once proposals go to the leader
@@ -159,6 +201,12 @@ def test_steady_fold_on_gpu(R):
 @pytest.mark.gpu
 def test_tokens_kill_truncate_on_gpu():
     case_tokens_kill_truncate(_gpu, G=2048)
+
+
+@pytest.mark.gpu
+def test_auto_truncate_on_gpu():
+    folded = case_auto_truncate(_gpu, G=4096)
+    assert folded[0] == 4096 and 0 < folded[-1] < 4096
 
 
 @pytest.mark.gpu

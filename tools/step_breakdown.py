@@ -14,9 +14,12 @@ import bench  # noqa: E402
 from josefine_b200 import abi  # noqa: E402
 
 
+EXPLICIT_TRUNCATE = False
+
+
 def measure(bn, label, G, R, steps, capture=True, flush=True, **kw):
     torch = bn.torch
-    eng = bn.steady_engine(G, R, abi.F_CAPTURE_FSM if capture else 0, **kw)
+    eng = bn.steady_engine(G, R, abi.F_CAPTURE_FSM if capture else 0, auto_truncate=not EXPLICIT_TRUNCATE, **kw)
     lib, h = eng._lib, eng._h
     S = bench.TICKS_PER_STEP
     now = bench.DT_MS * 17
@@ -32,9 +35,10 @@ def measure(bn, label, G, R, steps, capture=True, flush=True, **kw):
             bn.flush.fill_(1)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record(bn.stream)
-        eng.run(now, bench.DT_MS, S, 1)
+        eng.run(now, bench.DT_MS, S, 1)          # ends with its own truncation (jr_set_auto_truncate) unless --explicit-truncate
         ev[1].record(bn.stream)
-        eng.truncate(bench.TRUNC_MARGIN)
+        if EXPLICIT_TRUNCATE:
+            eng.truncate(bench.TRUNC_MARGIN)
         ev[2].record(bn.stream)
         if capture:
             assert lib.jr_fsm_records_async(h) == 0
@@ -65,7 +69,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("steps", nargs="?", type=int, default=60)
     ap.add_argument("--only", type=int, default=99, help="run only the first N variants")
+    ap.add_argument("--explicit-truncate", action="store_true", help="jr_truncate as its own call (the pre-fusion shape)")
     a = ap.parse_args()
+    global EXPLICIT_TRUNCATE
+    EXPLICIT_TRUNCATE = a.explicit_truncate
     bn = bench.Bench(argparse.Namespace())
     G, R = bench.GROUPS_PER_GPU, bench.REPLICAS
     variants = [("headline", G, {}), ("headline, no capture", G, {"capture": False}), ("scattered leaders", G, {"scattered": True}),
