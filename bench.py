@@ -68,7 +68,8 @@ L2_FLUSH_BYTES = 256 << 20
 CHAIN_WINDOW = 512          # block ids a replica's table may span above the floor (truncated every step)
 TRUNC_MARGIN = 8
 FSM_UNITS = 16              # record slots per replica between two drains (steady state uses <= 4)
-FOLD_THREADS = int(os.environ.get("JR_FOLD_THREADS", "4"))   # host threads folding a batch of Instruction records (jr_fsm_fold_mt, groups partitioned over threads)
+FOLD_THREADS = int(os.environ.get("JR_FOLD_THREADS", "0"))   # host threads folding a batch of Instruction records (jr_fsm_fold_mt, groups partitioned
+#                                                               over threads); 0 = what this rank's share of the usable host cores allows, at most 8
 
 
 def workload_name(G, R):
@@ -364,6 +365,9 @@ class Bench:
             os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")     # the 1 MB announce must not take SMs from a slot-bound kernel
             os.environ.setdefault("NCCL_MIN_NCHANNELS", "1")
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        global FOLD_THREADS
+        if FOLD_THREADS <= 0:     # the box's cgroup may allow far fewer cores than it shows: leave one for this rank's submitting thread
+            FOLD_THREADS = max(1, min(8, effective_cores() // self.world - 1))
         self.stream = torch.cuda.Stream()      # explicit non-default stream: handle 0 would mean "engine's own"
         torch.cuda.set_stream(self.stream)
         self.flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
@@ -564,16 +568,52 @@ class Bench:
 
         seq = [0]      # steps submitted so far (token bases advance with it, across warm-up and timed loops)
 
+        # JR_E2E_TWO_THREADS=1: consume on a second host thread (the engine allows it).  Measured here it is within a few percent
+        # of the single-threaded loop when few threads fold and much worse when many do, so the default stays one thread.
+        two_threads = os.environ.get("JR_E2E_TWO_THREADS", "0") == "1"
+
         def e2e_steps(n):
-            for j in range(min(NB - 1, n)):
-                submit(j)
+            """Step i is submitted by this thread and consumed (copy-out waited for, result read, Instruction records folded)
+            by a second one -- josefine's Raft task and fsm::Driver task (fsm.rs:52-88).  NB staging buffers: step i + NB is
+            not submitted before step i has been consumed."""
+            if not two_threads:
+                for j in range(min(NB - 1, n)):
+                    submit(j)
+                for i in range(n):
+                    if i + NB - 1 < n:
+                        ts = time.perf_counter()
+                        submit(i + NB - 1)
+                        if trace is not None:
+                            trace["submit"] += time.perf_counter() - ts
+                    consume(i)
+                return
+            free, ready, failed = threading.Semaphore(NB), threading.Semaphore(0), []
+
+            def consumer():
+                try:
+                    for i in range(n):
+                        ready.acquire()
+                        consume(i)
+                        free.release()
+                except BaseException as ex:      # noqa: BLE001 -- hand it to the submitting thread
+                    failed.append(ex)
+                    for _ in range(n + NB):
+                        free.release()
+
+            th = threading.Thread(target=consumer, name="fsm-driver")
+            th.start()
             for i in range(n):
-                if i + NB - 1 < n:
-                    ts = time.perf_counter()
-                    submit(i + NB - 1)
-                    if trace is not None:
-                        trace["submit"] += time.perf_counter() - ts
-                consume(i)
+                free.acquire()
+                if failed:
+                    break
+                ts = time.perf_counter()
+                submit(i)
+                if trace is not None:
+                    trace["submit"] += time.perf_counter() - ts
+                ready.release()
+            th.join()
+            if failed:
+                raise failed[0]
 
         e2e_steps(max(warmup, 4))
         eng.sync()
@@ -610,7 +650,8 @@ class Bench:
                         "api": "per step: " + ("jr_run_tokens(pinned u64 tokens[64][G]" if dense_input else "jr_run_token_runs(pinned jr_token_run[G]") +
                                ", routed to the last announced leader; ends with jr_truncate: jr_set_auto_truncate) + "
                                "jr_leader_table_async(pinned jr_leader_entry[G]) + jr_fsm_records_async; then jr_leader_table_wait + "
-                               f"jr_fsm_records_wait + jr_fsm_fold_mt over the batch on {FOLD_THREADS} host threads (apply watermark per replica); {NB} steps in flight",
+                               f"jr_fsm_records_wait + jr_fsm_fold_mt over the batch on {FOLD_THREADS} host threads (apply watermark per replica), "
+                               + ("on a second host thread (the fsm::Driver task); " if two_threads else "") + f"{NB} steps in flight",
                         "host_fold_threads": FOLD_THREADS})
         else:
             out["api"] = ("per step: jr_run_tokens (ends with jr_truncate) + jr_leader_table_async + jr_leader_table_wait; engine created without "

@@ -428,6 +428,11 @@ jr_status jr_drain_fsm(jr_engine* e, jr_fsm_instr* out, size_t cap, size_t* n);
  * and returns it: `*records` points into the engine's buffer and stays valid until the JR_STAGING_DEPTH-1'th
  * jr_fsm_records_async call after this one.  JR_E_CAPACITY (batch still returned) if records were dropped.  At
  * most JR_STAGING_DEPTH batches may be outstanding.  Requires JR_F_CAPTURE_FSM.
+ * Threads: an engine is driven by ONE submitting thread (josefine's event_loop task); jr_fsm_records_wait and
+ * jr_leader_table_wait (and the pure host functions jr_fsm_expand / jr_fsm_fold*) may be called from ONE other thread at
+ * the same time -- the counterpart of josefine's fsm::Driver task (fsm.rs:52-88), which consumes fsm_tx while the Raft
+ * task keeps stepping.  That thread must have returned a batch's buffer (be done reading it) before the submitting
+ * thread's JR_STAGING_DEPTH-1'th jr_fsm_records_async after it.
  */
 jr_status jr_fsm_records_async(jr_engine* e);
 jr_status jr_fsm_records_wait(jr_engine* e, const jr_fsm_record** records, jr_fsm_batch* batch);

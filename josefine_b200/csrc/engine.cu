@@ -788,6 +788,8 @@ struct jr_engine {
   int fsm_copy_by_sm = 0;                                     // JR_FSM_COPY=sm (A/B): fsm_copy_kernel instead of the copy engine
   bool fsm_used[NBUF] = {false, false};
   int fsm_i = 0, fsm_pending[NBUF] = {0, 0}, fsm_npending = 0;
+  std::mutex qmu;   // the two FIFOs of outstanding copy-outs (fsm_pending, tab_pending) and fsm_last_records: a second host thread may
+                    // sit in jr_fsm_records_wait / jr_leader_table_wait while the first one keeps submitting
   uint32_t fsm_epoch = 0;
   // symmetric-group fold
   uint8_t* symdone = nullptr;   // device, Gp entries
@@ -1289,7 +1291,12 @@ static jr_status capture_messages(jr_engine* e, int buf, std::vector<jr_msg>& ou
 static jr_status fsm_records_enqueue(jr_engine* e) {
   const Dev& d = e->d;
   if (!(d.flags & JR_F_CAPTURE_FSM)) { set_err("engine created without JR_F_CAPTURE_FSM"); return JR_E_INVAL; }
-  if (e->fsm_npending == jr_engine::NBUF) { set_err("%d batches outstanding: call jr_fsm_records_wait first", jr_engine::NBUF); return JR_E_INVAL; }
+  size_t last_records;
+  {
+    std::lock_guard<std::mutex> l(e->qmu);
+    if (e->fsm_npending == jr_engine::NBUF) { set_err("%d batches outstanding: call jr_fsm_records_wait first", jr_engine::NBUF); return JR_E_INVAL; }
+    last_records = e->fsm_last_records;
+  }
   const int b = e->fsm_i;
   e->fsm_i = (b + 1) % jr_engine::NBUF;
   const size_t plane = (size_t)d.R * d.Gp;
@@ -1318,22 +1325,27 @@ static jr_status fsm_records_enqueue(jr_engine* e) {
     // batch held plus a margin; fsm_records_take fetches the rest in the (rare) case the batch turned out larger.
     // (fsm_copy_kernel's stores to host memory share LSUs with the next step's kernel: one wave of CTAs, so the
     // slowest SM sets its duration.  A DMA copy takes nothing from the SMs.)
-    const size_t guess = std::min<size_t>(e->fsm_cap, std::max<size_t>(e->fsm_last_records + e->fsm_last_records / 8 + 1024, 16384));
+    const size_t guess = std::min<size_t>(e->fsm_cap, std::max<size_t>(last_records + last_records / 8 + 1024, 16384));
     if (guess) CK(cudaMemcpyAsync(e->fsm_host[b], e->fsm_stage[b], guess * sizeof(jr_fsm_record), cudaMemcpyDeviceToHost, e->d2h));
     CK(cudaMemcpyAsync(e->fsm_host_hdr[b], e->fsm_stage_hdr[b], sizeof(FsmHeader), cudaMemcpyDeviceToHost, e->d2h));
     e->fsm_copied[b] = guess;
   }
   CK(cudaEventRecord(e->fsm_landed[b], e->d2h));
   e->fsm_used[b] = true;
+  std::lock_guard<std::mutex> l(e->qmu);
   e->fsm_pending[e->fsm_npending++] = b;
   return JR_OK;
 }
 
 static jr_status fsm_records_take(jr_engine* e, const jr_fsm_record** recs, jr_fsm_batch* batch) {
-  if (e->fsm_npending == 0) { set_err("no batch outstanding"); return JR_E_INVAL; }
-  const int b = e->fsm_pending[0];
-  for (int k = 0; k + 1 < jr_engine::NBUF; ++k) e->fsm_pending[k] = e->fsm_pending[k + 1];
-  --e->fsm_npending;
+  int b;
+  {
+    std::lock_guard<std::mutex> l(e->qmu);
+    if (e->fsm_npending == 0) { set_err("no batch outstanding"); return JR_E_INVAL; }
+    b = e->fsm_pending[0];
+    for (int k = 0; k + 1 < jr_engine::NBUF; ++k) e->fsm_pending[k] = e->fsm_pending[k + 1];
+    --e->fsm_npending;
+  }
   CK(cudaEventSynchronize(e->fsm_landed[b]));
   const FsmHeader& h = *e->fsm_host_hdr[b];
   if (h.n_records > e->fsm_copied[b]) {   // the speculative copy was short: fetch the tail now (stage[b] is still intact)
@@ -1344,7 +1356,7 @@ static jr_status fsm_records_take(jr_engine* e, const jr_fsm_record** recs, jr_f
     CK(cudaEventSynchronize(e->fsm_landed[b]));
     e->fsm_copied[b] = h.n_records;
   }
-  e->fsm_last_records = h.n_records;
+  { std::lock_guard<std::mutex> l(e->qmu); e->fsm_last_records = h.n_records; }
   if (recs) *recs = reinterpret_cast<const jr_fsm_record*>(e->fsm_host[b]);
   if (batch) {
     memset(batch, 0, sizeof *batch);
@@ -1836,6 +1848,7 @@ jr_status jr_fsm_records_async(jr_engine* e) {
 
 jr_status jr_fsm_records_wait(jr_engine* e, const jr_fsm_record** records, jr_fsm_batch* batch) {
   if (!e) return JR_E_INVAL;
+  CK(cudaSetDevice(e->cfg.device));   // (may be a consumer thread of its own: the device is per thread)
   return fsm_records_take(e, records, batch);
 }
 
@@ -2246,6 +2259,7 @@ jr_status jr_leader_table_async(jr_engine* e, jr_leader_entry* host_out) {
   CK(cudaMemcpyAsync(host_out, e->leaders[b], (size_t)e->d.G * sizeof(jr_leader_entry), cudaMemcpyDeviceToHost, e->d2h));
   CK(cudaEventRecord(e->tab_free[b], e->d2h));
   e->tab_used[b] = true;
+  std::lock_guard<std::mutex> l(e->qmu);
   if (e->tab_npending == jr_engine::NBUF) {  // the oldest one is about to be overwritten anyway
     for (int k = 0; k + 1 < jr_engine::NBUF; ++k) e->tab_pending[k] = e->tab_pending[k + 1];
     --e->tab_npending;
@@ -2256,10 +2270,15 @@ jr_status jr_leader_table_async(jr_engine* e, jr_leader_entry* host_out) {
 
 jr_status jr_leader_table_wait(jr_engine* e) {
   if (!e) return JR_E_INVAL;
-  if (e->tab_npending == 0) return JR_OK;
-  const int b = e->tab_pending[0];
-  for (int k = 0; k + 1 < jr_engine::NBUF; ++k) e->tab_pending[k] = e->tab_pending[k + 1];
-  --e->tab_npending;
+  CK(cudaSetDevice(e->cfg.device));
+  int b;
+  {
+    std::lock_guard<std::mutex> l(e->qmu);
+    if (e->tab_npending == 0) return JR_OK;
+    b = e->tab_pending[0];
+    for (int k = 0; k + 1 < jr_engine::NBUF; ++k) e->tab_pending[k] = e->tab_pending[k + 1];
+    --e->tab_npending;
+  }
   CK(cudaEventSynchronize(e->tab_free[b]));
   return JR_OK;
 }

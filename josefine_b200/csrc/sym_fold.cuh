@@ -64,11 +64,13 @@ constexpr uint32_t SYM_SMEM_UNITS = 2 * SYM_ROWS + SYM_ENC_L + SYM_ENC_F;   // u
 // followers' -- because within a tick the two sides only depend on the mail of the PREVIOUS tick.  The kernel is latency
 // bound with 3.5 warps per SM sub-partition; this doubles the warps and halves each warp's serial chain.  The mail goes
 // through shared memory, double buffered, one __syncthreads() per tick:
-//   leader -> followers   A = {hb | ae << 1 | nb << 4 | abort << 8, hb_commit, leader's max key, id0}   B = {id1 .. id4}
+//   leader -> followers   A = {hb | ae << 1 | nb << 4 | abort << 8 | ids << 9 | mode << 10, commit, leader's max key, id0 / progress head}
+//                         B = {id1 .. id4}   (ids = 1: the AppendEntries' blocks are listed -- the mail sym_enter found in
+//                         flight; ids = 0: the follower lane derives them, see replicate())
 //   followers -> leader   C = {hbr | has << 1 | ar << 2 | abort << 8, hbr_commit, ar_head, -}
 constexpr uint32_t SYM2_GROUPS = 64;                                        // groups per CTA: 128 threads
 constexpr uint32_t SYM2_UNITS = SYM_SMEM_UNITS + 2 * 2 + 2 * 1;            // uint4 per group
-constexpr uint32_t SYM2_ABORT = 1u << 8;
+constexpr uint32_t SYM2_ABORT = 1u << 8, SYM2_IDS = 1u << 9, SYM2_MODE = 1u << 10;
 
 template <int R, bool SPLIT = false>
 struct SymGroup {
@@ -316,24 +318,33 @@ struct SymGroup {
       out.hb_commit = commit;
       hbtime = now;
     }
-    // replicate, leader.rs:124-174: Probe -> range(head..).nth(1); Replicate -> range(head..).skip(1).take(5)
-    const uint32_t take = mode_f ? JR_MAX_AE_BLOCKS : 1u;
-    uint32_t bid = max(ph_f, tbase), pulled = 0, nb = 0;
+    out.ae = 1;                                            // replicate() follows: one AppendEntries per peer
+    out.mk = maxkey;
+    if (!SPLIT) replicate<false>(ph_f, mode_f, maxkey, out);
+  }
+  // replicate, leader.rs:124-174: Probe -> range(head..).nth(1); Replicate -> range(head..).skip(1).take(5), over the
+  // leader's table as it stood when its largest key was `mk`.  The one-lane kernel runs it inside the leader's tick.  In
+  // sym2_kernel the FOLLOWER lane runs it (VIEW) at the start of the next tick, from the {progress head, mode, max key}
+  // the leader lane put in its mail -- the same rows, read through fetch_sent, the same blocks; it takes a sixth of the
+  // leader's chain off the critical lane.  (The leader lane runs it once itself, for the outbox the launch leaves behind.)
+  template <bool VIEW>
+  __device__ __forceinline__ void replicate(uint32_t phf, uint32_t modef, uint32_t mk, SymMail& out) {
+    const uint32_t take = modef ? JR_MAX_AE_BLOCKS : 1u;
+    uint32_t bid = max(phf, tbase), pulled = 0, nb = 0;
     while (pulled < 1 + take) {
       uint32_t nx = ABSENT; uint64_t tk = 0;
-      while (bid <= maxkey) {
-        fetch(L, bid, nx, tk);
+      while (bid <= mk) {
+        if (VIEW) fetch_sent(bid, mk, n_app, nx, tk);
+        else fetch(L, bid, nx, tk);
         if (nx != ABSENT) break;
         ++bid;
       }
-      if (bid > maxkey) break;
+      if (bid > mk) break;
       if (pulled >= 1) out.ae_id[nb++] = bid;
       ++pulled;
       ++bid;
     }
-    out.ae = 1;
     out.ae_nb = nb;
-    out.mk = maxkey;
   }
 
   // ---- follower (follower.rs), once for all R-1 of them ----------------------------------------------------------
@@ -782,7 +793,7 @@ __global__ void __launch_bounds__(2 * SYM2_GROUPS, JR_SYM2_MINCTAS) sym2_kernel(
       s.cache_fill(s.L, s.maxkey);
       s.enc_init_leader((d.flags & JR_F_CAPTURE_FSM) ? d.fc[s.rg(s.L)] : make_uint2(0u, 0u));
       // the mail in flight, where tick 0 looks for it
-      mail[2 * S] = make_uint4(a.hb | (a.ae << 1) | (a.ae_nb << 4), a.hb_commit, s.maxkey, a.ae_id[0]);
+      mail[2 * S] = make_uint4(a.hb | (a.ae << 1) | (a.ae_nb << 4) | SYM2_IDS, a.hb_commit, s.maxkey, a.ae_id[0]);
       mail[3 * S] = make_uint4(a.ae_id[1], a.ae_id[2], a.ae_id[3], a.ae_id[4]);
     } else {
       s.cache_fill(s.F0, s.fmaxkey);
@@ -828,21 +839,26 @@ __global__ void __launch_bounds__(2 * SYM2_GROUPS, JR_SYM2_MINCTAS) sym2_kernel(
           if (s.abort) dead = true;
           else {
             // (.y: the leader's commit -- what a Heartbeat of this tick carries, leader.rs:78-84; the last one also bounds the truncation)
-            mail[(2 * cur) * S] = make_uint4(out.hb | (out.ae << 1) | (out.ae_nb << 4), s.commit, s.maxkey, out.ae_id[0]);
-            mail[(2 * cur + 1) * S] = make_uint4(out.ae_id[1], out.ae_id[2], out.ae_id[3], out.ae_id[4]);
+            mail[(2 * cur) * S] = make_uint4(out.hb | (out.ae << 1) | (s.mode_f ? SYM2_MODE : 0u), s.commit, s.maxkey, s.ph_f);
           }
         }
       }
       if (dead) mail[(2 * cur) * S] = make_uint4(SYM2_ABORT, 0u, 0u, 0u);
     } else if (!lead && (JR_SYM2_ROLES & 2)) {
       if (!dead) {
-        const uint4 ma = mail[(2 * (1 - cur)) * S], mb = mail[(2 * (1 - cur) + 1) * S];
+        const uint4 ma = mail[(2 * (1 - cur)) * S];
         if (ma.x & SYM2_ABORT) dead = true;
         else {
           SymMail in{}, out{};
-          in.hb = ma.x & 1u; in.ae = (ma.x >> 1) & 1u; in.ae_nb = (ma.x >> 4) & 15u;
+          in.hb = ma.x & 1u; in.ae = (ma.x >> 1) & 1u;
           in.hb_commit = ma.y; in.mk = ma.z;
-          in.ae_id[0] = ma.w; in.ae_id[1] = mb.x; in.ae_id[2] = mb.y; in.ae_id[3] = mb.z; in.ae_id[4] = mb.w;
+          if (ma.x & SYM2_IDS) {                           // tick 0: the blocks sym_enter found in the leader's outbox
+            const uint4 mb = mail[(2 * (1 - cur) + 1) * S];
+            in.ae_nb = (ma.x >> 4) & 15u;
+            in.ae_id[0] = ma.w; in.ae_id[1] = mb.x; in.ae_id[2] = mb.y; in.ae_id[3] = mb.z; in.ae_id[4] = mb.w;
+          } else if (in.ae) {
+            s.template replicate<true>(ma.w, (ma.x & SYM2_MODE) ? 1u : 0u, ma.z, in);
+          }
           s.follower_tick(in, out);
           if (s.abort) dead = true;
           else mail[(4 + cur) * S] = make_uint4(out.hbr | (out.hbr_has << 1) | (out.ar << 2), out.hbr_commit, out.ar_head, 0u);
@@ -855,15 +871,15 @@ __global__ void __launch_bounds__(2 * SYM2_GROUPS, JR_SYM2_MINCTAS) sym2_kernel(
     cur ^= 1u;
   }
   const uint32_t lastb = cur ^ 1u;                         // the buffers the last tick wrote
-  const uint4 la = mail[(2 * lastb) * S], lb = mail[(2 * lastb + 1) * S], lc = mail[(4 + lastb) * S];
+  const uint4 la = mail[(2 * lastb) * S], lc = mail[(4 + lastb) * S];
   const bool ok = !dead && !((la.x | lc.x) & SYM2_ABORT);
   if (ok) {
     const int cur_last = p.cur ^ (int)((p.n_ticks - 1) & 1u);
     SymMail last{};
     if (lead) {
-      last.hb = la.x & 1u; last.ae = (la.x >> 1) & 1u; last.ae_nb = (la.x >> 4) & 15u;
+      last.hb = la.x & 1u; last.ae = (la.x >> 1) & 1u;
       last.hb_commit = la.y;
-      last.ae_id[0] = la.w; last.ae_id[1] = lb.x; last.ae_id[2] = lb.y; last.ae_id[3] = lb.z; last.ae_id[4] = lb.w;
+      if (last.ae) s.template replicate<false>(s.ph_f, s.mode_f, s.maxkey, last);   // what the last tick sent: the outbox it leaves behind
       sym_leave_leader(s, last, cur_last);
     } else {
       last.hbr = lc.x & 1u; last.hbr_has = (lc.x >> 1) & 1u; last.ar = (lc.x >> 2) & 1u;
