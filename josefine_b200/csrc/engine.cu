@@ -734,6 +734,7 @@ struct jr_engine {
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
   volatile uint32_t* h_scatter = nullptr;  // pinned + mapped: epoch of the last launch that saw scattered leaders (written by the kernel)
+  volatile uint32_t* h_unfolded = nullptr; // pinned + mapped: epoch of the last launch whose fold left some group to step_kernel (0: never)
   uint32_t ticket_sum = 0;                 // tickets taken so far (the counter is never reset: each launch gets its base)
   int force_sorted = 0;      // JR_STEP_VARIANT=sorted|plain pins the kernel variant (tests, A/B)
   uint64_t launches_sorted = 0, launches_total = 0, launches_split = 0;
@@ -919,6 +920,7 @@ static jr_status launch_step_once(jr_engine* e, const StepParams& p_in) {
   const uint32_t n_blocks = e->d.Gp / GROUPS_PER_CTA;
   const size_t smem = step_smem_bytes(e->d);
   StepParams p = p_in;
+  p.epoch = (uint32_t)(e->launches_total + 1) * 8u;
   if (fold_eligible(e, p)) {
     DISPATCH_R(e->cfg.n_replicas, (launch_sym_r<RR>(e, p)));
     CK(cudaGetLastError());
@@ -932,10 +934,14 @@ static jr_status launch_step_once(jr_engine* e, const StepParams& p_in) {
   }
   e->last_launch_folded = p.symdone != nullptr;
   p.n_parts = choose_parts(e, p, n_blocks);
+  // When the fold has been taking every group (no launch of the last two left one behind -- a hint the kernel stores in
+  // mapped host memory), step_kernel's CTAs only look at symblk and return: do not cut them in parts, which would cost
+  // each of them a ticket and two barriers first.  A wrong guess costs balance in that one launch, nothing else.
+  if (p.symdone && !e->sym_one_lane && e->h_unfolded && (*e->h_unfolded == 0 || p.epoch - *e->h_unfolded > 2u * 8u) && !e->force_parts)
+    if (!getenv("JR_NO_PARTS_HINT")) p.n_parts = 1;
   p.part_ticks = (p.n_ticks + p.n_parts - 1) / p.n_parts;
   p.n_parts = (p.n_ticks + p.part_ticks - 1) / p.part_ticks;  // no empty trailing part
   p.n_blocks = n_blocks;
-  p.epoch = (uint32_t)(e->launches_total + 1) * 8u;
   const uint32_t grid = n_blocks * p.n_parts;
   // Variant choice from the (possibly one launch stale) scatter flag: it only affects speed.
   // (the kernel stores its epoch into that mapped host word: no memset, no copy-back in the launch path)
@@ -1104,6 +1110,9 @@ jr_status jr_engine_create(const jr_config* cfg, jr_engine** out) {
     if (aerr == cudaSuccess) aerr = cudaHostAlloc((void**)&e->h_scatter, sizeof(uint32_t), cudaHostAllocMapped);
     if (aerr == cudaSuccess) *e->h_scatter = 0;
     if (aerr == cudaSuccess) aerr = cudaHostGetDevicePointer((void**)&e->d.hscat, (void*)e->h_scatter, 0);
+    if (aerr == cudaSuccess) aerr = cudaHostAlloc((void**)&e->h_unfolded, sizeof(uint32_t), cudaHostAllocMapped);
+    if (aerr == cudaSuccess) *e->h_unfolded = 0;
+    if (aerr == cudaSuccess) aerr = cudaHostGetDevicePointer((void**)&e->d.hunf, (void*)e->h_unfolded, 0);
     if (const char* ev = getenv("JR_NO_FOLD")) e->no_fold = atoi(ev);
     if (const char* ev = getenv("JR_SYM_ONE_LANE")) e->sym_one_lane = atoi(ev);
     if (const char* ev = getenv("JR_FSM_COPY")) e->fsm_copy_by_sm = strcmp(ev, "sm") == 0;
@@ -1195,6 +1204,7 @@ void jr_engine_destroy(jr_engine* e) {
     if (e->tokbuf[i]) cudaFree(e->tokbuf[i]);
   }
   if (e->h_scatter) cudaFreeHost((void*)e->h_scatter);
+  if (e->h_unfolded) cudaFreeHost((void*)e->h_unfolded);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   delete e;
 }

@@ -60,6 +60,7 @@ struct Dev {
   uint32_t Us, W;                  // shared-memory mailbox units per replica, table-cache entries (power of 2)
   uint32_t use_index;              // receivers use the delivery index (else scan whole mailboxes)
   uint32_t resident;               // bit r: replica index r is hosted here (others are inert, see jr_config)
+  uint32_t* hunf;                  // mapped HOST word: the epoch of the last launch in which sym2_kernel left a group to step_kernel
   uint32_t* hscat;                 // mapped HOST word: the epoch of the last launch in which some CTA saw leaders on >= 2 replica indices
   uint32_t* scatter;               // [0] set by a launch when some CTA has leaders on >= 2 replica indices;
                                    // [1] task ticket counter of the running step launch (both zeroed per launch)

@@ -766,6 +766,10 @@ __global__ void __launch_bounds__(SYM_LANES, 512 / SYM_LANES) sym_kernel(const D
 template <int R>
 __global__ void __launch_bounds__(2 * SYM2_GROUPS, JR_SYM2_MINCTAS) sym2_kernel(const Dev d, const StepParams p, uint8_t* symdone, uint8_t* symblk) {
   JR_DYN_SMEM(uint4, smem);
+  // One __syncthreads() per tick for both warp pairs of the CTA.  (A named barrier per pair -- `bar.sync 0/1, 64`, the
+  // pairs never need each other -- measured 3% SLOWER, twice; with a register operand for the id ptxas charges the CTA
+  // all 16 barriers and only one CTA fits an SM.)
+  auto pair_sync = [] { __syncthreads(); };
   constexpr uint32_t S = SYM2_GROUPS;
   const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31u;
   const bool lead = ((w ^ blockIdx.x) & 1u) == 0;          // roles alternate from CTA to CTA: no SM sub-partition gets leaders only
@@ -784,10 +788,10 @@ __global__ void __launch_bounds__(2 * SYM2_GROUPS, JR_SYM2_MINCTAS) sym2_kernel(
   s.cache_clear(lead ? 0u : SYM_ROWS, SYM_ROWS);
   const uint32_t blk = g / GROUPS_PER_CTA;                  // step_kernel's 32-group block of this warp pair
   if (lead && lane == 0 && g < d.Gp) symblk[blk] = 1;      // (cleared below by any lane whose group is not folded)
-  __syncthreads();
+  pair_sync();
   SymMail a;
   bool dead = !sym_enter(s, a, p, 1 - p.cur);
-  __syncthreads();                                         // the other lane's sym_enter may still be reading this lane's (empty) cache
+  pair_sync();                                         // the other lane's sym_enter may still be reading this lane's (empty) cache
   if (!dead) {
     if (lead) {
       s.cache_fill(s.L, s.maxkey);
@@ -808,7 +812,7 @@ __global__ void __launch_bounds__(2 * SYM2_GROUPS, JR_SYM2_MINCTAS) sym2_kernel(
       mail[5 * S] = make_uint4(a.hbr | (a.hbr_has << 1) | (a.ar << 2), a.hbr_commit, a.ar_head, 0u);
     }
   }
-  __syncthreads();
+  pair_sync();
   const jr_proposal* props = p.proposals;
   s.now = p.now;
   uint32_t cur = 0;                                        // mail buffer written this tick; 1 - cur is read
@@ -867,7 +871,7 @@ __global__ void __launch_bounds__(2 * SYM2_GROUPS, JR_SYM2_MINCTAS) sym2_kernel(
       if (dead) mail[(4 + cur) * S] = make_uint4(SYM2_ABORT, 0u, 0u, 0u);
     }
     s.now += p.dt;
-    __syncthreads();
+    pair_sync();
     cur ^= 1u;
   }
   const uint32_t lastb = cur ^ 1u;                         // the buffers the last tick wrote
@@ -889,7 +893,7 @@ __global__ void __launch_bounds__(2 * SYM2_GROUPS, JR_SYM2_MINCTAS) sym2_kernel(
   }
   if (p.trunc) {   // jr_truncate(margin) for this group (truncate_kernel, engine.cu): every replica is live, the
     //              leader's commit after the last tick travels in its last mail
-    __syncthreads();   // the leader lane's sym_leave may still be reading rows this is about to blank
+    pair_sync();   // the leader lane's sym_leave may still be reading rows this is about to blank
     if (ok && !lead) {
       const uint32_t lo = min(s.fcommit, la.y);
       const uint32_t floor = lo > p.trunc_margin ? lo - p.trunc_margin : 0u;
@@ -903,7 +907,10 @@ __global__ void __launch_bounds__(2 * SYM2_GROUPS, JR_SYM2_MINCTAS) sym2_kernel(
   }
   if (lead && g < d.Gp) {
     symdone[g] = ok ? 1 : 0;
-    if (!ok) symblk[blk] = 0;
+    if (!ok) {
+      symblk[blk] = 0;
+      if (g < d.G) *(volatile uint32_t*)d.hunf = p.epoch;   // advisory, for the host's choice of the next step_kernel grid
+    }
   }
 }
 

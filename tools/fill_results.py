@@ -63,7 +63,8 @@ def main():
     for name in ("BASELINE.md", "DESIGN.md"):
         p = os.path.join(ROOT, name)
         s = open(p).read()
-        new = re.sub(r"<!-- results:begin -->.*?<!-- results:end -->", "<!-- results:begin -->\n" + block + "\n<!-- results:end -->", s, flags=re.S)
+        new = re.sub(r"<!-- results:begin -->.*?<!-- results:end -->", lambda _m: "<!-- results:begin -->\n" + block + "\n<!-- results:end -->", s, flags=re.S)
+        new = re.sub(r"<!-- refbytes -->.*?<!-- /refbytes -->", lambda _m: f"<!-- refbytes -->{d['roofline']['algorithmic_bytes_per_group_tick']:.0f}<!-- /refbytes -->", new, flags=re.S)
         if new == s and "<!-- results:begin -->" not in s:
             print(f"{name}: no results block")
         open(p, "w").write(new)
