@@ -1163,6 +1163,8 @@ jr_status jr_engine_reset(jr_engine* e) {
   CK(cudaMemsetAsync(d.qt, 0, plane * JR_CLIENT_QUEUE_CAP * sizeof(uint4), e->stream));
   CK(cudaMemsetAsync(e->route, 0, (size_t)d.G * sizeof(uint32_t), e->stream));  // no leader announced yet
   CK(cudaMemsetAsync(d.done, 0, (size_t)(d.Gp / GROUPS_PER_CTA) * sizeof(uint32_t), e->stream));
+  CK(cudaMemsetAsync(d.scatter, 0, 2 * sizeof(uint32_t), e->stream));   // [1] = the ticket counter: from here on only launches move it,
+  e->ticket_sum = 0;                                                     //       and each one is told where it stands (ticket_base)
   JR_LAUNCH(init_kernel, (unsigned)((plane + 255) / 256), 256, e->stream, d);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(e->stream));
