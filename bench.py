@@ -362,8 +362,8 @@ class Bench:
         self.placement = bind_to_gpu_numa_node(self.local)     # before any pinned allocation (first touch)
         torch.cuda.set_device(self.local)
         if self.world > 1:
-            os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")     # the 1 MB announce must not take SMs from a slot-bound kernel
-            os.environ.setdefault("NCCL_MIN_NCHANNELS", "1")
+            # The 1 MB announce runs next to the step's drain kernels, never next to sym2_kernel (one_step below).
+            # (NCCL's own channel count: capped at 2 the 2 x 1 MB all-gather took 134 us, at 1 channel 255 us)
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
         global FOLD_THREADS
         if FOLD_THREADS <= 0:     # the box's cgroup may allow far fewer cores than it shows: leave one for this rank's submitting thread
@@ -430,19 +430,17 @@ class Bench:
             outstanding[0] -= 1
 
         def one_step():
+            if world > 1 and announce and announce_done[0] is not None:
+                # The previous announce must be over before the fused run starts: `leaders` is rewritten below, and sym2_kernel
+                # needs 1,024 of the GPU's 1,036 CTA slots in ONE wave -- an NCCL kernel still holding two SMs would push CTAs
+                # into a second wave and stretch the step by the collective's duration.
+                self.stream.wait_event(announce_done[0])
             eng.run(now[0], DT_MS, S, 1)          # (ends with jr_truncate: jr_set_auto_truncate)
             now[0] += DT_MS * S
-            if capture:
-                st = lib.jr_fsm_records_async(h)
-                assert st == 0, st
-                outstanding[0] += 1
-                if outstanding[0] == 2:      # consume the PREVIOUS step's stream while this step runs
-                    take()
             if world > 1 and announce:
-                # the one cross-shard exchange: leader announce, once per step (every 64 ticks).  The table is packed on
-                # the engine stream; the NCCL all-gather runs on a side stream and overlaps the next step's kernel.
-                if announce_done[0] is not None:
-                    self.stream.wait_event(announce_done[0])       # previous announce must be over before `leaders` is rewritten
+                # the one cross-shard exchange: leader announce, once per step (every 64 ticks).  The table is packed on the
+                # engine stream right behind the run; the NCCL all-gather runs on a side stream, next to the drain below (and, in
+                # this bench, the untimed L2 flush that follows); the last one of the timed region is waited for inside it.
                 eng.leader_table_device(leaders.data_ptr())
                 packed = torch.cuda.Event()
                 packed.record(self.stream)
@@ -452,6 +450,12 @@ class Bench:
                     ev = torch.cuda.Event()
                     ev.record(side)
                 announce_done[0] = ev
+            if capture:
+                st = lib.jr_fsm_records_async(h)
+                assert st == 0, st
+                outstanding[0] += 1
+                if outstanding[0] == 2:      # consume the PREVIOUS step's stream while this step runs
+                    take()
 
         for _ in range(max(warmup, 3)):
             self.flush.fill_(1)

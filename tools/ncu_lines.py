@@ -99,6 +99,9 @@ def by_function(rep, so, ksub, src, which=0, unit=1):
         m = re.search(r"__device__\s+(?:__forceinline__|__noinline__|inline)?\s*[\w:<>\*& ]+?\s+(\w+)\s*\(", line)
         if m and not line.strip().startswith("//"):
             cur = m.group(1)
+        g = re.search(r"__global__\s+void\s+(?:__launch_bounds__\([^)]*(?:\([^)]*\))?[^)]*\)\s*)?(\w+)\s*\(", line)
+        if g and not line.strip().startswith("//"):
+            cur = g.group(1) + " (kernel body)"
         fn_at[i] = cur
     base = os.path.basename(src)
     ex, samp = collections.Counter(), collections.Counter()

@@ -70,7 +70,7 @@ def main():
         print(f"# {tag}: per-function warp-instructions of {ksub}<5>, per 32 groups and tick "
               f"({groups // 32} x {ticks} ticks)")
         ncu_lines.by_function(rep, os.path.join(ROOT, "josefine_b200/csrc/libjosefine_b200.so"), ksub + "ILi5E",
-                              os.path.join(ROOT, "josefine_b200/csrc/sym_fold.cuh" if ksub == "sym_kernel" else "josefine_b200/csrc/raft_device.cuh"),
+                              os.path.join(ROOT, "josefine_b200/csrc/sym_fold.cuh" if ksub.startswith("sym") else "josefine_b200/csrc/raft_device.cuh"),
                               0, (groups // 32) * ticks)
     with open(os.path.join(ROOT, "profiles", f"{tag}_{ksub}_functions.txt"), "w") as f:
         f.write(buf.getvalue())
