@@ -324,9 +324,10 @@ struct SymGroup {
   }
   // replicate, leader.rs:124-174: Probe -> range(head..).nth(1); Replicate -> range(head..).skip(1).take(5), over the
   // leader's table as it stood when its largest key was `mk`.  The one-lane kernel runs it inside the leader's tick.  In
-  // sym2_kernel the FOLLOWER lane runs it (VIEW) at the start of the next tick, from the {progress head, mode, max key}
-  // the leader lane put in its mail -- the same rows, read through fetch_sent, the same blocks; it takes a sixth of the
-  // leader's chain off the critical lane.  (The leader lane runs it once itself, for the outbox the launch leaves behind.)
+  // sym2_kernel the FOLLOWER lane runs the same scan at the start of the next tick (follower_tick_view), from the
+  // {progress head, mode, max key} the leader lane put in its mail -- the same rows, read through fetch_sent, the same
+  // blocks; it takes a sixth of the leader's chain off the critical lane.  (The leader lane runs this once itself, for
+  // the outbox the launch leaves behind.)
   template <bool VIEW>
   __device__ __forceinline__ void replicate(uint32_t phf, uint32_t modef, uint32_t mk, SymMail& out) {
     const uint32_t take = modef ? JR_MAX_AE_BLOCKS : 1u;
@@ -348,48 +349,84 @@ struct SymGroup {
   }
 
   // ---- follower (follower.rs), once for all R-1 of them ----------------------------------------------------------
-  __device__ __forceinline__ void follower_tick(const SymMail& in, SymMail& out) {
-    if (in.hb) {                                           // follower.rs:178-217
-      ++n_hb;                                              // set_election_timeout: one RNG draw, timer restarted
-      last_hb = now;
-      const uint32_t c = in.hb_commit;
-      const bool hasc = has_f(c);
-      if (hasc && c > fcommit) {
-        const uint32_t prev = fcommit;
-        fckey = 1;
-        fcommit = c;
-        for (uint32_t b = max(prev, tbase); b < c; ++b) {  // range(prev..commit), key order
-          uint32_t nx; uint64_t tk;
-          fetch_f(b, nx, tk);
-          if (nx != ABSENT) emit_followers(b, nx, tk);
-        }
+  __device__ __forceinline__ void follower_heartbeat(const SymMail& in, SymMail& out) {   // follower.rs:178-217
+    ++n_hb;                                                // set_election_timeout: one RNG draw, timer restarted
+    last_hb = now;
+    const uint32_t c = in.hb_commit;
+    const bool hasc = has_f(c);
+    if (hasc && c > fcommit) {
+      const uint32_t prev = fcommit;
+      fckey = 1;
+      fcommit = c;
+      for (uint32_t b = max(prev, tbase); b < c; ++b) {    // range(prev..commit), key order
+        uint32_t nx; uint64_t tk;
+        fetch_f(b, nx, tk);
+        if (nx != ABSENT) emit_followers(b, nx, tk);
       }
-      out.hbr = 1;
-      out.hbr_commit = fcommit;
-      out.hbr_has = hasc ? 1u : 0u;
     }
+    out.hbr = 1;
+    out.hbr_commit = fcommit;
+    out.hbr_has = hasc ? 1u : 0u;
+  }
+  // one block of an AppendEntries, applied by every follower (follower.rs:156-173 -> chain.rs:180-190)
+  __device__ __forceinline__ void follower_extend(uint32_t bid, uint32_t nx, uint64_t tk) {
+    if (nx == ABSENT || !has_f(nx) || !in_window(bid)) { abort = true; return; }   // chain.rs:180-185 Err / window: step_kernel's business
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if ((uint32_t)r != L) {
+        d.cnext[row(r, bid)] = nx;
+        d.ctok[row(r, bid)] = tk;
+      }
+    cache_put(F0, bid, nx, tk);
+    if (bid > fmaxkey) fmaxkey = bid;
+    fhead = bid;                                           // chain.rs:188-190: unconditionally
+  }
+  __device__ __forceinline__ void follower_tick(const SymMail& in, SymMail& out) {
+    if (in.hb) follower_heartbeat(in, out);
     if (in.ae) {                                           // follower.rs:130-176 with voted_for == Some(leader)
-      for (uint32_t k = 0; k < in.ae_nb; ++k) {
+      for (uint32_t k = 0; k < in.ae_nb && !abort; ++k) {
         const uint32_t bid = in.ae_id[k];
         uint32_t nx; uint64_t tk;
         fetch_sent(bid, in.mk, n_app, nx, tk);             // the block as the leader sent it
-        if (nx == ABSENT || !has_f(nx) || !in_window(bid)) { abort = true; return; }   // chain.rs:180-185 Err / window: step_kernel's business
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-          if ((uint32_t)r != L) {
-            d.cnext[row(r, bid)] = nx;
-            d.ctok[row(r, bid)] = tk;
-          }
-        cache_put(F0, bid, nx, tk);
-        if (bid > fmaxkey) fmaxkey = bid;
-        fhead = bid;                                       // chain.rs:188-190: unconditionally
+        follower_extend(bid, nx, tk);
       }
+      if (abort) return;
       if (in.ae_nb) {
         out.ar = 1;
         out.ar_head = fhead;
       }
     }
     // Command::Tick: the election timer cannot have expired (sym_enter checked the bound)
+  }
+  // sym2_kernel, follower lane: the same tick when the AppendEntries' blocks are not listed in the mail.  The leader's
+  // replicate() (leader.rs:124-174: Probe -> range(head..).nth(1); Replicate -> range(head..).skip(1).take(5)) is run
+  // HERE, over the leader's table as it stood when its largest key was `mk`, and each block it yields is applied on the
+  // spot -- the same blocks in the same order as listing them first, without the list and without reading them twice.
+  __device__ __forceinline__ void follower_tick_view(const SymMail& in, uint32_t phf, uint32_t modef, uint32_t mk, SymMail& out) {
+    if (in.hb) follower_heartbeat(in, out);
+    if (!in.ae || abort) return;
+    const uint32_t take = modef ? JR_MAX_AE_BLOCKS : 1u;
+    uint32_t bid = max(phf, tbase), pulled = 0, nb = 0;
+    while (pulled < 1 + take) {
+      uint32_t nx = ABSENT; uint64_t tk = 0;
+      while (bid <= mk) {
+        fetch_sent(bid, mk, n_app, nx, tk);
+        if (nx != ABSENT) break;
+        ++bid;
+      }
+      if (bid > mk) break;
+      if (pulled >= 1) {
+        follower_extend(bid, nx, tk);
+        if (abort) return;
+        ++nb;
+      }
+      ++pulled;
+      ++bid;
+    }
+    if (nb) {
+      out.ar = 1;
+      out.ar_head = fhead;
+    }
   }
 };
 
@@ -860,10 +897,10 @@ __global__ void __launch_bounds__(2 * SYM2_GROUPS, JR_SYM2_MINCTAS) sym2_kernel(
             const uint4 mb = mail[(2 * (1 - cur) + 1) * S];
             in.ae_nb = (ma.x >> 4) & 15u;
             in.ae_id[0] = ma.w; in.ae_id[1] = mb.x; in.ae_id[2] = mb.y; in.ae_id[3] = mb.z; in.ae_id[4] = mb.w;
-          } else if (in.ae) {
-            s.template replicate<true>(ma.w, (ma.x & SYM2_MODE) ? 1u : 0u, ma.z, in);
+            s.follower_tick(in, out);
+          } else {
+            s.follower_tick_view(in, ma.w, (ma.x & SYM2_MODE) ? 1u : 0u, ma.z, out);
           }
-          s.follower_tick(in, out);
           if (s.abort) dead = true;
           else mail[(4 + cur) * S] = make_uint4(out.hbr | (out.hbr_has << 1) | (out.ar << 2), out.hbr_commit, out.ar_head, 0u);
         }
