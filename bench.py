@@ -14,13 +14,13 @@ HeartbeatResponse traffic between the co-resident replicas.  heartbeat_ms = tick
 and the reference compares with a strict `>` (leader.rs:78-84), so the leader heartbeats
 every SECOND tick; `variants.heartbeat_every_tick` (heartbeat_ms = 99) is the other reading.
 
-A bench "step" = TICKS_PER_STEP consecutive group-ticks of every group: one fused launch
-(jr_run / jr_run_tokens), then jr_truncate (deviation D7: the block-table window moves up, so
-an engine runs indefinitely -- no reset anywhere in this file) and the drain of the step's
-Instruction stream (jr_fsm_records_async: scan + pack on the engine stream, copy to pinned
-host memory on the copy stream).  L2 is flushed between timed steps (the working set is
-smaller than the 126 MB L2).  Device time is taken with CUDA events on the engine's stream,
-per step, flush excluded; max over ranks.
+A bench "step" = TICKS_PER_STEP consecutive group-ticks of every group: one fused call
+(jr_run / jr_run_token_runs) that ends with jr_truncate (jr_set_auto_truncate; deviation D7:
+the block-table window moves up, so an engine runs indefinitely -- no reset anywhere in this
+file), and the drain of the step's Instruction stream (jr_fsm_records_async: count + scan +
+pack on the engine stream, DMA to pinned host memory on the copy stream).  L2 is flushed
+between timed steps (the working set is smaller than the 126 MB L2).  Device time is taken
+with CUDA events on the engine's stream, per step, flush excluded; max over ranks.
 
 Arms:
   (default)          the CUDA engine.  `value` = device-resident throughput (proposals
@@ -28,7 +28,8 @@ Arms:
                      `e2e` = the same workload through the C ABI with HOST buffers, every
                      step: the step's proposals H2D from pinned memory in run-length form
                      (jr_run_token_runs: {base, stride} per group), the per-group leader
-                     table D2H, the step's Instruction records D2H and folded on the host.
+                     table D2H, the step's Instruction records D2H and folded on the host;
+                     three steps in flight (JR_STAGING_DEPTH).
                      `e2e_dense_input` = the same with one 8-byte token per group-tick
                      (jr_run_tokens, round 1's input); `e2e_no_output` = round 1's leg:
                      dense input, engine created without the Instruction stream.

@@ -6,6 +6,8 @@
 // Reference interfaces replaced are cited in include/josefine_raft_abi.h; the
 // replica state machine is in raft_device.cuh.
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -1779,47 +1781,74 @@ void fold_slice(FoldJob& j, uint32_t t) {
   j.nn[t] = nn;
 }
 class FoldPool {
+  // Workers SPIN for a little while after a job before they go to sleep: a host that folds a batch every few hundred
+  // microseconds (bench.py's end-to-end leg) then never pays the futex wake-up of seven threads -- which took as long as
+  // the fold itself.  A host that folds rarely finds them asleep on the condition variable, as before.
+  static constexpr long long SPIN_NS = 2'000'000;
  public:
   static FoldPool& get() { static FoldPool* p = new FoldPool(); return *p; }   // leaked on purpose (see above)
   void run(FoldJob& j) {
-    std::unique_lock<std::mutex> l(m_);
-    while (n_workers_ + 1 < j.parts) {   // worker k serves slice k + 1; the caller folds slice 0
-      const uint32_t k = n_workers_++;
-      std::thread th([this, k] { loop(k); });
-      th.detach();
+    {
+      std::lock_guard<std::mutex> l(m_);
+      while (n_workers_ + 1 < j.parts) {   // worker k serves slice k + 1; the caller folds slice 0
+        const uint32_t k = n_workers_++;
+        std::thread th([this, k] { loop(k); });
+        th.detach();
+      }
+      job_ = &j;
+      left_.store(j.parts - 1, std::memory_order_relaxed);
+      // one word says which job is current and how many slices it has: a worker decides from a single load
+      state_.store(((state_.load(std::memory_order_relaxed) >> 8) + 1) << 8 | j.parts, std::memory_order_release);
     }
-    job_ = &j;
-    left_ = j.parts - 1;
-    ++gen_;
-    l.unlock();
-    cv_.notify_all();
+    if (sleepers_.load(std::memory_order_acquire)) cv_.notify_all();
     fold_slice(j, 0);
-    l.lock();
-    done_.wait(l, [this] { return left_ == 0; });
-    job_ = nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    while (left_.load(std::memory_order_acquire) != 0) {
+      if (std::chrono::steady_clock::now() - t0 > std::chrono::nanoseconds(SPIN_NS)) {
+        std::unique_lock<std::mutex> l(m_);
+        done_.wait(l, [this] { return left_.load(std::memory_order_acquire) == 0; });
+        break;
+      }
+      cpu_relax();
+    }
   }
  private:
+  static void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+  }
   void loop(uint32_t k) {
-    uint64_t seen = 0;
+    uint64_t seen = 0;   // generation (state >> 8) this worker has dealt with
     for (;;) {
-      FoldJob* j;
-      {
-        std::unique_lock<std::mutex> l(m_);
-        cv_.wait(l, [&] { return gen_ != seen && job_ && k + 1 < job_->parts; });
-        seen = gen_;
-        j = job_;
+      uint64_t st = state_.load(std::memory_order_acquire);
+      const auto t0 = std::chrono::steady_clock::now();
+      while ((st >> 8) == seen) {
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::nanoseconds(SPIN_NS)) {
+          std::unique_lock<std::mutex> l(m_);
+          sleepers_.fetch_add(1, std::memory_order_acq_rel);
+          cv_.wait(l, [&] { return (state_.load(std::memory_order_acquire) >> 8) != seen; });
+          sleepers_.fetch_sub(1, std::memory_order_acq_rel);
+        } else {
+          cpu_relax();
+        }
+        st = state_.load(std::memory_order_acquire);
       }
-      fold_slice(*j, k + 1);
-      std::lock_guard<std::mutex> l(m_);
-      if (--left_ == 0) done_.notify_all();
+      seen = st >> 8;
+      if (k + 1 >= (uint32_t)(st & 255u)) continue;   // not one of this job's slices (and then job_ is not this worker's to touch)
+      fold_slice(*job_, k + 1);                         // (run() cannot return, nor the next job start, before left_ reaches 0)
+      if (left_.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+        std::lock_guard<std::mutex> l(m_);
+        done_.notify_all();
+      }
     }
   }
   std::mutex m_;
   std::condition_variable cv_, done_;
   uint32_t n_workers_ = 0;
   FoldJob* job_ = nullptr;
-  uint32_t left_ = 0;
-  uint64_t gen_ = 0;
+  std::atomic<uint32_t> left_{0}, sleepers_{0};
+  std::atomic<uint64_t> state_{0};   // generation << 8 | slices of the current job
 };
 }  // namespace
 

@@ -136,3 +136,40 @@ def test_full_size_stream_equals_oracle_65536x5_256_ticks():
         assert [key(r) for r in ra] == [key(r) for r in rb] and len(ra) >= sub * (S - 4)
     assert total > G * (R + 1) * S * LAUNCHES * 0.95
     assert eng.state_digest() == ora.state_digest() and eng.stream_digest() == ora.stream_digest()
+
+
+def test_fold_mt_equals_fold_on_every_thread_count():
+    """jr_fsm_fold_mt (a pool of spinning-then-sleeping workers, groups partitioned over threads) == jr_fsm_fold, call after
+    call, with the thread count changing between calls and pauses long enough for the workers to fall asleep."""
+    import ctypes as C
+    import random
+    import time
+    from josefine_b200 import abi
+    from josefine_b200.raft import load_engine_library
+    lib = load_engine_library()
+    G, R = 6000, 5
+    recs = (abi.FsmRecord * (G * 4))()
+    n = 0
+    for node in range(1, R + 1):
+        for g in range(G):
+            if node == 1:
+                for kind, cnt in ((0, 64), (1, 64)):
+                    r = recs[n]
+                    r.group, r.hdr, r.id0, r.addr = g, kind | (node << 2) | (cnt << 8), 100 + g % 7, 0
+                    n += 1
+            elif node == 2:                                   # one masked APPLY record for all four followers
+                r = recs[n]
+                r.group, r.hdr, r.id0, r.addr = g, 0 | (node << 2) | (60 << 8), 90 + g % 5, 0b11110
+                n += 1
+
+    def run(threads):
+        applied, tot = (C.c_uint32 * (G * R))(), (C.c_uint64 * 3)()
+        assert lib.jr_fsm_fold_mt(C.cast(recs, C.c_void_p), C.c_size_t(n), G, R, applied, tot, threads) == 0
+        return list(tot), list(applied)
+
+    ref = run(1)
+    rng = random.Random(5)
+    for rep in range(60):
+        assert run(rng.choice([2, 3, 4, 8])) == ref
+        if rep % 20 == 19:
+            time.sleep(0.01)                                  # > the workers' spin window: the next call has to wake them
