@@ -646,7 +646,8 @@ class Bench:
                         "run-length: one {base, stride} per group and step (jr_run_token_runs); the same tokens",
                "d2h_bytes_per_step": G * 16 + (rec_bytes[0] // steps if with_output else 0), "ms_per_step": dt * 1e3 / steps,
                "commit_last": checks[-1], "faulted_replicas": faults,
-               "timing": "host wall clock around all timed steps incl. the final sync, max over ranks"}
+               "timing": "host wall clock around all timed steps incl. the final sync, max over ranks",
+               "l2": "steps run back to back, no flush in between: one step moves ~0.4 GB through DRAM (profiles/, ncu), more than the 126 MB L2"}
         if trace is not None:
             out["host_ms_per_step"] = {k: v * 1e3 / steps for k, v in trace.items()}      # timed steps only
         if with_output:
