@@ -320,7 +320,7 @@ struct SymGroup {
     }
     out.ae = 1;                                            // replicate() follows: one AppendEntries per peer
     out.mk = maxkey;
-    if (!SPLIT) replicate<false>(ph_f, mode_f, maxkey, out);
+    if (!SPLIT) replicate(ph_f, mode_f, maxkey, out);
   }
   // replicate, leader.rs:124-174: Probe -> range(head..).nth(1); Replicate -> range(head..).skip(1).take(5), over the
   // leader's table as it stood when its largest key was `mk`.  The one-lane kernel runs it inside the leader's tick.  In
@@ -328,15 +328,13 @@ struct SymGroup {
   // {progress head, mode, max key} the leader lane put in its mail -- the same rows, read through fetch_sent, the same
   // blocks; it takes a sixth of the leader's chain off the critical lane.  (The leader lane runs this once itself, for
   // the outbox the launch leaves behind.)
-  template <bool VIEW>
   __device__ __forceinline__ void replicate(uint32_t phf, uint32_t modef, uint32_t mk, SymMail& out) {
     const uint32_t take = modef ? JR_MAX_AE_BLOCKS : 1u;
     uint32_t bid = max(phf, tbase), pulled = 0, nb = 0;
     while (pulled < 1 + take) {
       uint32_t nx = ABSENT; uint64_t tk = 0;
       while (bid <= mk) {
-        if (VIEW) fetch_sent(bid, mk, n_app, nx, tk);
-        else fetch(L, bid, nx, tk);
+        fetch(L, bid, nx, tk);
         if (nx != ABSENT) break;
         ++bid;
       }
@@ -920,7 +918,7 @@ __global__ void __launch_bounds__(2 * SYM2_GROUPS, JR_SYM2_MINCTAS) sym2_kernel(
     if (lead) {
       last.hb = la.x & 1u; last.ae = (la.x >> 1) & 1u;
       last.hb_commit = la.y;
-      if (last.ae) s.template replicate<false>(s.ph_f, s.mode_f, s.maxkey, last);   // what the last tick sent: the outbox it leaves behind
+      if (last.ae) s.replicate(s.ph_f, s.mode_f, s.maxkey, last);   // what the last tick sent: the outbox it leaves behind
       sym_leave_leader(s, last, cur_last);
     } else {
       last.hbr = lc.x & 1u; last.hbr_has = (lc.x >> 1) & 1u; last.ar = (lc.x >> 2) & 1u;
