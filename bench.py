@@ -367,8 +367,9 @@ class Bench:
             # (NCCL's own channel count: capped at 2 the 2 x 1 MB all-gather took 134 us, at 1 channel 255 us)
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
         global FOLD_THREADS
-        if FOLD_THREADS <= 0:     # the box's cgroup may allow far fewer cores than it shows: leave one for this rank's submitting thread
-            FOLD_THREADS = max(1, min(8, effective_cores() // self.world - 1))
+        if FOLD_THREADS <= 0:     # the box's cgroup may allow far fewer cores than it shows, and the fold pool's workers spin between two
+            #                       batches: stay clear of the quota (a throttled cgroup stalls every thread, the submitting one included)
+            FOLD_THREADS = max(1, min(8, effective_cores() // self.world - 2))
         self.stream = torch.cuda.Stream()      # explicit non-default stream: handle 0 would mean "engine's own"
         torch.cuda.set_stream(self.stream)
         self.flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
