@@ -505,6 +505,9 @@ __global__ void truncate_kernel(const Dev d, uint32_t margin, const uint8_t* ski
   if (floor <= old) return;
   for (uint32_t b = old; b < floor && b - old < d.cap; ++b)
     for (uint32_t r = 0; r < d.R; ++r) d.cnext[(size_t)(b & d.capm) * plane + (size_t)r * d.Gp + g] = ABSENT;
+  // a replica that was not waited for (silenced / faulted) may have lost every block it held: an empty table's largest key is 0
+  for (uint32_t r = 0; r < d.R; ++r)
+    if (d.mk[(size_t)r * d.Gp + g] < floor) d.mk[(size_t)r * d.Gp + g] = 0;
   d.tb[g] = floor;
 }
 

@@ -241,3 +241,96 @@ def test_token_runs_on_device_code():
 @pytest.mark.gpu
 def test_token_runs_on_gpu():
     assert case_token_runs_equal_tokens(_gpu, G=1500) == 1500
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Randomised scripts: every launch shape the fused calls have, with faults, silenced and revived nodes, proposals aimed at
+# followers, holes in the token grid, truncation (explicit and fused) and compaction thrown in -- so groups enter the
+# fold, abort out of it in the middle of a launch (either lane of sym2_kernel first), fall back to step_kernel and come
+# back.  After every launch the folding engine, the never-folding engine and the oracle must agree on everything.
+
+def _random_script(make, seed, rounds=9):
+    import random
+    rng = random.Random(seed)
+    G, R = rng.choice([(40, 3), (64, 5), (33, 5), (24, 7)])
+    cfg = dict(seed=seed, chain_capacity=512, fsm_units=512, fsm_host_records=G * R * 1024,
+               heartbeat_ms=rng.choice([100, 100, 99, 250]), mailbox_units=64)
+    apis = trio(make, G, R, **cfg)
+    lead = rng.choice([1, 2]) if seed % 3 else 1
+    for api in apis:
+        _bootstrap(api, G, R, node=lead)
+        api.run(100, 100, 10, 1)
+        api.leader_table()
+    now, tick = 1100, 0
+    auto = None
+    folded_any = unfolded_any = False
+    for rnd in range(rounds):
+        kind = rng.choice(["run", "run", "tokens", "token_runs", "proposals"])
+        ticks = rng.choice([2, 3, 7, 16, 21, 33])
+        if rng.random() < 0.25:                              # switch the fused truncation on / off / to another margin
+            auto = rng.choice([None, 3, 6, 9])
+            for api in apis:
+                api.set_auto_truncate(auto)
+        if kind == "run":
+            n_synth = rng.choice([0, 1, 1, 2])
+            for api in apis:
+                api.run(now, 100, ticks, n_synth)
+        elif kind == "tokens":
+            toks = strided_tokens(ticks, G, tick)
+            for k in range(ticks):
+                if rng.random() < 0.2:
+                    toks[k] = [0] * G                        # a tick without proposals
+                elif rng.random() < 0.2:
+                    toks[k] = [t if rng.random() < 0.7 else 0 for t in toks[k]]   # holes
+            for api in apis:
+                api.run_tokens(now, 100, toks)
+        elif kind == "token_runs":
+            runs = [(((rnd + 1) << 44) + g + 1 if rng.random() < 0.9 else 0, rng.choice([1, 1 << 20, 1 << 32])) for g in range(G)]
+            for api in apis:
+                api.run_token_runs(now, 100, ticks, runs)
+        else:                                                # dense proposals, some aimed at followers / nobody
+            props = [[(rng.choice([1, 1, 1, 2, 0, R]) if rng.random() < 0.15 else 1, 9000 + 1000 * rnd + 37 * k + g) for g in range(G)]
+                     for k in range(ticks)]
+            for api in apis:
+                api.run_proposals(now, 100, props)
+        now += 100 * ticks
+        tick += ticks
+        n = apis[0].fold_count()
+        folded_any |= n > 0
+        unfolded_any |= n < G
+        assert apis[1].fold_count() == 0
+        if auto is None and rng.random() < 0.5:
+            m = rng.choice([2, 5, 8])
+            for api in apis:
+                api.truncate(m)
+        same(apis, chain_ids=0)
+        r = rng.random()
+        if r < 0.2:
+            permille = rng.choice([100, 300])
+            assert len({api.kill_leaders(seed * 31 + rnd, permille) for api in apis}) == 1
+        elif r < 0.4:
+            g, node, alive = rng.randrange(G), rng.randrange(1, R + 1), rng.random() < 0.4
+            for api in apis:
+                api.set_alive(g, node, alive)
+        elif r < 0.5:
+            for api in apis:
+                api.compact()
+        if rng.random() < 0.5:
+            for api in apis:
+                api.leader_table()                           # re-announce: routes follow the (possibly silenced) leaders
+    reqs = [(g, n, max(int(apis[0].query(g, n).chain_floor), 0), 24) for g in range(0, G, 5) for n in (1, R)]
+    assert apis[0].chain_read_many(reqs) == apis[1].chain_read_many(reqs) == apis[2].chain_read_many(reqs)
+    return folded_any, unfolded_any
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_scripts_on_device_code(seed):
+    folded_any, _ = _random_script(_emu, seed)
+    assert folded_any
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [100, 101, 102, 103])
+def test_random_scripts_on_gpu(seed):
+    folded_any, _ = _random_script(_gpu, seed, rounds=12)
+    assert folded_any
