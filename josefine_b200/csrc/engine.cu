@@ -803,6 +803,7 @@ struct jr_engine {
   bool auto_trunc = false;      // jr_set_auto_truncate
   uint32_t auto_trunc_margin = 0;
   int no_fold = 0;              // JR_NO_FOLD=1 (A/B, tests)
+  int no_parts_hint = 0;        // JR_NO_PARTS_HINT=1 (A/B): always cut step_kernel's grid in parts, even while the fold takes every group
   int sym_one_lane = 0;         // JR_SYM_ONE_LANE=1 (A/B, tests): sym_kernel (one lane per group) instead of sym2_kernel
   uint64_t launches_folded = 0;
   bool last_launch_folded = false;
@@ -943,7 +944,7 @@ static jr_status launch_step_once(jr_engine* e, const StepParams& p_in) {
   // mapped host memory), step_kernel's CTAs only look at symblk and return: do not cut them in parts, which would cost
   // each of them a ticket and two barriers first.  A wrong guess costs balance in that one launch, nothing else.
   if (p.symdone && !e->sym_one_lane && e->h_unfolded && (*e->h_unfolded == 0 || p.epoch - *e->h_unfolded > 2u * 8u) && !e->force_parts)
-    if (!getenv("JR_NO_PARTS_HINT")) p.n_parts = 1;
+    if (!e->no_parts_hint) p.n_parts = 1;
   p.part_ticks = (p.n_ticks + p.n_parts - 1) / p.n_parts;
   p.n_parts = (p.n_ticks + p.part_ticks - 1) / p.part_ticks;  // no empty trailing part
   p.n_blocks = n_blocks;
@@ -1120,6 +1121,7 @@ jr_status jr_engine_create(const jr_config* cfg, jr_engine** out) {
     if (aerr == cudaSuccess) aerr = cudaHostGetDevicePointer((void**)&e->d.hunf, (void*)e->h_unfolded, 0);
     if (const char* ev = getenv("JR_NO_FOLD")) e->no_fold = atoi(ev);
     if (const char* ev = getenv("JR_SYM_ONE_LANE")) e->sym_one_lane = atoi(ev);
+    if (const char* ev = getenv("JR_NO_PARTS_HINT")) e->no_parts_hint = atoi(ev);
     if (const char* ev = getenv("JR_FSM_COPY")) e->fsm_copy_by_sm = strcmp(ev, "sm") == 0;
     if (const char* ev = getenv("JR_PARTS")) e->force_parts = (uint32_t)std::min(std::max(atoi(ev), 0), 8);
 #ifndef JR_EMU
