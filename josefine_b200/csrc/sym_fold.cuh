@@ -1,28 +1,34 @@
-// sym_fold.cuh -- the symmetric-group fold: a whole fused launch of a group in ONE lane.
+// sym_fold.cuh -- the symmetric-group fold: a whole fused launch of a group in TWO lanes (sym2_kernel), or in one
+// (sym_kernel, the first version: A/B and fallback, JR_SYM_ONE_LANE=1).
 //
 // In a healthy group every follower is in the same state: same term, same head and commit, the same mail from the
 // leader in flight, and the leader holds the same progress entry for each of them.  R-1 replicas then make the same
-// decisions on the same data, tick after tick.  This kernel exploits that symmetry exactly, not approximately:
-// one lane holds the leader's state and ONE follower state that stands for all R-1 followers, keeps the mail
-// between them in registers (it only ever has the shapes listed below), and applies the very handlers of
-// raft_device.cuh -- restated here for scalar operands, each citing the same reference lines -- for all n ticks
-// of the launch.  No mailboxes, no shared memory, no barriers, no divergence between roles; what is left is the data
-// that really has to move: the proposal tokens in, the block-table rows of every replica and the Instruction
-// stream out.
+// decisions on the same data, tick after tick.  These kernels exploit that symmetry exactly, not approximately:
+// the leader's state and ONE follower state that stands for all R-1 followers, the mail between them in its canonical
+// shapes (listed below), and the very handlers of raft_device.cuh -- restated here for scalar operands, each citing
+// the same reference lines -- for all n ticks of the launch.  No mailboxes in HBM, no divergence between roles; what
+// is left is the data that really has to move: the proposal tokens in, the block-table rows of every replica and the
+// Instruction stream out.  sym2_kernel runs the two sides in two lanes of two warps (within a tick they only depend on
+// the previous tick's mail), with the mail, the row caches and the Instruction encoders in shared memory and one
+// barrier per tick; sym_kernel runs both in one lane with the mail in registers.
 //
 // Exactness contract:
-//   * sym_kernel first CHECKS that a group is symmetric and that its mail in flight has the canonical shapes
-//     (sym_enter); every other group is left to step_kernel untouched.
-//   * If anything outside the canonical evolution would happen during the launch (a fault, an election timer
-//     that could fire, a HeartbeatResponse{has_committed: false}, ...) the lane ABORTS: it has only written
-//     block-table rows and raw Instruction entries that step_kernel writes identically when it re-runs the group
-//     from the untouched state planes, so an abort costs time, never correctness.
-//   * On success the lane writes the replicas' state planes, progress planes, the mailboxes of the last tick in the
-//     exact unit layout step_kernel produces, and encodes the Instruction streams with the same fsm_flush.
+//   * Both FIRST CHECK that a group is symmetric, that its followers' tables agree over every id the launch can read,
+//     and that its mail in flight has the canonical shapes (sym_enter); every other group is left to step_kernel
+//     untouched.
+//   * If anything outside the canonical evolution would happen during the launch (a fault, an election timer that
+//     could fire, a HeartbeatResponse{has_committed: false}, a read below the compared rows, ...) the lane ABORTS (in
+//     sym2_kernel: tells the other lane through the mail, and both check the other's last mail after the last
+//     barrier): it has only written block-table rows and Instruction records beyond the FIFO counters, which
+//     step_kernel writes identically when it re-runs the group from the untouched state planes -- an abort costs time,
+//     never correctness.
+//   * On success the replicas' state planes, progress planes and the mailboxes of the last tick are written in the
+//     exact unit layout step_kernel produces, and the Instruction streams leave through the same streaming encoder
+//     fsm_flush uses (fsm_enc_push), fed as the Instructions are produced.
 //   * Stream digests (JR_F_STREAM_DIGEST) need every Message in order, which this path never materialises: engines
 //     created with that flag, or with JR_F_SLED_COMMIT_KEY_STRICT / JR_F_NO_SYMMETRIC_FOLD, never take it.
 //     tests/test_sym_fold.py compares folded runs with step_kernel runs and with the oracle through everything else:
-//     replica state, block tables, leader tables, Instruction streams.
+//     replica state, block tables, leader tables, Instruction streams -- scenario by scenario and over random scripts.
 //
 // Canonical mail (all that can be in flight in a symmetric group):
 //   leader -> each follower, in this order:  [Heartbeat{term, commit}]  [AppendEntries{term, <= 5 blocks}]
