@@ -544,8 +544,8 @@ __global__ void node_restart_kernel(const Dev d, uint32_t g, uint32_t r, uint64_
 // ---- Instruction-stream drain -----------------------------------------------------------------
 // Records sit in per-replica FIFOs ([2*rec + half][replica][group]).  The drain packs them into one dense
 // array in thread order i = replica * Gp + group -- sorted by (node, group), FIFO per replica -- with an exclusive
-// scan over the per-replica counts, then writes them (to device memory, or straight into mapped pinned host
-// memory) and empties the FIFOs.
+// scan over the per-replica counts, writes them to a device staging buffer and empties the FIFOs; the copy engine
+// takes the batch to pinned host memory (fsm_records_enqueue).
 constexpr uint32_t SCAN_THREADS = 1024;
 struct FsmHeader {          // written by fsm_pack_kernel next to the records
   unsigned long long n_records, n_dropped, n_instructions;
