@@ -334,3 +334,11 @@ def test_random_scripts_on_device_code(seed):
 def test_random_scripts_on_gpu(seed):
     folded_any, _ = _random_script(_gpu, seed, rounds=12)
     assert folded_any
+
+
+@pytest.mark.parametrize("seed", [3, 8])
+def test_random_scripts_one_lane_kernel_on_device_code(seed, monkeypatch):
+    """The one-lane sym_kernel (JR_SYM_ONE_LANE=1: A/B and fallback) obeys the same contract."""
+    monkeypatch.setenv("JR_SYM_ONE_LANE", "1")
+    folded_any, _ = _random_script(_emu, seed)
+    assert folded_any
