@@ -249,12 +249,13 @@ def test_token_runs_on_gpu():
 # fold, abort out of it in the middle of a launch (either lane of sym2_kernel first), fall back to step_kernel and come
 # back.  After every launch the folding engine, the never-folding engine and the oracle must agree on everything.
 
-def _random_script(make, seed, rounds=9):
+def _random_script(make, seed, rounds=9, **cfg_over):
     import random
     rng = random.Random(seed)
     G, R = rng.choice([(40, 3), (64, 5), (33, 5), (24, 7)])
     cfg = dict(seed=seed, chain_capacity=512, fsm_units=512, fsm_host_records=G * R * 1024,
                heartbeat_ms=rng.choice([100, 100, 99, 250]), mailbox_units=64)
+    cfg.update(cfg_over)
     apis = trio(make, G, R, **cfg)
     lead = rng.choice([1, 2]) if seed % 3 else 1
     for api in apis:
