@@ -170,8 +170,8 @@ typedef struct jr_config {
                                 * config.rs:23) and reaches the others over TCP: non-resident
                                 * nodes are never stepped, and mail addressed to them is only
                                 * returned through out_msgs for the host to forward.           */
-  uint32_t fsm_host_records;   /* records one jr_fsm_records_async batch may hold (pinned host memory, two
-                                * buffers of this size); 0 = max(3 * n_groups * n_replicas + 1024,
+  uint32_t fsm_host_records;   /* records one jr_fsm_records_async batch may hold (pinned host memory,
+                                * JR_STAGING_DEPTH buffers of this size); 0 = max(3 * n_groups * n_replicas + 1024,
                                 * min(n_groups * n_replicas * fsm_units, 65536))                            */
   uint32_t fsm_raw_units;      /* scratch: raw Instructions one replica may emit per launch before they are encoded into
                                 * records at the launch's end; 0 = 192.  jr_run* cut their work into launches of at most
@@ -350,6 +350,11 @@ typedef struct jr_leader_entry {
 typedef struct jr_engine jr_engine;
 
 /* ---- lifecycle ------------------------------------------------------------- */
+/* Page-locked host memory for the buffers the asynchronous calls read or fill (jr_run_tokens / jr_run_token_runs input,
+ * jr_leader_table_async output): a host that binds this ABI over FFI has no CUDA runtime of its own to ask.  Pageable
+ * memory also works everywhere -- the copies are then staged and the calls block for their duration. */
+jr_status jr_host_alloc(size_t bytes, void** out);
+void jr_host_free(void* p);
 /* JR_E_INVAL for a configuration RaftConfig::validate (config.rs:60-84) rejects where the field exists here
  * (heartbeat_ms < 5, election_min_ms < 5), for an empty election range (follower.rs:103-108 gen_range would
  * panic) and for sizes outside the engine's limits. */

@@ -2148,6 +2148,21 @@ jr_status jr_truncate(jr_engine* e, uint32_t margin) {
   return JR_OK;
 }
 
+jr_status jr_host_alloc(size_t bytes, void** out) {
+  if (!out || !bytes) return JR_E_INVAL;
+  *out = nullptr;
+  cudaError_t err = cudaHostAlloc(out, bytes, 0);
+  if (err != cudaSuccess) {
+    set_err("cudaHostAlloc(%zu bytes): %s", bytes, cudaGetErrorString(err));
+    return err == cudaErrorMemoryAllocation ? JR_E_NOMEM : JR_E_CUDA;
+  }
+  return JR_OK;
+}
+
+void jr_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 jr_status jr_set_auto_truncate(jr_engine* e, int enabled, uint32_t margin) {
   if (!e) return JR_E_INVAL;
   e->auto_trunc = enabled != 0;

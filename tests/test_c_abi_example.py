@@ -10,16 +10,35 @@ from josefine_b200.raft import ENGINE_LIB_PATH
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _build(tmp_path):
-    exe = tmp_path / "multi_node"
+def _build(tmp_path, name="multi_node", lib=ENGINE_LIB_PATH):
+    exe = tmp_path / name
     subprocess.check_call(["gcc", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"),
-                           os.path.join(ROOT, "examples", "multi_node.c"), ENGINE_LIB_PATH,
-                           "-Wl,-rpath," + os.path.dirname(ENGINE_LIB_PATH), "-o", str(exe)])
+                           os.path.join(ROOT, "examples", name + ".c"), lib,
+                           "-Wl,-rpath," + os.path.dirname(lib), "-o", str(exe)])
     return exe
 
 
 def test_example_compiles_against_the_header(tmp_path):
     _build(tmp_path)      # CPU: the header is valid C and every symbol the example uses links
+    _build(tmp_path, "batched_quantum")
+
+
+def test_batched_quantum_example_runs_on_the_device_code(tmp_path):
+    """examples/batched_quantum.c -- the hot path's loop from plain C -- linked against the host build of
+    the device code (tests/emu): same C ABI, same kernels, no GPU."""
+    from tests.emu.emu import LIB_PATH as EMU_LIB_PATH
+    exe = _build(tmp_path, "batched_quantum", EMU_LIB_PATH)
+    out = subprocess.run([str(exe), "96", "4"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.strip().endswith("OK") and "96 of 96 groups elected a leader" in out.stdout
+
+
+@pytest.mark.gpu
+def test_batched_quantum_example_runs(tmp_path):
+    exe = _build(tmp_path, "batched_quantum")
+    out = subprocess.run([str(exe), "4096", "8"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.strip().endswith("OK") and "4096 of 4096 groups elected a leader" in out.stdout
 
 
 @pytest.mark.gpu
