@@ -166,6 +166,21 @@ extern "C" {
     fn jr_run_tokens(e: *mut c_void, now0_ms: u64, dt_ms: u32, n_steps: u32, tokens: *const u64) -> c_int;
     fn jr_query(e: *mut c_void, group: u32, node: u32, out: *mut JrReplicaState) -> c_int;
     fn jr_last_error() -> *const c_char;
+    // The batched calls a broker hosting many groups per process would use instead (INTEGRATION.md section 2a;
+    // examples/batched_quantum.c is that loop in C).  Declared for completeness: this shim keeps josefine's
+    // one-node-per-process shape and does not call them.
+    #[allow(dead_code)]
+    fn jr_host_alloc(bytes: usize, out: *mut *mut c_void) -> c_int;
+    #[allow(dead_code)]
+    fn jr_host_free(p: *mut c_void);
+    #[allow(dead_code)]
+    fn jr_set_auto_truncate(e: *mut c_void, enabled: c_int, margin: u32) -> c_int;
+    #[allow(dead_code)]
+    fn jr_run_token_runs(e: *mut c_void, now0_ms: u64, dt_ms: u32, n_steps: u32, runs: *const [u64; 2]) -> c_int;
+    #[allow(dead_code)]
+    fn jr_fsm_records_async(e: *mut c_void) -> c_int;
+    #[allow(dead_code)]
+    fn jr_fsm_records_wait(e: *mut c_void, records: *mut *const c_void, batch: *mut c_void) -> c_int;
 }
 
 // Command discriminants, in the order of `enum Command` (src/raft/mod.rs:160-227)
